@@ -1,0 +1,41 @@
+"""pytest configuration: markers, paths and shared fixtures.
+
+``-m "not gpu"`` : oracle vs golden vectors, host logic, C-ABI symbol checks (runs without a GPU).
+``-m gpu``       : parity tests proper -- the CUDA path through the C-ABI against the oracle.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REFERENCE = "/root/reference"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "reference: needs /root/reference (authoring container only)")
+
+
+def pytest_collection_modifyitems(config, items):
+    have_ref = os.path.isdir(os.path.join(REFERENCE, "nesr"))
+    for item in items:
+        if "reference" in item.keywords and not have_ref:
+            item.add_marker(pytest.mark.skip(reason="/root/reference not present"))
+
+
+@pytest.fixture(scope="session")
+def golden():
+    def load(name):
+        return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+    return load
+
+
+@pytest.fixture(scope="session")
+def photo_bgr(golden):
+    """64x80 natural-image crop (BGR u8) committed with the fixtures."""
+    return golden("esrgan_x2.npz")["crop_bgr"]
