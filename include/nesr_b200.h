@@ -1,0 +1,164 @@
+/*
+ * nesr_b200.h -- C ABI of libnesr_b200.so: the B200 (sm_100a) implementation of NESR's
+ * Real-ESRGAN x2plus upscaling stage.
+ *
+ * The reference (gddickinson/neural_enhanced_super_resolution) is pure Python and has no FFI layer;
+ * its operator boundary for this path is duck-typing on two third-party classes plus three methods
+ * of its own pipeline class.  Every entry point below names the reference interface it stands
+ * behind (paths are into the reference tree).  The ctypes binding a maintainer would add is in
+ * INTEGRATION.md; the shipped Python mirror is neural_enhanced_super_resolution_b200/_ffi.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative NESR_E_* code otherwise; the message is
+ *     available from nesr_b200_last_error().  No exceptions or abort() cross this boundary.
+ *   - the caller allocates all image buffers; the library owns weights, activation arenas, its
+ *     CUDA stream and its tensor maps.  A handle is bound to one CUDA device and may be used from
+ *     any ONE thread at a time (the reference calls from a QThread: nesr/gui/app.py:72-134).
+ *   - NESR_PTR_* flags say whether an image pointer is host or device memory.  Host pointers are
+ *     copied with cudaMemcpyAsync on the handle's stream (pinned memory makes that asynchronous).
+ *   - there is NO CPU fallback: without a CUDA device nesr_b200_create() fails.
+ */
+#ifndef NESR_B200_H_
+#define NESR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NESR_B200_ABI_VERSION 1
+
+enum {
+  NESR_OK = 0,
+  NESR_E_INVALID = -1,   /* bad argument / unsupported geometry */
+  NESR_E_CUDA = -2,      /* CUDA runtime or driver error */
+  NESR_E_WEIGHTS = -3,   /* unknown / mis-shaped / missing tensor */
+  NESR_E_STATE = -4,     /* call order (e.g. enhance before finalize) */
+  NESR_E_NOMEM = -5
+};
+
+enum {                   /* 16-bit operand formats of tcgen05 kind::f16 */
+  NESR_FMT_BF16 = 0,
+  NESR_FMT_FP16 = 1
+};
+
+enum {                   /* pointer-kind flags */
+  NESR_PTR_IN_DEVICE = 1,
+  NESR_PTR_OUT_DEVICE = 2
+};
+
+typedef struct nesr_b200_handle nesr_b200_handle;
+
+/* Architecture + precision.  Mirrors the constructor the reference calls:
+ *   RRDBNet(num_in_ch, num_out_ch, scale, num_feat, num_block, num_grow_ch)
+ *   -- nesr/nesr.py:216, standalone/direct_esrgan.py:104, standalone/superres_project.py:69.
+ * x2plus is {3, 3, 2, 64, 23, 32}.  This build supports scale == 2, num_feat == 64,
+ * num_grow_ch == 32, num_in_ch == num_out_ch == 3 and any num_block >= 1. */
+typedef struct nesr_b200_config {
+  int32_t abi_version;        /* NESR_B200_ABI_VERSION */
+  int32_t device;             /* CUDA ordinal */
+  int32_t num_in_ch;
+  int32_t num_out_ch;
+  int32_t scale;
+  int32_t num_feat;
+  int32_t num_block;
+  int32_t num_grow_ch;
+  int32_t body_format;        /* residual-dense-block convs: NESR_FMT_BF16 (default) | NESR_FMT_FP16 */
+  int32_t edge_format;        /* conv_first/body/up1/up2/hr/last:  NESR_FMT_FP16 (default) | NESR_FMT_BF16 */
+  int32_t conv_impl;          /* 0 = tcgen05/TMEM/TMA kernels (product).  1 = SIMT validation kernel:
+                                 test-only cross-check of the tensor path, never selected implicitly */
+  int32_t reserved0;
+  int64_t max_batch_pixels;   /* cap on feature-grid pixels resident per batch; 0 = default */
+} nesr_b200_config;
+
+typedef struct nesr_b200_stats {
+  int64_t kernel_launches;    /* kernels this handle launched since creation */
+  int64_t conv_launches;      /* ... of which tcgen05 conv kernels */
+  int64_t tiles_processed;
+  double  last_device_ms;     /* CUDA-event time of the last enhance/forward call (device part only) */
+  double  last_conv_ms;       /* ... conv kernels only (first to last conv of the call) */
+  int64_t arena_bytes;        /* activation arena currently allocated */
+} nesr_b200_stats;
+
+/* Fills *cfg with the x2plus defaults for `device`. */
+void nesr_b200_default_config(nesr_b200_config* cfg, int32_t device);
+
+/* Replaces: RRDBNet(...) construction + RealESRGANer.__init__ device placement
+ * (realesrgan/utils.py ctor; nesr/nesr.py:216-229). */
+int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out);
+int nesr_b200_destroy(nesr_b200_handle* h);
+
+/* Message of the most recent failure on this handle (h may be NULL: failure of create). */
+const char* nesr_b200_last_error(const nesr_b200_handle* h);
+
+/* Replaces: model.load_state_dict(loadnet['params_ema'|'params'], strict=True)
+ * (RealESRGANer.__init__; call site nesr/nesr.py:220-229).  `name` is the checkpoint key, e.g.
+ * "body.7.rdb2.conv3.weight"; data is host fp32, conv weights OIHW.  Unknown names and shape
+ * mismatches fail (strict).  finalize fails unless every tensor was supplied; it repacks the
+ * weights into the 16-bit K-major tap/chunk layout the kernels read and uploads them. */
+int nesr_b200_load_weight(nesr_b200_handle* h, const char* name, const float* data,
+                          const int64_t* shape, int32_t ndim);
+int nesr_b200_finalize_weights(nesr_b200_handle* h);
+
+/* Replaces: RealESRGANer.enhance(img, outscale=None) for 8-bit 3-channel input
+ * (standalone/superres_project.py:282, standalone/direct_esrgan.py:148, pre-HEAD nesr/nesr.py):
+ * BGR HWC u8 -> /255 -> RGB -> reflect pre_pad / mod-pad -> pixel_unshuffle(2) -> RRDBNet ->
+ * tile_process paste (tile > 0) -> post-crop -> clamp -> BGR -> round-half-even u8.
+ * in: H x W x 3 (in_stride bytes per row); out: 2H x 2W x 3.  tile == 0 processes the image whole.
+ * For scale 2 `tile` and `tile_pad` must be even (upstream's un-shuffle asserts the same). */
+int nesr_b200_enhance_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32_t H, int32_t W,
+                         int64_t in_stride, int32_t tile, int32_t tile_pad, int32_t pre_pad,
+                         uint8_t* out_bgr, int64_t out_stride, int32_t flags);
+
+/* Throughput mode (BASELINE config 4): n equally sized frames, each exactly as enhance_u8.
+ * Frame f starts at in + f*in_frame_stride / out + f*out_frame_stride. */
+int nesr_b200_enhance_batch_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32_t n_frames,
+                               int32_t H, int32_t W, int64_t in_stride, int64_t in_frame_stride,
+                               int32_t tile, int32_t tile_pad, int32_t pre_pad, uint8_t* out_bgr,
+                               int64_t out_stride, int64_t out_frame_stride, int32_t flags);
+
+/* Tile-sharded form of enhance_u8 (multi-GPU: BASELINE config 3).  Processes only tiles
+ * [tile_first, tile_first + tile_count) of upstream's row-major tile_process grid and pastes them
+ * into `out_bgr`, which addresses the FULL 2H x 2W output (pixels of other tiles are untouched).
+ * nesr_b200_tile_count reports the size of the grid. */
+int nesr_b200_tile_count(int32_t H, int32_t W, int32_t tile, int32_t pre_pad, int32_t scale);
+int nesr_b200_enhance_tiles_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32_t H, int32_t W,
+                               int64_t in_stride, int32_t tile, int32_t tile_pad, int32_t pre_pad,
+                               int32_t tile_first, int32_t tile_count, uint8_t* out_bgr,
+                               int64_t out_stride, int32_t flags);
+
+/* Replaces: RRDBNet.forward / `upsampler.model(x)` (nesr/nesr.py:887-891,930-935): device fp32
+ * NCHW [n, num_in_ch, H, W] in [0,1] -> device fp32 NCHW [n, num_out_ch, 2H, 2W], unclamped.
+ * Both pointers are device memory; `stream` is a cudaStream_t the call is ordered after and
+ * before (the torch current stream), or NULL for the handle's own stream. */
+int nesr_b200_forward_nchw_f32(nesr_b200_handle* h, const float* x, int32_t n, int32_t H,
+                               int32_t W, float* y, void* stream);
+
+/* Replaces: SuperResolutionPipeline._ensemble_results (nesr/nesr.py:1033-1054) for K >= 2
+ * equally sized H x W x 3 u8 members: acc(f32) += f64(img) * w[i] rounded to f32 per member,
+ * truncated to u8.  weights == NULL means the reference's uniform 1/K. */
+int nesr_b200_blend_u8(nesr_b200_handle* h, const uint8_t* const* members, int32_t K, int32_t H,
+                       int32_t W, const double* weights, uint8_t* out, int32_t flags);
+
+/* Replaces: SuperResolutionPipeline._postprocess_image with adaptive_sharpening on
+ * (nesr/nesr.py:1056-1084): RGB (or BGR with bgr != 0) H x W x 3 u8 -> same layout, bit-exact
+ * with cv2 4.13's fixed-point path. */
+int nesr_b200_sharpen_u8(nesr_b200_handle* h, const uint8_t* in, int32_t H, int32_t W,
+                         int32_t bgr, uint8_t* out, int32_t flags);
+
+int nesr_b200_get_stats(const nesr_b200_handle* h, nesr_b200_stats* out);
+int nesr_b200_synchronize(nesr_b200_handle* h);
+
+/* Test hook: run ONE 3x3 conv layer of the given geometry through the selected implementation
+ * on caller-provided device buffers (used by tests/ to compare the tcgen05 kernel with the SIMT
+ * validation kernel tap by tap).  See csrc/engine.cu. */
+int nesr_b200_debug_conv(nesr_b200_handle* h, int32_t impl, int32_t fmt, int32_t H, int32_t W,
+                         int32_t cin, int32_t cout, const float* weight_oihw, const float* bias,
+                         const float* x_nchw_host, int32_t lrelu, float* y_nchw_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NESR_B200_H_ */

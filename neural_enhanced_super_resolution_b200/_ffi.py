@@ -1,0 +1,279 @@
+"""ctypes binding of ``libnesr_b200.so`` (C ABI: ``include/nesr_b200.h``).
+
+This is the whole Python<->CUDA boundary: plain pointers and sizes, no torch types.  torch is used
+only by callers for device memory hand-off (``tensor.data_ptr()``).  There is no CPU fallback: a
+missing library or a missing CUDA device raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libnesr_b200.so")
+ABI_VERSION = 1
+FMT_BF16, FMT_FP16 = 0, 1
+PTR_IN_DEVICE, PTR_OUT_DEVICE = 1, 2
+
+EXPORTS = (
+    "nesr_b200_default_config", "nesr_b200_create", "nesr_b200_destroy", "nesr_b200_last_error",
+    "nesr_b200_load_weight", "nesr_b200_finalize_weights", "nesr_b200_enhance_u8",
+    "nesr_b200_enhance_batch_u8", "nesr_b200_tile_count", "nesr_b200_enhance_tiles_u8",
+    "nesr_b200_forward_nchw_f32", "nesr_b200_blend_u8", "nesr_b200_sharpen_u8", "nesr_b200_get_stats",
+    "nesr_b200_synchronize", "nesr_b200_debug_conv",
+)
+
+
+class Config(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("num_in_ch", C.c_int32),
+                ("num_out_ch", C.c_int32), ("scale", C.c_int32), ("num_feat", C.c_int32),
+                ("num_block", C.c_int32), ("num_grow_ch", C.c_int32), ("body_format", C.c_int32),
+                ("edge_format", C.c_int32), ("conv_impl", C.c_int32), ("reserved0", C.c_int32),
+                ("max_batch_pixels", C.c_int64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int64), ("conv_launches", C.c_int64), ("tiles_processed", C.c_int64),
+                ("last_device_ms", C.c_double), ("last_conv_ms", C.c_double), ("arena_bytes", C.c_int64)]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def load_library() -> C.CDLL:
+    """Load the shared library and declare every prototype.  Raises if it has not been built."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError(
+                f"{_LIB_PATH} not found: build it with `python -m neural_enhanced_super_resolution_b200._build` "
+                "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for this path.")
+        lib = C.CDLL(_LIB_PATH)
+        H = C.c_void_p
+        u8p, f32p, i64p = C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)
+        lib.nesr_b200_default_config.argtypes = [C.POINTER(Config), C.c_int32]
+        lib.nesr_b200_default_config.restype = None
+        lib.nesr_b200_create.argtypes = [C.POINTER(Config), C.POINTER(H)]
+        lib.nesr_b200_destroy.argtypes = [H]
+        lib.nesr_b200_last_error.argtypes = [H]
+        lib.nesr_b200_last_error.restype = C.c_char_p
+        lib.nesr_b200_load_weight.argtypes = [H, C.c_char_p, f32p, i64p, C.c_int32]
+        lib.nesr_b200_finalize_weights.argtypes = [H]
+        lib.nesr_b200_enhance_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                             C.c_int32, u8p, C.c_int64, C.c_int32]
+        lib.nesr_b200_enhance_batch_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                                   C.c_int32, C.c_int32, C.c_int32, u8p, C.c_int64, C.c_int64,
+                                                   C.c_int32]
+        lib.nesr_b200_tile_count.argtypes = [C.c_int32] * 5
+        lib.nesr_b200_enhance_tiles_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                                   C.c_int32, C.c_int32, C.c_int32, u8p, C.c_int64, C.c_int32]
+        lib.nesr_b200_forward_nchw_f32.argtypes = [H, f32p, C.c_int32, C.c_int32, C.c_int32, f32p, C.c_void_p]
+        lib.nesr_b200_blend_u8.argtypes = [H, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32,
+                                           C.POINTER(C.c_double), u8p, C.c_int32]
+        lib.nesr_b200_sharpen_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int32, u8p, C.c_int32]
+        lib.nesr_b200_get_stats.argtypes = [H, C.POINTER(Stats)]
+        lib.nesr_b200_synchronize.argtypes = [H]
+        lib.nesr_b200_debug_conv.argtypes = [H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                             f32p, f32p, f32p, C.c_int32, f32p]
+        for name in EXPORTS:
+            fn = getattr(lib, name)
+            if name not in ("nesr_b200_default_config", "nesr_b200_last_error"):
+                fn.restype = C.c_int
+        _lib = lib
+        return lib
+
+
+def _is_torch_cuda(x) -> bool:
+    return hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
+
+
+def _image_ptr(img):
+    """(address, is_device) of a contiguous u8 image held in numpy or in a torch CUDA tensor."""
+    if _is_torch_cuda(img):
+        if not img.is_contiguous() or str(img.dtype) != "torch.uint8":
+            raise ValueError("device images must be contiguous torch.uint8")
+        import torch
+        torch.cuda.current_stream(img.device).synchronize()   # the library works on its own stream
+        return img.data_ptr(), True
+    arr = img
+    if not isinstance(arr, np.ndarray) or arr.dtype != np.uint8 or not arr.flags["C_CONTIGUOUS"]:
+        raise ValueError("host images must be C-contiguous numpy uint8 arrays")
+    return arr.ctypes.data, False
+
+
+class Engine:
+    """One ``nesr_b200_handle``: weights + arenas + stream on one GPU.  Not thread-safe."""
+
+    def __init__(self, device: int = 0, num_block: int = 23, body_format: int = FMT_BF16,
+                 edge_format: int = FMT_FP16, conv_impl: int = 0, max_batch_pixels: int = 0,
+                 num_in_ch: int = 3, num_out_ch: int = 3, scale: int = 2, num_feat: int = 64,
+                 num_grow_ch: int = 32):
+        self._lib = load_library()
+        cfg = Config()
+        self._lib.nesr_b200_default_config(C.byref(cfg), int(device))
+        cfg.num_block, cfg.body_format, cfg.edge_format = int(num_block), int(body_format), int(edge_format)
+        cfg.conv_impl, cfg.max_batch_pixels = int(conv_impl), int(max_batch_pixels)
+        cfg.num_in_ch, cfg.num_out_ch, cfg.scale = int(num_in_ch), int(num_out_ch), int(scale)
+        cfg.num_feat, cfg.num_grow_ch = int(num_feat), int(num_grow_ch)
+        self.config = cfg
+        self.device = int(device)
+        self.scale = int(scale)
+        self._h = C.c_void_p()
+        rc = self._lib.nesr_b200_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.nesr_b200_last_error(None).decode()
+            self._h = C.c_void_p()
+            raise RuntimeError(f"nesr_b200_create failed ({rc}): {msg}")
+
+    # -- plumbing ----------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.nesr_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self._lib.nesr_b200_last_error(self._h).decode()}")
+
+    # -- weights -----------------------------------------------------------------------------
+    def load_state_dict(self, state_dict) -> None:
+        """strict load of a checkpoint ``state_dict`` (torch tensors or numpy arrays, fp32 OIHW)."""
+        for name, t in state_dict.items():
+            a = t.detach().cpu().float().contiguous().numpy() if hasattr(t, "detach") else np.ascontiguousarray(t, np.float32)
+            shape = (C.c_int64 * a.ndim)(*a.shape)
+            self._check(self._lib.nesr_b200_load_weight(self._h, name.encode(), a.ctypes.data, shape, a.ndim),
+                        f"load_weight({name})")
+        self._check(self._lib.nesr_b200_finalize_weights(self._h), "finalize_weights")
+
+    # -- RealESRGANer.enhance ----------------------------------------------------------------
+    def _alloc_like(self, img, shape):
+        if _is_torch_cuda(img):
+            import torch
+            return torch.empty(shape, dtype=torch.uint8, device=img.device)
+        return np.empty(shape, dtype=np.uint8)
+
+    def enhance_u8(self, img, tile: int = 0, tile_pad: int = 10, pre_pad: int = 0, out=None):
+        h, w = img.shape[:2]
+        if img.ndim != 3 or img.shape[2] != 3:
+            raise ValueError("enhance_u8 expects H x W x 3")
+        if out is None:
+            out = self._alloc_like(img, (h * self.scale, w * self.scale, 3))
+        ip, idev = _image_ptr(img)
+        op, odev = _image_ptr(out)
+        flags = (PTR_IN_DEVICE if idev else 0) | (PTR_OUT_DEVICE if odev else 0)
+        self._check(self._lib.nesr_b200_enhance_u8(self._h, ip, h, w, w * 3, tile, tile_pad, pre_pad, op,
+                                                   w * self.scale * 3, flags), "enhance_u8")
+        return out
+
+    def enhance_batch_u8(self, frames, tile: int = 0, tile_pad: int = 10, pre_pad: int = 0, out=None):
+        n, h, w = frames.shape[:3]
+        if out is None:
+            out = self._alloc_like(frames, (n, h * self.scale, w * self.scale, 3))
+        ip, idev = _image_ptr(frames)
+        op, odev = _image_ptr(out)
+        flags = (PTR_IN_DEVICE if idev else 0) | (PTR_OUT_DEVICE if odev else 0)
+        s = self.scale
+        self._check(self._lib.nesr_b200_enhance_batch_u8(self._h, ip, n, h, w, w * 3, h * w * 3, tile, tile_pad,
+                                                         pre_pad, op, w * s * 3, h * s * w * s * 3, flags),
+                    "enhance_batch_u8")
+        return out
+
+    def tile_count(self, h: int, w: int, tile: int, pre_pad: int = 0) -> int:
+        n = self._lib.nesr_b200_tile_count(h, w, tile, pre_pad, self.scale)
+        if n < 0:
+            raise ValueError("bad tile_count arguments")
+        return n
+
+    def enhance_tiles_u8(self, img, out, tile: int, tile_pad: int, pre_pad: int, first: int, count: int):
+        """Process tiles [first, first+count) of the tile grid into ``out`` (full-size output)."""
+        h, w = img.shape[:2]
+        ip, idev = _image_ptr(img)
+        op, odev = _image_ptr(out)
+        flags = (PTR_IN_DEVICE if idev else 0) | (PTR_OUT_DEVICE if odev else 0)
+        self._check(self._lib.nesr_b200_enhance_tiles_u8(self._h, ip, h, w, w * 3, tile, tile_pad, pre_pad, first,
+                                                         count, op, w * self.scale * 3, flags), "enhance_tiles_u8")
+        return out
+
+    # -- RRDBNet.forward ---------------------------------------------------------------------
+    def forward_nchw(self, x):
+        import torch
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
+            raise ValueError("forward_nchw expects a CUDA float32 NCHW tensor")
+        x = x.contiguous()
+        n, c, h, w = x.shape
+        if c != self.config.num_in_ch:
+            raise RuntimeError(f"expected {self.config.num_in_ch} input channels, got {c}")
+        y = torch.empty((n, self.config.num_out_ch, h * self.scale, w * self.scale), dtype=torch.float32, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        self._check(self._lib.nesr_b200_forward_nchw_f32(self._h, x.data_ptr(), n, h, w, y.data_ptr(),
+                                                         C.c_void_p(stream)), "forward_nchw_f32")
+        return y
+
+    # -- post-process ------------------------------------------------------------------------
+    def blend_u8(self, members, weights=None, out=None):
+        k = len(members)
+        h, w = members[0].shape[:2]
+        ptrs, dev = [], None
+        for m in members:
+            if tuple(m.shape) != (h, w, 3):
+                raise ValueError("blend members must share one H x W x 3 shape")
+            p, d = _image_ptr(m)
+            if dev is not None and d != dev:
+                raise ValueError("blend members must all be host or all be device images")
+            dev = d
+            ptrs.append(p)
+        if out is None:
+            out = self._alloc_like(members[0], (h, w, 3))
+        op, odev = _image_ptr(out)
+        arr = (C.c_void_p * k)(*ptrs)
+        wts = None if weights is None else (C.c_double * k)(*[float(v) for v in weights])
+        flags = (PTR_IN_DEVICE if dev else 0) | (PTR_OUT_DEVICE if odev else 0)
+        self._check(self._lib.nesr_b200_blend_u8(self._h, arr, k, h, w, wts, op, flags), "blend_u8")
+        return out
+
+    def sharpen_u8(self, img, bgr: bool = False, out=None):
+        h, w = img.shape[:2]
+        if out is None:
+            out = self._alloc_like(img, (h, w, 3))
+        ip, idev = _image_ptr(img)
+        op, odev = _image_ptr(out)
+        flags = (PTR_IN_DEVICE if idev else 0) | (PTR_OUT_DEVICE if odev else 0)
+        self._check(self._lib.nesr_b200_sharpen_u8(self._h, ip, h, w, int(bool(bgr)), op, flags), "sharpen_u8")
+        return out
+
+    # -- misc --------------------------------------------------------------------------------
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self._lib.nesr_b200_get_stats(self._h, C.byref(s)), "get_stats")
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def synchronize(self) -> None:
+        self._check(self._lib.nesr_b200_synchronize(self._h), "synchronize")
+
+    def debug_conv(self, x, weight, bias, lrelu: bool = False, impl: int = 0, fmt: int = FMT_BF16):
+        """One 3x3 conv on host fp32 arrays (x: C x H x W, weight: O x C x 3 x 3) -> O x H x W fp32."""
+        x = np.ascontiguousarray(x, np.float32)
+        weight = np.ascontiguousarray(weight, np.float32)
+        bias = np.ascontiguousarray(bias, np.float32)
+        cin, h, w = x.shape
+        cout = weight.shape[0]
+        y = np.empty((cout, h, w), np.float32)
+        self._check(self._lib.nesr_b200_debug_conv(self._h, impl, fmt, h, w, cin, cout, weight.ctypes.data,
+                                                   bias.ctypes.data, x.ctypes.data, int(bool(lrelu)), y.ctypes.data),
+                    "debug_conv")
+        return y

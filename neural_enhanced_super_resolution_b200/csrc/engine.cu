@@ -1,0 +1,867 @@
+// engine.cu -- host side of libnesr_b200.so: handle, weight repack, tile plan, activation arena,
+// layer schedule and the extern "C" entry points declared in include/nesr_b200.h.
+//
+// What it replaces in the reference stack (Python): RRDBNet construction + load_state_dict,
+// RealESRGANer.pre_process / tile_process / post_process / enhance (realesrgan 0.3.0, restated in
+// oracle/realesrganer.py) and RRDBNet.forward (basicsr 1.4.2, oracle/rrdbnet.py).
+//
+// Schedule: ALL tiles of a call (and all frames of a batch) advance through the network together,
+// one kernel launch per conv layer, so every launch has thousands of 128-pixel M-blocks to spread
+// over the 148 SMs.  The dense-block concat is two ping-pong [pixels][192] buffers written at
+// channel offsets; the residual trunk is carried in fp32 ([pixels][64]) next to its 16-bit copy.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "../../include/nesr_b200.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+using namespace nesr;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Layer {
+  std::string name;
+  int cin = 0, cout = 0;      // true channel counts
+  int cin16 = 0;              // cin rounded up to 16 (MMA K step)
+  int nchunk = 0;             // 64-channel chunks
+  int npad = 0;               // MMA N
+  int fmt = 0;                // NESR_FMT_*
+  int w_row0 = 0;             // first row in the packed arena
+  int bias_off = 0;           // floats into the bias arena
+};
+
+struct LevelPlan {
+  int64_t pixels = 0;         // flat pixels incl. guards
+  std::vector<BlockRef> blocks;
+  BlockRef* d_blocks = nullptr;
+};
+
+struct PlanKey {
+  int n_frames = -1, H = 0, W = 0, tile = 0, tile_pad = 0, pre_pad = 0, first = 0, count = 0, whole = 0;
+  bool operator==(const PlanKey& o) const {
+    return n_frames == o.n_frames && H == o.H && W == o.W && tile == o.tile && tile_pad == o.tile_pad &&
+           pre_pad == o.pre_pad && first == o.first && count == o.count && whole == o.whole;
+  }
+};
+
+struct Batch {
+  std::vector<TileGeom> tiles;
+  TileGeom* d_tiles = nullptr;
+  LevelPlan lv[3];
+};
+
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t bytes = 0;
+  // sub-buffers
+  void* x0 = nullptr;         // [P0][64] 16-bit network input (12 channels used)
+  void* d[2] = {nullptr, nullptr};   // [P0][192] dense-block ping-pong
+  float* trunk = nullptr;     // [P0][64] fp32 residual trunk
+  float* rrdb = nullptr;      // [P0][64] fp32 RRDB input
+  float* feat = nullptr;      // [P0][64] fp32 conv_first output (long skip)
+  void* g2 = nullptr;         // [P1][64]
+  void* g4[2] = {nullptr, nullptr};  // [P2][64]
+  int64_t P[3] = {0, 0, 0};
+  CUtensorMap m_x0, m_d[2], m_g2, m_g4[2];
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct nesr_b200_handle {
+  nesr_b200_config cfg{};
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evc0 = nullptr, evc1 = nullptr;
+  EncodeTiledFn encode = nullptr;
+  std::string error;
+
+  std::vector<Layer> layers;
+  std::map<std::string, std::vector<float>> staged;   // checkpoint tensors by name
+  std::map<std::string, std::vector<int64_t>> expect; // expected shapes
+  bool finalized = false;
+  uint16_t* d_wpack = nullptr;
+  int64_t w_rows = 0;
+  float* d_bias = nullptr;
+  CUtensorMap m_w[3];                                  // box rows 16 / 32 / 64
+
+  PlanKey key;
+  std::vector<Batch> batches;
+  Arena arena;
+
+  uint8_t* d_in = nullptr;  size_t d_in_bytes = 0;
+  uint8_t* d_out = nullptr; size_t d_out_bytes = 0;
+  uint8_t* d_tmp = nullptr; size_t d_tmp_bytes = 0;
+
+  nesr_b200_stats stats{};
+};
+
+namespace {
+
+int fail(nesr_b200_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->error = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                        \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      return fail(h, NESR_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+uint16_t to16(float v, int fmt) {
+  if (fmt == NESR_FMT_FP16) {
+    __half hh = __float2half_rn(v);
+    uint16_t r; memcpy(&r, &hh, 2); return r;
+  }
+  __nv_bfloat16 b = __float2bfloat16_rn(v);
+  uint16_t r; memcpy(&r, &b, 2); return r;
+}
+
+uint32_t hw_fmt(int fmt) { return fmt == NESR_FMT_BF16 ? 1u : 0u; }   // tcgen05 encoding: 0 = f16, 1 = bf16
+
+// ----------------------------------------------------------------------------------------------
+// layer table
+// ----------------------------------------------------------------------------------------------
+void add_layer(nesr_b200_handle* h, const std::string& name, int cin, int cout, int fmt) {
+  Layer L;
+  L.name = name; L.cin = cin; L.cout = cout; L.fmt = fmt;
+  L.cin16 = (int)round_up(cin, 16);
+  L.nchunk = (L.cin16 + kChunkChannels - 1) / kChunkChannels;
+  L.npad = cout <= 16 ? 16 : (cout <= 32 ? 32 : 64);
+  h->layers.push_back(L);
+  h->expect[name + ".weight"] = {cout, cin, 3, 3};
+  h->expect[name + ".bias"] = {cout};
+}
+
+void build_layers(nesr_b200_handle* h) {
+  const nesr_b200_config& c = h->cfg;
+  const int in_ch = c.num_in_ch * (c.scale == 2 ? 4 : 1);
+  add_layer(h, "conv_first", in_ch, c.num_feat, c.edge_format);
+  for (int i = 0; i < c.num_block; ++i)
+    for (int j = 1; j <= 3; ++j) {
+      const std::string p = "body." + std::to_string(i) + ".rdb" + std::to_string(j) + ".conv";
+      for (int k = 1; k <= 4; ++k) add_layer(h, p + std::to_string(k), c.num_feat + (k - 1) * c.num_grow_ch, c.num_grow_ch, c.body_format);
+      add_layer(h, p + "5", c.num_feat + 4 * c.num_grow_ch, c.num_feat, c.body_format);
+    }
+  add_layer(h, "conv_body", c.num_feat, c.num_feat, c.edge_format);
+  add_layer(h, "conv_up1", c.num_feat, c.num_feat, c.edge_format);
+  add_layer(h, "conv_up2", c.num_feat, c.num_feat, c.edge_format);
+  add_layer(h, "conv_hr", c.num_feat, c.num_feat, c.edge_format);
+  add_layer(h, "conv_last", c.num_feat, c.num_out_ch, c.edge_format);
+  int64_t rows = 0;
+  int boff = 0;
+  for (Layer& L : h->layers) {
+    L.w_row0 = (int)rows;
+    rows += (int64_t)9 * L.nchunk * L.npad;
+    L.bias_off = boff;
+    boff += 64;
+  }
+  h->w_rows = rows;
+}
+
+const Layer* find_layer(const nesr_b200_handle* h, const std::string& name) {
+  for (const Layer& L : h->layers) if (L.name == name) return &L;
+  return nullptr;
+}
+
+// Packed weight layout (16-bit): row ((tap*nchunk + chunk)*npad + n) holds the 64 input channels
+// [chunk*64, chunk*64+64) of output channel n at tap (ky,kx) -- K-major rows of 128 B, exactly one
+// TMA box [npad x 64] per (tap, chunk).  Padding channels are zero.
+void pack_layer(const Layer& L, const float* w_oihw, uint16_t* arena) {
+  for (int t = 0; t < 9; ++t)
+    for (int c = 0; c < L.nchunk; ++c)
+      for (int n = 0; n < L.npad; ++n) {
+        uint16_t* row = arena + ((int64_t)L.w_row0 + ((int64_t)t * L.nchunk + c) * L.npad + n) * 64;
+        for (int k = 0; k < 64; ++k) {
+          const int ci = c * 64 + k;
+          float v = 0.f;
+          if (n < L.cout && ci < L.cin) v = w_oihw[((int64_t)n * L.cin + ci) * 9 + t];
+          row[k] = to16(v, L.fmt);
+        }
+      }
+}
+
+int make_map(nesr_b200_handle* h, CUtensorMap* m, void* base, int64_t channels, int64_t rows, int box_rows) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)channels, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)channels * 2};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, NESR_E_CUDA, "cuTensorMapEncodeTiled failed (%d) ch=%lld rows=%lld", (int)r,
+                                     (long long)channels, (long long)rows);
+  return NESR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// tile plan (upstream RealESRGANer.pre_process + tile_process geometry, oracle/realesrganer.py)
+// ----------------------------------------------------------------------------------------------
+struct Grid {
+  int H2 = 0, W2 = 0, tiles_x = 1, tiles_y = 1;
+};
+
+Grid tile_grid_dims(int H, int W, int tile, int pre_pad, int scale) {
+  Grid g;
+  const int mod = scale == 2 ? 2 : 1;
+  g.H2 = (int)round_up(H + pre_pad, mod);
+  g.W2 = (int)round_up(W + pre_pad, mod);
+  if (tile > 0) {
+    g.tiles_x = (g.W2 + tile - 1) / tile;
+    g.tiles_y = (g.H2 + tile - 1) / tile;
+  }
+  return g;
+}
+
+void free_batches(nesr_b200_handle* h) {
+  for (Batch& b : h->batches) {
+    if (b.d_tiles) cudaFree(b.d_tiles);
+    for (LevelPlan& l : b.lv) if (l.d_blocks) cudaFree(l.d_blocks);
+  }
+  h->batches.clear();
+  h->key = PlanKey();
+}
+
+void layout_level(Batch& b, int level) {
+  int64_t cursor = 0;
+  int prev_pitch = 0;
+  LevelPlan& lp = b.lv[level];
+  lp.blocks.clear();
+  for (size_t i = 0; i < b.tiles.size(); ++i) {
+    LevelGeom& g = b.tiles[i].lv[level];
+    cursor += round_up(std::max(prev_pitch, g.pitch) + 1, kBlockPixels);   // zero guard
+    g.base = (int32_t)cursor;
+    const int64_t n = (int64_t)g.h * g.pitch;
+    for (int64_t j = 0; j < n; j += kBlockPixels) lp.blocks.push_back(BlockRef{(int32_t)(cursor + j), (int32_t)i});
+    cursor += round_up(n, kBlockPixels);
+    prev_pitch = g.pitch;
+  }
+  cursor += round_up(prev_pitch + 1, kBlockPixels);
+  lp.pixels = cursor;
+}
+
+int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
+  if (h->key == key && !h->batches.empty()) return NESR_OK;
+  free_batches(h);
+  const int scale = h->cfg.scale;
+  const Grid g = tile_grid_dims(key.H, key.W, key.tile, key.pre_pad, scale);
+  std::vector<TileGeom> all;
+  const int ntile = g.tiles_x * g.tiles_y;
+  const int first = key.whole ? 0 : key.first;
+  const int count = key.whole ? ntile : key.count;
+  if (first < 0 || count < 0 || first + count > ntile)
+    return fail(h, NESR_E_INVALID, "tile range [%d,%d) outside the %d-tile grid", first, first + count, ntile);
+  for (int f = 0; f < key.n_frames; ++f)
+    for (int ti = first; ti < first + count; ++ti) {
+      const int ty = ti / g.tiles_x, tx = ti % g.tiles_x;
+      int y0 = 0, y1 = g.H2, x0 = 0, x1 = g.W2, y0p = 0, y1p = g.H2, x0p = 0, x1p = g.W2;
+      if (key.tile > 0) {
+        x0 = tx * key.tile; y0 = ty * key.tile;
+        x1 = std::min(x0 + key.tile, g.W2); y1 = std::min(y0 + key.tile, g.H2);
+        x0p = std::max(x0 - key.tile_pad, 0); x1p = std::min(x1 + key.tile_pad, g.W2);
+        y0p = std::max(y0 - key.tile_pad, 0); y1p = std::min(y1 + key.tile_pad, g.H2);
+      }
+      const int th = y1p - y0p, tw = x1p - x0p;
+      if ((th | tw) & 1)
+        return fail(h, NESR_E_INVALID,
+                    "tile %d has odd extent %dx%d: pixel_unshuffle(2) needs even tiles (use even tile / tile_pad)", ti, tw, th);
+      TileGeom t{};
+      t.frame = f; t.src_y0 = y0p; t.src_x0 = x0p;
+      const int fh = th / 2, fw = tw / 2;
+      for (int l = 0; l < 3; ++l) {
+        t.lv[l].h = fh << l; t.lv[l].w = fw << l; t.lv[l].pitch = (fw << l) + 1; t.lv[l].base = 0;
+      }
+      t.crop_y = (y0 - y0p) * scale; t.crop_x = (x0 - x0p) * scale;
+      t.out_y0 = y0 * scale; t.out_x0 = x0 * scale;
+      t.crop_h = std::max(0, std::min((y1 - y0) * scale, out_h - t.out_y0));
+      t.crop_w = std::max(0, std::min((x1 - x0) * scale, out_w - t.out_x0));
+      all.push_back(t);
+    }
+  // split into batches bounded by feature pixels
+  const int64_t cap = h->cfg.max_batch_pixels > 0 ? h->cfg.max_batch_pixels : (int64_t)3 << 20;
+  size_t i = 0;
+  while (i < all.size()) {
+    Batch b;
+    int64_t px = 0;
+    while (i < all.size()) {
+      const int64_t n = (int64_t)all[i].lv[0].h * all[i].lv[0].pitch;
+      if (!b.tiles.empty() && px + n > cap) break;
+      b.tiles.push_back(all[i]);
+      px += n;
+      ++i;
+    }
+    for (int l = 0; l < 3; ++l) layout_level(b, l);
+    if (b.lv[2].pixels >= ((int64_t)1 << 31) - 4096) return fail(h, NESR_E_INVALID, "batch too large for 32-bit pixel indices");
+    h->batches.push_back(std::move(b));
+  }
+  // upload
+  int64_t P[3] = {0, 0, 0};
+  for (Batch& b : h->batches) {
+    CUDA_TRY(h, cudaMalloc(&b.d_tiles, b.tiles.size() * sizeof(TileGeom)));
+    CUDA_TRY(h, cudaMemcpyAsync(b.d_tiles, b.tiles.data(), b.tiles.size() * sizeof(TileGeom), cudaMemcpyHostToDevice, h->stream));
+    for (int l = 0; l < 3; ++l) {
+      LevelPlan& lp = b.lv[l];
+      CUDA_TRY(h, cudaMalloc(&lp.d_blocks, std::max<size_t>(1, lp.blocks.size()) * sizeof(BlockRef)));
+      CUDA_TRY(h, cudaMemcpyAsync(lp.d_blocks, lp.blocks.data(), lp.blocks.size() * sizeof(BlockRef), cudaMemcpyHostToDevice, h->stream));
+      P[l] = std::max(P[l], lp.pixels);
+    }
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));      // host vectors may now be reused
+  // arena (sized for the largest batch)
+  Arena& a = h->arena;
+  const size_t sz_x0 = round_up(P[0] * 64 * 2, 1024), sz_d = round_up(P[0] * kDense * 2, 1024);
+  const size_t sz_f = round_up(P[0] * 64 * 4, 1024), sz_g2 = round_up(P[1] * 64 * 2, 1024), sz_g4 = round_up(P[2] * 64 * 2, 1024);
+  const size_t need = sz_x0 + 2 * sz_d + 3 * sz_f + sz_g2 + 2 * sz_g4;
+  if (need > a.bytes) {
+    if (a.base) cudaFree(a.base);
+    a.base = nullptr; a.bytes = 0;
+    cudaError_t e = cudaMalloc(&a.base, need);
+    if (e != cudaSuccess) return fail(h, NESR_E_NOMEM, "activation arena of %zu bytes: %s", need, cudaGetErrorString(e));
+    a.bytes = need;
+  }
+  uint8_t* p = a.base;
+  a.x0 = p; p += sz_x0;
+  a.d[0] = p; p += sz_d; a.d[1] = p; p += sz_d;
+  a.g2 = p; p += sz_g2;
+  a.g4[0] = p; p += sz_g4; a.g4[1] = p; p += sz_g4;
+  const size_t zero_bytes = (size_t)(p - a.base);     // every buffer a conv reads: pads must be zero
+  a.trunk = (float*)p; p += sz_f; a.rrdb = (float*)p; p += sz_f; a.feat = (float*)p; p += sz_f;
+  for (int l = 0; l < 3; ++l) a.P[l] = P[l];
+  CUDA_TRY(h, cudaMemsetAsync(a.base, 0, zero_bytes, h->stream));
+  int rc;
+  if ((rc = make_map(h, &a.m_x0, a.x0, 64, P[0], kBlockPixels))) return rc;
+  for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.m_d[i2], a.d[i2], kDense, P[0], kBlockPixels))) return rc;
+  if ((rc = make_map(h, &a.m_g2, a.g2, 64, P[1], kBlockPixels))) return rc;
+  for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.m_g4[i2], a.g4[i2], 64, P[2], kBlockPixels))) return rc;
+  h->stats.arena_bytes = (int64_t)a.bytes;
+  h->key = key;
+  return NESR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// network schedule
+// ----------------------------------------------------------------------------------------------
+struct ConvIO {
+  const CUtensorMap* amap = nullptr;
+  const void* src = nullptr;
+  int src_pitch = 0;
+  int level = 0;
+};
+
+int run_conv(nesr_b200_handle* h, const Batch& b, const Layer& L, const ConvIO& io, ConvParams p, cudaStream_t s) {
+  const LevelPlan& lp = b.lv[io.level];
+  p.blocks = lp.d_blocks; p.tiles = b.d_tiles; p.nblk = (int)lp.blocks.size(); p.level = io.level;
+  p.src = io.src; p.src_pitch = io.src_pitch; p.cin = L.cin16;
+  p.wpack = h->d_wpack; p.w_row0 = L.w_row0; p.npad = L.npad; p.fmt = L.fmt;
+  p.idesc = umma_idesc_f16(hw_fmt(L.fmt), (uint32_t)L.npad);
+  p.bias = h->d_bias + L.bias_off; p.cout = L.cout;
+  cudaError_t e;
+  if (h->cfg.conv_impl == 1) {
+    e = launch_conv3x3_simt(p, s);
+  } else {
+    const CUtensorMap& wm = h->m_w[L.npad == 16 ? 0 : (L.npad == 32 ? 1 : 2)];
+    e = launch_conv3x3_tc(*io.amap, wm, p, h->num_sms, s);
+    h->stats.conv_launches++;
+  }
+  h->stats.kernel_launches++;
+  if (e != cudaSuccess) return fail(h, NESR_E_CUDA, "conv %s launch failed: %s", L.name.c_str(), cudaGetErrorString(e));
+  return NESR_OK;
+}
+
+struct Sink {
+  uint8_t* out_u8 = nullptr; int64_t out_stride = 0, out_frame_stride = 0;
+  float* out_f32 = nullptr; int out_h = 0, out_w = 0;
+};
+
+int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in, const Sink& sink, cudaStream_t s,
+                  bool time_convs) {
+  Arena& a = h->arena;
+  const nesr_b200_config& c = h->cfg;
+  int rc;
+  PackParams pk = pack_in;
+  pk.blocks = b.lv[0].d_blocks; pk.tiles = b.d_tiles; pk.nblk = (int)b.lv[0].blocks.size();
+  pk.x0 = a.x0; pk.fmt = c.edge_format;
+  cudaError_t e = launch_pack(pk, s);
+  h->stats.kernel_launches++;
+  if (e != cudaSuccess) return fail(h, NESR_E_CUDA, "pack launch failed: %s", cudaGetErrorString(e));
+  if (time_convs) cudaEventRecord(h->evc0, s);
+
+  size_t li = 0;
+  auto next = [&]() -> const Layer& { return h->layers[li++]; };
+  {  // conv_first: x0 -> trunk (fp32), feat (fp32), d[0][0:64] (16-bit copy for the first RDB)
+    ConvParams p{};
+    p.dst32a = a.trunk; p.dst32b = a.feat;
+    p.dst16 = a.d[0]; p.dst16_pitch = kDense; p.dst16_coff = 0; p.dst16_fmt = c.body_format;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_x0, a.x0, 64, 0}, p, s))) return rc;
+  }
+  int cur = 0;
+  const int nrdb = c.num_block * 3;
+  for (int r = 0; r < nrdb; ++r) {
+    const ConvIO io{&a.m_d[cur], a.d[cur], kDense, 0};
+    for (int k = 1; k <= 4; ++k) {   // x_k = lrelu(conv_k(cat(x, x1..x_{k-1})))  -> channels [64+32(k-1), +32)
+      ConvParams p{};
+      p.lrelu = 1;
+      p.dst16 = a.d[cur]; p.dst16_pitch = kDense; p.dst16_coff = kFeat + (k - 1) * kGrow; p.dst16_fmt = c.body_format;
+      if ((rc = run_conv(h, b, next(), io, p, s))) return rc;
+    }
+    ConvParams p{};                  // x5*0.2 + x  (+ RRDB skip on every third block)
+    p.res1 = a.trunk; p.s1 = 0.2f;
+    p.dst32a = a.trunk;
+    if (r % 3 == 2) {
+      p.res2 = (r == 2) ? a.feat : a.rrdb; p.s2 = 0.2f;
+      p.dst32b = a.rrdb;
+    }
+    p.dst16 = a.d[cur ^ 1]; p.dst16_pitch = kDense; p.dst16_coff = 0;
+    p.dst16_fmt = (r == nrdb - 1) ? c.edge_format : c.body_format;    // conv_body reads the last one
+    if ((rc = run_conv(h, b, next(), io, p, s))) return rc;
+    cur ^= 1;
+  }
+  {  // conv_body + long skip, stored nearest-x2 upsampled into level 1
+    ConvParams p{};
+    p.res1 = a.feat; p.s1 = 1.0f;
+    p.dst16 = a.g2; p.dst16_pitch = 64; p.dst16_fmt = c.edge_format; p.dst16_up = 1;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_d[cur], a.d[cur], kDense, 0}, p, s))) return rc;
+  }
+  {  // conv_up1 + lrelu, stored upsampled into level 2
+    ConvParams p{};
+    p.lrelu = 1;
+    p.dst16 = a.g4[0]; p.dst16_pitch = 64; p.dst16_fmt = c.edge_format; p.dst16_up = 1;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g2, a.g2, 64, 1}, p, s))) return rc;
+  }
+  {  // conv_up2 + lrelu
+    ConvParams p{};
+    p.lrelu = 1;
+    p.dst16 = a.g4[1]; p.dst16_pitch = 64; p.dst16_fmt = c.edge_format;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], a.g4[0], 64, 2}, p, s))) return rc;
+  }
+  {  // conv_hr + lrelu
+    ConvParams p{};
+    p.lrelu = 1;
+    p.dst16 = a.g4[0]; p.dst16_pitch = 64; p.dst16_fmt = c.edge_format;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[1], a.g4[1], 64, 2}, p, s))) return rc;
+  }
+  {  // conv_last -> clamp, BGR, u8, halo crop + stitch  (or unclamped fp32 NCHW)
+    ConvParams p{};
+    p.out_u8 = sink.out_u8; p.out_stride = sink.out_stride; p.out_frame_stride = sink.out_frame_stride;
+    p.out_f32 = sink.out_f32; p.out_h = sink.out_h; p.out_w = sink.out_w;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], a.g4[0], 64, 2}, p, s))) return rc;
+  }
+  if (time_convs) cudaEventRecord(h->evc1, s);
+  h->stats.tiles_processed += (int64_t)b.tiles.size();
+  return NESR_OK;
+}
+
+int ensure(nesr_b200_handle* h, uint8_t** buf, size_t* cap, size_t need) {
+  if (need <= *cap) return NESR_OK;
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr; *cap = 0;
+  cudaError_t e = cudaMalloc(buf, need);
+  if (e != cudaSuccess) return fail(h, NESR_E_NOMEM, "device image buffer of %zu bytes: %s", need, cudaGetErrorString(e));
+  *cap = need;
+  return NESR_OK;
+}
+
+int enhance_impl(nesr_b200_handle* h, const uint8_t* in, int n_frames, int H, int W, int64_t in_stride,
+                 int64_t in_frame_stride, int tile, int tile_pad, int pre_pad, int first, int count, int whole,
+                 uint8_t* out, int64_t out_stride, int64_t out_frame_stride, int flags) {
+  if (!h) return NESR_E_INVALID;
+  if (!h->finalized) return fail(h, NESR_E_STATE, "weights not finalized");
+  if (!in || !out || n_frames < 1 || H < 2 || W < 2) return fail(h, NESR_E_INVALID, "bad image arguments (H=%d W=%d n=%d)", H, W, n_frames);
+  if (tile < 0 || tile_pad < 0 || pre_pad < 0 || pre_pad >= H || pre_pad >= W)
+    return fail(h, NESR_E_INVALID, "bad tile/pad arguments (tile=%d tile_pad=%d pre_pad=%d)", tile, tile_pad, pre_pad);
+  if (in_stride < (int64_t)W * 3 || out_stride < (int64_t)W * h->cfg.scale * 3) return fail(h, NESR_E_INVALID, "row stride smaller than a row");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const int s = h->cfg.scale, OH = H * s, OW = W * s;
+  PlanKey key; key.n_frames = n_frames; key.H = H; key.W = W; key.tile = tile; key.tile_pad = tile_pad;
+  key.pre_pad = pre_pad; key.first = first; key.count = count; key.whole = whole;
+  int rc = build_plan(h, key, OH, OW);
+  if (rc) return rc;
+
+  const uint8_t* d_in = in;
+  int64_t d_in_stride = in_stride, d_in_fs = in_frame_stride;
+  if (!(flags & NESR_PTR_IN_DEVICE)) {
+    d_in_stride = (int64_t)W * 3; d_in_fs = d_in_stride * H;
+    if ((rc = ensure(h, &h->d_in, &h->d_in_bytes, (size_t)d_in_fs * n_frames))) return rc;
+    for (int f = 0; f < n_frames; ++f)
+      CUDA_TRY(h, cudaMemcpy2DAsync(h->d_in + f * d_in_fs, d_in_stride, in + f * in_frame_stride, in_stride, (size_t)W * 3, H,
+                                    cudaMemcpyHostToDevice, h->stream));
+    d_in = h->d_in;
+  }
+  uint8_t* d_out = out;
+  int64_t d_out_stride = out_stride, d_out_fs = out_frame_stride;
+  if (!(flags & NESR_PTR_OUT_DEVICE)) {
+    d_out_stride = (int64_t)OW * 3; d_out_fs = d_out_stride * OH;
+    if ((rc = ensure(h, &h->d_out, &h->d_out_bytes, (size_t)d_out_fs * n_frames))) return rc;
+    d_out = h->d_out;
+    if (!whole)   // partial tile range: untouched pixels must round-trip unchanged
+      for (int f = 0; f < n_frames; ++f)
+        CUDA_TRY(h, cudaMemcpy2DAsync(d_out + f * d_out_fs, d_out_stride, out + f * out_frame_stride, out_stride, (size_t)OW * 3, OH,
+                                      cudaMemcpyHostToDevice, h->stream));
+  }
+  cudaEventRecord(h->ev0, h->stream);
+  PackParams pk{};
+  pk.in_u8 = d_in; pk.in_stride = d_in_stride; pk.in_frame_stride = d_in_fs; pk.H = H; pk.W = W; pk.pre_pad = pre_pad;
+  Sink sink; sink.out_u8 = d_out; sink.out_stride = d_out_stride; sink.out_frame_stride = d_out_fs;
+  for (size_t bi = 0; bi < h->batches.size(); ++bi)
+    if ((rc = forward_batch(h, h->batches[bi], pk, sink, h->stream, bi == 0))) return rc;
+  cudaEventRecord(h->ev1, h->stream);
+  if (!(flags & NESR_PTR_OUT_DEVICE))
+    for (int f = 0; f < n_frames; ++f)
+      CUDA_TRY(h, cudaMemcpy2DAsync(out + f * out_frame_stride, out_stride, d_out + f * d_out_fs, d_out_stride, (size_t)OW * 3, OH,
+                                    cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->stats.last_device_ms = ms;
+  if (cudaEventElapsedTime(&ms, h->evc0, h->evc1) == cudaSuccess) h->stats.last_conv_ms = ms;
+  return NESR_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+void nesr_b200_default_config(nesr_b200_config* cfg, int32_t device) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof *cfg);
+  cfg->abi_version = NESR_B200_ABI_VERSION;
+  cfg->device = device;
+  cfg->num_in_ch = 3; cfg->num_out_ch = 3; cfg->scale = 2;
+  cfg->num_feat = 64; cfg->num_block = 23; cfg->num_grow_ch = 32;
+  cfg->body_format = NESR_FMT_BF16; cfg->edge_format = NESR_FMT_FP16;
+  cfg->conv_impl = 0; cfg->max_batch_pixels = 0;
+}
+
+int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
+  if (!cfg || !out) return fail(nullptr, NESR_E_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != NESR_B200_ABI_VERSION) return fail(nullptr, NESR_E_INVALID, "ABI version %d != %d", cfg->abi_version, NESR_B200_ABI_VERSION);
+  if (cfg->scale != 2 || cfg->num_feat != 64 || cfg->num_grow_ch != 32 || cfg->num_in_ch != 3 || cfg->num_out_ch != 3 || cfg->num_block < 1)
+    return fail(nullptr, NESR_E_INVALID, "unsupported architecture: this build implements RRDBNet(3,3,scale=2,num_feat=64,num_grow_ch=32)");
+  if ((cfg->body_format | cfg->edge_format) & ~1) return fail(nullptr, NESR_E_INVALID, "bad operand format");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, NESR_E_CUDA, "no CUDA device (%s): libnesr_b200 has no CPU fallback", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, NESR_E_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+  if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail(nullptr, NESR_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) return fail(nullptr, NESR_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, NESR_E_CUDA, "device %d is sm_%d%d; libnesr_b200 is built for sm_100a (B200) only", cfg->device, prop.major, prop.minor);
+  nesr_b200_handle* h = new nesr_b200_handle();
+  h->cfg = *cfg;
+  h->num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    delete h;
+    return fail(nullptr, NESR_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  }
+  h->encode = (EncodeTiledFn)fn;
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
+      (e = cudaEventCreate(&h->evc0)) != cudaSuccess || (e = cudaEventCreate(&h->evc1)) != cudaSuccess ||
+      (e = conv3x3_tc_configure()) != cudaSuccess) {
+    std::string msg = cudaGetErrorString(e);
+    nesr_b200_destroy(h);
+    return fail(nullptr, NESR_E_CUDA, "device setup failed: %s", msg.c_str());
+  }
+  build_layers(h);
+  *out = h;
+  return NESR_OK;
+}
+
+int nesr_b200_destroy(nesr_b200_handle* h) {
+  if (!h) return NESR_OK;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  free_batches(h);
+  if (h->arena.base) cudaFree(h->arena.base);
+  if (h->d_wpack) cudaFree(h->d_wpack);
+  if (h->d_bias) cudaFree(h->d_bias);
+  if (h->d_in) cudaFree(h->d_in);
+  if (h->d_out) cudaFree(h->d_out);
+  if (h->d_tmp) cudaFree(h->d_tmp);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->evc0) cudaEventDestroy(h->evc0);
+  if (h->evc1) cudaEventDestroy(h->evc1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return NESR_OK;
+}
+
+const char* nesr_b200_last_error(const nesr_b200_handle* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int nesr_b200_load_weight(nesr_b200_handle* h, const char* name, const float* data, const int64_t* shape, int32_t ndim) {
+  if (!h || !name || !data || !shape) return fail(h, NESR_E_INVALID, "null argument");
+  auto it = h->expect.find(name);
+  if (it == h->expect.end()) return fail(h, NESR_E_WEIGHTS, "unexpected key in state_dict: %s", name);
+  const std::vector<int64_t>& want = it->second;
+  bool ok = (size_t)ndim == want.size();
+  int64_t numel = 1;
+  for (int i = 0; ok && i < ndim; ++i) { ok = shape[i] == want[i]; numel *= shape[i]; }
+  if (!ok) return fail(h, NESR_E_WEIGHTS, "size mismatch for %s", name);
+  h->staged[name].assign(data, data + numel);
+  h->finalized = false;
+  return NESR_OK;
+}
+
+int nesr_b200_finalize_weights(nesr_b200_handle* h) {
+  if (!h) return NESR_E_INVALID;
+  for (const auto& kv : h->expect)
+    if (!h->staged.count(kv.first)) return fail(h, NESR_E_WEIGHTS, "missing key in state_dict: %s", kv.first.c_str());
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  std::vector<uint16_t> arena((size_t)h->w_rows * 64, 0);
+  std::vector<float> bias(h->layers.size() * 64, 0.f);
+  for (const Layer& L : h->layers) {
+    pack_layer(L, h->staged[L.name + ".weight"].data(), arena.data());
+    const std::vector<float>& bv = h->staged[L.name + ".bias"];
+    std::copy(bv.begin(), bv.end(), bias.begin() + L.bias_off);
+  }
+  if (!h->d_wpack) CUDA_TRY(h, cudaMalloc(&h->d_wpack, arena.size() * 2));
+  if (!h->d_bias) CUDA_TRY(h, cudaMalloc(&h->d_bias, bias.size() * 4));
+  CUDA_TRY(h, cudaMemcpy(h->d_wpack, arena.data(), arena.size() * 2, cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+  const int box[3] = {16, 32, 64};
+  for (int i = 0; i < 3; ++i) {
+    int rc = make_map(h, &h->m_w[i], h->d_wpack, 64, h->w_rows, box[i]);
+    if (rc) return rc;
+  }
+  h->finalized = true;
+  return NESR_OK;
+}
+
+int nesr_b200_enhance_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32_t H, int32_t W, int64_t in_stride, int32_t tile,
+                         int32_t tile_pad, int32_t pre_pad, uint8_t* out_bgr, int64_t out_stride, int32_t flags) {
+  return enhance_impl(h, in_bgr, 1, H, W, in_stride, 0, tile, tile_pad, pre_pad, 0, 0, 1, out_bgr, out_stride, 0, flags);
+}
+
+int nesr_b200_enhance_batch_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32_t n_frames, int32_t H, int32_t W,
+                               int64_t in_stride, int64_t in_frame_stride, int32_t tile, int32_t tile_pad, int32_t pre_pad,
+                               uint8_t* out_bgr, int64_t out_stride, int64_t out_frame_stride, int32_t flags) {
+  return enhance_impl(h, in_bgr, n_frames, H, W, in_stride, in_frame_stride, tile, tile_pad, pre_pad, 0, 0, 1, out_bgr,
+                      out_stride, out_frame_stride, flags);
+}
+
+int nesr_b200_tile_count(int32_t H, int32_t W, int32_t tile, int32_t pre_pad, int32_t scale) {
+  if (H < 1 || W < 1 || tile < 0 || pre_pad < 0) return NESR_E_INVALID;
+  const Grid g = tile_grid_dims(H, W, tile, pre_pad, scale);
+  return g.tiles_x * g.tiles_y;
+}
+
+int nesr_b200_enhance_tiles_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32_t H, int32_t W, int64_t in_stride, int32_t tile,
+                               int32_t tile_pad, int32_t pre_pad, int32_t tile_first, int32_t tile_count, uint8_t* out_bgr,
+                               int64_t out_stride, int32_t flags) {
+  if (tile_count == 0) return NESR_OK;
+  return enhance_impl(h, in_bgr, 1, H, W, in_stride, 0, tile, tile_pad, pre_pad, tile_first, tile_count, 0, out_bgr, out_stride, 0, flags);
+}
+
+int nesr_b200_forward_nchw_f32(nesr_b200_handle* h, const float* x, int32_t n, int32_t H, int32_t W, float* y, void* stream) {
+  if (!h) return NESR_E_INVALID;
+  if (!h->finalized) return fail(h, NESR_E_STATE, "weights not finalized");
+  if (!x || !y || n < 1 || H < 2 || W < 2) return fail(h, NESR_E_INVALID, "bad tensor arguments");
+  if ((H | W) & 1) return fail(h, NESR_E_INVALID, "pixel_unshuffle(2): H and W must be even (got %dx%d)", H, W);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  const int sc = h->cfg.scale;
+  PlanKey key; key.n_frames = n; key.H = H; key.W = W; key.tile = 0; key.whole = 1;
+  int rc = build_plan(h, key, H * sc, W * sc);
+  if (rc) return rc;
+  if (s != h->stream) CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // plan uploads / memset ran on our stream
+  PackParams pk{};
+  pk.in_f32 = x; pk.H = H; pk.W = W; pk.pre_pad = 0;
+  Sink sink; sink.out_f32 = y; sink.out_h = H * sc; sink.out_w = W * sc;
+  for (const Batch& b : h->batches)
+    if ((rc = forward_batch(h, b, pk, sink, s, false))) return rc;
+  return NESR_OK;
+}
+
+int nesr_b200_blend_u8(nesr_b200_handle* h, const uint8_t* const* members, int32_t K, int32_t H, int32_t W, const double* weights,
+                       uint8_t* out, int32_t flags) {
+  if (!h) return NESR_E_INVALID;
+  if (!members || !out || K < 2 || K > kMaxBlendMembers || H < 1 || W < 1) return fail(h, NESR_E_INVALID, "blend: need 2..%d members", kMaxBlendMembers);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const int64_t n = (int64_t)H * W * 3;
+  BlendParams p{};
+  p.k = K; p.nbytes = n;
+  for (int i = 0; i < K; ++i) p.weights[i] = weights ? weights[i] : 1.0 / K;
+  int rc;
+  if (!(flags & NESR_PTR_IN_DEVICE)) {
+    const size_t slot = (size_t)round_up(n, 256);
+    if ((rc = ensure(h, &h->d_in, &h->d_in_bytes, slot * K))) return rc;
+    for (int i = 0; i < K; ++i) {
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_in + slot * i, members[i], n, cudaMemcpyHostToDevice, h->stream));
+      p.members[i] = h->d_in + slot * i;
+    }
+  } else {
+    for (int i = 0; i < K; ++i) p.members[i] = members[i];
+  }
+  if (!(flags & NESR_PTR_OUT_DEVICE)) {
+    if ((rc = ensure(h, &h->d_out, &h->d_out_bytes, (size_t)n))) return rc;
+    p.out = h->d_out;
+  } else {
+    p.out = out;
+  }
+  cudaEventRecord(h->ev0, h->stream);
+  cudaError_t e = launch_blend(p, h->stream);
+  cudaEventRecord(h->ev1, h->stream);
+  h->stats.kernel_launches++;
+  if (e != cudaSuccess) return fail(h, NESR_E_CUDA, "blend launch failed: %s", cudaGetErrorString(e));
+  if (!(flags & NESR_PTR_OUT_DEVICE)) CUDA_TRY(h, cudaMemcpyAsync(out, h->d_out, n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->stats.last_device_ms = ms;
+  return NESR_OK;
+}
+
+int nesr_b200_sharpen_u8(nesr_b200_handle* h, const uint8_t* in, int32_t H, int32_t W, int32_t bgr, uint8_t* out, int32_t flags) {
+  if (!h) return NESR_E_INVALID;
+  if (!in || !out || H < 1 || W < 1) return fail(h, NESR_E_INVALID, "sharpen: bad arguments");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const int64_t n = (int64_t)H * W * 3;
+  const uint8_t* d_in = in;
+  uint8_t* d_out = out;
+  int rc;
+  if (!(flags & NESR_PTR_IN_DEVICE)) {
+    if ((rc = ensure(h, &h->d_in, &h->d_in_bytes, (size_t)n))) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_in, in, n, cudaMemcpyHostToDevice, h->stream));
+    d_in = h->d_in;
+  }
+  if (!(flags & NESR_PTR_OUT_DEVICE)) {
+    if ((rc = ensure(h, &h->d_out, &h->d_out_bytes, (size_t)n))) return rc;
+    d_out = h->d_out;
+  }
+  if (d_in == d_out) return fail(h, NESR_E_INVALID, "sharpen: in-place operation is not supported");
+  cudaEventRecord(h->ev0, h->stream);
+  cudaError_t e = launch_sharpen(d_in, d_out, H, W, bgr, h->stream);
+  cudaEventRecord(h->ev1, h->stream);
+  h->stats.kernel_launches++;
+  if (e != cudaSuccess) return fail(h, NESR_E_CUDA, "sharpen launch failed: %s", cudaGetErrorString(e));
+  if (!(flags & NESR_PTR_OUT_DEVICE)) CUDA_TRY(h, cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->stats.last_device_ms = ms;
+  return NESR_OK;
+}
+
+int nesr_b200_get_stats(const nesr_b200_handle* h, nesr_b200_stats* out) {
+  if (!h || !out) return NESR_E_INVALID;
+  *out = h->stats;
+  return NESR_OK;
+}
+
+int nesr_b200_synchronize(nesr_b200_handle* h) {
+  if (!h) return NESR_E_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return NESR_OK;
+}
+
+// One conv layer on a single H x W "tile" (level-0 geometry), fp32 NCHW in/out on the host; operands
+// are rounded to `fmt`, accumulation is fp32, the result is returned un-rounded (dst32a path).
+int nesr_b200_debug_conv(nesr_b200_handle* h, int32_t impl, int32_t fmt, int32_t H, int32_t W, int32_t cin, int32_t cout,
+                         const float* weight_oihw, const float* bias, const float* x_nchw, int32_t lrelu, float* y_nchw) {
+  if (!h) return NESR_E_INVALID;
+  if (!weight_oihw || !bias || !x_nchw || !y_nchw || H < 1 || W < 1 || cin < 1 || cin > kDense || cout < 1 || cout > 64 || (fmt & ~1))
+    return fail(h, NESR_E_INVALID, "debug_conv: bad arguments");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  Layer L;
+  L.name = "debug"; L.cin = cin; L.cout = cout; L.fmt = fmt;
+  L.cin16 = (int)round_up(cin, 16); L.nchunk = (L.cin16 + 63) / 64; L.npad = cout <= 16 ? 16 : (cout <= 32 ? 32 : 64);
+  L.w_row0 = 0; L.bias_off = 0;
+  const int64_t rows = (int64_t)9 * L.nchunk * L.npad;
+  std::vector<uint16_t> wp((size_t)rows * 64, 0);
+  pack_layer(L, weight_oihw, wp.data());
+  std::vector<float> bpad(64, 0.f);
+  std::copy(bias, bias + cout, bpad.begin());
+  Batch b;
+  TileGeom t{};
+  t.lv[0].h = H; t.lv[0].w = W; t.lv[0].pitch = W + 1;
+  t.lv[1] = t.lv[0]; t.lv[2] = t.lv[0];
+  b.tiles.push_back(t);
+  layout_level(b, 0);
+  const int64_t P = b.lv[0].pixels;
+  const int src_pitch = L.nchunk * 64;
+  std::vector<uint16_t> xs((size_t)P * src_pitch, 0);
+  const LevelGeom g = b.tiles[0].lv[0];
+  for (int c = 0; c < cin; ++c)
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x)
+        xs[((size_t)g.base + (size_t)y * g.pitch + x) * src_pitch + c] = to16(x_nchw[((size_t)c * H + y) * W + x], fmt);
+  uint16_t *d_w = nullptr, *d_x = nullptr;
+  float *d_b = nullptr, *d_y = nullptr;
+  TileGeom* d_t = nullptr; BlockRef* d_blk = nullptr;
+  int rc = NESR_OK;
+  auto cleanup = [&]() {
+    cudaFree(d_w); cudaFree(d_x); cudaFree(d_b); cudaFree(d_y); cudaFree(d_t); cudaFree(d_blk);
+  };
+#define DBG_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(h, NESR_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); } } while (0)
+  DBG_TRY(cudaMalloc(&d_w, wp.size() * 2));
+  DBG_TRY(cudaMalloc(&d_x, xs.size() * 2));
+  DBG_TRY(cudaMalloc(&d_b, 64 * 4));
+  DBG_TRY(cudaMalloc(&d_y, (size_t)P * 64 * 4));
+  DBG_TRY(cudaMalloc(&d_t, sizeof(TileGeom)));
+  DBG_TRY(cudaMalloc(&d_blk, b.lv[0].blocks.size() * sizeof(BlockRef)));
+  DBG_TRY(cudaMemcpy(d_w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+  DBG_TRY(cudaMemcpy(d_x, xs.data(), xs.size() * 2, cudaMemcpyHostToDevice));
+  DBG_TRY(cudaMemcpy(d_b, bpad.data(), 64 * 4, cudaMemcpyHostToDevice));
+  DBG_TRY(cudaMemset(d_y, 0, (size_t)P * 64 * 4));
+  DBG_TRY(cudaMemcpy(d_t, b.tiles.data(), sizeof(TileGeom), cudaMemcpyHostToDevice));
+  DBG_TRY(cudaMemcpy(d_blk, b.lv[0].blocks.data(), b.lv[0].blocks.size() * sizeof(BlockRef), cudaMemcpyHostToDevice));
+  ConvParams p{};
+  p.blocks = d_blk; p.tiles = d_t; p.nblk = (int)b.lv[0].blocks.size(); p.level = 0;
+  p.src = d_x; p.src_pitch = src_pitch; p.cin = L.cin16; p.wpack = d_w; p.w_row0 = 0; p.npad = L.npad; p.fmt = fmt;
+  p.idesc = umma_idesc_f16(hw_fmt(fmt), (uint32_t)L.npad);
+  p.bias = d_b; p.cout = cout; p.lrelu = lrelu; p.dst32a = d_y;
+  cudaError_t e;
+  if (impl == 1) {
+    e = launch_conv3x3_simt(p, h->stream);
+  } else {
+    CUtensorMap am, wm;
+    if ((rc = make_map(h, &am, d_x, src_pitch, P, kBlockPixels)) || (rc = make_map(h, &wm, d_w, 64, rows, L.npad))) { cleanup(); return rc; }
+    e = launch_conv3x3_tc(am, wm, p, h->num_sms, h->stream);
+  }
+  h->stats.kernel_launches++;
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) { cleanup(); return fail(h, NESR_E_CUDA, "debug_conv kernel: %s", cudaGetErrorString(e)); }
+  std::vector<float> ys((size_t)P * 64);
+  DBG_TRY(cudaMemcpy(ys.data(), d_y, ys.size() * 4, cudaMemcpyDeviceToHost));
+  for (int c = 0; c < cout; ++c)
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x)
+        y_nchw[((size_t)c * H + y) * W + x] = ys[((size_t)g.base + (size_t)y * g.pitch + x) * 64 + c];
+  cleanup();
+#undef DBG_TRY
+  return NESR_OK;
+}
+
+}  // extern "C"

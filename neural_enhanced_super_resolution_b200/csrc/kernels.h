@@ -1,0 +1,46 @@
+// kernels.h -- host-callable launchers of every CUDA kernel in libnesr_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "layout.h"
+
+namespace nesr {
+
+// --- conv3x3_tc.cu : tcgen05 / TMEM / TMA implicit-GEMM conv (the product path) -----------------
+cudaError_t conv3x3_tc_configure();
+cudaError_t launch_conv3x3_tc(const CUtensorMap& amap, const CUtensorMap& wmap, const ConvParams& p, int num_sms,
+                              cudaStream_t stream);
+
+// --- conv3x3_simt.cu : plain CUDA-core conv over the same buffers (test-only cross-check) -------
+cudaError_t launch_conv3x3_simt(const ConvParams& p, cudaStream_t stream);
+
+// --- pixel_io.cu : image -> level-0 input features (BGR->RGB, /255, reflect pad, pixel_unshuffle) -
+struct PackParams {
+  const BlockRef* blocks;
+  const TileGeom* tiles;
+  int32_t nblk;
+  const uint8_t* in_u8;        // BGR HWC frames, or null
+  int64_t in_stride, in_frame_stride;
+  const float* in_f32;         // RGB NCHW frames, or null
+  int32_t H, W;                // un-padded frame size
+  int32_t pre_pad;             // reflect pad (right/bottom) applied before the mod pad
+  void* x0;                    // [pixels][64] 16-bit, channels 0..11 written
+  int32_t fmt;
+};
+cudaError_t launch_pack(const PackParams& p, cudaStream_t stream);
+
+// --- stencil.cu : bit-exact integer post-process kernels ----------------------------------------
+constexpr int kMaxBlendMembers = 16;
+struct BlendParams {
+  const uint8_t* members[kMaxBlendMembers];
+  double weights[kMaxBlendMembers];
+  int32_t k;
+  int64_t nbytes;
+  uint8_t* out;
+};
+cudaError_t launch_blend(const BlendParams& p, cudaStream_t stream);
+cudaError_t launch_sharpen(const uint8_t* in, uint8_t* out, int32_t H, int32_t W, int32_t bgr, cudaStream_t stream);
+
+}  // namespace nesr

@@ -1,0 +1,80 @@
+// layout.h -- data layout shared by the host engine and every kernel.
+//
+// FLAT ZERO-PADDED NHWC.  All tiles of a batch live in one flat pixel array per resolution level
+// (level 0 = feature grid h x w, level 1 = 2h x 2w, level 2 = 4h x 4w).  Tile t occupies flat pixels
+// [base, base + h*pitch) with pitch = w + 1: pixel (y, x) sits at base + y*pitch + x and column
+// x == w is a pad column that is zero and never written.  `base` is a multiple of 128 and at least
+// pitch+1 zero pixels separate consecutive tiles.  Consequences:
+//   * a 3x3 tap (dy, dx) is the flat shift dy*pitch + dx, and conv zero padding at every tile
+//     border -- upstream tile_process forwards each tile independently -- is plain data;
+//   * an MMA M-block is 128 consecutive flat pixels (it may span rows), so M tiles are always full;
+//   * one 2-D TMA tensor map [pixels][channels] per buffer serves every tile and every tap.
+#pragma once
+#include <stdint.h>
+
+namespace nesr {
+
+constexpr int kBlockPixels = 128;       // MMA M
+constexpr int kChunkChannels = 64;      // one 128-byte swizzle row of 16-bit channels
+constexpr int kFeat = 64;               // num_feat
+constexpr int kGrow = 32;               // num_grow_ch
+constexpr int kDense = kFeat + 4 * kGrow;   // 192 channels of a dense-block buffer
+
+struct LevelGeom {
+  int32_t base;    // flat pixel index of (0,0); multiple of 128
+  int32_t pitch;   // w + 1
+  int32_t h, w;
+};
+
+struct TileGeom {
+  LevelGeom lv[3];
+  int32_t frame;               // source / destination frame of the batch
+  int32_t src_y0, src_x0;      // top-left of the padded tile window in the (pre/mod-padded) input, pixels
+  // level-2 pixels [crop_y, crop_y+crop_h) x [crop_x, crop_x+crop_w) are pasted at (out_y0, out_x0)
+  int32_t crop_y, crop_x, crop_h, crop_w;
+  int32_t out_y0, out_x0;
+};
+
+// One unit of conv work: 128 flat pixels starting at `px` (multiple of 128) inside tile `tile`.
+struct BlockRef {
+  int32_t px;
+  int32_t tile;
+};
+
+struct ConvParams {
+  const BlockRef* blocks;
+  const TileGeom* tiles;
+  int32_t nblk;
+  int32_t level;
+  // operands
+  const void* src;             // [pixels][src_pitch] 16-bit (SIMT validation kernel reads it directly)
+  int32_t src_pitch;           // channels per pixel in src
+  int32_t cin;                 // input channels, multiple of 16
+  const void* wpack;           // packed weights arena base (16-bit), rows of 64
+  int32_t w_row0;              // first arena row of this layer
+  int32_t npad;                // padded Cout = MMA N (16 / 32 / 64)
+  int32_t fmt;                 // NESR_FMT_* of src and weights
+  uint32_t idesc;
+  // epilogue:  v = acc + bias; lrelu?; v = v*s1 + res1; v = v*s2 + res2
+  const float* bias;           // [npad]
+  int32_t cout;
+  int32_t lrelu;
+  const float* res1;           // fp32 [pixels][64] or null
+  const float* res2;
+  float s1, s2;
+  float* dst32a;               // fp32 [pixels][64] or null
+  float* dst32b;
+  void* dst16;                 // 16-bit [pixels][dst16_pitch] or null
+  int32_t dst16_pitch;
+  int32_t dst16_coff;
+  int32_t dst16_fmt;
+  int32_t dst16_up;            // 1: nearest x2 -- write the 2x2 replicas into level+1's layout
+  // final layer
+  uint8_t* out_u8;             // BGR HWC frames or null
+  int64_t out_stride;          // bytes per row
+  int64_t out_frame_stride;    // bytes per frame
+  float* out_f32;              // NCHW frames (unclamped) or null
+  int32_t out_h, out_w;        // frame dims for out_f32
+};
+
+}  // namespace nesr

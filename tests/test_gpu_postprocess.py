@@ -1,0 +1,64 @@
+"""Blend and adaptive-sharpen kernels: bit-exact against the integer oracle (itself pinned to the
+reference's cv2/numpy code) and against the committed reference outputs."""
+import numpy as np
+import pytest
+import torch
+
+from neural_enhanced_super_resolution_b200 import _ffi
+from oracle import postprocess as O
+from gpu_common import natural_image
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    eng = _ffi.Engine(device=0, num_block=1)
+    yield eng
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["photo_crop", "photo_small", "noise_ragged", "noise_tiny", "noise_row", "noise_col", "flat"])
+def test_sharpen_matches_reference_golden(engine, golden, name):
+    g = golden("postprocess.npz")
+    assert np.array_equal(engine.sharpen_u8(np.ascontiguousarray(g[name + "_in"])), g[name + "_out"])
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (2, 3), (31, 33), (64, 64), (65, 129), (200, 77), (1080, 1920)])
+def test_sharpen_matches_oracle(engine, shape):
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    img = rng.integers(0, 256, (*shape, 3), dtype=np.uint8) if shape[0] < 1000 else natural_image(*shape, seed=1)
+    assert np.array_equal(engine.sharpen_u8(img), O.postprocess_image(img))
+
+
+def test_sharpen_bgr_flag_and_device_tensors(engine):
+    img = natural_image(90, 70, seed=3)                      # treat as RGB
+    want = O.postprocess_image(img)
+    got_bgr = engine.sharpen_u8(np.ascontiguousarray(img[:, :, ::-1]), bgr=True)
+    assert np.array_equal(got_bgr[:, :, ::-1], want)
+    dev = torch.from_numpy(img).cuda()
+    out = engine.sharpen_u8(dev)
+    assert out.is_cuda and np.array_equal(out.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_blend_matches_reference_golden(engine, golden, k):
+    g = golden("ensemble.npz")
+    members = [np.ascontiguousarray(m) for m in g[f"k{k}_in"]]
+    assert np.array_equal(engine.blend_u8(members), g[f"k{k}_out"])
+
+
+def test_blend_lattice_and_sizes(engine, golden):
+    g = golden("ensemble.npz")
+    assert np.array_equal(engine.blend_u8([np.ascontiguousarray(m) for m in g["lattice3_in"]]), g["lattice3_out"])
+    rng = np.random.default_rng(9)
+    for shape, k in (((1, 1), 2), ((7, 5), 3), ((33, 17), 5), ((301, 203), 7), ((64, 64), 16)):
+        ms = [rng.integers(0, 256, (*shape, 3), dtype=np.uint8) for _ in range(k)]
+        assert np.array_equal(engine.blend_u8(ms), O.ensemble_results(ms))
+    ms = [rng.integers(0, 256, (20, 20, 3), dtype=np.uint8) for _ in range(3)]
+    w = [0.5, 0.25, 0.25]
+    assert np.array_equal(engine.blend_u8(ms, weights=w), O.ensemble_results(ms, weights=w))
+    dev = [torch.from_numpy(m).cuda() for m in ms]
+    assert np.array_equal(engine.blend_u8(dev).cpu().numpy(), O.ensemble_results(ms))
+    with pytest.raises(RuntimeError):
+        engine.blend_u8([ms[0]])
