@@ -131,8 +131,9 @@ int nesr_b200_enhance_tiles_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32
 
 /* Replaces: RRDBNet.forward / `upsampler.model(x)` (nesr/nesr.py:887-891,930-935): device fp32
  * NCHW [n, num_in_ch, H, W] in [0,1] -> device fp32 NCHW [n, num_out_ch, 2H, 2W], unclamped.
- * Both pointers are device memory; `stream` is a cudaStream_t the call is ordered after and
- * before (the torch current stream), or NULL for the handle's own stream. */
+ * Both pointers are device memory; the work is enqueued on `stream` (a cudaStream_t, taken literally:
+ * NULL is the legacy default stream -- pass torch.cuda.current_stream().cuda_stream) and the call
+ * returns without synchronising it. */
 int nesr_b200_forward_nchw_f32(nesr_b200_handle* h, const float* x, int32_t n, int32_t H,
                                int32_t W, float* y, void* stream);
 

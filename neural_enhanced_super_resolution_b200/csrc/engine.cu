@@ -65,6 +65,7 @@ struct Batch {
 struct Arena {
   uint8_t* base = nullptr;
   size_t bytes = 0;
+  size_t zero_bytes = 0;      // prefix holding every buffer a conv reads (pads must stay zero)
   // sub-buffers
   void* x0 = nullptr;         // [P0][64] 16-bit network input (12 channels used)
   void* d[2] = {nullptr, nullptr};   // [P0][192] dense-block ping-pong
@@ -183,10 +184,6 @@ void build_layers(nesr_b200_handle* h) {
   h->w_rows = rows;
 }
 
-const Layer* find_layer(const nesr_b200_handle* h, const std::string& name) {
-  for (const Layer& L : h->layers) if (L.name == name) return &L;
-  return nullptr;
-}
 
 // Packed weight layout (16-bit): row ((tap*nchunk + chunk)*npad + n) holds the 64 input channels
 // [chunk*64, chunk*64+64) of output channel n at tap (ky,kx) -- K-major rows of 128 B, exactly one
@@ -348,10 +345,10 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
   a.d[0] = p; p += sz_d; a.d[1] = p; p += sz_d;
   a.g2 = p; p += sz_g2;
   a.g4[0] = p; p += sz_g4; a.g4[1] = p; p += sz_g4;
-  const size_t zero_bytes = (size_t)(p - a.base);     // every buffer a conv reads: pads must be zero
+  a.zero_bytes = (size_t)(p - a.base);                // every buffer a conv reads: pads must be zero
   a.trunk = (float*)p; p += sz_f; a.rrdb = (float*)p; p += sz_f; a.feat = (float*)p; p += sz_f;
   for (int l = 0; l < 3; ++l) a.P[l] = P[l];
-  CUDA_TRY(h, cudaMemsetAsync(a.base, 0, zero_bytes, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(a.base, 0, a.zero_bytes, h->stream));
   int rc;
   if ((rc = make_map(h, &a.m_x0, a.x0, 64, P[0], kBlockPixels))) return rc;
   for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.m_d[i2], a.d[i2], kDense, P[0], kBlockPixels))) return rc;
@@ -402,6 +399,10 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
   Arena& a = h->arena;
   const nesr_b200_config& c = h->cfg;
   int rc;
+  if (h->batches.size() > 1) {   // batches have different flat layouts: re-establish the zero pads
+    cudaError_t ez = cudaMemsetAsync(a.base, 0, a.zero_bytes, s);
+    if (ez != cudaSuccess) return fail(h, NESR_E_CUDA, "arena memset failed: %s", cudaGetErrorString(ez));
+  }
   PackParams pk = pack_in;
   pk.blocks = b.lv[0].d_blocks; pk.tiles = b.d_tiles; pk.nblk = (int)b.lv[0].blocks.size();
   pk.x0 = a.x0; pk.fmt = c.edge_format;
@@ -691,12 +692,12 @@ int nesr_b200_forward_nchw_f32(nesr_b200_handle* h, const float* x, int32_t n, i
   if (!x || !y || n < 1 || H < 2 || W < 2) return fail(h, NESR_E_INVALID, "bad tensor arguments");
   if ((H | W) & 1) return fail(h, NESR_E_INVALID, "pixel_unshuffle(2): H and W must be even (got %dx%d)", H, W);
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  cudaStream_t s = (cudaStream_t)stream;      // literally the caller's stream; NULL is the legacy default stream
   const int sc = h->cfg.scale;
   PlanKey key; key.n_frames = n; key.H = H; key.W = W; key.tile = 0; key.whole = 1;
   int rc = build_plan(h, key, H * sc, W * sc);
   if (rc) return rc;
-  if (s != h->stream) CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // plan uploads / memset ran on our stream
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // plan uploads / memset ran on our own stream
   PackParams pk{};
   pk.in_f32 = x; pk.H = H; pk.W = W; pk.pre_pad = 0;
   Sink sink; sink.out_f32 = y; sink.out_h = H * sc; sink.out_w = W * sc;

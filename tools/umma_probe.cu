@@ -82,19 +82,28 @@ shift_probe_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
   if (warp == 0) tmem_dealloc(tmem, 32);
 }
 
-// Throughput: `iters` back-to-back MMAs (M=128, K=16) with N = n on operands resident in smem.
-// mode 0: same A every time; mode 1: A start cycles over 9 row-shifted views (as the conv taps do).
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int mode, long long* cycles) {
+// Throughput: MMAs (M=128, K=16, N=n) on operands resident in smem, issue loop fully unrolled so the
+// issuing thread does ~2 integer instructions per MMA (descriptor = base + immediate).
+//   NACC  : number of independent TMEM accumulators the MMAs rotate over
+//   ORDER : 0 = accumulator index fastest (consecutive MMAs hit DIFFERENT accumulators)
+//           1 = k-step, then tap, then accumulator (36 consecutive MMAs chain on the SAME accumulator)
+//   AVIEW : 0 = one A view / one B view; 2 = nine A views shifted by the flat 3x3 tap offsets of a
+//           pitch-267 tile (NOT 1024-B aligned) and nine B (weight) views -- the conv's real pattern
+__device__ __forceinline__ constexpr int tap_rows(int t) { return (t / 3) * 267 + (t % 3); }
+
+template <int NACC, int ORDER, int AVIEW>
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int reps, long long* cycles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sa = smem;                       // 64 KB of A rows
-  uint8_t* sb = smem + 65536;               // 256 rows x 128 B
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(sb + 32768);
+  constexpr int kABytes = 96 * 1024, kBBytes = 9 * 32 * 128 + 256 * 128;
+  uint8_t* sa = smem;
+  uint8_t* sb = smem + kABytes;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sb + kBBytes);
   uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 1);
   const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < (65536 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  for (int i = threadIdx.x; i < (kABytes + kBBytes) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
   if (threadIdx.x == 0) { mbar_init(mbar, 1); fence_barrier_init(); }
-  if (warp == 0) { tmem_alloc(slot, 256); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(slot, 512); tmem_relinquish(); }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -102,12 +111,31 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int 
   const uint32_t tmem = *slot;
   if (threadIdx.x == 0) {
     const uint32_t idesc = umma_idesc_f16(1, n);
-    const uint64_t bd = umma_smem_desc_sw128(smem_u32(sb), 1024);
+    const uint64_t a0 = umma_smem_desc_sw128(smem_u32(sa), 1024);
+    const uint64_t b0 = umma_smem_desc_sw128(smem_u32(sb), 1024);
     const long long t0 = clock64();
-    for (int i = 0; i < iters; ++i) {
-      const int view = mode ? (i % 9) : 0;
-      const uint64_t ad = umma_smem_desc_sw128(smem_u32(sa) + view * 2048, 1024) + 2 * (i & 3);
-      umma_f16(tmem, ad, bd + 2 * (i & 3), idesc, 1);
+    for (int r = 0; r < reps; ++r) {
+      if (ORDER == 0) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int acc = 0; acc < NACC; ++acc) {
+              const int rows = (AVIEW ? tap_rows(tap) : 0) + acc * 8;
+              umma_f16(tmem + acc * n, a0 + (rows * 128 >> 4) + 2 * k, b0 + (AVIEW ? (tap * 32 * 128 >> 4) : 0) + 2 * k, idesc, 1);
+            }
+      } else {
+#pragma unroll
+        for (int acc = 0; acc < NACC; ++acc)
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int rows = (AVIEW ? tap_rows(tap) : 0) + acc * 8;
+              umma_f16(tmem + acc * n, a0 + (rows * 128 >> 4) + 2 * k, b0 + (AVIEW ? (tap * 32 * 128 >> 4) : 0) + 2 * k, idesc, 1);
+            }
+      }
     }
     umma_commit(mbar);
     mbar_wait(mbar, 0);
@@ -118,7 +146,26 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int NACC, int ORDER, int AVIEW>
+void run_rate(int n, int sms, long long* dc, std::vector<long long>& hc) {
+  if (NACC * n > 512) return;
+  const int smem2 = 96 * 1024 + 9 * 32 * 128 + 256 * 128 + 64 + 1024;
+  CK(cudaFuncSetAttribute(mma_rate_kernel<NACC, ORDER, AVIEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+  const int reps = 16;
+  mma_rate_kernel<NACC, ORDER, AVIEW><<<sms, 128, smem2>>>(n, reps, dc);
+  mma_rate_kernel<NACC, ORDER, AVIEW><<<sms, 128, smem2>>>(n, reps, dc);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("rate kernel failed: %s\n", cudaGetErrorString(e)); exit(3); }
+  CK(cudaMemcpy(hc.data(), dc, sms * sizeof(long long), cudaMemcpyDeviceToHost));
+  long long mx = 0;
+  for (int i = 0; i < sms; ++i) mx = hc[i] > mx ? hc[i] : mx;
+  const double cyc = (double)mx / (reps * 36 * NACC);
+  const double macs = 128.0 * n * 16 / cyc;
+  printf("aview=%d order=%d N=%3d nacc=%2d : %6.2f cyc/MMA  %4.0f MAC/clk/SM (%5.1f%%)  smem operand B/clk=%.0f\n", AVIEW, ORDER, n, NACC, cyc,
+         macs, 100.0 * macs / 4096.0, (4096.0 + n * 32.0) / cyc);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -197,32 +244,29 @@ int main() {
       printf("\n");
     }
 
-  // ---- (2) MMA issue rate vs N ----
+  // ---- (2) MMA rate vs N, accumulator interleave and A-view pattern ----
   printf("== tcgen05.mma rate, M=128 K=16, SS operands, 1 CTA/SM on all SMs ==\n");
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   long long* dc;
   CK(cudaMalloc(&dc, sms * sizeof(long long)));
-  const int smem2 = 65536 + 32768 + 64 + 1024;
-  CK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
   std::vector<long long> hc(sms);
-  const int ns[] = {16, 32, 48, 64, 96, 128, 192, 256};
-  for (int mode = 0; mode < 2; ++mode)
-    for (int grid : {1, sms})
-      for (int n : ns) {
-        const int iters = 8192;
-        mma_rate_kernel<<<grid, 128, smem2>>>(n, iters, mode, dc);   // warm
-        mma_rate_kernel<<<grid, 128, smem2>>>(n, iters, mode, dc);
-        cudaError_t e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) { printf("rate kernel failed: %s\n", cudaGetErrorString(e)); return 3; }
-        CK(cudaMemcpy(hc.data(), dc, grid * sizeof(long long), cudaMemcpyDeviceToHost));
-        long long mx = 0;
-        for (int i = 0; i < grid; ++i) mx = hc[i] > mx ? hc[i] : mx;
-        const double cyc = (double)mx / iters;
-        const double macs = 128.0 * n * 16 / cyc;
-        printf("mode=%d grid=%3d N=%3d : %.2f cyc/MMA  %.0f MAC/clk/SM  (%.1f%% of 4096)  smem operand B/clk=%.0f\n", mode, grid, n,
-               cyc, macs, 100.0 * macs / 4096.0, (4096.0 + n * 32.0) / cyc);
-      }
+  for (int n : {16, 32, 64, 96, 128, 192, 256}) {
+    run_rate<1, 0, 0>(n, sms, dc, hc);
+    run_rate<2, 0, 0>(n, sms, dc, hc);
+    run_rate<4, 0, 0>(n, sms, dc, hc);
+    run_rate<8, 0, 0>(n, sms, dc, hc);
+    run_rate<4, 1, 0>(n, sms, dc, hc);
+    run_rate<8, 1, 0>(n, sms, dc, hc);
+  }
+  for (int n : {16, 32, 64}) {            // B views are 32 rows apart: N <= 64 keeps them inside the region
+    run_rate<1, 0, 2>(n, sms, dc, hc);
+    run_rate<2, 0, 2>(n, sms, dc, hc);
+    run_rate<4, 0, 2>(n, sms, dc, hc);
+    run_rate<8, 0, 2>(n, sms, dc, hc);
+    run_rate<4, 1, 2>(n, sms, dc, hc);
+    run_rate<8, 1, 2>(n, sms, dc, hc);
+  }
   printf("probe done\n");
   return 0;
 }
