@@ -67,8 +67,9 @@ typedef struct nesr_b200_config {
   int32_t num_grow_ch;
   int32_t body_format;        /* residual-dense-block convs: NESR_FMT_BF16 (default) | NESR_FMT_FP16 */
   int32_t edge_format;        /* conv_first/body/up1/up2/hr/last:  NESR_FMT_FP16 (default) | NESR_FMT_BF16 */
-  int32_t conv_impl;          /* 0 = tcgen05/TMEM/TMA kernels (product).  1 = SIMT validation kernel:
-                                 test-only cross-check of the tensor path, never selected implicitly */
+  int32_t conv_impl;          /* 0 = row-folded tcgen05/TMEM/TMA kernel (product).  Test-only cross-checks,
+                                 never selected implicitly: 1 = SIMT validation kernel, 2 = first-generation
+                                 per-tap tcgen05 kernel */
   int32_t reserved0;
   int64_t max_batch_pixels;   /* cap on feature-grid pixels resident per batch; 0 = default */
 } nesr_b200_config;

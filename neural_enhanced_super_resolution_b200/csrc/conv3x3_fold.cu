@@ -1,0 +1,303 @@
+// conv3x3_fold.cu -- the production 3x3 conv: row-folded implicit GEMM on tcgen05 / TMEM / TMA.
+//
+// Why "folded".  Measured on B200 (tools/umma_probe.cu, profiles/r1_umma_probe_rates.log): a
+// tcgen05.mma with M=128, K=16 and both operands in shared memory never issues faster than one per
+// ~54 cycles, whatever N <= 64 is -- the 4 KB A-operand read is the cost.  A conv with Cout = 32 as a
+// plain implicit GEMM (N = 32) is therefore capped at 30 % of the tensor peak, Cout = 64 at 59 %.
+// Folding the three VERTICAL taps into N fixes that: for one input row segment (128 pixels, one A
+// tile) and one horizontal shift dx,
+//
+//      [ out(y-1) | out(y) | out(y+1) ]  +=  A(y, dx) * [ W(dy=+1,dx) | W(dy=0,dx) | W(dy=-1,dx) ]^T
+//
+// is ONE MMA with N = 3*Cout (96 -> 85 %, 192 -> 99 % of peak in the same probe) whose accumulator
+// is three consecutive row slots of a TMEM ring.  Each A byte fetched from shared memory now feeds
+// 3x the MACs, and each activation row is loaded from L2 exactly once per strip (no tap re-reads).
+//
+// Work decomposition.  A tile is cut into 128-pixel-wide column strips and the strips into bands
+// of consecutive rows (host: engine.cu build_fold_schedule, balanced over the SMs).  A CTA streams
+// down its bands: the TMA producer loads one 136-pixel row slab [136 px x 64 ch] per (row, channel
+// chunk) into a ring; the MMA thread issues 3 (dx) x ksteps MMAs per slab, the dx shift being a
+// 128-byte offset of the A descriptor into the slab (address-based swizzle makes un-aligned views
+// legal: profiles/r1_umma_probe_shifted_views.log); the folded weights of the whole layer pass stay
+// resident in shared memory.  Output row r is complete once input row r+1 has been issued, so the
+// four epilogue warps drain rows in order while the MMAs run ahead: tcgen05.ld -> fused epilogue
+// (epilogue.cuh) -> tcgen05.st zeros (every MMA accumulates; a slot is handed back zeroed).
+// Rows just outside a band are "virtual": they receive partial sums and are dropped.
+//
+// Layers with Cout = 64 and Cin > 64 (RDB conv5) run as two passes of 32 output channels so that
+// the resident weights (3*nchunk boxes of [96 x 64]) fit next to the activation ring.
+#include <stdio.h>
+
+#include "epilogue.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace nesr {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kSlabPx = 136;                       // 1 + 128 + 1 halo pixels, rounded to 8-row groups
+constexpr int kSlabBytes = kSlabPx * 128;          // 17408 = 17 * 1024
+constexpr int kMaxStages = 8;
+constexpr int kMaxSlots = 16;
+constexpr int kSmemBudget = 232448;                // 227 KB
+
+template <int COUT>
+struct FoldCfg {
+  static constexpr int kN3 = 3 * COUT;
+  static constexpr int kSlots = (512 / COUT) > kMaxSlots ? kMaxSlots : (512 / COUT);   // 16, 16, 8
+  static constexpr int kCols = kSlots * COUT;                                         // 256, 512, 512
+  static constexpr int kWBoxBytes = kN3 * 128;                                        // one (dx, chunk) weight box
+};
+
+constexpr int kBarrierBytes = (1 + 2 * kMaxStages + 2 * kMaxSlots) * 8 + 16;
+
+template <int COUT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_fold_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap wmap,
+                    const ConvParams p) {
+  using Cfg = FoldCfg<COUT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nchunk = (p.cin + kChunkChannels - 1) / kChunkChannels;
+  const int wbytes = 3 * nchunk * Cfg::kWBoxBytes;
+  const int nstage = p.fold_stages;
+  uint8_t* wsm = smem;                                         // resident folded weights
+  uint8_t* ring = smem + wbytes;                               // activation row slabs
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(ring + nstage * kSlabBytes);
+  uint64_t* full = wbar + 1;
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* tfull = empty + kMaxStages;
+  uint64_t* tempty = tfull + kMaxSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kMaxSlots);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&amap);
+    tma_prefetch_desc(&wmap);
+    mbar_init(wbar, 1);
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kMaxSlots; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 2) {                                             // every MMA accumulates: start from zero
+    const uint32_t t0 = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    for (int c = 0; c < Cfg::kCols; c += 16) tmem_st16_zero(t0 + c);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const int band_begin = p.cta_band_off[blockIdx.x];
+  const int band_end = p.cta_band_off[blockIdx.x + 1];
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, wbytes);
+      for (int b = 0; b < 3 * nchunk; ++b)
+        tma_load_2d(wsm + b * Cfg::kWBoxBytes, &wmap, wbar, 0, p.w_row0 + b * Cfg::kN3);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int bi = band_begin; bi < band_end; ++bi) {
+        const FoldBand band = p.bands[bi];
+        const LevelGeom g = p.tiles[band.tile].lv[p.level];
+        for (int i = 0; i < band.rows + 2; ++i) {
+          const int px0 = g.base + (band.r0 - 1 + i) * g.pitch + band.x0 - 1;
+          for (int c = 0; c < nchunk; ++c) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], kSlabBytes);
+            tma_load_2d(ring + stage * kSlabBytes, &amap, &full[stage], c * kChunkChannels, px0);
+            if (++stage == nstage) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    if (lane == 0) {
+      const uint32_t hw = (p.idesc >> 7) & 7u;                 // operand format bits of the layer
+      const uint32_t idesc1 = umma_idesc_f16(hw, COUT), idesc2 = umma_idesc_f16(hw, 2 * COUT),
+                     idesc3 = umma_idesc_f16(hw, 3 * COUT);
+      const uint32_t w_addr = smem_u32(wsm);
+      mbar_wait(wbar, 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t u = 0;                                          // running row-slot counter
+      for (int bi = band_begin; bi < band_end; ++bi) {
+        const int rows = p.bands[bi].rows;
+        for (int j = 0; j < 2; ++j) {                          // slots of the first two (virtual) output rows
+          const uint32_t v = u + j;
+          mbar_wait(&tempty[v % Cfg::kSlots], ((v / Cfg::kSlots) & 1) ^ 1);
+        }
+        for (int i = 0; i < rows + 2; ++i) {
+          {                                                    // slot of output row i+2 must be drained + zeroed
+            const uint32_t v = u + i + 2;
+            mbar_wait(&tempty[v % Cfg::kSlots], ((v / Cfg::kSlots) & 1) ^ 1);
+          }
+          tc_fence_after();
+          const uint32_t q = (u + i) % Cfg::kSlots;
+          const uint32_t d0 = tmem_base + q * COUT;
+          for (int c = 0; c < nchunk; ++c) {
+            const int rem = (p.cin - c * kChunkChannels) >> 4;
+            const int ksteps = rem < 4 ? rem : 4;
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(ring + stage * kSlabBytes);
+#pragma unroll
+            for (int dxi = 0; dxi < 3; ++dxi) {
+              const uint64_t ad = umma_smem_desc_sw128(a_addr + dxi * 128, 1024);
+              const uint32_t wb = w_addr + (dxi * nchunk + c) * Cfg::kWBoxBytes;
+              if (q + 3 <= Cfg::kSlots) {
+                const uint64_t bd = umma_smem_desc_sw128(wb, 1024);
+                for (int k = 0; k < ksteps; ++k) umma_f16(d0, ad + 2 * k, bd + 2 * k, idesc3, 1);
+              } else if (q + 2 == Cfg::kSlots) {               // ring wrap: rows (y-1, y) | (y+1)
+                const uint64_t bd = umma_smem_desc_sw128(wb, 1024);
+                const uint64_t bd2 = umma_smem_desc_sw128(wb + 2 * COUT * 128, 1024);
+                for (int k = 0; k < ksteps; ++k) {
+                  umma_f16(d0, ad + 2 * k, bd + 2 * k, idesc2, 1);
+                  umma_f16(tmem_base, ad + 2 * k, bd2 + 2 * k, idesc1, 1);
+                }
+              } else {                                         // ring wrap: row (y-1) | (y, y+1)
+                const uint64_t bd = umma_smem_desc_sw128(wb, 1024);
+                const uint64_t bd2 = umma_smem_desc_sw128(wb + COUT * 128, 1024);
+                for (int k = 0; k < ksteps; ++k) {
+                  umma_f16(d0, ad + 2 * k, bd + 2 * k, idesc1, 1);
+                  umma_f16(tmem_base, ad + 2 * k, bd2 + 2 * k, idesc2, 1);
+                }
+              }
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == nstage) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tfull[q]);                              // output row i has all its contributions
+          if (i == rows + 1) {
+            umma_commit(&tfull[(u + i + 1) % Cfg::kSlots]);
+            umma_commit(&tfull[(u + i + 2) % Cfg::kSlots]);
+          }
+        }
+        u += rows + 4;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ epilogue ----------------------------------
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;                         // A row == TMEM lane == pixel x0 + m
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    uint32_t u = 0;
+    for (int bi = band_begin; bi < band_end; ++bi) {
+      const FoldBand band = p.bands[bi];
+      const TileGeom& tg = p.tiles[band.tile];
+      const LevelGeom g = tg.lv[p.level];
+      const int x = band.x0 + m;
+      for (int j = 0; j < band.rows + 4; ++j) {
+        const uint32_t v = u + j;
+        const uint32_t slot = v % Cfg::kSlots;
+        mbar_wait(&tfull[slot], (v / Cfg::kSlots) & 1);
+        tc_fence_after();
+        __syncwarp();
+        const uint32_t taddr = lane_base + slot * COUT;
+        uint32_t r[COUT / 16][16];
+#pragma unroll
+        for (int c = 0; c < COUT / 16; ++c) tmem_ld16(taddr + c * 16, r[c]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < COUT / 16; ++c) tmem_st16_zero(taddr + c * 16);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&tempty[slot]);
+        const int y = band.r0 - 2 + j;
+        if (j >= 2 && j < band.rows + 2 && x < g.w) {
+          PixelRef px;
+          px.P = g.base + y * g.pitch + x;
+          px.y = y; px.x = x; px.valid = true;
+#pragma unroll
+          for (int c = 0; c < COUT / 16; ++c) {
+            if (c * 16 < p.cout) {
+              float vals[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) vals[e] = __uint_as_float(r[c][e]);
+              epilogue16(p, tg, px, c * 16, vals);
+            }
+          }
+        }
+      }
+      u += band.rows + 4;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int COUT>
+int stages_for(int nchunk) {
+  const int wbytes = 3 * nchunk * FoldCfg<COUT>::kWBoxBytes;
+  int s = (kSmemBudget - 1024 - kBarrierBytes - wbytes) / kSlabBytes;
+  return s > kMaxStages ? kMaxStages : s;
+}
+
+template <int COUT>
+cudaError_t launch_c(const CUtensorMap& amap, const CUtensorMap& wmap, ConvParams p, int grid, cudaStream_t stream) {
+  const int nchunk = (p.cin + kChunkChannels - 1) / kChunkChannels;
+  p.fold_stages = stages_for<COUT>(nchunk);
+  if (p.fold_stages < 2) return cudaErrorInvalidConfiguration;
+  const int smem = 3 * nchunk * FoldCfg<COUT>::kWBoxBytes + p.fold_stages * kSlabBytes + kBarrierBytes + 1024;
+  conv3x3_fold_kernel<COUT><<<grid, kThreads, smem, stream>>>(amap, wmap, p);
+  return cudaGetLastError();
+}
+
+template <int COUT>
+cudaError_t configure_c() {
+  return cudaFuncSetAttribute(conv3x3_fold_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+}
+
+}  // namespace
+
+cudaError_t conv3x3_fold_configure() {
+  cudaError_t e = configure_c<16>();
+  if (e == cudaSuccess) e = configure_c<32>();
+  if (e == cudaSuccess) e = configure_c<64>();
+  return e;
+}
+
+// Can a (cin16, npad) layer pass keep its folded weights resident with at least 3 ring stages?
+bool conv3x3_fold_fits(int cin16, int npad) {
+  const int nchunk = (cin16 + kChunkChannels - 1) / kChunkChannels;
+  switch (npad) {
+    case 16: return stages_for<16>(nchunk) >= 3;
+    case 32: return stages_for<32>(nchunk) >= 3;
+    case 64: return stages_for<64>(nchunk) >= 3;
+    default: return false;
+  }
+}
+
+cudaError_t launch_conv3x3_fold(const CUtensorMap& amap, const CUtensorMap& wmap, const ConvParams& p, int grid,
+                                cudaStream_t stream) {
+  if (grid <= 0) return cudaSuccess;
+  switch (p.npad) {
+    case 16: return launch_c<16>(amap, wmap, p, grid, stream);
+    case 32: return launch_c<32>(amap, wmap, p, grid, stream);
+    case 64: return launch_c<64>(amap, wmap, p, grid, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace nesr

@@ -38,14 +38,24 @@ struct Layer {
   int nchunk = 0;             // 64-channel chunks
   int npad = 0;               // MMA N
   int fmt = 0;                // NESR_FMT_*
-  int w_row0 = 0;             // first row in the packed arena
+  int w_row0 = 0;             // first row in the packed (per-tap) arena
   int bias_off = 0;           // floats into the bias arena
+  // row-folded kernel: 1 pass, or 2 passes of 32 output channels when the weights would not fit
+  int fold_passes = 1;
+  int fold_npad = 0;          // Cout per pass (16 / 32 / 64)
+  int fold_row0[2] = {0, 0};  // first row of each pass in the folded arena
 };
 
 struct LevelPlan {
   int64_t pixels = 0;         // flat pixels incl. guards
   std::vector<BlockRef> blocks;
   BlockRef* d_blocks = nullptr;
+  // row-folded kernel schedule: bands grouped by CTA
+  std::vector<FoldBand> bands;
+  std::vector<int32_t> cta_off;
+  FoldBand* d_bands = nullptr;
+  int32_t* d_cta_off = nullptr;
+  int fold_grid = 0;
 };
 
 struct PlanKey {
@@ -75,7 +85,8 @@ struct Arena {
   void* g2 = nullptr;         // [P1][64]
   void* g4[2] = {nullptr, nullptr};  // [P2][64]
   int64_t P[3] = {0, 0, 0};
-  CUtensorMap m_x0, m_d[2], m_g2, m_g4[2];
+  CUtensorMap m_x0, m_d[2], m_g2, m_g4[2];             // box 128 px (per-tap kernel)
+  CUtensorMap f_x0, f_d[2], f_g2, f_g4[2];             // box 136 px (row-folded kernel)
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -100,6 +111,9 @@ struct nesr_b200_handle {
   int64_t w_rows = 0;
   float* d_bias = nullptr;
   CUtensorMap m_w[3];                                  // box rows 16 / 32 / 64
+  uint16_t* d_wfold = nullptr;                         // folded weights [dx][chunk][dy: +1,0,-1][cout][64]
+  int64_t wfold_rows = 0;
+  CUtensorMap m_wf[3];                                 // box rows 48 / 96 / 192
 
   PlanKey key;
   std::vector<Batch> batches;
@@ -182,6 +196,17 @@ void build_layers(nesr_b200_handle* h) {
     boff += 64;
   }
   h->w_rows = rows;
+  int64_t frows = 0;
+  for (Layer& L : h->layers) {
+    const bool fits = conv3x3_fold_fits(L.cin16, L.npad);
+    L.fold_passes = fits ? 1 : 2;
+    L.fold_npad = fits ? L.npad : L.npad / 2;
+    for (int ps = 0; ps < L.fold_passes; ++ps) {
+      L.fold_row0[ps] = (int)frows;
+      frows += (int64_t)3 * L.nchunk * 3 * L.fold_npad;
+    }
+  }
+  h->wfold_rows = frows;
 }
 
 
@@ -200,6 +225,27 @@ void pack_layer(const Layer& L, const float* w_oihw, uint16_t* arena) {
           row[k] = to16(v, L.fmt);
         }
       }
+}
+
+// Folded layout of one pass (output channels [n_off, n_off + npad)): row
+//   ((dx*nchunk + chunk)*3 + g)*npad + n      g = 0,1,2 <-> dy = +1,0,-1 <-> ky = 2,1,0
+// holds input channels [chunk*64, +64) of tap (ky, kx = dx).  One TMA box [3*npad x 64] per (dx, chunk)
+// is the B operand of the folded MMA: its three column groups feed output rows y-1, y, y+1.
+void pack_layer_fold(const Layer& L, int pass, const float* w_oihw, uint16_t* arena) {
+  const int npad = L.fold_npad, n_off = pass * npad;
+  for (int dx = 0; dx < 3; ++dx)
+    for (int c = 0; c < L.nchunk; ++c)
+      for (int g = 0; g < 3; ++g)
+        for (int n = 0; n < npad; ++n) {
+          uint16_t* row = arena + ((int64_t)L.fold_row0[pass] + (((int64_t)dx * L.nchunk + c) * 3 + g) * npad + n) * 64;
+          const int ky = 2 - g, co = n_off + n;
+          for (int k = 0; k < 64; ++k) {
+            const int ci = c * 64 + k;
+            float v = 0.f;
+            if (co < L.cout && ci < L.cin) v = w_oihw[((int64_t)co * L.cin + ci) * 9 + ky * 3 + dx];
+            row[k] = to16(v, L.fmt);
+          }
+        }
 }
 
 int make_map(nesr_b200_handle* h, CUtensorMap* m, void* base, int64_t channels, int64_t rows, int box_rows) {
@@ -237,7 +283,11 @@ Grid tile_grid_dims(int H, int W, int tile, int pre_pad, int scale) {
 void free_batches(nesr_b200_handle* h) {
   for (Batch& b : h->batches) {
     if (b.d_tiles) cudaFree(b.d_tiles);
-    for (LevelPlan& l : b.lv) if (l.d_blocks) cudaFree(l.d_blocks);
+    for (LevelPlan& l : b.lv) {
+      if (l.d_blocks) cudaFree(l.d_blocks);
+      if (l.d_bands) cudaFree(l.d_bands);
+      if (l.d_cta_off) cudaFree(l.d_cta_off);
+    }
   }
   h->batches.clear();
   h->key = PlanKey();
@@ -259,6 +309,43 @@ void layout_level(Batch& b, int level) {
   }
   cursor += round_up(prev_pitch + 1, kBlockPixels);
   lp.pixels = cursor;
+}
+
+// Row-folded kernel schedule: every tile is cut into 128-pixel column strips, every strip into bands
+// of consecutive rows (about two bands per SM so the load balances), and the bands are dealt to the
+// CTAs longest-first.  A band costs rows + 2 input row slabs.
+void build_fold_schedule(Batch& b, int level, int num_sms) {
+  LevelPlan& lp = b.lv[level];
+  int64_t total_rows = 0;
+  for (const TileGeom& t : b.tiles) total_rows += (int64_t)t.lv[level].h * ((t.lv[level].w + kBlockPixels - 1) / kBlockPixels);
+  const int target = (int)std::max<int64_t>(8, (total_rows + 2 * num_sms - 1) / (2 * num_sms));
+  std::vector<FoldBand> all;
+  for (size_t ti = 0; ti < b.tiles.size(); ++ti) {
+    const LevelGeom& g = b.tiles[ti].lv[level];
+    const int nb = (g.h + target - 1) / target;
+    for (int x0 = 0; x0 < g.w; x0 += kBlockPixels)
+      for (int k = 0; k < nb; ++k) {
+        const int r0 = (int)((int64_t)g.h * k / nb), r1 = (int)((int64_t)g.h * (k + 1) / nb);
+        if (r1 > r0) all.push_back(FoldBand{(int32_t)ti, x0, r0, r1 - r0});
+      }
+  }
+  std::stable_sort(all.begin(), all.end(), [](const FoldBand& a, const FoldBand& c) { return a.rows > c.rows; });
+  const int grid = (int)std::min<size_t>((size_t)num_sms, all.size());
+  std::vector<std::vector<FoldBand>> per(grid);
+  std::vector<int64_t> load(grid, 0);
+  for (const FoldBand& band : all) {
+    int best = 0;
+    for (int c = 1; c < grid; ++c) if (load[c] < load[best]) best = c;
+    per[best].push_back(band);
+    load[best] += band.rows + 2;
+  }
+  lp.bands.clear();
+  lp.cta_off.assign(1, 0);
+  for (int c = 0; c < grid; ++c) {
+    lp.bands.insert(lp.bands.end(), per[c].begin(), per[c].end());
+    lp.cta_off.push_back((int32_t)lp.bands.size());
+  }
+  lp.fold_grid = grid;
 }
 
 int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
@@ -311,7 +398,7 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
       px += n;
       ++i;
     }
-    for (int l = 0; l < 3; ++l) layout_level(b, l);
+    for (int l = 0; l < 3; ++l) { layout_level(b, l); build_fold_schedule(b, l, h->num_sms); }
     if (b.lv[2].pixels >= ((int64_t)1 << 31) - 4096) return fail(h, NESR_E_INVALID, "batch too large for 32-bit pixel indices");
     h->batches.push_back(std::move(b));
   }
@@ -324,6 +411,10 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
       LevelPlan& lp = b.lv[l];
       CUDA_TRY(h, cudaMalloc(&lp.d_blocks, std::max<size_t>(1, lp.blocks.size()) * sizeof(BlockRef)));
       CUDA_TRY(h, cudaMemcpyAsync(lp.d_blocks, lp.blocks.data(), lp.blocks.size() * sizeof(BlockRef), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(h, cudaMalloc(&lp.d_bands, std::max<size_t>(1, lp.bands.size()) * sizeof(FoldBand)));
+      CUDA_TRY(h, cudaMemcpyAsync(lp.d_bands, lp.bands.data(), lp.bands.size() * sizeof(FoldBand), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(h, cudaMalloc(&lp.d_cta_off, lp.cta_off.size() * sizeof(int32_t)));
+      CUDA_TRY(h, cudaMemcpyAsync(lp.d_cta_off, lp.cta_off.data(), lp.cta_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
       P[l] = std::max(P[l], lp.pixels);
     }
   }
@@ -354,6 +445,11 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
   for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.m_d[i2], a.d[i2], kDense, P[0], kBlockPixels))) return rc;
   if ((rc = make_map(h, &a.m_g2, a.g2, 64, P[1], kBlockPixels))) return rc;
   for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.m_g4[i2], a.g4[i2], 64, P[2], kBlockPixels))) return rc;
+  constexpr int kSlab = 136;                                   // row slab of the folded kernel
+  if ((rc = make_map(h, &a.f_x0, a.x0, 64, P[0], kSlab))) return rc;
+  for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.f_d[i2], a.d[i2], kDense, P[0], kSlab))) return rc;
+  if ((rc = make_map(h, &a.f_g2, a.g2, 64, P[1], kSlab))) return rc;
+  for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.f_g4[i2], a.g4[i2], 64, P[2], kSlab))) return rc;
   h->stats.arena_bytes = (int64_t)a.bytes;
   h->key = key;
   return NESR_OK;
@@ -363,7 +459,8 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
 // network schedule
 // ----------------------------------------------------------------------------------------------
 struct ConvIO {
-  const CUtensorMap* amap = nullptr;
+  const CUtensorMap* amap = nullptr;     // box 128 px
+  const CUtensorMap* fmap = nullptr;     // box 136 px
   const void* src = nullptr;
   int src_pitch = 0;
   int level = 0;
@@ -376,13 +473,30 @@ int run_conv(nesr_b200_handle* h, const Batch& b, const Layer& L, const ConvIO& 
   p.wpack = h->d_wpack; p.w_row0 = L.w_row0; p.npad = L.npad; p.fmt = L.fmt;
   p.idesc = umma_idesc_f16(hw_fmt(L.fmt), (uint32_t)L.npad);
   p.bias = h->d_bias + L.bias_off; p.cout = L.cout;
-  cudaError_t e;
+  cudaError_t e = cudaSuccess;
   if (h->cfg.conv_impl == 1) {
     e = launch_conv3x3_simt(p, s);
-  } else {
+  } else if (h->cfg.conv_impl == 2) {
     const CUtensorMap& wm = h->m_w[L.npad == 16 ? 0 : (L.npad == 32 ? 1 : 2)];
     e = launch_conv3x3_tc(*io.amap, wm, p, h->num_sms, s);
     h->stats.conv_launches++;
+  } else {
+    p.bands = lp.d_bands; p.cta_band_off = lp.d_cta_off;
+    const float* bias0 = p.bias;
+    const int coff0 = p.dst16_coff;
+    for (int ps = 0; ps < L.fold_passes && e == cudaSuccess; ++ps) {
+      p.npad = L.fold_npad;
+      p.c_off = ps * L.fold_npad;
+      p.bias = bias0 + p.c_off;
+      p.dst16_coff = coff0 + p.c_off;
+      p.cout = std::min(L.cout - p.c_off, L.fold_npad);
+      p.w_row0 = L.fold_row0[ps];
+      p.idesc = umma_idesc_f16(hw_fmt(L.fmt), (uint32_t)L.fold_npad);
+      const CUtensorMap& wm = h->m_wf[L.fold_npad == 16 ? 0 : (L.fold_npad == 32 ? 1 : 2)];
+      e = launch_conv3x3_fold(*io.fmap, wm, p, lp.fold_grid, s);
+      h->stats.conv_launches++;
+      if (ps + 1 < L.fold_passes) h->stats.kernel_launches++;
+    }
   }
   h->stats.kernel_launches++;
   if (e != cudaSuccess) return fail(h, NESR_E_CUDA, "conv %s launch failed: %s", L.name.c_str(), cudaGetErrorString(e));
@@ -417,12 +531,12 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
     ConvParams p{};
     p.dst32a = a.trunk; p.dst32b = a.feat;
     p.dst16 = a.d[0]; p.dst16_pitch = kDense; p.dst16_coff = 0; p.dst16_fmt = c.body_format;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_x0, a.x0, 64, 0}, p, s))) return rc;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_x0, &a.f_x0, a.x0, 64, 0}, p, s))) return rc;
   }
   int cur = 0;
   const int nrdb = c.num_block * 3;
   for (int r = 0; r < nrdb; ++r) {
-    const ConvIO io{&a.m_d[cur], a.d[cur], kDense, 0};
+    const ConvIO io{&a.m_d[cur], &a.f_d[cur], a.d[cur], kDense, 0};
     for (int k = 1; k <= 4; ++k) {   // x_k = lrelu(conv_k(cat(x, x1..x_{k-1})))  -> channels [64+32(k-1), +32)
       ConvParams p{};
       p.lrelu = 1;
@@ -445,31 +559,31 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
     ConvParams p{};
     p.res1 = a.feat; p.s1 = 1.0f;
     p.dst16 = a.g2; p.dst16_pitch = 64; p.dst16_fmt = c.edge_format; p.dst16_up = 1;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_d[cur], a.d[cur], kDense, 0}, p, s))) return rc;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_d[cur], &a.f_d[cur], a.d[cur], kDense, 0}, p, s))) return rc;
   }
   {  // conv_up1 + lrelu, stored upsampled into level 2
     ConvParams p{};
     p.lrelu = 1;
     p.dst16 = a.g4[0]; p.dst16_pitch = 64; p.dst16_fmt = c.edge_format; p.dst16_up = 1;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g2, a.g2, 64, 1}, p, s))) return rc;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g2, &a.f_g2, a.g2, 64, 1}, p, s))) return rc;
   }
   {  // conv_up2 + lrelu
     ConvParams p{};
     p.lrelu = 1;
     p.dst16 = a.g4[1]; p.dst16_pitch = 64; p.dst16_fmt = c.edge_format;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], a.g4[0], 64, 2}, p, s))) return rc;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], &a.f_g4[0], a.g4[0], 64, 2}, p, s))) return rc;
   }
   {  // conv_hr + lrelu
     ConvParams p{};
     p.lrelu = 1;
     p.dst16 = a.g4[0]; p.dst16_pitch = 64; p.dst16_fmt = c.edge_format;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[1], a.g4[1], 64, 2}, p, s))) return rc;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[1], &a.f_g4[1], a.g4[1], 64, 2}, p, s))) return rc;
   }
   {  // conv_last -> clamp, BGR, u8, halo crop + stitch  (or unclamped fp32 NCHW)
     ConvParams p{};
     p.out_u8 = sink.out_u8; p.out_stride = sink.out_stride; p.out_frame_stride = sink.out_frame_stride;
     p.out_f32 = sink.out_f32; p.out_h = sink.out_h; p.out_w = sink.out_w;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], a.g4[0], 64, 2}, p, s))) return rc;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], &a.f_g4[0], a.g4[0], 64, 2}, p, s))) return rc;
   }
   if (time_convs) cudaEventRecord(h->evc1, s);
   h->stats.tiles_processed += (int64_t)b.tiles.size();
@@ -590,7 +704,7 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
       (e = cudaEventCreate(&h->evc0)) != cudaSuccess || (e = cudaEventCreate(&h->evc1)) != cudaSuccess ||
-      (e = conv3x3_tc_configure()) != cudaSuccess) {
+      (e = conv3x3_tc_configure()) != cudaSuccess || (e = conv3x3_fold_configure()) != cudaSuccess) {
     std::string msg = cudaGetErrorString(e);
     nesr_b200_destroy(h);
     return fail(nullptr, NESR_E_CUDA, "device setup failed: %s", msg.c_str());
@@ -608,6 +722,7 @@ int nesr_b200_destroy(nesr_b200_handle* h) {
   if (h->arena.base) cudaFree(h->arena.base);
   if (h->d_wpack) cudaFree(h->d_wpack);
   if (h->d_bias) cudaFree(h->d_bias);
+  if (h->d_wfold) cudaFree(h->d_wfold);
   if (h->d_in) cudaFree(h->d_in);
   if (h->d_out) cudaFree(h->d_out);
   if (h->d_tmp) cudaFree(h->d_tmp);
@@ -647,6 +762,16 @@ int nesr_b200_finalize_weights(nesr_b200_handle* h) {
     pack_layer(L, h->staged[L.name + ".weight"].data(), arena.data());
     const std::vector<float>& bv = h->staged[L.name + ".bias"];
     std::copy(bv.begin(), bv.end(), bias.begin() + L.bias_off);
+  }
+  std::vector<uint16_t> farena((size_t)h->wfold_rows * 64, 0);
+  for (const Layer& L : h->layers)
+    for (int ps = 0; ps < L.fold_passes; ++ps) pack_layer_fold(L, ps, h->staged[L.name + ".weight"].data(), farena.data());
+  if (!h->d_wfold) CUDA_TRY(h, cudaMalloc(&h->d_wfold, farena.size() * 2));
+  CUDA_TRY(h, cudaMemcpy(h->d_wfold, farena.data(), farena.size() * 2, cudaMemcpyHostToDevice));
+  const int fbox[3] = {48, 96, 192};
+  for (int i = 0; i < 3; ++i) {
+    int rc = make_map(h, &h->m_wf[i], h->d_wfold, 64, h->wfold_rows, fbox[i]);
+    if (rc) return rc;
   }
   if (!h->d_wpack) CUDA_TRY(h, cudaMalloc(&h->d_wpack, arena.size() * 2));
   if (!h->d_bias) CUDA_TRY(h, cudaMalloc(&h->d_bias, bias.size() * 4));
@@ -799,9 +924,18 @@ int nesr_b200_debug_conv(nesr_b200_handle* h, int32_t impl, int32_t fmt, int32_t
   L.name = "debug"; L.cin = cin; L.cout = cout; L.fmt = fmt;
   L.cin16 = (int)round_up(cin, 16); L.nchunk = (L.cin16 + 63) / 64; L.npad = cout <= 16 ? 16 : (cout <= 32 ? 32 : 64);
   L.w_row0 = 0; L.bias_off = 0;
-  const int64_t rows = (int64_t)9 * L.nchunk * L.npad;
+  const bool fits = conv3x3_fold_fits(L.cin16, L.npad);
+  L.fold_passes = fits ? 1 : 2;
+  L.fold_npad = fits ? L.npad : L.npad / 2;
+  const int64_t pass_rows = (int64_t)3 * L.nchunk * 3 * L.fold_npad;
+  L.fold_row0[0] = 0; L.fold_row0[1] = (int)pass_rows;
+  const int64_t rows = impl == 0 ? pass_rows * L.fold_passes : (int64_t)9 * L.nchunk * L.npad;
   std::vector<uint16_t> wp((size_t)rows * 64, 0);
-  pack_layer(L, weight_oihw, wp.data());
+  if (impl == 0) {
+    for (int ps = 0; ps < L.fold_passes; ++ps) pack_layer_fold(L, ps, weight_oihw, wp.data());
+  } else {
+    pack_layer(L, weight_oihw, wp.data());
+  }
   std::vector<float> bpad(64, 0.f);
   std::copy(bias, bias + cout, bpad.begin());
   Batch b;
@@ -810,7 +944,9 @@ int nesr_b200_debug_conv(nesr_b200_handle* h, int32_t impl, int32_t fmt, int32_t
   t.lv[1] = t.lv[0]; t.lv[2] = t.lv[0];
   b.tiles.push_back(t);
   layout_level(b, 0);
-  const int64_t P = b.lv[0].pixels;
+  build_fold_schedule(b, 0, h->num_sms);
+  const LevelPlan& lp = b.lv[0];
+  const int64_t P = lp.pixels;
   const int src_pitch = L.nchunk * 64;
   std::vector<uint16_t> xs((size_t)P * src_pitch, 0);
   const LevelGeom g = b.tiles[0].lv[0];
@@ -820,10 +956,10 @@ int nesr_b200_debug_conv(nesr_b200_handle* h, int32_t impl, int32_t fmt, int32_t
         xs[((size_t)g.base + (size_t)y * g.pitch + x) * src_pitch + c] = to16(x_nchw[((size_t)c * H + y) * W + x], fmt);
   uint16_t *d_w = nullptr, *d_x = nullptr;
   float *d_b = nullptr, *d_y = nullptr;
-  TileGeom* d_t = nullptr; BlockRef* d_blk = nullptr;
+  TileGeom* d_t = nullptr; BlockRef* d_blk = nullptr; FoldBand* d_bands = nullptr; int32_t* d_off = nullptr;
   int rc = NESR_OK;
   auto cleanup = [&]() {
-    cudaFree(d_w); cudaFree(d_x); cudaFree(d_b); cudaFree(d_y); cudaFree(d_t); cudaFree(d_blk);
+    cudaFree(d_w); cudaFree(d_x); cudaFree(d_b); cudaFree(d_y); cudaFree(d_t); cudaFree(d_blk); cudaFree(d_bands); cudaFree(d_off);
   };
 #define DBG_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(h, NESR_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); } } while (0)
   DBG_TRY(cudaMalloc(&d_w, wp.size() * 2));
@@ -831,25 +967,39 @@ int nesr_b200_debug_conv(nesr_b200_handle* h, int32_t impl, int32_t fmt, int32_t
   DBG_TRY(cudaMalloc(&d_b, 64 * 4));
   DBG_TRY(cudaMalloc(&d_y, (size_t)P * 64 * 4));
   DBG_TRY(cudaMalloc(&d_t, sizeof(TileGeom)));
-  DBG_TRY(cudaMalloc(&d_blk, b.lv[0].blocks.size() * sizeof(BlockRef)));
+  DBG_TRY(cudaMalloc(&d_blk, lp.blocks.size() * sizeof(BlockRef)));
+  DBG_TRY(cudaMalloc(&d_bands, lp.bands.size() * sizeof(FoldBand)));
+  DBG_TRY(cudaMalloc(&d_off, lp.cta_off.size() * sizeof(int32_t)));
   DBG_TRY(cudaMemcpy(d_w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
   DBG_TRY(cudaMemcpy(d_x, xs.data(), xs.size() * 2, cudaMemcpyHostToDevice));
   DBG_TRY(cudaMemcpy(d_b, bpad.data(), 64 * 4, cudaMemcpyHostToDevice));
   DBG_TRY(cudaMemset(d_y, 0, (size_t)P * 64 * 4));
   DBG_TRY(cudaMemcpy(d_t, b.tiles.data(), sizeof(TileGeom), cudaMemcpyHostToDevice));
-  DBG_TRY(cudaMemcpy(d_blk, b.lv[0].blocks.data(), b.lv[0].blocks.size() * sizeof(BlockRef), cudaMemcpyHostToDevice));
+  DBG_TRY(cudaMemcpy(d_blk, lp.blocks.data(), lp.blocks.size() * sizeof(BlockRef), cudaMemcpyHostToDevice));
+  DBG_TRY(cudaMemcpy(d_bands, lp.bands.data(), lp.bands.size() * sizeof(FoldBand), cudaMemcpyHostToDevice));
+  DBG_TRY(cudaMemcpy(d_off, lp.cta_off.data(), lp.cta_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   ConvParams p{};
-  p.blocks = d_blk; p.tiles = d_t; p.nblk = (int)b.lv[0].blocks.size(); p.level = 0;
+  p.blocks = d_blk; p.tiles = d_t; p.nblk = (int)lp.blocks.size(); p.level = 0;
   p.src = d_x; p.src_pitch = src_pitch; p.cin = L.cin16; p.wpack = d_w; p.w_row0 = 0; p.npad = L.npad; p.fmt = fmt;
   p.idesc = umma_idesc_f16(hw_fmt(fmt), (uint32_t)L.npad);
   p.bias = d_b; p.cout = cout; p.lrelu = lrelu; p.dst32a = d_y;
-  cudaError_t e;
+  cudaError_t e = cudaSuccess;
   if (impl == 1) {
     e = launch_conv3x3_simt(p, h->stream);
-  } else {
+  } else if (impl == 2) {
     CUtensorMap am, wm;
     if ((rc = make_map(h, &am, d_x, src_pitch, P, kBlockPixels)) || (rc = make_map(h, &wm, d_w, 64, rows, L.npad))) { cleanup(); return rc; }
     e = launch_conv3x3_tc(am, wm, p, h->num_sms, h->stream);
+  } else {
+    CUtensorMap am, wm;
+    if ((rc = make_map(h, &am, d_x, src_pitch, P, 136)) || (rc = make_map(h, &wm, d_w, 64, rows, 3 * L.fold_npad))) { cleanup(); return rc; }
+    p.bands = d_bands; p.cta_band_off = d_off;
+    for (int ps = 0; ps < L.fold_passes && e == cudaSuccess; ++ps) {
+      p.npad = L.fold_npad; p.c_off = ps * L.fold_npad; p.bias = d_b + p.c_off;
+      p.cout = std::min(cout - p.c_off, L.fold_npad); p.w_row0 = L.fold_row0[ps];
+      p.idesc = umma_idesc_f16(hw_fmt(fmt), (uint32_t)L.fold_npad);
+      if (p.cout > 0) e = launch_conv3x3_fold(am, wm, p, lp.fold_grid, h->stream);
+    }
   }
   h->stats.kernel_launches++;
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);

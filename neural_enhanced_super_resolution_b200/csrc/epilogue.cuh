@@ -64,7 +64,7 @@ __device__ __forceinline__ void epilogue16(const ConvParams& p, const TileGeom& 
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = v[i] >= 0.f ? v[i] : 0.2f * v[i];
   }
-  const size_t t64 = static_cast<size_t>(px.P) * kFeat + n0;
+  const size_t t64 = static_cast<size_t>(px.P) * kFeat + p.c_off + n0;
   if (p.res1) {
     const float4* r4 = reinterpret_cast<const float4*>(p.res1 + t64);
 #pragma unroll

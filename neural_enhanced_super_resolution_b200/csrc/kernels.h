@@ -8,10 +8,16 @@
 
 namespace nesr {
 
-// --- conv3x3_tc.cu : tcgen05 / TMEM / TMA implicit-GEMM conv (the product path) -----------------
+// --- conv3x3_tc.cu : per-tap tcgen05 implicit-GEMM conv (first-generation kernel, conv_impl = 2) --
 cudaError_t conv3x3_tc_configure();
 cudaError_t launch_conv3x3_tc(const CUtensorMap& amap, const CUtensorMap& wmap, const ConvParams& p, int num_sms,
                               cudaStream_t stream);
+
+// --- conv3x3_fold.cu : row-folded tcgen05 conv, N = 3*Cout (the production kernel) ---------------
+cudaError_t conv3x3_fold_configure();
+bool conv3x3_fold_fits(int cin16, int npad);
+cudaError_t launch_conv3x3_fold(const CUtensorMap& amap, const CUtensorMap& wmap, const ConvParams& p, int grid,
+                                cudaStream_t stream);
 
 // --- conv3x3_simt.cu : plain CUDA-core conv over the same buffers (test-only cross-check) -------
 cudaError_t launch_conv3x3_simt(const ConvParams& p, cudaStream_t stream);

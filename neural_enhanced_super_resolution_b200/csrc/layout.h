@@ -41,6 +41,12 @@ struct BlockRef {
   int32_t tile;
 };
 
+// One unit of work of the row-folded conv kernel: output rows [r0, r0+rows) of the 128-pixel-wide
+// column strip starting at x0 of tile `tile`.
+struct FoldBand {
+  int32_t tile, x0, r0, rows;
+};
+
 struct ConvParams {
   const BlockRef* blocks;
   const TileGeom* tiles;
@@ -75,6 +81,11 @@ struct ConvParams {
   int64_t out_frame_stride;    // bytes per frame
   float* out_f32;              // NCHW frames (unclamped) or null
   int32_t out_h, out_w;        // frame dims for out_f32
+  // row-folded kernel (conv3x3_fold.cu)
+  const FoldBand* bands;       // all bands of the level, grouped by CTA
+  const int32_t* cta_band_off; // [grid + 1] first band of each CTA
+  int32_t c_off;               // first output channel of this pass inside the 64-channel fp32 buffers
+  int32_t fold_stages;         // activation ring depth (host-computed from the shared-memory budget)
 };
 
 }  // namespace nesr

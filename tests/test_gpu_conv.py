@@ -33,20 +33,27 @@ CASES = [  # cin, cout, H, W
     (64, 64, 40, 67),     # conv_body / up / hr, several M-blocks per row group
     (64, 3, 15, 33),      # conv_last (N padded to 16)
     (64, 32, 1, 1),       # degenerate
-    (64, 32, 3, 300),     # wide: pitch > 128
+    (64, 32, 3, 300),     # wide: pitch > 128, three column strips
+    (192, 64, 70, 140),   # conv5 as two folded passes, several bands per strip, ring wraps
+    (64, 64, 45, 129),    # Cout 64 ring (8 slots) wraps many times; 1-pixel second strip
+    (160, 32, 37, 128),   # exactly one full strip
 ]
 
 
+FOLD, SIMT, PERTAP = 0, 1, 2      # conv_impl: row-folded tcgen05 (product), SIMT validation, per-tap tcgen05
+
+
+@pytest.mark.parametrize("impl", [FOLD, PERTAP])
 @pytest.mark.parametrize("fmt", [_ffi.FMT_BF16, _ffi.FMT_FP16])
 @pytest.mark.parametrize("cin,cout,h,w", CASES)
-def test_tc_conv_matches_torch(engine, cin, cout, h, w, fmt):
+def test_tc_conv_matches_torch(engine, cin, cout, h, w, fmt, impl):
     g = torch.Generator().manual_seed(cin * 1000 + cout * 10 + h)
     x = torch.randn(cin, h, w, generator=g)
     wt = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
     b = torch.randn(cout, generator=g) * 0.1
     want = F.conv2d(_round(x, fmt).unsqueeze(0).double(), _round(wt, fmt).double(), b.double(), padding=1)[0]
     want = F.leaky_relu(want, 0.2).float().numpy()
-    got = engine.debug_conv(x.numpy(), wt.numpy(), b.numpy(), lrelu=True, impl=0, fmt=fmt)
+    got = engine.debug_conv(x.numpy(), wt.numpy(), b.numpy(), lrelu=True, impl=impl, fmt=fmt)
     assert got.shape == want.shape
     err = np.abs(got - want).max()
     assert err < 2e-4 * max(1.0, np.abs(want).max()), f"max err {err}"
@@ -58,9 +65,9 @@ def test_tc_conv_matches_simt_validation_kernel(engine, cin, cout, h, w):
     x = torch.randn(cin, h, w, generator=g).numpy()
     wt = (torch.randn(cout, cin, 3, 3, generator=g) * 0.05).numpy()
     b = torch.randn(cout, generator=g).numpy()
-    tc = engine.debug_conv(x, wt, b, impl=0)
-    simt = engine.debug_conv(x, wt, b, impl=1)
-    assert np.abs(tc - simt).max() < 1e-4
+    simt = engine.debug_conv(x, wt, b, impl=SIMT)
+    for impl in (FOLD, PERTAP):
+        assert np.abs(engine.debug_conv(x, wt, b, impl=impl) - simt).max() < 1e-4
 
 
 def test_conv_is_linear_and_translation_consistent(engine):

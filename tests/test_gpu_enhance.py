@@ -131,12 +131,13 @@ def test_device_tensor_in_out(up_random):
     assert dev.is_cuda and mode == "RGB" and np.array_equal(dev.cpu().numpy(), host)
 
 
-def test_simt_validation_path_agrees_with_tensor_path():
-    img = natural_image(32, 48, seed=3)
-    tc, _ = gpu_up("calibrated").enhance(img)
-    simt, _ = gpu_up("calibrated", conv_impl=1).enhance(img)
-    d = np.abs(tc.astype(int) - simt.astype(int))
-    assert d.max() <= 1 and (d > 0).mean() < 5e-2
+def test_validation_kernels_agree_with_the_product_kernel():
+    img = natural_image(40, 140, seed=3)                      # two column strips
+    fold, _ = gpu_up("calibrated").enhance(img)
+    for impl in (1, 2):                                        # SIMT validation kernel, per-tap tcgen05 kernel
+        other, _ = gpu_up("calibrated", conv_impl=impl).enhance(img)
+        d = np.abs(fold.astype(int) - other.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 5e-2
 
 
 # ---------------------------------------------------------------------------------------------
