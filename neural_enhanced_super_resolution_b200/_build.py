@@ -19,6 +19,8 @@ SOURCES = ["conv3x3_fold.cu", "conv3x3_tc.cu", "conv3x3_simt.cu", "pixel_io.cu",
 HEADERS = ["ptx.cuh", "layout.h", "epilogue.cuh", "kernels.h", os.path.join("..", "..", "include", "nesr_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+if os.environ.get("NESR_B200_PROF") == "1":          # device printf + per-role cycle accounting (timing experiments)
+    FLAGS.append("-DNESR_PROF=1")
 
 
 def _nvcc() -> str:

@@ -36,7 +36,23 @@ namespace nesr {
 
 namespace {
 
-constexpr int kThreads = 192;
+// NESR_PROF build + debug_flags & 32: block 0 prints where each role spent its cycles (timing experiments only)
+#if NESR_PROF
+#define PROF_DECL long long prof_t = 0, prof_acc[4] = {0, 0, 0, 0}; const bool prof_on = (p.debug_flags & 32) && blockIdx.x == 0
+#define PROF_BEGIN() do { if (prof_on) prof_t = clock64(); } while (0)
+#define PROF_END(k) do { if (prof_on) { const long long t__ = clock64(); prof_acc[k] += t__ - prof_t; prof_t = t__; } } while (0)
+#define PROF_PRINT(...) do { if (prof_on) printf(__VA_ARGS__); } while (0)
+#define PROF_NOW() clock64()
+#else
+#define PROF_DECL do {} while (0)
+#define PROF_BEGIN() do {} while (0)
+#define PROF_END(k) do {} while (0)
+#define PROF_PRINT(...) do {} while (0)
+#define PROF_NOW() 0LL
+#endif
+
+constexpr int kEpiGroups = 2;                      // epilogue warp-groups (4 warps each) alternating over rows
+constexpr int kThreads = 64 + 128 * kEpiGroups;
 constexpr int kSlabPx = 136;                       // 1 + 128 + 1 halo pixels, rounded to 8-row groups
 constexpr int kSlabBytes = kSlabPx * 128;          // 17408 = 17 * 1024
 constexpr int kMaxStages = 8;
@@ -91,7 +107,7 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (warp >= 2) {                                             // every MMA accumulates: start from zero
+  if (warp >= 2 && warp < 6 && !(p.debug_flags & 128)) {       // every MMA accumulates: start from zero
     const uint32_t t0 = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     for (int c = 0; c < Cfg::kCols; c += 16) tmem_st16_zero(t0 + c);
     tmem_st_wait();
@@ -102,104 +118,145 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
 
   const int band_begin = p.cta_band_off[blockIdx.x];
   const int band_end = p.cta_band_off[blockIdx.x + 1];
+  pdl_launch_dependents();        // the next layer may start its prologue on SMs this grid has left
 
   if (warp == 0) {
-    // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
-      mbar_arrive_expect_tx(wbar, wbytes);
-      for (int b = 0; b < 3 * nchunk; ++b)
-        tma_load_2d(wsm + b * Cfg::kWBoxBytes, &wmap, wbar, 0, p.w_row0 + b * Cfg::kN3);
+    // ------------------------------ TMA producer (warp-wide, one elected lane issues) ----------
+    {
+      if (elect_one()) {
+        if (p.debug_flags & 64) {
+          mbar_arrive(wbar);
+        } else {
+          mbar_arrive_expect_tx(wbar, wbytes);
+          for (int b = 0; b < 3 * nchunk; ++b)
+            tma_load_2d(wsm + b * Cfg::kWBoxBytes, &wmap, wbar, 0, p.w_row0 + b * Cfg::kN3);
+        }
+      }
+      pdl_wait();                  // activations below were written by the previous layer
+      // Band geometry is read once per band; inside a band the slab coordinate advances by the row
+      // pitch in registers.  (Fetching it per slab made the producer latency-bound on its own
+      // metadata loads whenever the epilogue kept the memory system busy: profiles/r1_fold_role_timing.txt.)
       int stage = 0;
       uint32_t phase = 0;
+      PROF_DECL;
+      [[maybe_unused]] const long long prof_start = PROF_NOW();
       for (int bi = band_begin; bi < band_end; ++bi) {
         const FoldBand band = p.bands[bi];
         const LevelGeom g = p.tiles[band.tile].lv[p.level];
-        for (int i = 0; i < band.rows + 2; ++i) {
-          const int px0 = g.base + (band.r0 - 1 + i) * g.pitch + band.x0 - 1;
+        int px0 = g.base + (band.r0 - 1) * g.pitch + band.x0 - 1;
+        for (int i = 0; i < band.rows + 2; ++i, px0 += g.pitch) {
           for (int c = 0; c < nchunk; ++c) {
+            PROF_BEGIN();
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], kSlabBytes);
-            tma_load_2d(ring + stage * kSlabBytes, &amap, &full[stage], c * kChunkChannels, px0);
+            PROF_END(0);
+            if (elect_one()) {
+              if (p.debug_flags & 4) {
+                mbar_arrive(&full[stage]);
+              } else {
+                mbar_arrive_expect_tx(&full[stage], kSlabBytes);
+                tma_load_2d(ring + stage * kSlabBytes, &amap, &full[stage], 0, c * p.src_plane_px + px0);
+              }
+            }
             if (++stage == nstage) { stage = 0; phase ^= 1; }
           }
         }
       }
+      if (lane == 0)
+        PROF_PRINT("[fold cin=%d cout=%d] producer: total %lld  wait_empty %lld\n", p.cin, COUT, PROF_NOW() - prof_start, prof_acc[0]);
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
+    // ------------------------------ MMA issuer (warp-wide, one elected lane issues) ------------
+    {
       const uint32_t hw = (p.idesc >> 7) & 7u;                 // operand format bits of the layer
       const uint32_t idesc1 = umma_idesc_f16(hw, COUT), idesc2 = umma_idesc_f16(hw, 2 * COUT),
                      idesc3 = umma_idesc_f16(hw, 3 * COUT);
-      const uint32_t w_addr = smem_u32(wsm);
+      const uint32_t hi = umma_desc_hi_sw128();
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(ring));
+      const uint32_t w_lo0 = umma_desc_lo(smem_u32(wsm));
+      constexpr uint32_t kSlabLo = kSlabBytes >> 4, kBoxLo = Cfg::kWBoxBytes >> 4;
       mbar_wait(wbar, 0);
       tc_fence_after();
       int stage = 0;
       uint32_t phase = 0;
       uint32_t u = 0;                                          // running row-slot counter
+      PROF_DECL;
+      [[maybe_unused]] const long long prof_start = PROF_NOW();
+      [[maybe_unused]] int prof_rows = 0;
       for (int bi = band_begin; bi < band_end; ++bi) {
         const int rows = p.bands[bi].rows;
+        prof_rows += rows + 2;
         for (int j = 0; j < 2; ++j) {                          // slots of the first two (virtual) output rows
           const uint32_t v = u + j;
           mbar_wait(&tempty[v % Cfg::kSlots], ((v / Cfg::kSlots) & 1) ^ 1);
         }
         for (int i = 0; i < rows + 2; ++i) {
+          PROF_BEGIN();
           {                                                    // slot of output row i+2 must be drained + zeroed
             const uint32_t v = u + i + 2;
             mbar_wait(&tempty[v % Cfg::kSlots], ((v / Cfg::kSlots) & 1) ^ 1);
           }
+          PROF_END(0);
           tc_fence_after();
           const uint32_t q = (u + i) % Cfg::kSlots;
+          // accumulator = row slots (q, q+1, q+2); at the ring end it splits into two narrower MMAs
           const uint32_t d0 = tmem_base + q * COUT;
+          uint32_t id0 = idesc3, id1 = 0, b1 = 0;
+          if (q + 2 == Cfg::kSlots) { id0 = idesc2; id1 = idesc1; b1 = (2 * COUT * 128) >> 4; }
+          else if (q + 1 == Cfg::kSlots) { id0 = idesc1; id1 = idesc2; b1 = (COUT * 128) >> 4; }
           for (int c = 0; c < nchunk; ++c) {
             const int rem = (p.cin - c * kChunkChannels) >> 4;
             const int ksteps = rem < 4 ? rem : 4;
+            PROF_BEGIN();
             mbar_wait(&full[stage], phase);
+            PROF_END(1);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(ring + stage * kSlabBytes);
+            const uint32_t a_lo = a_lo0 + stage * kSlabLo;
+            const uint32_t b_lo = w_lo0 + c * kBoxLo;
+            if (!(p.debug_flags & 2) && elect_one()) {
+              if (ksteps == 4) {
 #pragma unroll
-            for (int dxi = 0; dxi < 3; ++dxi) {
-              const uint64_t ad = umma_smem_desc_sw128(a_addr + dxi * 128, 1024);
-              const uint32_t wb = w_addr + (dxi * nchunk + c) * Cfg::kWBoxBytes;
-              if (q + 3 <= Cfg::kSlots) {
-                const uint64_t bd = umma_smem_desc_sw128(wb, 1024);
-                for (int k = 0; k < ksteps; ++k) umma_f16(d0, ad + 2 * k, bd + 2 * k, idesc3, 1);
-              } else if (q + 2 == Cfg::kSlots) {               // ring wrap: rows (y-1, y) | (y+1)
-                const uint64_t bd = umma_smem_desc_sw128(wb, 1024);
-                const uint64_t bd2 = umma_smem_desc_sw128(wb + 2 * COUT * 128, 1024);
-                for (int k = 0; k < ksteps; ++k) {
-                  umma_f16(d0, ad + 2 * k, bd + 2 * k, idesc2, 1);
-                  umma_f16(tmem_base, ad + 2 * k, bd2 + 2 * k, idesc1, 1);
+                for (int dxi = 0; dxi < 3; ++dxi) {
+                  umma_f16_ksteps<4>(d0, a_lo + dxi * 8, b_lo + dxi * nchunk * kBoxLo, hi, id0);
+                  if (id1) umma_f16_ksteps<4>(tmem_base, a_lo + dxi * 8, b_lo + dxi * nchunk * kBoxLo + b1, hi, id1);
                 }
-              } else {                                         // ring wrap: row (y-1) | (y, y+1)
-                const uint64_t bd = umma_smem_desc_sw128(wb, 1024);
-                const uint64_t bd2 = umma_smem_desc_sw128(wb + COUT * 128, 1024);
-                for (int k = 0; k < ksteps; ++k) {
-                  umma_f16(d0, ad + 2 * k, bd + 2 * k, idesc1, 1);
-                  umma_f16(tmem_base, ad + 2 * k, bd2 + 2 * k, idesc2, 1);
+              } else {
+#pragma unroll
+                for (int dxi = 0; dxi < 3; ++dxi) {
+                  umma_f16_ksteps_rt(ksteps, d0, a_lo + dxi * 8, b_lo + dxi * nchunk * kBoxLo, hi, id0);
+                  if (id1) umma_f16_ksteps_rt(ksteps, tmem_base, a_lo + dxi * 8, b_lo + dxi * nchunk * kBoxLo + b1, hi, id1);
                 }
               }
             }
-            umma_commit(&empty[stage]);
+            if (elect_one()) umma_commit(&empty[stage]);
+            PROF_END(2);
             if (++stage == nstage) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tfull[q]);                              // output row i has all its contributions
-          if (i == rows + 1) {
-            umma_commit(&tfull[(u + i + 1) % Cfg::kSlots]);
-            umma_commit(&tfull[(u + i + 2) % Cfg::kSlots]);
+          if (elect_one()) {
+            umma_commit(&tfull[q]);                            // output row i has all its contributions
+            if (i == rows + 1) {
+              umma_commit(&tfull[(u + i + 1) % Cfg::kSlots]);
+              umma_commit(&tfull[(u + i + 2) % Cfg::kSlots]);
+            }
           }
         }
         u += rows + 4;
       }
+      if (lane == 0)
+        PROF_PRINT("[fold cin=%d cout=%d] mma: input rows %d total %lld  wait_tempty %lld  wait_full %lld  issue %lld\n", p.cin, COUT,
+                   prof_rows, PROF_NOW() - prof_start, prof_acc[0], prof_acc[1], prof_acc[2]);
     }
     __syncwarp();
   } else {
     // ------------------------------ epilogue ----------------------------------
     const int quarter = warp & 3;
+    const int group = (warp - 2) >> 2;                         // rows alternate between the epilogue groups
     const int m = quarter * 32 + lane;                         // A row == TMEM lane == pixel x0 + m
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t u = 0;
+    PROF_DECL;
+    pdl_wait();                    // residual reads / stores must not overtake the previous layer
+    [[maybe_unused]] const long long prof_start = PROF_NOW();
     for (int bi = band_begin; bi < band_end; ++bi) {
       const FoldBand band = p.bands[bi];
       const TileGeom& tg = p.tiles[band.tile];
@@ -207,8 +264,29 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
       const int x = band.x0 + m;
       for (int j = 0; j < band.rows + 4; ++j) {
         const uint32_t v = u + j;
+        if (static_cast<int>(v % kEpiGroups) != group) continue;
         const uint32_t slot = v % Cfg::kSlots;
+        const int y = band.r0 - 2 + j;
+        const bool active = j >= 2 && j < band.rows + 2 && x < g.w && !(p.debug_flags & 1);
+        PixelRef px;
+        px.P = g.base + y * g.pitch + x;
+        px.y = y; px.x = x; px.valid = true;
+        // residual rows are fetched BEFORE waiting for the accumulator: their latency hides behind the MMAs
+        constexpr bool kPrefetchR2 = COUT <= 32;                // 64-wide layers never carry a second residual
+        float r1[COUT], r2[kPrefetchR2 ? COUT : 1];
+        if (active && p.res1) {
+#pragma unroll
+          for (int c = 0; c < COUT / 16; ++c) load_trunk16(p.res1, px.P, p.c_off + c * 16, &r1[c * 16]);
+        }
+        if constexpr (kPrefetchR2) {
+          if (active && p.res2) {
+#pragma unroll
+            for (int c = 0; c < COUT / 16; ++c) load_trunk16(p.res2, px.P, p.c_off + c * 16, &r2[c * 16]);
+          }
+        }
+        PROF_BEGIN();
         mbar_wait(&tfull[slot], (v / Cfg::kSlots) & 1);
+        PROF_END(0);
         tc_fence_after();
         __syncwarp();
         const uint32_t taddr = lane_base + slot * COUT;
@@ -216,29 +294,33 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
 #pragma unroll
         for (int c = 0; c < COUT / 16; ++c) tmem_ld16(taddr + c * 16, r[c]);
         tmem_ld_wait();
+        if (!(p.debug_flags & 8)) {
 #pragma unroll
-        for (int c = 0; c < COUT / 16; ++c) tmem_st16_zero(taddr + c * 16);
-        tmem_st_wait();
+          for (int c = 0; c < COUT / 16; ++c) tmem_st16_zero(taddr + c * 16);
+          tmem_st_wait();
+        }
         tc_fence_before();
         mbar_arrive(&tempty[slot]);
-        const int y = band.r0 - 2 + j;
-        if (j >= 2 && j < band.rows + 2 && x < g.w) {
-          PixelRef px;
-          px.P = g.base + y * g.pitch + x;
-          px.y = y; px.x = x; px.valid = true;
+        PROF_END(1);
+        if (active) {
 #pragma unroll
           for (int c = 0; c < COUT / 16; ++c) {
             if (c * 16 < p.cout) {
               float vals[16];
 #pragma unroll
               for (int e = 0; e < 16; ++e) vals[e] = __uint_as_float(r[c][e]);
-              epilogue16(p, tg, px, c * 16, vals);
+              epilogue16(p, tg, px, c * 16, vals, p.res1 ? &r1[c * 16] : nullptr,
+                         (kPrefetchR2 && p.res2) ? &r2[kPrefetchR2 ? c * 16 : 0] : nullptr);
             }
           }
         }
+        PROF_END(2);
       }
       u += band.rows + 4;
     }
+    if (lane == 0 && (warp == 2 || warp == 6))
+      PROF_PRINT("[fold cin=%d cout=%d] epilogue warp %d: total %lld  wait_tfull %lld  ld+zero+arrive %lld  math+stores %lld\n", p.cin, COUT,
+                 warp, PROF_NOW() - prof_start, prof_acc[0], prof_acc[1], prof_acc[2]);
   }
 
   tc_fence_before();
@@ -260,8 +342,17 @@ cudaError_t launch_c(const CUtensorMap& amap, const CUtensorMap& wmap, ConvParam
   p.fold_stages = stages_for<COUT>(nchunk);
   if (p.fold_stages < 2) return cudaErrorInvalidConfiguration;
   const int smem = 3 * nchunk * FoldCfg<COUT>::kWBoxBytes + p.fold_stages * kSlabBytes + kBarrierBytes + 1024;
-  conv3x3_fold_kernel<COUT><<<grid, kThreads, smem, stream>>>(amap, wmap, p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv3x3_fold_kernel<COUT>, amap, wmap, p);
 }
 
 template <int COUT>

@@ -25,8 +25,8 @@ __global__ void __launch_bounds__(kBlockPixels) conv3x3_simt_kernel(const ConvPa
   for (int t = 0; t < 9; ++t) {
     const long long ps = static_cast<long long>(px.P) + (t / 3 - 1) * g.pitch + (t % 3 - 1);
     for (int ch = 0; ch < p.cin; ++ch) {
-      const float a = load16(p.src, static_cast<size_t>(ps) * p.src_pitch + ch, fp16);
       const int chunk = ch >> 6, k = ch & 63;
+      const float a = load16(p.src, (static_cast<size_t>(chunk) * p.src_plane_px + static_cast<size_t>(ps)) * 64 + k, fp16);
       const size_t wrow = static_cast<size_t>(p.w_row0) + static_cast<size_t>(t * nchunk + chunk) * p.npad + n0;
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[j] = fmaf(a, load16(p.wpack, (wrow + j) * 64 + k, fp16), acc[j]);

@@ -88,7 +88,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-            tma_load_2d(sa, &amap, &full[stage], c * kChunkChannels, b.px + (t / 3 - 1) * pitch + (t % 3 - 1));
+            tma_load_2d(sa, &amap, &full[stage], 0, c * p.src_plane_px + b.px + (t / 3 - 1) * pitch + (t % 3 - 1));
             tma_load_2d(sa + kABytes, &wmap, &full[stage], 0, p.w_row0 + (t * nchunk + c) * N);
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }

@@ -22,6 +22,7 @@
 #include <cuda_fp16.h>
 
 #include "../../include/nesr_b200.h"
+#include "epilogue.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -78,7 +79,7 @@ struct Arena {
   size_t zero_bytes = 0;      // prefix holding every buffer a conv reads (pads must stay zero)
   // sub-buffers
   void* x0 = nullptr;         // [P0][64] 16-bit network input (12 channels used)
-  void* d[2] = {nullptr, nullptr};   // [P0][192] dense-block ping-pong
+  void* d[2] = {nullptr, nullptr};   // [3][P0][64] dense-block ping-pong (three 64-channel planes)
   float* trunk = nullptr;     // [P0][64] fp32 residual trunk
   float* rrdb = nullptr;      // [P0][64] fp32 RRDB input
   float* feat = nullptr;      // [P0][64] fp32 conv_first output (long skip)
@@ -124,6 +125,7 @@ struct nesr_b200_handle {
   uint8_t* d_tmp = nullptr; size_t d_tmp_bytes = 0;
 
   nesr_b200_stats stats{};
+  int debug_flags = 0;        // NESR_B200_DEBUG_FLAGS: timing experiments (results are wrong when set)
 };
 
 namespace {
@@ -311,38 +313,40 @@ void layout_level(Batch& b, int level) {
   lp.pixels = cursor;
 }
 
-// Row-folded kernel schedule: every tile is cut into 128-pixel column strips, every strip into bands
-// of consecutive rows (about two bands per SM so the load balances), and the bands are dealt to the
-// CTAs longest-first.  A band costs rows + 2 input row slabs.
+// Row-folded kernel schedule.  Every tile is cut into 128-pixel column strips; the strips of the
+// whole batch are laid end to end into one sequence of strip-rows and that sequence is cut into one
+// contiguous, equally long run per CTA (split into bands where it crosses a strip boundary).  Every
+// CTA gets the same number of rows +-1 and at most a few bands, so no SM waits for a straggler
+// (a longest-first deal of fixed-size bands left 12 of 148 CTAs with 35 % more work), and the two
+// halo rows a band costs are paid as rarely as possible.
 void build_fold_schedule(Batch& b, int level, int num_sms) {
   LevelPlan& lp = b.lv[level];
+  struct Strip { int32_t tile, x0, h; };
+  std::vector<Strip> strips;
   int64_t total_rows = 0;
-  for (const TileGeom& t : b.tiles) total_rows += (int64_t)t.lv[level].h * ((t.lv[level].w + kBlockPixels - 1) / kBlockPixels);
-  const int target = (int)std::max<int64_t>(8, (total_rows + 2 * num_sms - 1) / (2 * num_sms));
-  std::vector<FoldBand> all;
   for (size_t ti = 0; ti < b.tiles.size(); ++ti) {
     const LevelGeom& g = b.tiles[ti].lv[level];
-    const int nb = (g.h + target - 1) / target;
-    for (int x0 = 0; x0 < g.w; x0 += kBlockPixels)
-      for (int k = 0; k < nb; ++k) {
-        const int r0 = (int)((int64_t)g.h * k / nb), r1 = (int)((int64_t)g.h * (k + 1) / nb);
-        if (r1 > r0) all.push_back(FoldBand{(int32_t)ti, x0, r0, r1 - r0});
-      }
+    for (int x0 = 0; x0 < g.w; x0 += kBlockPixels) {
+      strips.push_back(Strip{(int32_t)ti, x0, g.h});
+      total_rows += g.h;
+    }
   }
-  std::stable_sort(all.begin(), all.end(), [](const FoldBand& a, const FoldBand& c) { return a.rows > c.rows; });
-  const int grid = (int)std::min<size_t>((size_t)num_sms, all.size());
-  std::vector<std::vector<FoldBand>> per(grid);
-  std::vector<int64_t> load(grid, 0);
-  for (const FoldBand& band : all) {
-    int best = 0;
-    for (int c = 1; c < grid; ++c) if (load[c] < load[best]) best = c;
-    per[best].push_back(band);
-    load[best] += band.rows + 2;
-  }
+  const int min_rows = 4;                                      // do not spread tiny work over every SM
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms, total_rows / min_rows));
   lp.bands.clear();
   lp.cta_off.assign(1, 0);
+  size_t si = 0;
+  int64_t strip_start = 0;                                     // sequence position of strips[si] row 0
   for (int c = 0; c < grid; ++c) {
-    lp.bands.insert(lp.bands.end(), per[c].begin(), per[c].end());
+    int64_t lo = total_rows * c / grid, hi = total_rows * (c + 1) / grid;
+    while (lo < hi) {
+      while (si < strips.size() && strip_start + strips[si].h <= lo) { strip_start += strips[si].h; ++si; }
+      const Strip& st = strips[si];
+      const int r0 = (int)(lo - strip_start);
+      const int n = (int)std::min<int64_t>(hi - lo, st.h - r0);
+      lp.bands.push_back(FoldBand{st.tile, st.x0, r0, n});
+      lo += n;
+    }
     lp.cta_off.push_back((int32_t)lp.bands.size());
   }
   lp.fold_grid = grid;
@@ -442,12 +446,12 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
   CUDA_TRY(h, cudaMemsetAsync(a.base, 0, a.zero_bytes, h->stream));
   int rc;
   if ((rc = make_map(h, &a.m_x0, a.x0, 64, P[0], kBlockPixels))) return rc;
-  for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.m_d[i2], a.d[i2], kDense, P[0], kBlockPixels))) return rc;
+  for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.m_d[i2], a.d[i2], 64, 3 * P[0], kBlockPixels))) return rc;
   if ((rc = make_map(h, &a.m_g2, a.g2, 64, P[1], kBlockPixels))) return rc;
   for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.m_g4[i2], a.g4[i2], 64, P[2], kBlockPixels))) return rc;
   constexpr int kSlab = 136;                                   // row slab of the folded kernel
   if ((rc = make_map(h, &a.f_x0, a.x0, 64, P[0], kSlab))) return rc;
-  for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.f_d[i2], a.d[i2], kDense, P[0], kSlab))) return rc;
+  for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.f_d[i2], a.d[i2], 64, 3 * P[0], kSlab))) return rc;
   if ((rc = make_map(h, &a.f_g2, a.g2, 64, P[1], kSlab))) return rc;
   for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.f_g4[i2], a.g4[i2], 64, P[2], kSlab))) return rc;
   h->stats.arena_bytes = (int64_t)a.bytes;
@@ -462,14 +466,14 @@ struct ConvIO {
   const CUtensorMap* amap = nullptr;     // box 128 px
   const CUtensorMap* fmap = nullptr;     // box 136 px
   const void* src = nullptr;
-  int src_pitch = 0;
+  int planes = 1;
   int level = 0;
 };
 
 int run_conv(nesr_b200_handle* h, const Batch& b, const Layer& L, const ConvIO& io, ConvParams p, cudaStream_t s) {
   const LevelPlan& lp = b.lv[io.level];
   p.blocks = lp.d_blocks; p.tiles = b.d_tiles; p.nblk = (int)lp.blocks.size(); p.level = io.level;
-  p.src = io.src; p.src_pitch = io.src_pitch; p.cin = L.cin16;
+  p.src = io.src; p.src_plane_px = (int)h->arena.P[io.level]; p.cin = L.cin16;
   p.wpack = h->d_wpack; p.w_row0 = L.w_row0; p.npad = L.npad; p.fmt = L.fmt;
   p.idesc = umma_idesc_f16(hw_fmt(L.fmt), (uint32_t)L.npad);
   p.bias = h->d_bias + L.bias_off; p.cout = L.cout;
@@ -482,6 +486,7 @@ int run_conv(nesr_b200_handle* h, const Batch& b, const Layer& L, const ConvIO& 
     h->stats.conv_launches++;
   } else {
     p.bands = lp.d_bands; p.cta_band_off = lp.d_cta_off;
+    p.debug_flags = h->debug_flags;
     const float* bias0 = p.bias;
     const int coff0 = p.dst16_coff;
     for (int ps = 0; ps < L.fold_passes && e == cudaSuccess; ++ps) {
@@ -530,17 +535,17 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
   {  // conv_first: x0 -> trunk (fp32), feat (fp32), d[0][0:64] (16-bit copy for the first RDB)
     ConvParams p{};
     p.dst32a = a.trunk; p.dst32b = a.feat;
-    p.dst16 = a.d[0]; p.dst16_pitch = kDense; p.dst16_coff = 0; p.dst16_fmt = c.body_format;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_x0, &a.f_x0, a.x0, 64, 0}, p, s))) return rc;
+    p.dst16 = a.d[0]; p.dst16_plane_px = (int)a.P[0]; p.dst16_coff = 0; p.dst16_fmt = c.body_format;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_x0, &a.f_x0, a.x0, 1, 0}, p, s))) return rc;
   }
   int cur = 0;
   const int nrdb = c.num_block * 3;
   for (int r = 0; r < nrdb; ++r) {
-    const ConvIO io{&a.m_d[cur], &a.f_d[cur], a.d[cur], kDense, 0};
+    const ConvIO io{&a.m_d[cur], &a.f_d[cur], a.d[cur], 3, 0};
     for (int k = 1; k <= 4; ++k) {   // x_k = lrelu(conv_k(cat(x, x1..x_{k-1})))  -> channels [64+32(k-1), +32)
       ConvParams p{};
       p.lrelu = 1;
-      p.dst16 = a.d[cur]; p.dst16_pitch = kDense; p.dst16_coff = kFeat + (k - 1) * kGrow; p.dst16_fmt = c.body_format;
+      p.dst16 = a.d[cur]; p.dst16_plane_px = (int)a.P[0]; p.dst16_coff = kFeat + (k - 1) * kGrow; p.dst16_fmt = c.body_format;
       if ((rc = run_conv(h, b, next(), io, p, s))) return rc;
     }
     ConvParams p{};                  // x5*0.2 + x  (+ RRDB skip on every third block)
@@ -550,7 +555,7 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
       p.res2 = (r == 2) ? a.feat : a.rrdb; p.s2 = 0.2f;
       p.dst32b = a.rrdb;
     }
-    p.dst16 = a.d[cur ^ 1]; p.dst16_pitch = kDense; p.dst16_coff = 0;
+    p.dst16 = a.d[cur ^ 1]; p.dst16_plane_px = (int)a.P[0]; p.dst16_coff = 0;
     p.dst16_fmt = (r == nrdb - 1) ? c.edge_format : c.body_format;    // conv_body reads the last one
     if ((rc = run_conv(h, b, next(), io, p, s))) return rc;
     cur ^= 1;
@@ -558,32 +563,32 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
   {  // conv_body + long skip, stored nearest-x2 upsampled into level 1
     ConvParams p{};
     p.res1 = a.feat; p.s1 = 1.0f;
-    p.dst16 = a.g2; p.dst16_pitch = 64; p.dst16_fmt = c.edge_format; p.dst16_up = 1;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_d[cur], &a.f_d[cur], a.d[cur], kDense, 0}, p, s))) return rc;
+    p.dst16 = a.g2; p.dst16_plane_px = (int)a.P[1]; p.dst16_fmt = c.edge_format; p.dst16_up = 1;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_d[cur], &a.f_d[cur], a.d[cur], 3, 0}, p, s))) return rc;
   }
   {  // conv_up1 + lrelu, stored upsampled into level 2
     ConvParams p{};
     p.lrelu = 1;
-    p.dst16 = a.g4[0]; p.dst16_pitch = 64; p.dst16_fmt = c.edge_format; p.dst16_up = 1;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g2, &a.f_g2, a.g2, 64, 1}, p, s))) return rc;
+    p.dst16 = a.g4[0]; p.dst16_plane_px = (int)a.P[2]; p.dst16_fmt = c.edge_format; p.dst16_up = 1;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g2, &a.f_g2, a.g2, 1, 1}, p, s))) return rc;
   }
   {  // conv_up2 + lrelu
     ConvParams p{};
     p.lrelu = 1;
-    p.dst16 = a.g4[1]; p.dst16_pitch = 64; p.dst16_fmt = c.edge_format;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], &a.f_g4[0], a.g4[0], 64, 2}, p, s))) return rc;
+    p.dst16 = a.g4[1]; p.dst16_plane_px = (int)a.P[2]; p.dst16_fmt = c.edge_format;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], &a.f_g4[0], a.g4[0], 1, 2}, p, s))) return rc;
   }
   {  // conv_hr + lrelu
     ConvParams p{};
     p.lrelu = 1;
-    p.dst16 = a.g4[0]; p.dst16_pitch = 64; p.dst16_fmt = c.edge_format;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[1], &a.f_g4[1], a.g4[1], 64, 2}, p, s))) return rc;
+    p.dst16 = a.g4[0]; p.dst16_plane_px = (int)a.P[2]; p.dst16_fmt = c.edge_format;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[1], &a.f_g4[1], a.g4[1], 1, 2}, p, s))) return rc;
   }
   {  // conv_last -> clamp, BGR, u8, halo crop + stitch  (or unclamped fp32 NCHW)
     ConvParams p{};
     p.out_u8 = sink.out_u8; p.out_stride = sink.out_stride; p.out_frame_stride = sink.out_frame_stride;
     p.out_f32 = sink.out_f32; p.out_h = sink.out_h; p.out_w = sink.out_w;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], &a.f_g4[0], a.g4[0], 64, 2}, p, s))) return rc;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], &a.f_g4[0], a.g4[0], 1, 2}, p, s))) return rc;
   }
   if (time_convs) cudaEventRecord(h->evc1, s);
   h->stats.tiles_processed += (int64_t)b.tiles.size();
@@ -710,6 +715,7 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
     return fail(nullptr, NESR_E_CUDA, "device setup failed: %s", msg.c_str());
   }
   build_layers(h);
+  if (const char* dbg = getenv("NESR_B200_DEBUG_FLAGS")) h->debug_flags = atoi(dbg);
   *out = h;
   return NESR_OK;
 }
@@ -947,13 +953,12 @@ int nesr_b200_debug_conv(nesr_b200_handle* h, int32_t impl, int32_t fmt, int32_t
   build_fold_schedule(b, 0, h->num_sms);
   const LevelPlan& lp = b.lv[0];
   const int64_t P = lp.pixels;
-  const int src_pitch = L.nchunk * 64;
-  std::vector<uint16_t> xs((size_t)P * src_pitch, 0);
+  std::vector<uint16_t> xs((size_t)L.nchunk * P * 64, 0);      // [plane][pixel][64]
   const LevelGeom g = b.tiles[0].lv[0];
   for (int c = 0; c < cin; ++c)
     for (int y = 0; y < H; ++y)
       for (int x = 0; x < W; ++x)
-        xs[((size_t)g.base + (size_t)y * g.pitch + x) * src_pitch + c] = to16(x_nchw[((size_t)c * H + y) * W + x], fmt);
+        xs[((size_t)(c >> 6) * P + (size_t)g.base + (size_t)y * g.pitch + x) * 64 + (c & 63)] = to16(x_nchw[((size_t)c * H + y) * W + x], fmt);
   uint16_t *d_w = nullptr, *d_x = nullptr;
   float *d_b = nullptr, *d_y = nullptr;
   TileGeom* d_t = nullptr; BlockRef* d_blk = nullptr; FoldBand* d_bands = nullptr; int32_t* d_off = nullptr;
@@ -980,7 +985,7 @@ int nesr_b200_debug_conv(nesr_b200_handle* h, int32_t impl, int32_t fmt, int32_t
   DBG_TRY(cudaMemcpy(d_off, lp.cta_off.data(), lp.cta_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   ConvParams p{};
   p.blocks = d_blk; p.tiles = d_t; p.nblk = (int)lp.blocks.size(); p.level = 0;
-  p.src = d_x; p.src_pitch = src_pitch; p.cin = L.cin16; p.wpack = d_w; p.w_row0 = 0; p.npad = L.npad; p.fmt = fmt;
+  p.src = d_x; p.src_plane_px = (int)P; p.cin = L.cin16; p.wpack = d_w; p.w_row0 = 0; p.npad = L.npad; p.fmt = fmt;
   p.idesc = umma_idesc_f16(hw_fmt(fmt), (uint32_t)L.npad);
   p.bias = d_b; p.cout = cout; p.lrelu = lrelu; p.dst32a = d_y;
   cudaError_t e = cudaSuccess;
@@ -988,11 +993,11 @@ int nesr_b200_debug_conv(nesr_b200_handle* h, int32_t impl, int32_t fmt, int32_t
     e = launch_conv3x3_simt(p, h->stream);
   } else if (impl == 2) {
     CUtensorMap am, wm;
-    if ((rc = make_map(h, &am, d_x, src_pitch, P, kBlockPixels)) || (rc = make_map(h, &wm, d_w, 64, rows, L.npad))) { cleanup(); return rc; }
+    if ((rc = make_map(h, &am, d_x, 64, (int64_t)L.nchunk * P, kBlockPixels)) || (rc = make_map(h, &wm, d_w, 64, rows, L.npad))) { cleanup(); return rc; }
     e = launch_conv3x3_tc(am, wm, p, h->num_sms, h->stream);
   } else {
     CUtensorMap am, wm;
-    if ((rc = make_map(h, &am, d_x, src_pitch, P, 136)) || (rc = make_map(h, &wm, d_w, 64, rows, 3 * L.fold_npad))) { cleanup(); return rc; }
+    if ((rc = make_map(h, &am, d_x, 64, (int64_t)L.nchunk * P, 136)) || (rc = make_map(h, &wm, d_w, 64, rows, 3 * L.fold_npad))) { cleanup(); return rc; }
     p.bands = d_bands; p.cta_band_off = d_off;
     for (int ps = 0; ps < L.fold_passes && e == cudaSuccess; ++ps) {
       p.npad = L.fold_npad; p.c_off = ps * L.fold_npad; p.bias = d_b + p.c_off;
@@ -1009,7 +1014,7 @@ int nesr_b200_debug_conv(nesr_b200_handle* h, int32_t impl, int32_t fmt, int32_t
   for (int c = 0; c < cout; ++c)
     for (int y = 0; y < H; ++y)
       for (int x = 0; x < W; ++x)
-        y_nchw[((size_t)c * H + y) * W + x] = ys[((size_t)g.base + (size_t)y * g.pitch + x) * 64 + c];
+        y_nchw[((size_t)c * H + y) * W + x] = ys[trunk_offset((int)(g.base + (int64_t)y * g.pitch + x), c)];
   cleanup();
 #undef DBG_TRY
   return NESR_OK;

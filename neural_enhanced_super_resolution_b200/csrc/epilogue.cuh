@@ -51,9 +51,44 @@ __device__ __forceinline__ PixelRef locate(const LevelGeom& g, int P) {
   return r;
 }
 
-// Channels [n0, n0+16) of one pixel.
+// ---------------------------------------------------------------------------------------------
+// fp32 trunk buffers (trunk / rrdb / feat) are touched only by epilogues, one pixel per lane, so they
+// use a BLOCKED layout that makes that access coalesced: [pixel/32][channel/8][pixel%32][channel%8].
+// A warp reading 8 channels of 32 consecutive pixels moves 1 KB of (nearly) contiguous memory with
+// one 256-bit access per lane instead of 32 scattered lines.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ size_t trunk_offset(int P, int ch) {
+  return (static_cast<size_t>(P >> 5) * 8 + (ch >> 3)) * 256 + (static_cast<size_t>(P & 31) << 3) + (ch & 7);
+}
+__device__ __forceinline__ void ldg256(const float* ptr, float* v) {
+  uint32_t r[8];
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(ptr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void stg256(void* ptr, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void stg256f(float* ptr, const float* v) {
+  uint32_t r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(v[i]);
+  stg256(ptr, r);
+}
+// 16 residual channels [ch0, ch0+16) of pixel P (ch0 multiple of 8).
+__device__ __forceinline__ void load_trunk16(const float* buf, int P, int ch0, float* r) {
+  ldg256(buf + trunk_offset(P, ch0), r);
+  ldg256(buf + trunk_offset(P, ch0 + 8), r + 8);
+}
+
+// Channels [n0, n0+16) of one pixel.  r1pre / r2pre: residual values the caller already fetched
+// (the fold kernel issues those loads before it waits for the accumulator), or null.
 __device__ __forceinline__ void epilogue16(const ConvParams& p, const TileGeom& tg, const PixelRef& px, int n0,
-                                           float (&v)[16]) {
+                                           float (&v)[16], const float* r1pre = nullptr, const float* r2pre = nullptr) {
   const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -64,45 +99,35 @@ __device__ __forceinline__ void epilogue16(const ConvParams& p, const TileGeom& 
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = v[i] >= 0.f ? v[i] : 0.2f * v[i];
   }
-  const size_t t64 = static_cast<size_t>(px.P) * kFeat + p.c_off + n0;
+  const int ch0 = p.c_off + n0;
   if (p.res1) {
-    const float4* r4 = reinterpret_cast<const float4*>(p.res1 + t64);
+    float r[16];
+    if (!r1pre) { load_trunk16(p.res1, px.P, ch0, r); r1pre = r; }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 r = r4[i];
-      v[4 * i + 0] = fmaf(v[4 * i + 0], p.s1, r.x); v[4 * i + 1] = fmaf(v[4 * i + 1], p.s1, r.y);
-      v[4 * i + 2] = fmaf(v[4 * i + 2], p.s1, r.z); v[4 * i + 3] = fmaf(v[4 * i + 3], p.s1, r.w);
-    }
+    for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], p.s1, r1pre[i]);
   }
   if (p.res2) {
-    const float4* r4 = reinterpret_cast<const float4*>(p.res2 + t64);
+    float r[16];
+    if (!r2pre) { load_trunk16(p.res2, px.P, ch0, r); r2pre = r; }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 r = r4[i];
-      v[4 * i + 0] = fmaf(v[4 * i + 0], p.s2, r.x); v[4 * i + 1] = fmaf(v[4 * i + 1], p.s2, r.y);
-      v[4 * i + 2] = fmaf(v[4 * i + 2], p.s2, r.z); v[4 * i + 3] = fmaf(v[4 * i + 3], p.s2, r.w);
-    }
+    for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], p.s2, r2pre[i]);
   }
   if (p.dst32a) {
-    float4* d4 = reinterpret_cast<float4*>(p.dst32a + t64);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    stg256f(p.dst32a + trunk_offset(px.P, ch0), v);
+    stg256f(p.dst32a + trunk_offset(px.P, ch0 + 8), v + 8);
   }
   if (p.dst32b) {
-    float4* d4 = reinterpret_cast<float4*>(p.dst32b + t64);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    stg256f(p.dst32b + trunk_offset(px.P, ch0), v);
+    stg256f(p.dst32b + trunk_offset(px.P, ch0 + 8), v + 8);
   }
   if (p.dst16) {
-    uint4 lo, hi;
-    lo.x = pack2(v[0], v[1], p.dst16_fmt);   lo.y = pack2(v[2], v[3], p.dst16_fmt);
-    lo.z = pack2(v[4], v[5], p.dst16_fmt);   lo.w = pack2(v[6], v[7], p.dst16_fmt);
-    hi.x = pack2(v[8], v[9], p.dst16_fmt);   hi.y = pack2(v[10], v[11], p.dst16_fmt);
-    hi.z = pack2(v[12], v[13], p.dst16_fmt); hi.w = pack2(v[14], v[15], p.dst16_fmt);
-    uint16_t* base = reinterpret_cast<uint16_t*>(p.dst16) + p.dst16_coff + n0;
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = pack2(v[2 * i], v[2 * i + 1], p.dst16_fmt);
+    const int dch = p.dst16_coff + n0;                                             // 16 channels, 32-byte aligned
+    uint16_t* base = reinterpret_cast<uint16_t*>(p.dst16) + static_cast<size_t>(dch >> 6) * p.dst16_plane_px * 64 + (dch & 63);
     if (!p.dst16_up) {
-      uint4* d = reinterpret_cast<uint4*>(base + static_cast<size_t>(px.P) * p.dst16_pitch);
-      d[0] = lo; d[1] = hi;
+      stg256(base + static_cast<size_t>(px.P) * 64, w);
     } else {
       const LevelGeom g2 = tg.lv[p.level + 1];
 #pragma unroll
@@ -110,8 +135,7 @@ __device__ __forceinline__ void epilogue16(const ConvParams& p, const TileGeom& 
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
           const size_t P2 = static_cast<size_t>(g2.base) + static_cast<size_t>(2 * px.y + a) * g2.pitch + (2 * px.x + b);
-          uint4* d = reinterpret_cast<uint4*>(base + P2 * p.dst16_pitch);
-          d[0] = lo; d[1] = hi;
+          stg256(base + P2 * 64, w);
         }
     }
   }

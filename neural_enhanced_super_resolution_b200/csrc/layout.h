@@ -8,7 +8,13 @@
 //   * a 3x3 tap (dy, dx) is the flat shift dy*pitch + dx, and conv zero padding at every tile
 //     border -- upstream tile_process forwards each tile independently -- is plain data;
 //   * an MMA M-block is 128 consecutive flat pixels (it may span rows), so M tiles are always full;
-//   * one 2-D TMA tensor map [pixels][channels] per buffer serves every tile and every tap.
+//   * one 2-D TMA tensor map per buffer serves every tile and every tap.
+//
+// CHANNEL PLANES.  16-bit activation buffers are stored as planes of 64 channels:
+// [plane][pixel][64] (the 192-channel dense-block buffer has three).  A conv reads a channel PREFIX
+// of the dense block, i.e. whole planes, so every TMA row slab (136 pixels x 128 B) is one contiguous
+// 17 KB run of memory -- interleaving the planes ([pixel][192]) made every 128-byte request hop
+// 384 bytes and held HBM efficiency near 45 % (profiles/r1_fold_role_timing.txt).
 #pragma once
 #include <stdint.h>
 
@@ -53,8 +59,8 @@ struct ConvParams {
   int32_t nblk;
   int32_t level;
   // operands
-  const void* src;             // [pixels][src_pitch] 16-bit (SIMT validation kernel reads it directly)
-  int32_t src_pitch;           // channels per pixel in src
+  const void* src;             // [planes][pixels][64] 16-bit, plane = 64-channel chunk (SIMT kernel reads it directly)
+  int32_t src_plane_px;        // pixels per plane of src
   int32_t cin;                 // input channels, multiple of 16
   const void* wpack;           // packed weights arena base (16-bit), rows of 64
   int32_t w_row0;              // first arena row of this layer
@@ -70,8 +76,8 @@ struct ConvParams {
   float s1, s2;
   float* dst32a;               // fp32 [pixels][64] or null
   float* dst32b;
-  void* dst16;                 // 16-bit [pixels][dst16_pitch] or null
-  int32_t dst16_pitch;
+  void* dst16;                 // 16-bit [planes][pixels][64] or null
+  int32_t dst16_plane_px;      // pixels per plane of dst16
   int32_t dst16_coff;
   int32_t dst16_fmt;
   int32_t dst16_up;            // 1: nearest x2 -- write the 2x2 replicas into level+1's layout
@@ -86,6 +92,7 @@ struct ConvParams {
   const int32_t* cta_band_off; // [grid + 1] first band of each CTA
   int32_t c_off;               // first output channel of this pass inside the 64-channel fp32 buffers
   int32_t fold_stages;         // activation ring depth (host-computed from the shared-memory budget)
+  int32_t debug_flags;         // NESR_B200_DEBUG_FLAGS (timing experiments only): 1 no epilogue stores, 2 no MMA, 4 no TMA, 8 no TMEM re-zero
 };
 
 }  // namespace nesr

@@ -7,11 +7,39 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef NESR_PROF
+#define NESR_PROF 0     // 1: build with device printf + per-role cycle accounting (NESR_B200_PROF=1 python -m ..._build)
+#endif
+
 namespace nesr {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+
+// One lane of a fully converged warp.  The async-proxy instructions (TMA, tcgen05.mma/commit) take
+// their operands from UNIFORM registers: code that runs warp-wide with uniform values and elects a
+// lane only around the instruction itself compiles to plain UMOV/R2UR, whereas code nested under
+// `if (lane == 0)` gets a per-instruction ELECT/R2UR/BRA "waterfall" loop (seen in SASS: ~17
+// instructions per MMA), which made the issuing thread the bottleneck of the first fold kernel.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// Programmatic dependent launch: a kernel launched with programmaticStreamSerialization may start
+// (prologue, weight loads) while its predecessor in the stream is still draining; pdl_wait() blocks
+// until the predecessor has completed and its writes are visible, pdl_launch_dependents() lets the
+// successor begin as soon as this grid's CTAs free their SMs.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------
 // mbarrier
@@ -51,8 +79,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > NESR_HANG_GUARD_CYCLES) {
+#if NESR_PROF
       printf("nesr_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-      __trap();
+#endif
+      __trap();                     // surfaces as a failed launch (cudaErrorLaunchFailure), never a hang
     }
   }
 }
@@ -70,6 +100,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+
+// Fire-and-forget prefetch of a 2-D box into L2 (no shared-memory destination, no barrier).
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1)
+               : "memory");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -124,6 +161,48 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// KS back-to-back accumulating MMAs (k-steps of one 64-channel chunk) from ONE asm block: the
+// descriptors differ only in the low word (+32 B = +2 per k-step), so the issuing thread spends a
+// handful of integer instructions per MMA instead of rebuilding 64-bit descriptors.
+// lo = (addr >> 4) | LBO field; hi = SBO | version | swizzle (same for A and B here).
+__device__ __forceinline__ constexpr uint32_t umma_desc_hi_sw128(uint32_t sbo_bytes = 1024) {
+  return (sbo_bytes >> 4) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+
+#define NESR_UMMA_STEP(K)                                              \
+  "add.u32 ta, %1, " #K ";\n\t"                                        \
+  "add.u32 tb, %2, " #K ";\n\t"                                        \
+  "mov.b64 da, {ta, %3};\n\t"                                          \
+  "mov.b64 db, {tb, %3};\n\t"                                          \
+  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+
+template <int KS>
+__device__ __forceinline__ void umma_f16_ksteps(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+  static_assert(KS >= 1 && KS <= 4, "one 64-channel chunk has at most 4 k-steps");
+  if constexpr (KS == 1) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 ta, tb;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 NESR_UMMA_STEP(0) "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc) : "memory");
+  } else if constexpr (KS == 2) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 ta, tb;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 NESR_UMMA_STEP(0) NESR_UMMA_STEP(2) "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc) : "memory");
+  } else if constexpr (KS == 3) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 ta, tb;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 NESR_UMMA_STEP(0) NESR_UMMA_STEP(2) NESR_UMMA_STEP(4) "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 ta, tb;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 NESR_UMMA_STEP(0) NESR_UMMA_STEP(2) NESR_UMMA_STEP(4) NESR_UMMA_STEP(6) "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc) : "memory");
+  }
+}
+__device__ __forceinline__ void umma_f16_ksteps_rt(int ks, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+  switch (ks) {
+    case 4: umma_f16_ksteps<4>(tmem_d, a_lo, b_lo, hi, idesc); break;
+    case 2: umma_f16_ksteps<2>(tmem_d, a_lo, b_lo, hi, idesc); break;
+    case 1: umma_f16_ksteps<1>(tmem_d, a_lo, b_lo, hi, idesc); break;
+    default: umma_f16_ksteps<3>(tmem_d, a_lo, b_lo, hi, idesc); break;
+  }
+}
+
 // Arrive on an mbarrier when all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
