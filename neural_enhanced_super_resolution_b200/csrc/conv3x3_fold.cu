@@ -71,9 +71,12 @@ constexpr int kBarrierBytes = (1 + 2 * kMaxStages + 2 * kMaxSlots) * 8 + 16;
 
 template <int COUT>
 __global__ void __launch_bounds__(kThreads, 1)
-conv3x3_fold_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap wmap,
-                    const ConvParams p) {
+conv3x3_fold_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap amap8,
+                    const __grid_constant__ CUtensorMap wmap, const ConvParams p) {
   using Cfg = FoldCfg<COUT>;
+#if NESR_PROF
+  unsigned long long prof_cta_start; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_cta_start));
+#endif
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nchunk = (p.cin + kChunkChannels - 1) / kChunkChannels;
@@ -93,6 +96,7 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&amap);
+    tma_prefetch_desc(&amap8);
     tma_prefetch_desc(&wmap);
     mbar_init(wbar, 1);
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -142,9 +146,26 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
       [[maybe_unused]] const long long prof_start = PROF_NOW();
       for (int bi = band_begin; bi < band_end; ++bi) {
         const FoldBand band = p.bands[bi];
-        const LevelGeom g = p.tiles[band.tile].lv[p.level];
-        int px0 = g.base + (band.r0 - 1) * g.pitch + band.x0 - 1;
-        for (int i = 0; i < band.rows + 2; ++i, px0 += g.pitch) {
+        // per segment: flat pixel of (row r0-1, x0-1), row pitch, slab byte offset, number of 8-pixel boxes
+        int seg_px[kMaxFoldSegs], seg_pitch[kMaxFoldSegs], seg_off[kMaxFoldSegs], seg_n8[kMaxFoldSegs];
+        bool full_strip = false;
+        uint32_t row_bytes = 0;
+#pragma unroll
+        for (int sgi = 0; sgi < kMaxFoldSegs; ++sgi) {
+          seg_px[sgi] = seg_pitch[sgi] = seg_off[sgi] = seg_n8[sgi] = 0;
+          if (sgi < band.nseg) {
+            const FoldSeg sg = p.segs[band.seg0 + sgi];
+            const LevelGeom g = p.tiles[sg.tile].lv[p.level];
+            seg_px[sgi] = g.base + (band.r0 - 1) * g.pitch + sg.x0 - 1;
+            seg_pitch[sgi] = g.pitch;
+            seg_off[sgi] = sg.lane0 * 128;
+            seg_n8[sgi] = (sg.width + 2 + 7) >> 3;
+            if (sg.width == kBlockPixels) full_strip = true;      // a 128-pixel segment is always alone
+            row_bytes += seg_n8[sgi] * 1024;
+          }
+        }
+        if (full_strip) row_bytes = kSlabBytes;
+        for (int i = 0; i < band.rows + 2; ++i) {
           for (int c = 0; c < nchunk; ++c) {
             PROF_BEGIN();
             mbar_wait(&empty[stage], phase ^ 1);
@@ -153,8 +174,18 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
               if (p.debug_flags & 4) {
                 mbar_arrive(&full[stage]);
               } else {
-                mbar_arrive_expect_tx(&full[stage], kSlabBytes);
-                tma_load_2d(ring + stage * kSlabBytes, &amap, &full[stage], 0, c * p.src_plane_px + px0);
+                mbar_arrive_expect_tx(&full[stage], row_bytes);
+                uint8_t* slab = ring + stage * kSlabBytes;
+                const int plane = c * p.src_plane_px;
+                if (full_strip) {
+                  tma_load_2d(slab, &amap, &full[stage], 0, plane + seg_px[0] + i * seg_pitch[0]);
+                } else {
+#pragma unroll
+                  for (int sgi = 0; sgi < kMaxFoldSegs; ++sgi)
+                    for (int k = 0; k < seg_n8[sgi]; ++k)
+                      tma_load_2d(slab + seg_off[sgi] + k * 1024, &amap8, &full[stage], 0,
+                                  plane + seg_px[sgi] + i * seg_pitch[sgi] + k * 8);
+                }
               }
             }
             if (++stage == nstage) { stage = 0; phase ^= 1; }
@@ -259,9 +290,13 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
     [[maybe_unused]] const long long prof_start = PROF_NOW();
     for (int bi = band_begin; bi < band_end; ++bi) {
       const FoldBand band = p.bands[bi];
-      const TileGeom& tg = p.tiles[band.tile];
+      int my_tile = 0, x = 1 << 20;                            // this lane's pixel column (none: masked lane)
+      for (int sgi = 0; sgi < band.nseg; ++sgi) {
+        const FoldSeg sg = p.segs[band.seg0 + sgi];
+        if (m >= sg.lane0 && m < sg.lane0 + sg.width) { my_tile = sg.tile; x = sg.x0 + (m - sg.lane0); }
+      }
+      const TileGeom& tg = p.tiles[my_tile];
       const LevelGeom g = tg.lv[p.level];
-      const int x = band.x0 + m;
       for (int j = 0; j < band.rows + 4; ++j) {
         const uint32_t v = u + j;
         if (static_cast<int>(v % kEpiGroups) != group) continue;
@@ -327,6 +362,16 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
   __syncthreads();
   tc_fence_after();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+#if NESR_PROF
+  if ((p.debug_flags & 256) && threadIdx.x == 0) {       // per-CTA lifetime: who are the stragglers?
+    unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    int nrows = 0;
+    for (int bi = band_begin; bi < band_end; ++bi) nrows += p.bands[bi].rows + 2;
+    printf("[cta cin=%d cout=%d] blk %d sm %u start_ns %llu end_ns %llu bands %d inrows %d\n", p.cin, COUT, (int)blockIdx.x, smid,
+           prof_cta_start, t1, band_end - band_begin, nrows);
+  }
+#endif
 }
 
 template <int COUT>
@@ -337,7 +382,8 @@ int stages_for(int nchunk) {
 }
 
 template <int COUT>
-cudaError_t launch_c(const CUtensorMap& amap, const CUtensorMap& wmap, ConvParams p, int grid, cudaStream_t stream) {
+cudaError_t launch_c(const CUtensorMap& amap, const CUtensorMap& amap8, const CUtensorMap& wmap, ConvParams p, int grid,
+                     cudaStream_t stream) {
   const int nchunk = (p.cin + kChunkChannels - 1) / kChunkChannels;
   p.fold_stages = stages_for<COUT>(nchunk);
   if (p.fold_stages < 2) return cudaErrorInvalidConfiguration;
@@ -352,7 +398,7 @@ cudaError_t launch_c(const CUtensorMap& amap, const CUtensorMap& wmap, ConvParam
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv3x3_fold_kernel<COUT>, amap, wmap, p);
+  return cudaLaunchKernelEx(&cfg, conv3x3_fold_kernel<COUT>, amap, amap8, wmap, p);
 }
 
 template <int COUT>
@@ -380,13 +426,13 @@ bool conv3x3_fold_fits(int cin16, int npad) {
   }
 }
 
-cudaError_t launch_conv3x3_fold(const CUtensorMap& amap, const CUtensorMap& wmap, const ConvParams& p, int grid,
-                                cudaStream_t stream) {
+cudaError_t launch_conv3x3_fold(const CUtensorMap& amap, const CUtensorMap& amap8, const CUtensorMap& wmap,
+                                const ConvParams& p, int grid, cudaStream_t stream) {
   if (grid <= 0) return cudaSuccess;
   switch (p.npad) {
-    case 16: return launch_c<16>(amap, wmap, p, grid, stream);
-    case 32: return launch_c<32>(amap, wmap, p, grid, stream);
-    case 64: return launch_c<64>(amap, wmap, p, grid, stream);
+    case 16: return launch_c<16>(amap, amap8, wmap, p, grid, stream);
+    case 32: return launch_c<32>(amap, amap8, wmap, p, grid, stream);
+    case 64: return launch_c<64>(amap, amap8, wmap, p, grid, stream);
     default: return cudaErrorInvalidValue;
   }
 }

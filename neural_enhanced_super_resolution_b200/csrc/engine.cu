@@ -53,8 +53,10 @@ struct LevelPlan {
   BlockRef* d_blocks = nullptr;
   // row-folded kernel schedule: bands grouped by CTA
   std::vector<FoldBand> bands;
+  std::vector<FoldSeg> segs;
   std::vector<int32_t> cta_off;
   FoldBand* d_bands = nullptr;
+  FoldSeg* d_segs = nullptr;
   int32_t* d_cta_off = nullptr;
   int fold_grid = 0;
 };
@@ -87,7 +89,8 @@ struct Arena {
   void* g4[2] = {nullptr, nullptr};  // [P2][64]
   int64_t P[3] = {0, 0, 0};
   CUtensorMap m_x0, m_d[2], m_g2, m_g4[2];             // box 128 px (per-tap kernel)
-  CUtensorMap f_x0, f_d[2], f_g2, f_g4[2];             // box 136 px (row-folded kernel)
+  CUtensorMap f_x0, f_d[2], f_g2, f_g4[2];             // box 136 px (row-folded kernel, full strips)
+  CUtensorMap e_x0, e_d[2], e_g2, e_g4[2];             // box 8 px (row-folded kernel, packed remainder strips)
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -288,6 +291,7 @@ void free_batches(nesr_b200_handle* h) {
     for (LevelPlan& l : b.lv) {
       if (l.d_blocks) cudaFree(l.d_blocks);
       if (l.d_bands) cudaFree(l.d_bands);
+      if (l.d_segs) cudaFree(l.d_segs);
       if (l.d_cta_off) cudaFree(l.d_cta_off);
     }
   }
@@ -321,16 +325,39 @@ void layout_level(Batch& b, int level) {
 // halo rows a band costs are paid as rarely as possible.
 void build_fold_schedule(Batch& b, int level, int num_sms) {
   LevelPlan& lp = b.lv[level];
-  struct Strip { int32_t tile, x0, h; };
+  struct Strip { int32_t seg0, nseg, h; };
   std::vector<Strip> strips;
-  int64_t total_rows = 0;
+  lp.segs.clear();
+  // full 128-pixel strips: one segment each
   for (size_t ti = 0; ti < b.tiles.size(); ++ti) {
     const LevelGeom& g = b.tiles[ti].lv[level];
-    for (int x0 = 0; x0 < g.w; x0 += kBlockPixels) {
-      strips.push_back(Strip{(int32_t)ti, x0, g.h});
-      total_rows += g.h;
+    for (int x0 = 0; x0 + kBlockPixels <= g.w; x0 += kBlockPixels) {
+      strips.push_back(Strip{(int32_t)lp.segs.size(), 1, g.h});
+      lp.segs.push_back(FoldSeg{(int32_t)ti, x0, kBlockPixels, 0});
     }
   }
+  // right-hand remainders: packed side by side (with their halo pixels) among tiles of equal height
+  std::vector<bool> done(b.tiles.size(), false);
+  for (size_t ti = 0; ti < b.tiles.size(); ++ti) {
+    const LevelGeom& g = b.tiles[ti].lv[level];
+    if (done[ti] || g.w % kBlockPixels == 0) continue;
+    Strip st{(int32_t)lp.segs.size(), 0, g.h};
+    int lane = 0;
+    for (size_t tj = ti; tj < b.tiles.size() && st.nseg < kMaxFoldSegs; ++tj) {
+      const LevelGeom& gj = b.tiles[tj].lv[level];
+      const int rem = gj.w % kBlockPixels;
+      if (done[tj] || rem == 0 || gj.h != g.h) continue;
+      const int span = (rem + 2 + 7) / 8 * 8;                  // slab rows incl. halo, in 8-pixel TMA boxes
+      if (lane + span > 136 || lane + rem > kBlockPixels) continue;   // slab rows and MMA lanes available
+      lp.segs.push_back(FoldSeg{(int32_t)tj, gj.w - rem, rem, lane});
+      lane += span;
+      ++st.nseg;
+      done[tj] = true;
+    }
+    strips.push_back(st);
+  }
+  int64_t total_rows = 0;
+  for (const Strip& st : strips) total_rows += st.h;
   const int min_rows = 4;                                      // do not spread tiny work over every SM
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms, total_rows / min_rows));
   lp.bands.clear();
@@ -344,7 +371,7 @@ void build_fold_schedule(Batch& b, int level, int num_sms) {
       const Strip& st = strips[si];
       const int r0 = (int)(lo - strip_start);
       const int n = (int)std::min<int64_t>(hi - lo, st.h - r0);
-      lp.bands.push_back(FoldBand{st.tile, st.x0, r0, n});
+      lp.bands.push_back(FoldBand{st.seg0, st.nseg, r0, n});
       lo += n;
     }
     lp.cta_off.push_back((int32_t)lp.bands.size());
@@ -417,6 +444,8 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
       CUDA_TRY(h, cudaMemcpyAsync(lp.d_blocks, lp.blocks.data(), lp.blocks.size() * sizeof(BlockRef), cudaMemcpyHostToDevice, h->stream));
       CUDA_TRY(h, cudaMalloc(&lp.d_bands, std::max<size_t>(1, lp.bands.size()) * sizeof(FoldBand)));
       CUDA_TRY(h, cudaMemcpyAsync(lp.d_bands, lp.bands.data(), lp.bands.size() * sizeof(FoldBand), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(h, cudaMalloc(&lp.d_segs, std::max<size_t>(1, lp.segs.size()) * sizeof(FoldSeg)));
+      CUDA_TRY(h, cudaMemcpyAsync(lp.d_segs, lp.segs.data(), lp.segs.size() * sizeof(FoldSeg), cudaMemcpyHostToDevice, h->stream));
       CUDA_TRY(h, cudaMalloc(&lp.d_cta_off, lp.cta_off.size() * sizeof(int32_t)));
       CUDA_TRY(h, cudaMemcpyAsync(lp.d_cta_off, lp.cta_off.data(), lp.cta_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
       P[l] = std::max(P[l], lp.pixels);
@@ -454,6 +483,10 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
   for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.f_d[i2], a.d[i2], 64, 3 * P[0], kSlab))) return rc;
   if ((rc = make_map(h, &a.f_g2, a.g2, 64, P[1], kSlab))) return rc;
   for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.f_g4[i2], a.g4[i2], 64, P[2], kSlab))) return rc;
+  if ((rc = make_map(h, &a.e_x0, a.x0, 64, P[0], 8))) return rc;
+  for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.e_d[i2], a.d[i2], 64, 3 * P[0], 8))) return rc;
+  if ((rc = make_map(h, &a.e_g2, a.g2, 64, P[1], 8))) return rc;
+  for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.e_g4[i2], a.g4[i2], 64, P[2], 8))) return rc;
   h->stats.arena_bytes = (int64_t)a.bytes;
   h->key = key;
   return NESR_OK;
@@ -465,6 +498,7 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
 struct ConvIO {
   const CUtensorMap* amap = nullptr;     // box 128 px
   const CUtensorMap* fmap = nullptr;     // box 136 px
+  const CUtensorMap* emap = nullptr;     // box 8 px
   const void* src = nullptr;
   int planes = 1;
   int level = 0;
@@ -485,7 +519,7 @@ int run_conv(nesr_b200_handle* h, const Batch& b, const Layer& L, const ConvIO& 
     e = launch_conv3x3_tc(*io.amap, wm, p, h->num_sms, s);
     h->stats.conv_launches++;
   } else {
-    p.bands = lp.d_bands; p.cta_band_off = lp.d_cta_off;
+    p.bands = lp.d_bands; p.segs = lp.d_segs; p.cta_band_off = lp.d_cta_off;
     p.debug_flags = h->debug_flags;
     const float* bias0 = p.bias;
     const int coff0 = p.dst16_coff;
@@ -498,7 +532,7 @@ int run_conv(nesr_b200_handle* h, const Batch& b, const Layer& L, const ConvIO& 
       p.w_row0 = L.fold_row0[ps];
       p.idesc = umma_idesc_f16(hw_fmt(L.fmt), (uint32_t)L.fold_npad);
       const CUtensorMap& wm = h->m_wf[L.fold_npad == 16 ? 0 : (L.fold_npad == 32 ? 1 : 2)];
-      e = launch_conv3x3_fold(*io.fmap, wm, p, lp.fold_grid, s);
+      e = launch_conv3x3_fold(*io.fmap, *io.emap, wm, p, lp.fold_grid, s);
       h->stats.conv_launches++;
       if (ps + 1 < L.fold_passes) h->stats.kernel_launches++;
     }
@@ -536,12 +570,12 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
     ConvParams p{};
     p.dst32a = a.trunk; p.dst32b = a.feat;
     p.dst16 = a.d[0]; p.dst16_plane_px = (int)a.P[0]; p.dst16_coff = 0; p.dst16_fmt = c.body_format;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_x0, &a.f_x0, a.x0, 1, 0}, p, s))) return rc;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_x0, &a.f_x0, &a.e_x0, a.x0, 1, 0}, p, s))) return rc;
   }
   int cur = 0;
   const int nrdb = c.num_block * 3;
   for (int r = 0; r < nrdb; ++r) {
-    const ConvIO io{&a.m_d[cur], &a.f_d[cur], a.d[cur], 3, 0};
+    const ConvIO io{&a.m_d[cur], &a.f_d[cur], &a.e_d[cur], a.d[cur], 3, 0};
     for (int k = 1; k <= 4; ++k) {   // x_k = lrelu(conv_k(cat(x, x1..x_{k-1})))  -> channels [64+32(k-1), +32)
       ConvParams p{};
       p.lrelu = 1;
@@ -564,31 +598,31 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
     ConvParams p{};
     p.res1 = a.feat; p.s1 = 1.0f;
     p.dst16 = a.g2; p.dst16_plane_px = (int)a.P[1]; p.dst16_fmt = c.edge_format; p.dst16_up = 1;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_d[cur], &a.f_d[cur], a.d[cur], 3, 0}, p, s))) return rc;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_d[cur], &a.f_d[cur], &a.e_d[cur], a.d[cur], 3, 0}, p, s))) return rc;
   }
   {  // conv_up1 + lrelu, stored upsampled into level 2
     ConvParams p{};
     p.lrelu = 1;
     p.dst16 = a.g4[0]; p.dst16_plane_px = (int)a.P[2]; p.dst16_fmt = c.edge_format; p.dst16_up = 1;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g2, &a.f_g2, a.g2, 1, 1}, p, s))) return rc;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g2, &a.f_g2, &a.e_g2, a.g2, 1, 1}, p, s))) return rc;
   }
   {  // conv_up2 + lrelu
     ConvParams p{};
     p.lrelu = 1;
     p.dst16 = a.g4[1]; p.dst16_plane_px = (int)a.P[2]; p.dst16_fmt = c.edge_format;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], &a.f_g4[0], a.g4[0], 1, 2}, p, s))) return rc;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], &a.f_g4[0], &a.e_g4[0], a.g4[0], 1, 2}, p, s))) return rc;
   }
   {  // conv_hr + lrelu
     ConvParams p{};
     p.lrelu = 1;
     p.dst16 = a.g4[0]; p.dst16_plane_px = (int)a.P[2]; p.dst16_fmt = c.edge_format;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[1], &a.f_g4[1], a.g4[1], 1, 2}, p, s))) return rc;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[1], &a.f_g4[1], &a.e_g4[1], a.g4[1], 1, 2}, p, s))) return rc;
   }
   {  // conv_last -> clamp, BGR, u8, halo crop + stitch  (or unclamped fp32 NCHW)
     ConvParams p{};
     p.out_u8 = sink.out_u8; p.out_stride = sink.out_stride; p.out_frame_stride = sink.out_frame_stride;
     p.out_f32 = sink.out_f32; p.out_h = sink.out_h; p.out_w = sink.out_w;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], &a.f_g4[0], a.g4[0], 1, 2}, p, s))) return rc;
+    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], &a.f_g4[0], &a.e_g4[0], a.g4[0], 1, 2}, p, s))) return rc;
   }
   if (time_convs) cudaEventRecord(h->evc1, s);
   h->stats.tiles_processed += (int64_t)b.tiles.size();
@@ -961,10 +995,10 @@ int nesr_b200_debug_conv(nesr_b200_handle* h, int32_t impl, int32_t fmt, int32_t
         xs[((size_t)(c >> 6) * P + (size_t)g.base + (size_t)y * g.pitch + x) * 64 + (c & 63)] = to16(x_nchw[((size_t)c * H + y) * W + x], fmt);
   uint16_t *d_w = nullptr, *d_x = nullptr;
   float *d_b = nullptr, *d_y = nullptr;
-  TileGeom* d_t = nullptr; BlockRef* d_blk = nullptr; FoldBand* d_bands = nullptr; int32_t* d_off = nullptr;
+  TileGeom* d_t = nullptr; BlockRef* d_blk = nullptr; FoldBand* d_bands = nullptr; FoldSeg* d_segs = nullptr; int32_t* d_off = nullptr;
   int rc = NESR_OK;
   auto cleanup = [&]() {
-    cudaFree(d_w); cudaFree(d_x); cudaFree(d_b); cudaFree(d_y); cudaFree(d_t); cudaFree(d_blk); cudaFree(d_bands); cudaFree(d_off);
+    cudaFree(d_w); cudaFree(d_x); cudaFree(d_b); cudaFree(d_y); cudaFree(d_t); cudaFree(d_blk); cudaFree(d_bands); cudaFree(d_segs); cudaFree(d_off);
   };
 #define DBG_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(h, NESR_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); } } while (0)
   DBG_TRY(cudaMalloc(&d_w, wp.size() * 2));
@@ -975,6 +1009,8 @@ int nesr_b200_debug_conv(nesr_b200_handle* h, int32_t impl, int32_t fmt, int32_t
   DBG_TRY(cudaMalloc(&d_blk, lp.blocks.size() * sizeof(BlockRef)));
   DBG_TRY(cudaMalloc(&d_bands, lp.bands.size() * sizeof(FoldBand)));
   DBG_TRY(cudaMalloc(&d_off, lp.cta_off.size() * sizeof(int32_t)));
+  DBG_TRY(cudaMalloc(&d_segs, lp.segs.size() * sizeof(FoldSeg)));
+  DBG_TRY(cudaMemcpy(d_segs, lp.segs.data(), lp.segs.size() * sizeof(FoldSeg), cudaMemcpyHostToDevice));
   DBG_TRY(cudaMemcpy(d_w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
   DBG_TRY(cudaMemcpy(d_x, xs.data(), xs.size() * 2, cudaMemcpyHostToDevice));
   DBG_TRY(cudaMemcpy(d_b, bpad.data(), 64 * 4, cudaMemcpyHostToDevice));
@@ -996,14 +1032,15 @@ int nesr_b200_debug_conv(nesr_b200_handle* h, int32_t impl, int32_t fmt, int32_t
     if ((rc = make_map(h, &am, d_x, 64, (int64_t)L.nchunk * P, kBlockPixels)) || (rc = make_map(h, &wm, d_w, 64, rows, L.npad))) { cleanup(); return rc; }
     e = launch_conv3x3_tc(am, wm, p, h->num_sms, h->stream);
   } else {
-    CUtensorMap am, wm;
-    if ((rc = make_map(h, &am, d_x, 64, (int64_t)L.nchunk * P, 136)) || (rc = make_map(h, &wm, d_w, 64, rows, 3 * L.fold_npad))) { cleanup(); return rc; }
-    p.bands = d_bands; p.cta_band_off = d_off;
+    CUtensorMap am, am8, wm;
+    if ((rc = make_map(h, &am, d_x, 64, (int64_t)L.nchunk * P, 136)) || (rc = make_map(h, &am8, d_x, 64, (int64_t)L.nchunk * P, 8)) ||
+        (rc = make_map(h, &wm, d_w, 64, rows, 3 * L.fold_npad))) { cleanup(); return rc; }
+    p.bands = d_bands; p.segs = d_segs; p.cta_band_off = d_off;
     for (int ps = 0; ps < L.fold_passes && e == cudaSuccess; ++ps) {
       p.npad = L.fold_npad; p.c_off = ps * L.fold_npad; p.bias = d_b + p.c_off;
       p.cout = std::min(cout - p.c_off, L.fold_npad); p.w_row0 = L.fold_row0[ps];
       p.idesc = umma_idesc_f16(hw_fmt(fmt), (uint32_t)L.fold_npad);
-      if (p.cout > 0) e = launch_conv3x3_fold(am, wm, p, lp.fold_grid, h->stream);
+      if (p.cout > 0) e = launch_conv3x3_fold(am, am8, wm, p, lp.fold_grid, h->stream);
     }
   }
   h->stats.kernel_launches++;

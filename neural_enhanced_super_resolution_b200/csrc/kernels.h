@@ -16,8 +16,8 @@ cudaError_t launch_conv3x3_tc(const CUtensorMap& amap, const CUtensorMap& wmap, 
 // --- conv3x3_fold.cu : row-folded tcgen05 conv, N = 3*Cout (the production kernel) ---------------
 cudaError_t conv3x3_fold_configure();
 bool conv3x3_fold_fits(int cin16, int npad);
-cudaError_t launch_conv3x3_fold(const CUtensorMap& amap, const CUtensorMap& wmap, const ConvParams& p, int grid,
-                                cudaStream_t stream);
+cudaError_t launch_conv3x3_fold(const CUtensorMap& amap136, const CUtensorMap& amap8, const CUtensorMap& wmap,
+                                const ConvParams& p, int grid, cudaStream_t stream);
 
 // --- conv3x3_simt.cu : plain CUDA-core conv over the same buffers (test-only cross-check) -------
 cudaError_t launch_conv3x3_simt(const ConvParams& p, cudaStream_t stream);

@@ -47,10 +47,20 @@ struct BlockRef {
   int32_t tile;
 };
 
-// One unit of work of the row-folded conv kernel: output rows [r0, r0+rows) of the 128-pixel-wide
-// column strip starting at x0 of tile `tile`.
+// Row-folded conv kernel work units.  A strip is 128 MMA lanes wide.  A full strip is one segment of
+// 128 pixels of one tile; the narrow right-hand remainders of several tiles that share a height
+// (the tiles of one tile-row) are PACKED side by side into one combined strip, each with its own
+// halo pixels, so ragged tile widths cost neither MMA lanes nor memory traffic.
+struct FoldSeg {
+  int32_t tile;    // tile the pixels belong to
+  int32_t x0;      // first pixel column
+  int32_t width;   // pixels (<= 128)
+  int32_t lane0;   // MMA lane of pixel x0 (multiple of 8).  Slab rows [lane0, lane0+width+2) hold pixels x0-1 .. x0+width
+};
+constexpr int kMaxFoldSegs = 8;
+// One band: output rows [r0, r0+rows) of a strip made of segments segs[seg0 .. seg0+nseg).
 struct FoldBand {
-  int32_t tile, x0, r0, rows;
+  int32_t seg0, nseg, r0, rows;
 };
 
 struct ConvParams {
@@ -89,6 +99,7 @@ struct ConvParams {
   int32_t out_h, out_w;        // frame dims for out_f32
   // row-folded kernel (conv3x3_fold.cu)
   const FoldBand* bands;       // all bands of the level, grouped by CTA
+  const FoldSeg* segs;         // segments referenced by the bands
   const int32_t* cta_band_off; // [grid + 1] first band of each CTA
   int32_t c_off;               // first output channel of this pass inside the 64-channel fp32 buffers
   int32_t fold_stages;         // activation ring depth (host-computed from the shared-memory budget)
