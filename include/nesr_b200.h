@@ -67,9 +67,11 @@ typedef struct nesr_b200_config {
   int32_t num_grow_ch;
   int32_t body_format;        /* residual-dense-block convs: NESR_FMT_BF16 (default) | NESR_FMT_FP16 */
   int32_t edge_format;        /* conv_first/body/up1/up2/hr/last:  NESR_FMT_FP16 (default) | NESR_FMT_BF16 */
-  int32_t conv_impl;          /* 0 = row-folded tcgen05/TMEM/TMA kernel (product).  Test-only cross-checks,
-                                 never selected implicitly: 1 = SIMT validation kernel, 2 = first-generation
-                                 per-tap tcgen05 kernel */
+  int32_t conv_impl;          /* 0 = row-folded tcgen05/TMEM/TMA kernels (product): one persistent launch for
+                                 the 69 residual dense blocks, one launch per edge layer.  Test-only
+                                 cross-checks, never selected implicitly: 1 = SIMT validation kernel,
+                                 2 = first-generation per-tap tcgen05 kernel, 3 = row-folded kernel with one
+                                 launch per layer pass */
   int32_t reserved0;
   int64_t max_batch_pixels;   /* cap on feature-grid pixels resident per batch; 0 = default */
 } nesr_b200_config;

@@ -1,73 +1,20 @@
-// conv3x3_fold.cu -- the production 3x3 conv: row-folded implicit GEMM on tcgen05 / TMEM / TMA.
+// conv3x3_fold.cu -- one 3x3 conv layer pass per launch: row-folded implicit GEMM on tcgen05 / TMEM / TMA.
 //
-// Why "folded".  Measured on B200 (tools/umma_probe.cu, profiles/r1_umma_probe_rates.log): a
-// tcgen05.mma with M=128, K=16 and both operands in shared memory never issues faster than one per
-// ~54 cycles, whatever N <= 64 is -- the 4 KB A-operand read is the cost.  A conv with Cout = 32 as a
-// plain implicit GEMM (N = 32) is therefore capped at 30 % of the tensor peak, Cout = 64 at 59 %.
-// Folding the three VERTICAL taps into N fixes that: for one input row segment (128 pixels, one A
-// tile) and one horizontal shift dx,
-//
-//      [ out(y-1) | out(y) | out(y+1) ]  +=  A(y, dx) * [ W(dy=+1,dx) | W(dy=0,dx) | W(dy=-1,dx) ]^T
-//
-// is ONE MMA with N = 3*Cout (96 -> 85 %, 192 -> 99 % of peak in the same probe) whose accumulator
-// is three consecutive row slots of a TMEM ring.  Each A byte fetched from shared memory now feeds
-// 3x the MACs, and each activation row is loaded from L2 exactly once per strip (no tap re-reads).
-//
-// Work decomposition.  A tile is cut into 128-pixel-wide column strips and the strips into bands
-// of consecutive rows (host: engine.cu build_fold_schedule, balanced over the SMs).  A CTA streams
-// down its bands: the TMA producer loads one 136-pixel row slab [136 px x 64 ch] per (row, channel
-// chunk) into a ring; the MMA thread issues 3 (dx) x ksteps MMAs per slab, the dx shift being a
-// 128-byte offset of the A descriptor into the slab (address-based swizzle makes un-aligned views
-// legal: profiles/r1_umma_probe_shifted_views.log); the folded weights of the whole layer pass stay
-// resident in shared memory.  Output row r is complete once input row r+1 has been issued, so the
-// four epilogue warps drain rows in order while the MMAs run ahead: tcgen05.ld -> fused epilogue
-// (epilogue.cuh) -> tcgen05.st zeros (every MMA accumulates; a slot is handed back zeroed).
-// Rows just outside a band are "virtual": they receive partial sums and are dropped.
+// The roles (TMA producer, MMA issuer, epilogue warps) and the reasoning behind the row fold live in
+// fold_roles.cuh.  This kernel runs the six edge layers of the network (conv_first, conv_body,
+// conv_up1/2, conv_hr, conv_last); the 69 residual dense blocks in between run inside the persistent
+// kernel of conv3x3_body.cu, which uses the same roles.  (conv_impl = 3 runs every layer through this
+// kernel -- the previous production path, kept as a cross-check.)
 //
 // Layers with Cout = 64 and Cin > 64 (RDB conv5) run as two passes of 32 output channels so that
 // the resident weights (3*nchunk boxes of [96 x 64]) fit next to the activation ring.
-#include <stdio.h>
-
-#include "epilogue.cuh"
-#include "kernels.h"
-#include "ptx.cuh"
+#include "fold_roles.cuh"
 
 namespace nesr {
 
 namespace {
 
-// NESR_PROF build + debug_flags & 32: block 0 prints where each role spent its cycles (timing experiments only)
-#if NESR_PROF
-#define PROF_DECL long long prof_t = 0, prof_acc[4] = {0, 0, 0, 0}; const bool prof_on = (p.debug_flags & 32) && blockIdx.x == 0
-#define PROF_BEGIN() do { if (prof_on) prof_t = clock64(); } while (0)
-#define PROF_END(k) do { if (prof_on) { const long long t__ = clock64(); prof_acc[k] += t__ - prof_t; prof_t = t__; } } while (0)
-#define PROF_PRINT(...) do { if (prof_on) printf(__VA_ARGS__); } while (0)
-#define PROF_NOW() clock64()
-#else
-#define PROF_DECL do {} while (0)
-#define PROF_BEGIN() do {} while (0)
-#define PROF_END(k) do {} while (0)
-#define PROF_PRINT(...) do {} while (0)
-#define PROF_NOW() 0LL
-#endif
-
-constexpr int kEpiGroups = 2;                      // epilogue warp-groups (4 warps each) alternating over rows
-constexpr int kThreads = 64 + 128 * kEpiGroups;
-constexpr int kSlabPx = 136;                       // 1 + 128 + 1 halo pixels, rounded to 8-row groups
-constexpr int kSlabBytes = kSlabPx * 128;          // 17408 = 17 * 1024
-constexpr int kMaxStages = 8;
-constexpr int kMaxSlots = 16;
-constexpr int kSmemBudget = 232448;                // 227 KB
-
-template <int COUT>
-struct FoldCfg {
-  static constexpr int kN3 = 3 * COUT;
-  static constexpr int kSlots = (512 / COUT) > kMaxSlots ? kMaxSlots : (512 / COUT);   // 16, 16, 8
-  static constexpr int kCols = kSlots * COUT;                                         // 256, 512, 512
-  static constexpr int kWBoxBytes = kN3 * 128;                                        // one (dx, chunk) weight box
-};
-
-constexpr int kBarrierBytes = (1 + 2 * kMaxStages + 2 * kMaxSlots) * 8 + 16;
+using namespace fold;
 
 template <int COUT>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -80,288 +27,39 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nchunk = (p.cin + kChunkChannels - 1) / kChunkChannels;
-  const int wbytes = 3 * nchunk * Cfg::kWBoxBytes;
-  const int nstage = p.fold_stages;
-  uint8_t* wsm = smem;                                         // resident folded weights
-  uint8_t* ring = smem + wbytes;                               // activation row slabs
-  uint64_t* wbar = reinterpret_cast<uint64_t*>(ring + nstage * kSlabBytes);
-  uint64_t* full = wbar + 1;
-  uint64_t* empty = full + kMaxStages;
-  uint64_t* tfull = empty + kMaxStages;
-  uint64_t* tempty = tfull + kMaxSlots;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kMaxSlots);
+  Pipe s = carve_pipe(smem, 3 * nchunk * Cfg::kWBoxBytes, p.fold_stages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&amap);
     tma_prefetch_desc(&amap8);
     tma_prefetch_desc(&wmap);
-    mbar_init(wbar, 1);
-    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < kMaxSlots; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
-    fence_barrier_init();
   }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (warp >= 2 && warp < 6 && !(p.debug_flags & 128)) {       // every MMA accumulates: start from zero
-    const uint32_t t0 = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    for (int c = 0; c < Cfg::kCols; c += 16) tmem_st16_zero(t0 + c);
-    tmem_st_wait();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
+  pipe_setup<COUT>(s, warp, lane, !(p.debug_flags & 128));
 
   const int band_begin = p.cta_band_off[blockIdx.x];
   const int band_end = p.cta_band_off[blockIdx.x + 1];
   pdl_launch_dependents();        // the next layer may start its prologue on SMs this grid has left
 
   if (warp == 0) {
-    // ------------------------------ TMA producer (warp-wide, one elected lane issues) ----------
-    {
-      if (elect_one()) {
-        if (p.debug_flags & 64) {
-          mbar_arrive(wbar);
-        } else {
-          mbar_arrive_expect_tx(wbar, wbytes);
-          for (int b = 0; b < 3 * nchunk; ++b)
-            tma_load_2d(wsm + b * Cfg::kWBoxBytes, &wmap, wbar, 0, p.w_row0 + b * Cfg::kN3);
-        }
-      }
-      pdl_wait();                  // activations below were written by the previous layer
-      // Band geometry is read once per band; inside a band the slab coordinate advances by the row
-      // pitch in registers.  (Fetching it per slab made the producer latency-bound on its own
-      // metadata loads whenever the epilogue kept the memory system busy: profiles/r1_fold_role_timing.txt.)
-      int stage = 0;
-      uint32_t phase = 0;
-      PROF_DECL;
-      [[maybe_unused]] const long long prof_start = PROF_NOW();
-      for (int bi = band_begin; bi < band_end; ++bi) {
-        const FoldBand band = p.bands[bi];
-        // per segment: flat pixel of (row r0-1, x0-1), row pitch, slab byte offset, number of 8-pixel boxes
-        int seg_px[kMaxFoldSegs], seg_pitch[kMaxFoldSegs], seg_off[kMaxFoldSegs], seg_n8[kMaxFoldSegs];
-        bool full_strip = false;
-        uint32_t row_bytes = 0;
-#pragma unroll
-        for (int sgi = 0; sgi < kMaxFoldSegs; ++sgi) {
-          seg_px[sgi] = seg_pitch[sgi] = seg_off[sgi] = seg_n8[sgi] = 0;
-          if (sgi < band.nseg) {
-            const FoldSeg sg = p.segs[band.seg0 + sgi];
-            const LevelGeom g = p.tiles[sg.tile].lv[p.level];
-            seg_px[sgi] = g.base + (band.r0 - 1) * g.pitch + sg.x0 - 1;
-            seg_pitch[sgi] = g.pitch;
-            seg_off[sgi] = sg.lane0 * 128;
-            seg_n8[sgi] = (sg.width + 2 + 7) >> 3;
-            if (sg.width == kBlockPixels) full_strip = true;      // a 128-pixel segment is always alone
-            row_bytes += seg_n8[sgi] * 1024;
-          }
-        }
-        if (full_strip) row_bytes = kSlabBytes;
-        for (int i = 0; i < band.rows + 2; ++i) {
-          for (int c = 0; c < nchunk; ++c) {
-            PROF_BEGIN();
-            mbar_wait(&empty[stage], phase ^ 1);
-            PROF_END(0);
-            if (elect_one()) {
-              if (p.debug_flags & 4) {
-                mbar_arrive(&full[stage]);
-              } else {
-                mbar_arrive_expect_tx(&full[stage], row_bytes);
-                uint8_t* slab = ring + stage * kSlabBytes;
-                const int plane = c * p.src_plane_px;
-                if (full_strip) {
-                  tma_load_2d(slab, &amap, &full[stage], 0, plane + seg_px[0] + i * seg_pitch[0]);
-                } else {
-#pragma unroll
-                  for (int sgi = 0; sgi < kMaxFoldSegs; ++sgi)
-                    for (int k = 0; k < seg_n8[sgi]; ++k)
-                      tma_load_2d(slab + seg_off[sgi] + k * 1024, &amap8, &full[stage], 0,
-                                  plane + seg_px[sgi] + i * seg_pitch[sgi] + k * 8);
-                }
-              }
-            }
-            if (++stage == nstage) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-      if (lane == 0)
-        PROF_PRINT("[fold cin=%d cout=%d] producer: total %lld  wait_empty %lld\n", p.cin, COUT, PROF_NOW() - prof_start, prof_acc[0]);
-    }
+    load_weights<COUT>(p, &wmap, s);
+    pdl_wait();                    // activations below were written by the previous layer
+    RingPos rp;
+    producer_bands(p, &amap, &amap8, s, rp, band_begin, band_end);
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer (warp-wide, one elected lane issues) ------------
-    {
-      const uint32_t hw = (p.idesc >> 7) & 7u;                 // operand format bits of the layer
-      const uint32_t idesc1 = umma_idesc_f16(hw, COUT), idesc2 = umma_idesc_f16(hw, 2 * COUT),
-                     idesc3 = umma_idesc_f16(hw, 3 * COUT);
-      const uint32_t hi = umma_desc_hi_sw128();
-      const uint32_t a_lo0 = umma_desc_lo(smem_u32(ring));
-      const uint32_t w_lo0 = umma_desc_lo(smem_u32(wsm));
-      constexpr uint32_t kSlabLo = kSlabBytes >> 4, kBoxLo = Cfg::kWBoxBytes >> 4;
-      mbar_wait(wbar, 0);
-      tc_fence_after();
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t u = 0;                                          // running row-slot counter
-      PROF_DECL;
-      [[maybe_unused]] const long long prof_start = PROF_NOW();
-      [[maybe_unused]] int prof_rows = 0;
-      for (int bi = band_begin; bi < band_end; ++bi) {
-        const int rows = p.bands[bi].rows;
-        prof_rows += rows + 2;
-        for (int j = 0; j < 2; ++j) {                          // slots of the first two (virtual) output rows
-          const uint32_t v = u + j;
-          mbar_wait(&tempty[v % Cfg::kSlots], ((v / Cfg::kSlots) & 1) ^ 1);
-        }
-        for (int i = 0; i < rows + 2; ++i) {
-          PROF_BEGIN();
-          {                                                    // slot of output row i+2 must be drained + zeroed
-            const uint32_t v = u + i + 2;
-            mbar_wait(&tempty[v % Cfg::kSlots], ((v / Cfg::kSlots) & 1) ^ 1);
-          }
-          PROF_END(0);
-          tc_fence_after();
-          const uint32_t q = (u + i) % Cfg::kSlots;
-          // accumulator = row slots (q, q+1, q+2); at the ring end it splits into two narrower MMAs
-          const uint32_t d0 = tmem_base + q * COUT;
-          uint32_t id0 = idesc3, id1 = 0, b1 = 0;
-          if (q + 2 == Cfg::kSlots) { id0 = idesc2; id1 = idesc1; b1 = (2 * COUT * 128) >> 4; }
-          else if (q + 1 == Cfg::kSlots) { id0 = idesc1; id1 = idesc2; b1 = (COUT * 128) >> 4; }
-          for (int c = 0; c < nchunk; ++c) {
-            const int rem = (p.cin - c * kChunkChannels) >> 4;
-            const int ksteps = rem < 4 ? rem : 4;
-            PROF_BEGIN();
-            mbar_wait(&full[stage], phase);
-            PROF_END(1);
-            tc_fence_after();
-            const uint32_t a_lo = a_lo0 + stage * kSlabLo;
-            const uint32_t b_lo = w_lo0 + c * kBoxLo;
-            if (!(p.debug_flags & 2) && elect_one()) {
-              if (ksteps == 4) {
-#pragma unroll
-                for (int dxi = 0; dxi < 3; ++dxi) {
-                  umma_f16_ksteps<4>(d0, a_lo + dxi * 8, b_lo + dxi * nchunk * kBoxLo, hi, id0);
-                  if (id1) umma_f16_ksteps<4>(tmem_base, a_lo + dxi * 8, b_lo + dxi * nchunk * kBoxLo + b1, hi, id1);
-                }
-              } else {
-#pragma unroll
-                for (int dxi = 0; dxi < 3; ++dxi) {
-                  umma_f16_ksteps_rt(ksteps, d0, a_lo + dxi * 8, b_lo + dxi * nchunk * kBoxLo, hi, id0);
-                  if (id1) umma_f16_ksteps_rt(ksteps, tmem_base, a_lo + dxi * 8, b_lo + dxi * nchunk * kBoxLo + b1, hi, id1);
-                }
-              }
-            }
-            if (elect_one()) umma_commit(&empty[stage]);
-            PROF_END(2);
-            if (++stage == nstage) { stage = 0; phase ^= 1; }
-          }
-          if (elect_one()) {
-            umma_commit(&tfull[q]);                            // output row i has all its contributions
-            if (i == rows + 1) {
-              umma_commit(&tfull[(u + i + 1) % Cfg::kSlots]);
-              umma_commit(&tfull[(u + i + 2) % Cfg::kSlots]);
-            }
-          }
-        }
-        u += rows + 4;
-      }
-      if (lane == 0)
-        PROF_PRINT("[fold cin=%d cout=%d] mma: input rows %d total %lld  wait_tempty %lld  wait_full %lld  issue %lld\n", p.cin, COUT,
-                   prof_rows, PROF_NOW() - prof_start, prof_acc[0], prof_acc[1], prof_acc[2]);
-    }
+    RingPos rp;
+    uint32_t u = 0;
+    mma_bands<COUT>(p, s, rp, u, 0, band_begin, band_end);
     __syncwarp();
   } else {
-    // ------------------------------ epilogue ----------------------------------
-    const int quarter = warp & 3;
-    const int group = (warp - 2) >> 2;                         // rows alternate between the epilogue groups
-    const int m = quarter * 32 + lane;                         // A row == TMEM lane == pixel x0 + m
-    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    uint32_t u = 0;
-    PROF_DECL;
     pdl_wait();                    // residual reads / stores must not overtake the previous layer
-    [[maybe_unused]] const long long prof_start = PROF_NOW();
-    for (int bi = band_begin; bi < band_end; ++bi) {
-      const FoldBand band = p.bands[bi];
-      int my_tile = 0, x = 1 << 20;                            // this lane's pixel column (none: masked lane)
-      for (int sgi = 0; sgi < band.nseg; ++sgi) {
-        const FoldSeg sg = p.segs[band.seg0 + sgi];
-        if (m >= sg.lane0 && m < sg.lane0 + sg.width) { my_tile = sg.tile; x = sg.x0 + (m - sg.lane0); }
-      }
-      const TileGeom& tg = p.tiles[my_tile];
-      const LevelGeom g = tg.lv[p.level];
-      for (int j = 0; j < band.rows + 4; ++j) {
-        const uint32_t v = u + j;
-        if (static_cast<int>(v % kEpiGroups) != group) continue;
-        const uint32_t slot = v % Cfg::kSlots;
-        const int y = band.r0 - 2 + j;
-        const bool active = j >= 2 && j < band.rows + 2 && x < g.w && !(p.debug_flags & 1);
-        PixelRef px;
-        px.P = g.base + y * g.pitch + x;
-        px.y = y; px.x = x; px.valid = true;
-        // residual rows are fetched BEFORE waiting for the accumulator: their latency hides behind the MMAs
-        constexpr bool kPrefetchR2 = COUT <= 32;                // 64-wide layers never carry a second residual
-        float r1[COUT], r2[kPrefetchR2 ? COUT : 1];
-        if (active && p.res1) {
-#pragma unroll
-          for (int c = 0; c < COUT / 16; ++c) load_trunk16(p.res1, px.P, p.c_off + c * 16, &r1[c * 16]);
-        }
-        if constexpr (kPrefetchR2) {
-          if (active && p.res2) {
-#pragma unroll
-            for (int c = 0; c < COUT / 16; ++c) load_trunk16(p.res2, px.P, p.c_off + c * 16, &r2[c * 16]);
-          }
-        }
-        PROF_BEGIN();
-        mbar_wait(&tfull[slot], (v / Cfg::kSlots) & 1);
-        PROF_END(0);
-        tc_fence_after();
-        __syncwarp();
-        const uint32_t taddr = lane_base + slot * COUT;
-        uint32_t r[COUT / 16][16];
-#pragma unroll
-        for (int c = 0; c < COUT / 16; ++c) tmem_ld16(taddr + c * 16, r[c]);
-        tmem_ld_wait();
-        if (!(p.debug_flags & 8)) {
-#pragma unroll
-          for (int c = 0; c < COUT / 16; ++c) tmem_st16_zero(taddr + c * 16);
-          tmem_st_wait();
-        }
-        tc_fence_before();
-        mbar_arrive(&tempty[slot]);
-        PROF_END(1);
-        if (active) {
-#pragma unroll
-          for (int c = 0; c < COUT / 16; ++c) {
-            if (c * 16 < p.cout) {
-              float vals[16];
-#pragma unroll
-              for (int e = 0; e < 16; ++e) vals[e] = __uint_as_float(r[c][e]);
-              epilogue16(p, tg, px, c * 16, vals, p.res1 ? &r1[c * 16] : nullptr,
-                         (kPrefetchR2 && p.res2) ? &r2[kPrefetchR2 ? c * 16 : 0] : nullptr);
-            }
-          }
-        }
-        PROF_END(2);
-      }
-      u += band.rows + 4;
-    }
-    if (lane == 0 && (warp == 2 || warp == 6))
-      PROF_PRINT("[fold cin=%d cout=%d] epilogue warp %d: total %lld  wait_tfull %lld  ld+zero+arrive %lld  math+stores %lld\n", p.cin, COUT,
-                 warp, PROF_NOW() - prof_start, prof_acc[0], prof_acc[1], prof_acc[2]);
+    uint32_t u = 0;
+    epilogue_bands<COUT>(p, s, u, warp, lane, band_begin, band_end);
   }
 
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  pipe_teardown(s, warp);
 #if NESR_PROF
   if ((p.debug_flags & 256) && threadIdx.x == 0) {       // per-CTA lifetime: who are the stragglers?
     unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -397,7 +95,7 @@ cudaError_t launch_c(const CUtensorMap& amap, const CUtensorMap& amap8, const CU
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (p.debug_flags & 512) ? 0 : 1;      // 512: no programmatic dependent launch (timing experiments)
   return cudaLaunchKernelEx(&cfg, conv3x3_fold_kernel<COUT>, amap, amap8, wmap, p);
 }
 

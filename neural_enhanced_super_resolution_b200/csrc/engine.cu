@@ -73,6 +73,8 @@ struct Batch {
   std::vector<TileGeom> tiles;
   TileGeom* d_tiles = nullptr;
   LevelPlan lv[3];
+  ConvParams* d_body_passes = nullptr;   // persistent trunk kernel: one ConvParams per RDB layer pass
+  int n_body_passes = 0;
 };
 
 struct Arena {
@@ -126,6 +128,8 @@ struct nesr_b200_handle {
   uint8_t* d_in = nullptr;  size_t d_in_bytes = 0;
   uint8_t* d_out = nullptr; size_t d_out_bytes = 0;
   uint8_t* d_tmp = nullptr; size_t d_tmp_bytes = 0;
+
+  unsigned* d_gbar = nullptr;                          // arrival counter of the persistent trunk kernel
 
   nesr_b200_stats stats{};
   int debug_flags = 0;        // NESR_B200_DEBUG_FLAGS: timing experiments (results are wrong when set)
@@ -288,6 +292,7 @@ Grid tile_grid_dims(int H, int W, int tile, int pre_pad, int scale) {
 void free_batches(nesr_b200_handle* h) {
   for (Batch& b : h->batches) {
     if (b.d_tiles) cudaFree(b.d_tiles);
+    if (b.d_body_passes) cudaFree(b.d_body_passes);
     for (LevelPlan& l : b.lv) {
       if (l.d_blocks) cudaFree(l.d_blocks);
       if (l.d_bands) cudaFree(l.d_bands);
@@ -378,6 +383,8 @@ void build_fold_schedule(Batch& b, int level, int num_sms) {
   }
   lp.fold_grid = grid;
 }
+
+int build_body_passes(nesr_b200_handle* h, Batch& b);
 
 int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
   if (h->key == key && !h->batches.empty()) return NESR_OK;
@@ -488,6 +495,9 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
   if ((rc = make_map(h, &a.e_g2, a.g2, 64, P[1], 8))) return rc;
   for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.e_g4[i2], a.g4[i2], 64, P[2], 8))) return rc;
   h->stats.arena_bytes = (int64_t)a.bytes;
+  if (h->cfg.conv_impl == 0)
+    for (Batch& b : h->batches)
+      if ((rc = build_body_passes(h, b))) return rc;
   h->key = key;
   return NESR_OK;
 }
@@ -504,13 +514,38 @@ struct ConvIO {
   int level = 0;
 };
 
-int run_conv(nesr_b200_handle* h, const Batch& b, const Layer& L, const ConvIO& io, ConvParams p, cudaStream_t s) {
+// Fills the layer-dependent fields of `p` (operands, weights, bias) for layer L read through `io`.
+void bind_layer(nesr_b200_handle* h, const Batch& b, const Layer& L, const ConvIO& io, ConvParams& p) {
   const LevelPlan& lp = b.lv[io.level];
   p.blocks = lp.d_blocks; p.tiles = b.d_tiles; p.nblk = (int)lp.blocks.size(); p.level = io.level;
   p.src = io.src; p.src_plane_px = (int)h->arena.P[io.level]; p.cin = L.cin16;
   p.wpack = h->d_wpack; p.w_row0 = L.w_row0; p.npad = L.npad; p.fmt = L.fmt;
   p.idesc = umma_idesc_f16(hw_fmt(L.fmt), (uint32_t)L.npad);
   p.bias = h->d_bias + L.bias_off; p.cout = L.cout;
+  p.bands = lp.d_bands; p.segs = lp.d_segs; p.cta_band_off = lp.d_cta_off;
+  p.debug_flags = h->debug_flags;
+}
+
+// Narrows a bound ConvParams to pass `ps` of the row-folded kernel (Cout split when the folded weights
+// of the whole layer would not fit in shared memory).
+void select_fold_pass(const Layer& L, int ps, const ConvParams& bound, ConvParams& p) {
+  p = bound;
+  p.npad = L.fold_npad;
+  p.c_off = ps * L.fold_npad;
+  p.bias = bound.bias + p.c_off;
+  p.dst16_coff = bound.dst16_coff + p.c_off;
+  p.cout = std::min(L.cout - p.c_off, L.fold_npad);
+  p.w_row0 = L.fold_row0[ps];
+  p.idesc = umma_idesc_f16((bound.idesc >> 7) & 7u, (uint32_t)L.fold_npad);
+}
+
+const CUtensorMap& fold_weight_map(const nesr_b200_handle* h, int fold_npad) {
+  return h->m_wf[fold_npad == 16 ? 0 : (fold_npad == 32 ? 1 : 2)];
+}
+
+int run_conv(nesr_b200_handle* h, const Batch& b, const Layer& L, const ConvIO& io, ConvParams p, cudaStream_t s) {
+  const LevelPlan& lp = b.lv[io.level];
+  bind_layer(h, b, L, io, p);
   cudaError_t e = cudaSuccess;
   if (h->cfg.conv_impl == 1) {
     e = launch_conv3x3_simt(p, s);
@@ -519,26 +554,76 @@ int run_conv(nesr_b200_handle* h, const Batch& b, const Layer& L, const ConvIO& 
     e = launch_conv3x3_tc(*io.amap, wm, p, h->num_sms, s);
     h->stats.conv_launches++;
   } else {
-    p.bands = lp.d_bands; p.segs = lp.d_segs; p.cta_band_off = lp.d_cta_off;
-    p.debug_flags = h->debug_flags;
-    const float* bias0 = p.bias;
-    const int coff0 = p.dst16_coff;
     for (int ps = 0; ps < L.fold_passes && e == cudaSuccess; ++ps) {
-      p.npad = L.fold_npad;
-      p.c_off = ps * L.fold_npad;
-      p.bias = bias0 + p.c_off;
-      p.dst16_coff = coff0 + p.c_off;
-      p.cout = std::min(L.cout - p.c_off, L.fold_npad);
-      p.w_row0 = L.fold_row0[ps];
-      p.idesc = umma_idesc_f16(hw_fmt(L.fmt), (uint32_t)L.fold_npad);
-      const CUtensorMap& wm = h->m_wf[L.fold_npad == 16 ? 0 : (L.fold_npad == 32 ? 1 : 2)];
-      e = launch_conv3x3_fold(*io.fmap, *io.emap, wm, p, lp.fold_grid, s);
+      ConvParams q;
+      select_fold_pass(L, ps, p, q);
+      e = launch_conv3x3_fold(*io.fmap, *io.emap, fold_weight_map(h, L.fold_npad), q, lp.fold_grid, s);
       h->stats.conv_launches++;
       if (ps + 1 < L.fold_passes) h->stats.kernel_launches++;
     }
   }
   h->stats.kernel_launches++;
   if (e != cudaSuccess) return fail(h, NESR_E_CUDA, "conv %s launch failed: %s", L.name.c_str(), cudaGetErrorString(e));
+  return NESR_OK;
+}
+
+// Epilogue wiring of the 5 convs of residual dense block r (0-based over the whole trunk) reading
+// dense buffer `cur`: conv1-4 append 32 channels to the same buffer (torch.cat as addressing), conv5
+// writes 0.2*x5 + x (+ the RRDB skip on every third block) as the next block's channels [0,64).
+ConvParams rdb_conv_params(const nesr_b200_handle* h, int r, int k, int cur) {
+  const Arena& a = h->arena;
+  const nesr_b200_config& c = h->cfg;
+  const int nrdb = c.num_block * 3;
+  ConvParams p{};
+  p.dst16_plane_px = (int)a.P[0];
+  if (k <= 4) {                      // x_k = lrelu(conv_k(cat(x, x1..x_{k-1})))  -> channels [64+32(k-1), +32)
+    p.lrelu = 1;
+    p.dst16 = a.d[cur]; p.dst16_coff = kFeat + (k - 1) * kGrow; p.dst16_fmt = c.body_format;
+  } else {                           // x5*0.2 + x  (+ RRDB skip on every third block)
+    p.res1 = a.trunk; p.s1 = 0.2f;
+    p.dst32a = a.trunk;
+    if (r % 3 == 2) {
+      p.res2 = (r == 2) ? a.feat : a.rrdb; p.s2 = 0.2f;
+      p.dst32b = a.rrdb;
+    }
+    p.dst16 = a.d[cur ^ 1]; p.dst16_coff = 0;
+    p.dst16_fmt = (r == nrdb - 1) ? c.edge_format : c.body_format;    // conv_body reads the last one
+  }
+  return p;
+}
+
+// One ConvParams per layer pass of the trunk, in execution order, for the persistent kernel.
+int build_body_passes(nesr_b200_handle* h, Batch& b) {
+  const Arena& a = h->arena;
+  const int nrdb = h->cfg.num_block * 3;
+  std::vector<ConvParams> passes;
+  size_t li = 1;                     // layers[0] is conv_first
+  int cur = 0;
+  for (int r = 0; r < nrdb; ++r) {
+    const ConvIO io{&a.m_d[cur], &a.f_d[cur], &a.e_d[cur], a.d[cur], 3, 0};
+    for (int k = 1; k <= 5; ++k) {
+      const Layer& L = h->layers[li++];
+      if (L.fold_npad != 32 || L.fmt != h->cfg.body_format)
+        return fail(h, NESR_E_STATE, "persistent trunk kernel: layer %s is not a 32-channel pass", L.name.c_str());
+      ConvParams bound = rdb_conv_params(h, r, k, cur);
+      bind_layer(h, b, L, io, bound);
+      const int first = (int)passes.size();
+      for (int ps = 0; ps < L.fold_passes; ++ps) {
+        ConvParams q;
+        select_fold_pass(L, ps, bound, q);
+        q.src_sel = cur;
+        q.sync_passes = first;       // passes of one layer read the same input and write disjoint channels
+        passes.push_back(q);
+      }
+    }
+    cur ^= 1;
+  }
+  if (b.d_body_passes) cudaFree(b.d_body_passes);
+  b.d_body_passes = nullptr;
+  b.n_body_passes = (int)passes.size();
+  CUDA_TRY(h, cudaMalloc(&b.d_body_passes, passes.size() * sizeof(ConvParams)));
+  CUDA_TRY(h, cudaMemcpyAsync(b.d_body_passes, passes.data(), passes.size() * sizeof(ConvParams), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return NESR_OK;
 }
 
@@ -574,25 +659,21 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
   }
   int cur = 0;
   const int nrdb = c.num_block * 3;
-  for (int r = 0; r < nrdb; ++r) {
-    const ConvIO io{&a.m_d[cur], &a.f_d[cur], &a.e_d[cur], a.d[cur], 3, 0};
-    for (int k = 1; k <= 4; ++k) {   // x_k = lrelu(conv_k(cat(x, x1..x_{k-1})))  -> channels [64+32(k-1), +32)
-      ConvParams p{};
-      p.lrelu = 1;
-      p.dst16 = a.d[cur]; p.dst16_plane_px = (int)a.P[0]; p.dst16_coff = kFeat + (k - 1) * kGrow; p.dst16_fmt = c.body_format;
-      if ((rc = run_conv(h, b, next(), io, p, s))) return rc;
+  if (c.conv_impl == 0) {            // all RDB layer passes in one persistent cooperative launch
+    cudaError_t eb = launch_conv3x3_body(a.f_d[0], a.f_d[1], a.e_d[0], a.e_d[1], fold_weight_map(h, 32), b.d_body_passes,
+                                         b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s);
+    if (eb != cudaSuccess) return fail(h, NESR_E_CUDA, "trunk kernel launch failed: %s", cudaGetErrorString(eb));
+    h->stats.kernel_launches++;
+    h->stats.conv_launches++;
+    li += (size_t)nrdb * 5;
+    cur = nrdb & 1;
+  } else {
+    for (int r = 0; r < nrdb; ++r) {
+      const ConvIO io{&a.m_d[cur], &a.f_d[cur], &a.e_d[cur], a.d[cur], 3, 0};
+      for (int k = 1; k <= 5; ++k)
+        if ((rc = run_conv(h, b, next(), io, rdb_conv_params(h, r, k, cur), s))) return rc;
+      cur ^= 1;
     }
-    ConvParams p{};                  // x5*0.2 + x  (+ RRDB skip on every third block)
-    p.res1 = a.trunk; p.s1 = 0.2f;
-    p.dst32a = a.trunk;
-    if (r % 3 == 2) {
-      p.res2 = (r == 2) ? a.feat : a.rrdb; p.s2 = 0.2f;
-      p.dst32b = a.rrdb;
-    }
-    p.dst16 = a.d[cur ^ 1]; p.dst16_plane_px = (int)a.P[0]; p.dst16_coff = 0;
-    p.dst16_fmt = (r == nrdb - 1) ? c.edge_format : c.body_format;    // conv_body reads the last one
-    if ((rc = run_conv(h, b, next(), io, p, s))) return rc;
-    cur ^= 1;
   }
   {  // conv_body + long skip, stored nearest-x2 upsampled into level 1
     ConvParams p{};
@@ -743,7 +824,8 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
       (e = cudaEventCreate(&h->evc0)) != cudaSuccess || (e = cudaEventCreate(&h->evc1)) != cudaSuccess ||
-      (e = conv3x3_tc_configure()) != cudaSuccess || (e = conv3x3_fold_configure()) != cudaSuccess) {
+      (e = conv3x3_tc_configure()) != cudaSuccess || (e = conv3x3_fold_configure()) != cudaSuccess ||
+      (e = conv3x3_body_configure()) != cudaSuccess || (e = cudaMalloc(&h->d_gbar, 256)) != cudaSuccess) {
     std::string msg = cudaGetErrorString(e);
     nesr_b200_destroy(h);
     return fail(nullptr, NESR_E_CUDA, "device setup failed: %s", msg.c_str());
@@ -763,6 +845,7 @@ int nesr_b200_destroy(nesr_b200_handle* h) {
   if (h->d_wpack) cudaFree(h->d_wpack);
   if (h->d_bias) cudaFree(h->d_bias);
   if (h->d_wfold) cudaFree(h->d_wfold);
+  if (h->d_gbar) cudaFree(h->d_gbar);
   if (h->d_in) cudaFree(h->d_in);
   if (h->d_out) cudaFree(h->d_out);
   if (h->d_tmp) cudaFree(h->d_tmp);

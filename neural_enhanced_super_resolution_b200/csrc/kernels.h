@@ -13,11 +13,17 @@ cudaError_t conv3x3_tc_configure();
 cudaError_t launch_conv3x3_tc(const CUtensorMap& amap, const CUtensorMap& wmap, const ConvParams& p, int num_sms,
                               cudaStream_t stream);
 
-// --- conv3x3_fold.cu : row-folded tcgen05 conv, N = 3*Cout (the production kernel) ---------------
+// --- conv3x3_fold.cu : row-folded tcgen05 conv, N = 3*Cout, one layer pass per launch ------------
 cudaError_t conv3x3_fold_configure();
 bool conv3x3_fold_fits(int cin16, int npad);
 cudaError_t launch_conv3x3_fold(const CUtensorMap& amap136, const CUtensorMap& amap8, const CUtensorMap& wmap,
                                 const ConvParams& p, int grid, cudaStream_t stream);
+
+// --- conv3x3_body.cu : all RDB layer passes of a batch in one persistent cooperative launch ----------
+cudaError_t conv3x3_body_configure();
+cudaError_t launch_conv3x3_body(const CUtensorMap& d0_136, const CUtensorMap& d1_136, const CUtensorMap& d0_8,
+                                const CUtensorMap& d1_8, const CUtensorMap& wmap96, const ConvParams* d_passes, int npass,
+                                unsigned* d_gbar, int grid, cudaStream_t stream);
 
 // --- conv3x3_simt.cu : plain CUDA-core conv over the same buffers (test-only cross-check) -------
 cudaError_t launch_conv3x3_simt(const ConvParams& p, cudaStream_t stream);

@@ -103,6 +103,9 @@ struct ConvParams {
   const int32_t* cta_band_off; // [grid + 1] first band of each CTA
   int32_t c_off;               // first output channel of this pass inside the 64-channel fp32 buffers
   int32_t fold_stages;         // activation ring depth (host-computed from the shared-memory budget)
+  // persistent trunk kernel (conv3x3_body.cu)
+  int32_t src_sel;             // which of the two dense-block buffers (tensor maps) this pass reads
+  int32_t sync_passes;         // passes [0, sync_passes) of every CTA must be complete before this pass loads activations
   int32_t debug_flags;         // NESR_B200_DEBUG_FLAGS (timing experiments only): 1 no epilogue stores, 2 no MMA, 4 no TMA, 8 no TMEM re-zero
 };
 

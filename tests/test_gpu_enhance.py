@@ -131,6 +131,21 @@ def test_device_tensor_in_out(up_random):
     assert dev.is_cuda and mode == "RGB" and np.array_equal(dev.cpu().numpy(), host)
 
 
+def test_persistent_trunk_kernel_is_bit_identical_to_per_layer_launches():
+    """conv_impl 0 (one cooperative launch for the 69 RDBs, grid-wide arrival counter between layer
+    passes) and conv_impl 3 (one launch per layer pass) run the same roles on the same schedule."""
+    img = natural_image(300, 420, seed=11)                    # 6 tiles, several strips and bands per CTA
+    for tile, pad in ((0, 10), (160, 10)):
+        a, _ = gpu_up("calibrated", tile, pad).enhance(img)
+        b, _ = gpu_up("calibrated", tile, pad, conv_impl=3).enhance(img)
+        assert np.array_equal(a, b)
+    up = gpu_up("calibrated", 160, 10)
+    first, _ = up.enhance(img)
+    for _ in range(3):                                        # repeated launches reuse the counter and the arena
+        again, _ = up.enhance(img)
+        assert np.array_equal(first, again)
+
+
 def test_validation_kernels_agree_with_the_product_kernel():
     img = natural_image(40, 140, seed=3)                      # two column strips
     fold, _ = gpu_up("calibrated").enhance(img)

@@ -13,7 +13,7 @@ import neural_enhanced_super_resolution_b200 as pkg  # noqa: E402
 
 H, W, tile, pad, steps = ([int(a) for a in sys.argv[1:6]] + [1080, 1920, 512, 10, 5][len(sys.argv) - 1:])[:5]
 torch.manual_seed(0)
-net = pkg.RRDBNet(3, 3, scale=2, num_block=int(os.environ.get("NESR_NUM_BLOCK", "23")), conv_impl=int(os.environ.get("NESR_CONV_IMPL", "0"))).cuda().eval()
+net = pkg.RRDBNet(3, 3, scale=2, num_block=int(os.environ.get("NESR_NUM_BLOCK", "23")), conv_impl=int(os.environ.get("NESR_CONV_IMPL", "0")), max_batch_pixels=int(os.environ.get("NESR_MAX_BATCH_PX", "0"))).cuda().eval()
 eng = net.engine()
 rng = np.random.default_rng(0)
 img = torch.from_numpy(rng.integers(0, 256, (H, W, 3), dtype=np.uint8)).cuda()
