@@ -41,6 +41,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, h) for h in HEADERS]
+    stamp = os.path.join(OBJ, "flags.txt")                    # a different flag set (e.g. NESR_B200_PROF) rebuilds everything
+    flags_now = " ".join(ARCH + FLAGS)
+    if not os.path.exists(stamp) or open(stamp).read() != flags_now:
+        force = True
+        with open(stamp, "w") as fh:
+            fh.write(flags_now)
     objs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)

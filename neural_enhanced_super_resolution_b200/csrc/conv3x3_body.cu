@@ -70,6 +70,8 @@ conv3x3_body_kernel(const __grid_constant__ CUtensorMap amap_d0, const __grid_co
   uint32_t u = 0;                                              // running row-slot counter of the TMEM ring
 
   for (int pass = 0; pass < npass; ++pass) {
+    [[maybe_unused]] const long long prof_t0 = PROF_NOW();
+    [[maybe_unused]] long long prof_t1 = 0, prof_t2 = 0, prof_t3 = 0;
     if (warp == 0) {
       const uint32_t* src = reinterpret_cast<const uint32_t*>(passes + pass);
       uint32_t* dst = reinterpret_cast<uint32_t*>(&sp);
@@ -95,7 +97,9 @@ conv3x3_body_kernel(const __grid_constant__ CUtensorMap amap_d0, const __grid_co
         __syncwarp();
         fence_proxy_async_all();
       }
+      prof_t1 = PROF_NOW();
       producer_bands(p, p.src_sel ? &amap_d1 : &amap_d0, p.src_sel ? &amap8_d1 : &amap8_d0, s, rp, band_begin, band_end);
+      prof_t2 = PROF_NOW();
     } else if (warp == 1) {
       mma_bands<COUT>(p, s, rp, u, static_cast<uint32_t>(pass & 1), band_begin, band_end);
     } else {
@@ -112,6 +116,14 @@ conv3x3_body_kernel(const __grid_constant__ CUtensorMap amap_d0, const __grid_co
       __threadfence();
       red_release_gpu_add(gbar, 1u);
     }
+#if NESR_PROF
+    if ((sp.debug_flags & 1024) && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 77) && pass < 48) {
+      prof_t3 = PROF_NOW();
+      printf("[body blk %d pass %d cin=%d] params+wload+spin %lld  producer %lld  drain+sync %lld  total %lld\n", (int)blockIdx.x, pass,
+             sp.cin, prof_t1 - prof_t0, prof_t2 - prof_t1, prof_t3 - prof_t2, prof_t3 - prof_t0);
+    }
+    __syncthreads();                 // sp.debug_flags above must be read before the next pass overwrites sp
+#endif
   }
 
   pipe_teardown(s, warp);

@@ -272,10 +272,12 @@ __device__ __forceinline__ void mma_bands(const ConvParams& p, const Pipe& s, Ri
             }
           }
         }
-        if (elect_one()) umma_commit(&s.empty[rp.stage]);
         PROF_END(2);
+        if (elect_one()) umma_commit(&s.empty[rp.stage]);
+        PROF_END(3);
         if (++rp.stage == s.nstage) { rp.stage = 0; rp.phase ^= 1; }
       }
+      PROF_BEGIN();
       if (elect_one()) {
         umma_commit(&s.tfull[q]);                            // output row i has all its contributions
         if (i == rows + 1) {
@@ -283,12 +285,13 @@ __device__ __forceinline__ void mma_bands(const ConvParams& p, const Pipe& s, Ri
           umma_commit(&s.tfull[(u + i + 2) % Cfg::kSlots]);
         }
       }
+      PROF_END(3);
     }
     u += rows + 4;
   }
   if ((threadIdx.x & 31) == 0)
-    PROF_PRINT("[fold cin=%d cout=%d] mma: input rows %d total %lld  wait_tempty %lld  wait_full %lld  issue %lld\n", p.cin, COUT,
-               prof_rows, PROF_NOW() - prof_start, prof_acc[0], prof_acc[1], prof_acc[2]);
+    PROF_PRINT("[fold cin=%d cout=%d] mma: input rows %d total %lld  wait_tempty %lld  wait_full %lld  issue %lld  commit %lld\n", p.cin, COUT,
+               prof_rows, PROF_NOW() - prof_start, prof_acc[0], prof_acc[1], prof_acc[2], prof_acc[3]);
 }
 
 // ------------------------------ epilogue (warps 2..9) ---------------------------------------------
