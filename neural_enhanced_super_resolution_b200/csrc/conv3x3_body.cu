@@ -103,7 +103,7 @@ conv3x3_body_kernel(const __grid_constant__ CUtensorMap amap_d0, const __grid_co
     } else if (warp == 1) {
       mma_bands<COUT>(p, s, rp, u, static_cast<uint32_t>(pass & 1), band_begin, band_end);
     } else {
-      epilogue_bands<COUT>(p, s, u, warp, lane, band_begin, band_end);
+      epilogue_bands<COUT, true>(p, s, u, warp, lane, band_begin, band_end);
       fence_proxy_async_all();                                 // generic-proxy stores -> later TMA (async proxy) reads
     }
 

@@ -56,7 +56,7 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
   } else {
     pdl_wait();                    // residual reads / stores must not overtake the previous layer
     uint32_t u = 0;
-    epilogue_bands<COUT>(p, s, u, warp, lane, band_begin, band_end);
+    epilogue_bands<COUT, false>(p, s, u, warp, lane, band_begin, band_end);
   }
 
   pipe_teardown(s, warp);

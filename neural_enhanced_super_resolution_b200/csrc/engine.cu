@@ -59,6 +59,8 @@ struct LevelPlan {
   FoldSeg* d_segs = nullptr;
   int32_t* d_cta_off = nullptr;
   int fold_grid = 0;
+  std::vector<int32_t> deps;   // level 0 only: [grid][kTrunkMaxDeps] halo dependencies of the trunk kernel (empty: too many)
+  int32_t* d_deps = nullptr;
 };
 
 struct PlanKey {
@@ -75,6 +77,7 @@ struct Batch {
   LevelPlan lv[3];
   ConvParams* d_body_passes = nullptr;   // persistent trunk kernel: one ConvParams per RDB layer pass
   int n_body_passes = 0;
+  bool trunk_fits = false;               // level-0 schedule fits the TMEM-resident trunk kernel (conv3x3_trunk.cu)
 };
 
 struct Arena {
@@ -93,6 +96,7 @@ struct Arena {
   CUtensorMap m_x0, m_d[2], m_g2, m_g4[2];             // box 128 px (per-tap kernel)
   CUtensorMap f_x0, f_d[2], f_g2, f_g4[2];             // box 136 px (row-folded kernel, full strips)
   CUtensorMap e_x0, e_d[2], e_g2, e_g4[2];             // box 8 px (row-folded kernel, packed remainder strips)
+  CUtensorMap b_d[2][4];                               // boxes 8 / 16 / 32 / 64 px of the dense-block buffers (trunk kernel)
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -133,6 +137,7 @@ struct nesr_b200_handle {
 
   nesr_b200_stats stats{};
   int debug_flags = 0;        // NESR_B200_DEBUG_FLAGS: timing experiments (results are wrong when set)
+  int l2_pin_chunks = 1;      // NESR_B200_L2_PIN: dense-block planes whose loads are tagged evict_last in the trunk passes
 };
 
 namespace {
@@ -298,6 +303,7 @@ void free_batches(nesr_b200_handle* h) {
       if (l.d_bands) cudaFree(l.d_bands);
       if (l.d_segs) cudaFree(l.d_segs);
       if (l.d_cta_off) cudaFree(l.d_cta_off);
+      if (l.d_deps) cudaFree(l.d_deps);
     }
   }
   h->batches.clear();
@@ -365,26 +371,75 @@ void build_fold_schedule(Batch& b, int level, int num_sms) {
   for (const Strip& st : strips) total_rows += st.h;
   const int min_rows = 4;                                      // do not spread tiny work over every SM
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms, total_rows / min_rows));
-  lp.bands.clear();
-  lp.cta_off.assign(1, 0);
-  size_t si = 0;
-  int64_t strip_start = 0;                                     // sequence position of strips[si] row 0
-  for (int c = 0; c < grid; ++c) {
-    int64_t lo = total_rows * c / grid, hi = total_rows * (c + 1) / grid;
-    while (lo < hi) {
-      while (si < strips.size() && strip_start + strips[si].h <= lo) { strip_start += strips[si].h; ++si; }
-      const Strip& st = strips[si];
-      const int r0 = (int)(lo - strip_start);
-      const int n = (int)std::min<int64_t>(hi - lo, st.h - r0);
-      lp.bands.push_back(FoldBand{st.seg0, st.nseg, r0, n});
-      lo += n;
+  // Contiguous runs of equal COST: a band of n rows costs n + 2 slab rows (its halo), so a CTA whose run crosses a
+  // strip boundary gets fewer output rows.  The smallest per-CTA budget that covers everything is found by bisection.
+  auto deal = [&](int64_t budget, std::vector<FoldBand>* bands, std::vector<int32_t>* cta_off) -> bool {
+    size_t si = 0;
+    int r = 0;                                                 // next row of strips[si]
+    if (bands) { bands->clear(); cta_off->assign(1, 0); }
+    for (int c = 0; c < grid; ++c) {
+      int64_t left = budget;
+      while (si < strips.size() && left >= 3) {
+        const int n = (int)std::min<int64_t>(left - 2, strips[si].h - r);
+        if (bands) bands->push_back(FoldBand{strips[si].seg0, strips[si].nseg, r, n});
+        left -= n + 2;
+        r += n;
+        if (r == strips[si].h) { ++si; r = 0; }
+      }
+      if (cta_off) cta_off->push_back((int32_t)bands->size());
     }
-    lp.cta_off.push_back((int32_t)lp.bands.size());
+    return si == strips.size();
+  };
+  int64_t lo = 3, hi = total_rows + 2 * (int64_t)strips.size() + 3;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) / 2;
+    if (deal(mid, nullptr, nullptr)) hi = mid; else lo = mid + 1;
   }
+  deal(lo, &lp.bands, &lp.cta_off);
   lp.fold_grid = grid;
 }
 
 int build_body_passes(nesr_b200_handle* h, Batch& b);
+
+// conv3x3_trunk.cu keeps all output rows of a CTA in TMEM: at most kTrunkMaxRows rows in kTrunkMaxBands bands.
+// Halo dependencies of the trunk kernel: CTA c must not load activations another pass wrote before every CTA owning a
+// pixel of its bands' input halos (one pixel around each segment, inside the tile) has published that pass.
+void build_trunk_deps(LevelPlan& lp) {
+  const int grid = lp.fold_grid;
+  struct Rect { int tile, x0, x1, y0, y1, cta; };              // inclusive pixel rectangle of one segment of one band
+  std::vector<Rect> rects;
+  for (int c = 0; c < grid; ++c)
+    for (int b = lp.cta_off[c]; b < lp.cta_off[c + 1]; ++b) {
+      const FoldBand& band = lp.bands[b];
+      for (int sgi = 0; sgi < band.nseg; ++sgi) {
+        const FoldSeg& sg = lp.segs[band.seg0 + sgi];
+        rects.push_back(Rect{sg.tile, sg.x0, sg.x0 + sg.width - 1, band.r0, band.r0 + band.rows - 1, c});
+      }
+    }
+  lp.deps.assign((size_t)grid * kTrunkMaxDeps, 0);
+  std::vector<std::vector<int32_t>> dep(grid);
+  for (const Rect& a : rects)
+    for (const Rect& o : rects) {
+      if (o.tile != a.tile || o.cta == a.cta) continue;
+      if (o.x1 < a.x0 - 1 || o.x0 > a.x1 + 1 || o.y1 < a.y0 - 1 || o.y0 > a.y1 + 1) continue;
+      if (std::find(dep[a.cta].begin(), dep[a.cta].end(), o.cta) == dep[a.cta].end()) dep[a.cta].push_back(o.cta);
+    }
+  for (int c = 0; c < grid; ++c) {
+    if ((int)dep[c].size() + 1 > kTrunkMaxDeps) { lp.deps.clear(); return; }
+    for (int k = 0; k < kTrunkMaxDeps; ++k) lp.deps[(size_t)c * kTrunkMaxDeps + k] = k < (int)dep[c].size() ? dep[c][k] : c;
+  }
+}
+
+bool trunk_schedule_fits(const LevelPlan& lp) {
+  for (int c = 0; c < lp.fold_grid; ++c) {
+    const int b0 = lp.cta_off[c], b1 = lp.cta_off[c + 1];
+    if (b1 - b0 > kTrunkMaxBands) return false;
+    int rows = 0;
+    for (int b = b0; b < b1; ++b) rows += lp.bands[b].rows;
+    if (rows > kTrunkMaxRows) return false;
+  }
+  return true;
+}
 
 int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
   if (h->key == key && !h->batches.empty()) return NESR_OK;
@@ -423,8 +478,11 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
       t.crop_w = std::max(0, std::min((x1 - x0) * scale, out_w - t.out_x0));
       all.push_back(t);
     }
-  // split into batches bounded by feature pixels
-  const int64_t cap = h->cfg.max_batch_pixels > 0 ? h->cfg.max_batch_pixels : (int64_t)3 << 20;
+  // Split into batches (tile groups) bounded by feature pixels.  Product path (conv_impl 0): a group's dense-block
+  // working set (~512 B per feature pixel) should stay in the 126 MB L2 across all 414 trunk passes, and its
+  // level-0 schedule must fit the TMEM-resident trunk kernel; other paths keep the whole frame in one batch.
+  const bool l2_groups = h->cfg.conv_impl == 0;
+  const int64_t cap = h->cfg.max_batch_pixels > 0 ? h->cfg.max_batch_pixels : (l2_groups ? (int64_t)150000 : (int64_t)3 << 20);
   size_t i = 0;
   while (i < all.size()) {
     Batch b;
@@ -433,10 +491,31 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
       const int64_t n = (int64_t)all[i].lv[0].h * all[i].lv[0].pitch;
       if (!b.tiles.empty() && px + n > cap) break;
       b.tiles.push_back(all[i]);
+      if (l2_groups && b.tiles.size() > 1) {                    // would the group still fit the trunk kernel?
+        layout_level(b, 0); build_fold_schedule(b, 0, h->num_sms);
+        if (!trunk_schedule_fits(b.lv[0])) { b.tiles.pop_back(); break; }
+      }
       px += n;
       ++i;
     }
     for (int l = 0; l < 3; ++l) { layout_level(b, l); build_fold_schedule(b, l, h->num_sms); }
+    if (l2_groups && i == all.size() && !h->batches.empty() && px * 5 < cap * 2) {
+      // A small tail group pays the trunk's per-pass latency (414 dependent passes) for almost no work: fold it into the
+      // previous group when the combined schedule still fits the trunk kernel.
+      Batch m = h->batches.back();
+      m.tiles.insert(m.tiles.end(), b.tiles.begin(), b.tiles.end());
+      layout_level(m, 0); build_fold_schedule(m, 0, h->num_sms);
+      if (trunk_schedule_fits(m.lv[0])) {
+        h->batches.pop_back();
+        b = std::move(m);
+        for (int l = 0; l < 3; ++l) { layout_level(b, l); build_fold_schedule(b, l, h->num_sms); }
+      }
+    }
+    b.trunk_fits = l2_groups && trunk_schedule_fits(b.lv[0]);
+    if (b.trunk_fits) {
+      build_trunk_deps(b.lv[0]);
+      b.trunk_fits = !b.lv[0].deps.empty();
+    }
     if (b.lv[2].pixels >= ((int64_t)1 << 31) - 4096) return fail(h, NESR_E_INVALID, "batch too large for 32-bit pixel indices");
     h->batches.push_back(std::move(b));
   }
@@ -453,6 +532,10 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
       CUDA_TRY(h, cudaMemcpyAsync(lp.d_bands, lp.bands.data(), lp.bands.size() * sizeof(FoldBand), cudaMemcpyHostToDevice, h->stream));
       CUDA_TRY(h, cudaMalloc(&lp.d_segs, std::max<size_t>(1, lp.segs.size()) * sizeof(FoldSeg)));
       CUDA_TRY(h, cudaMemcpyAsync(lp.d_segs, lp.segs.data(), lp.segs.size() * sizeof(FoldSeg), cudaMemcpyHostToDevice, h->stream));
+      if (!lp.deps.empty()) {
+        CUDA_TRY(h, cudaMalloc(&lp.d_deps, lp.deps.size() * sizeof(int32_t)));
+        CUDA_TRY(h, cudaMemcpyAsync(lp.d_deps, lp.deps.data(), lp.deps.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+      }
       CUDA_TRY(h, cudaMalloc(&lp.d_cta_off, lp.cta_off.size() * sizeof(int32_t)));
       CUDA_TRY(h, cudaMemcpyAsync(lp.d_cta_off, lp.cta_off.data(), lp.cta_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
       P[l] = std::max(P[l], lp.pixels);
@@ -492,10 +575,12 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
   for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.f_g4[i2], a.g4[i2], 64, P[2], kSlab))) return rc;
   if ((rc = make_map(h, &a.e_x0, a.x0, 64, P[0], 8))) return rc;
   for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.e_d[i2], a.d[i2], 64, 3 * P[0], 8))) return rc;
+  for (int i2 = 0; i2 < 2; ++i2)
+    for (int k = 0; k < 4; ++k) if ((rc = make_map(h, &a.b_d[i2][k], a.d[i2], 64, 3 * P[0], 8 << k))) return rc;
   if ((rc = make_map(h, &a.e_g2, a.g2, 64, P[1], 8))) return rc;
   for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.e_g4[i2], a.g4[i2], 64, P[2], 8))) return rc;
   h->stats.arena_bytes = (int64_t)a.bytes;
-  if (h->cfg.conv_impl == 0)
+  if (h->cfg.conv_impl == 0 || h->cfg.conv_impl == 4)
     for (Batch& b : h->batches)
       if ((rc = build_body_passes(h, b))) return rc;
   h->key = key;
@@ -613,6 +698,14 @@ int build_body_passes(nesr_b200_handle* h, Batch& b) {
         select_fold_pass(L, ps, bound, q);
         q.src_sel = cur;
         q.sync_passes = first;       // passes of one layer read the same input and write disjoint channels
+        // trunk kernel: which passes must be complete everywhere before input chunk c may be loaded.  Chunk 0 is x
+        // (previous block's conv5, both halves), chunk 1 holds x1|x2 (conv1, conv2), chunk 2 holds x3|x4 (conv3, conv4).
+        const int rb = r * 6;
+        q.need[0] = rb;
+        q.need[1] = k == 2 ? rb + 1 : rb + 2;
+        q.need[2] = k == 4 ? rb + 3 : rb + 4;
+        q.trunk_deps = b.lv[0].d_deps;
+        q.l2_pin_chunks = h->l2_pin_chunks;
         passes.push_back(q);
       }
     }
@@ -633,7 +726,7 @@ struct Sink {
 };
 
 int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in, const Sink& sink, cudaStream_t s,
-                  bool time_convs) {
+                  bool time_begin, bool time_end) {
   Arena& a = h->arena;
   const nesr_b200_config& c = h->cfg;
   int rc;
@@ -647,7 +740,7 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
   cudaError_t e = launch_pack(pk, s);
   h->stats.kernel_launches++;
   if (e != cudaSuccess) return fail(h, NESR_E_CUDA, "pack launch failed: %s", cudaGetErrorString(e));
-  if (time_convs) cudaEventRecord(h->evc0, s);
+  if (time_begin) cudaEventRecord(h->evc0, s);
 
   size_t li = 0;
   auto next = [&]() -> const Layer& { return h->layers[li++]; };
@@ -659,9 +752,19 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
   }
   int cur = 0;
   const int nrdb = c.num_block * 3;
-  if (c.conv_impl == 0) {            // all RDB layer passes in one persistent cooperative launch
-    cudaError_t eb = launch_conv3x3_body(a.f_d[0], a.f_d[1], a.e_d[0], a.e_d[1], fold_weight_map(h, 32), b.d_body_passes,
-                                         b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s);
+  if (c.conv_impl == 0 || c.conv_impl == 4) {   // all RDB layer passes in one persistent cooperative launch
+    TrunkMaps tm;
+    if (b.trunk_fits) {
+      for (int i2 = 0; i2 < 2; ++i2) {
+        tm.full[i2] = a.f_d[i2];
+        for (int k = 0; k < 4; ++k) tm.box[i2][k] = a.b_d[i2][k];
+      }
+      tm.w = fold_weight_map(h, 32);
+    }
+    cudaError_t eb = b.trunk_fits
+        ? launch_conv3x3_trunk(tm, b.d_body_passes, b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s)
+        : launch_conv3x3_body(a.f_d[0], a.f_d[1], a.e_d[0], a.e_d[1], fold_weight_map(h, 32), b.d_body_passes,
+                              b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s);
     if (eb != cudaSuccess) return fail(h, NESR_E_CUDA, "trunk kernel launch failed: %s", cudaGetErrorString(eb));
     h->stats.kernel_launches++;
     h->stats.conv_launches++;
@@ -705,7 +808,7 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
     p.out_f32 = sink.out_f32; p.out_h = sink.out_h; p.out_w = sink.out_w;
     if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], &a.f_g4[0], &a.e_g4[0], a.g4[0], 1, 2}, p, s))) return rc;
   }
-  if (time_convs) cudaEventRecord(h->evc1, s);
+  if (time_end) cudaEventRecord(h->evc1, s);
   h->stats.tiles_processed += (int64_t)b.tiles.size();
   return NESR_OK;
 }
@@ -762,7 +865,7 @@ int enhance_impl(nesr_b200_handle* h, const uint8_t* in, int n_frames, int H, in
   pk.in_u8 = d_in; pk.in_stride = d_in_stride; pk.in_frame_stride = d_in_fs; pk.H = H; pk.W = W; pk.pre_pad = pre_pad;
   Sink sink; sink.out_u8 = d_out; sink.out_stride = d_out_stride; sink.out_frame_stride = d_out_fs;
   for (size_t bi = 0; bi < h->batches.size(); ++bi)
-    if ((rc = forward_batch(h, h->batches[bi], pk, sink, h->stream, bi == 0))) return rc;
+    if ((rc = forward_batch(h, h->batches[bi], pk, sink, h->stream, bi == 0, bi + 1 == h->batches.size()))) return rc;
   cudaEventRecord(h->ev1, h->stream);
   if (!(flags & NESR_PTR_OUT_DEVICE))
     for (int f = 0; f < n_frames; ++f)
@@ -813,6 +916,14 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
   nesr_b200_handle* h = new nesr_b200_handle();
   h->cfg = *cfg;
   h->num_sms = prop.multiProcessorCount;
+  // evict_last cache hints only hold lines inside the persisting-L2 set-aside, which defaults to zero
+  if (const char* ps = getenv("NESR_B200_L2_PERSIST_MB")) {
+    size_t want = (size_t)atoi(ps) << 20;
+    if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+    cudaError_t el = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    fprintf(stderr, "nesr_b200: persisting L2 set-aside %zu MB (max %d MB, L2 %d MB): %s\n", want >> 20,
+            prop.persistingL2CacheMaxSize >> 20, prop.l2CacheSize >> 20, cudaGetErrorString(el));
+  }
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -825,13 +936,14 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
       (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
       (e = cudaEventCreate(&h->evc0)) != cudaSuccess || (e = cudaEventCreate(&h->evc1)) != cudaSuccess ||
       (e = conv3x3_tc_configure()) != cudaSuccess || (e = conv3x3_fold_configure()) != cudaSuccess ||
-      (e = conv3x3_body_configure()) != cudaSuccess || (e = cudaMalloc(&h->d_gbar, 256)) != cudaSuccess) {
+      (e = conv3x3_body_configure()) != cudaSuccess || (e = conv3x3_trunk_configure()) != cudaSuccess || (e = cudaMalloc(&h->d_gbar, 1024 * 128)) != cudaSuccess) {
     std::string msg = cudaGetErrorString(e);
     nesr_b200_destroy(h);
     return fail(nullptr, NESR_E_CUDA, "device setup failed: %s", msg.c_str());
   }
   build_layers(h);
   if (const char* dbg = getenv("NESR_B200_DEBUG_FLAGS")) h->debug_flags = atoi(dbg);
+  if (const char* pin = getenv("NESR_B200_L2_PIN")) h->l2_pin_chunks = atoi(pin);
   *out = h;
   return NESR_OK;
 }
@@ -950,7 +1062,7 @@ int nesr_b200_forward_nchw_f32(nesr_b200_handle* h, const float* x, int32_t n, i
   pk.in_f32 = x; pk.H = H; pk.W = W; pk.pre_pad = 0;
   Sink sink; sink.out_f32 = y; sink.out_h = H * sc; sink.out_w = W * sc;
   for (const Batch& b : h->batches)
-    if ((rc = forward_batch(h, b, pk, sink, s, false))) return rc;
+    if ((rc = forward_batch(h, b, pk, sink, s, false, false))) return rc;
   return NESR_OK;
 }
 

@@ -68,6 +68,21 @@ __device__ __forceinline__ void ldg256(const float* ptr, float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// Streaming variants for the fp32 trunk (touched once per dense block): evict-first in L2, no L1 allocation.
+__device__ __forceinline__ void ldg256_stream(const float* ptr, float* v) {
+  uint32_t r[8];
+  asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(ptr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void stg256f_stream(float* ptr, const float* v) {
+  asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(__float_as_uint(v[0])),
+               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+               "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
 __device__ __forceinline__ void stg256(void* ptr, const uint32_t (&r)[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
                "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -81,13 +96,51 @@ __device__ __forceinline__ void stg256f(float* ptr, const float* v) {
 }
 // 16 residual channels [ch0, ch0+16) of pixel P (ch0 multiple of 8).
 __device__ __forceinline__ void load_trunk16(const float* buf, int P, int ch0, float* r) {
-  ldg256(buf + trunk_offset(P, ch0), r);
-  ldg256(buf + trunk_offset(P, ch0 + 8), r + 8);
+  ldg256_stream(buf + trunk_offset(P, ch0), r);
+  ldg256_stream(buf + trunk_offset(P, ch0 + 8), r + 8);
+}
+
+// The epilogue's view of a layer pass, held in REGISTERS.  The persistent trunk kernel keeps the
+// ConvParams of the current pass in shared memory; reading its fields through that copy cost one
+// dependent LDS (+ branch) per field per row, re-issued after every mbarrier wait (asm memory
+// clobber) -- most of the 1500 cycles a row's "math + stores" took (profiles/r1_fold_role_timing.txt).
+// kTrunk: a residual-dense-block pass never upsamples and never writes the output frame; those
+// fields become compile-time constants and their code disappears.
+struct EpiRegs {
+  const float* bias;
+  int32_t cout, lrelu, c_off, level;
+  const float* res1;
+  const float* res2;
+  float s1, s2;
+  float* dst32a;
+  float* dst32b;
+  void* dst16;
+  int32_t dst16_plane_px, dst16_coff, dst16_fmt, dst16_up;
+  uint8_t* out_u8;
+  int64_t out_stride, out_frame_stride;
+  float* out_f32;
+  int32_t out_h, out_w;
+  int32_t debug_flags;
+};
+template <bool kTrunk>
+__device__ __forceinline__ EpiRegs make_epi_regs(const ConvParams& p) {
+  EpiRegs e;
+  e.bias = p.bias; e.cout = p.cout; e.lrelu = p.lrelu; e.c_off = p.c_off; e.level = kTrunk ? 0 : p.level;
+  e.res1 = p.res1; e.res2 = p.res2; e.s1 = p.s1; e.s2 = p.s2;
+  e.dst32a = p.dst32a; e.dst32b = p.dst32b;
+  e.dst16 = p.dst16; e.dst16_plane_px = p.dst16_plane_px; e.dst16_coff = p.dst16_coff; e.dst16_fmt = p.dst16_fmt;
+  e.dst16_up = kTrunk ? 0 : p.dst16_up;
+  e.out_u8 = kTrunk ? nullptr : p.out_u8; e.out_stride = p.out_stride; e.out_frame_stride = p.out_frame_stride;
+  e.out_f32 = kTrunk ? nullptr : p.out_f32; e.out_h = p.out_h; e.out_w = p.out_w;
+  e.debug_flags = p.debug_flags;
+  return e;
 }
 
 // Channels [n0, n0+16) of one pixel.  r1pre / r2pre: residual values the caller already fetched
 // (the fold kernel issues those loads before it waits for the accumulator), or null.
-__device__ __forceinline__ void epilogue16(const ConvParams& p, const TileGeom& tg, const PixelRef& px, int n0,
+// Params is ConvParams (kernel parameter space) or EpiRegs (registers).
+template <class Params>
+__device__ __forceinline__ void epilogue16(const Params& p, const TileGeom& tg, const PixelRef& px, int n0,
                                            float (&v)[16], const float* r1pre = nullptr, const float* r2pre = nullptr) {
   const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
@@ -112,15 +165,15 @@ __device__ __forceinline__ void epilogue16(const ConvParams& p, const TileGeom& 
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], p.s2, r2pre[i]);
   }
-  if (p.dst32a) {
-    stg256f(p.dst32a + trunk_offset(px.P, ch0), v);
-    stg256f(p.dst32a + trunk_offset(px.P, ch0 + 8), v + 8);
+  if (p.dst32a && !(p.debug_flags & 4096)) {                 // 4096: no fp32 trunk stores (timing experiments)
+    stg256f_stream(p.dst32a + trunk_offset(px.P, ch0), v);
+    stg256f_stream(p.dst32a + trunk_offset(px.P, ch0 + 8), v + 8);
   }
   if (p.dst32b) {
-    stg256f(p.dst32b + trunk_offset(px.P, ch0), v);
-    stg256f(p.dst32b + trunk_offset(px.P, ch0 + 8), v + 8);
+    stg256f_stream(p.dst32b + trunk_offset(px.P, ch0), v);
+    stg256f_stream(p.dst32b + trunk_offset(px.P, ch0 + 8), v + 8);
   }
-  if (p.dst16) {
+  if (p.dst16 && !(p.debug_flags & 16)) {                    // 16: no 16-bit activation stores (timing experiments)
     uint32_t w[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) w[i] = pack2(v[2 * i], v[2 * i + 1], p.dst16_fmt);

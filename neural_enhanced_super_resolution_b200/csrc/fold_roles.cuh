@@ -151,13 +151,26 @@ __device__ __forceinline__ void load_weights(const ConvParams& p, const CUtensor
 // Band geometry is read once per band; inside a band the slab coordinate advances by the row pitch
 // in registers.  (Fetching it per slab made the producer latency-bound on its own metadata loads
 // whenever the epilogue kept the memory system busy: profiles/r1_fold_role_timing.txt.)
+// Every role copies the ConvParams fields it uses into registers first: in the persistent kernel `p`
+// lives in shared memory and each asm memory clobber (every barrier op) would force a reload.
 __device__ __forceinline__ void producer_bands(const ConvParams& p, const CUtensorMap* amap, const CUtensorMap* amap8,
                                                const Pipe& s, RingPos& rp, int band_begin, int band_end) {
   const int nchunk = (p.cin + kChunkChannels - 1) / kChunkChannels;
+  const int plane_px = p.src_plane_px, level = p.level, dbg = p.debug_flags;
+  const FoldBand* const bands = p.bands;
+  const FoldSeg* const segs = p.segs;
+  const TileGeom* const tiles = p.tiles;
+  const int nstage = s.nstage;
+  // L2 policy (frame-wide passes: the 213 MB dense-block buffer cannot live in the 126 MB L2, but its first plane --
+  // x, read by all six passes of a dense block -- can): chunk 0 loads ask to stay (evict_last), chunks 1, 2 stream.
+  // debug_flags & 2048 disables the hints (timing experiments).
+  const bool hints = nchunk > 0 && !(dbg & 2048) && p.l2_pin_chunks > 0;
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+  const int pin_chunks = p.l2_pin_chunks;
   PROF_DECL;
   [[maybe_unused]] const long long prof_start = PROF_NOW();
   for (int bi = band_begin; bi < band_end; ++bi) {
-    const FoldBand band = p.bands[bi];
+    const FoldBand band = bands[bi];
     // per segment: flat pixel of (row r0-1, x0-1), row pitch, slab byte offset, number of 8-pixel boxes
     int seg_px[kMaxFoldSegs], seg_pitch[kMaxFoldSegs], seg_off[kMaxFoldSegs], seg_n8[kMaxFoldSegs];
     bool full_strip = false;
@@ -166,8 +179,8 @@ __device__ __forceinline__ void producer_bands(const ConvParams& p, const CUtens
     for (int sgi = 0; sgi < kMaxFoldSegs; ++sgi) {
       seg_px[sgi] = seg_pitch[sgi] = seg_off[sgi] = seg_n8[sgi] = 0;
       if (sgi < band.nseg) {
-        const FoldSeg sg = p.segs[band.seg0 + sgi];
-        const LevelGeom g = p.tiles[sg.tile].lv[p.level];
+        const FoldSeg sg = segs[band.seg0 + sgi];
+        const LevelGeom g = tiles[sg.tile].lv[level];
         seg_px[sgi] = g.base + (band.r0 - 1) * g.pitch + sg.x0 - 1;
         seg_pitch[sgi] = g.pitch;
         seg_off[sgi] = sg.lane0 * 128;
@@ -183,13 +196,24 @@ __device__ __forceinline__ void producer_bands(const ConvParams& p, const CUtens
         mbar_wait(&s.empty[rp.stage], rp.phase ^ 1);
         PROF_END(0);
         if (elect_one()) {
-          if (p.debug_flags & 4) {
+          if (dbg & 4) {
             mbar_arrive(&s.full[rp.stage]);
           } else {
             mbar_arrive_expect_tx(&s.full[rp.stage], row_bytes);
             uint8_t* slab = s.ring + rp.stage * kSlabBytes;
-            const int plane = c * p.src_plane_px;
-            if (full_strip) {
+            const int plane = c * plane_px;
+            if (hints) {
+              const uint64_t pol = c < pin_chunks ? pol_keep : pol_stream;
+              if (full_strip) {
+                tma_load_2d_hint(slab, amap, &s.full[rp.stage], 0, plane + seg_px[0] + i * seg_pitch[0], pol);
+              } else {
+#pragma unroll
+                for (int sgi = 0; sgi < kMaxFoldSegs; ++sgi)
+                  for (int k = 0; k < seg_n8[sgi]; ++k)
+                    tma_load_2d_hint(slab + seg_off[sgi] + k * 1024, amap8, &s.full[rp.stage], 0,
+                                     plane + seg_px[sgi] + i * seg_pitch[sgi] + k * 8, pol);
+              }
+            } else if (full_strip) {
               tma_load_2d(slab, amap, &s.full[rp.stage], 0, plane + seg_px[0] + i * seg_pitch[0]);
             } else {
 #pragma unroll
@@ -200,7 +224,7 @@ __device__ __forceinline__ void producer_bands(const ConvParams& p, const CUtens
             }
           }
         }
-        if (++rp.stage == s.nstage) { rp.stage = 0; rp.phase ^= 1; }
+        if (++rp.stage == nstage) { rp.stage = 0; rp.phase ^= 1; }
       }
     }
   }
@@ -210,17 +234,29 @@ __device__ __forceinline__ void producer_bands(const ConvParams& p, const CUtens
 
 // ------------------------------ MMA issuer (warp-wide, one elected lane issues) ------------------
 // `u` is the running row-slot counter of the TMEM ring; `wphase` the parity of the weight barrier.
+//
+// The issuing thread must stay LEAN: the tensor pipe's instruction queue is shallow, so every ~100
+// cycles the thread spends outside the issue sequence (a barrier poll, an elect + divergent branch +
+// reconvergence -- tools/commit_probe.cu measures ~110 cycles per separately elected commit) is a
+// bubble in the MMA stream.  One input row is therefore ONE elected region: the barrier waits for all
+// of the row's slabs come first (warp-wide), then a single lane issues the row's 3 x k-steps MMAs of
+// every chunk, the commits that free the slabs and the commit that completes the output row.
 template <int COUT>
 __device__ __forceinline__ void mma_bands(const ConvParams& p, const Pipe& s, RingPos& rp, uint32_t& u, uint32_t wphase,
                                           int band_begin, int band_end) {
   using Cfg = FoldCfg<COUT>;
-  const int nchunk = (p.cin + kChunkChannels - 1) / kChunkChannels;
+  const int cin = p.cin, dbg = p.debug_flags;
+  const FoldBand* const bands = p.bands;
+  const int nchunk = (cin + kChunkChannels - 1) / kChunkChannels;
+  const int last_ks = (cin - (nchunk - 1) * kChunkChannels) >> 4;   // k-steps of the last chunk (1..4)
   const uint32_t hw = (p.idesc >> 7) & 7u;                 // operand format bits of the layer
   const uint32_t idesc1 = umma_idesc_f16(hw, COUT), idesc2 = umma_idesc_f16(hw, 2 * COUT), idesc3 = umma_idesc_f16(hw, 3 * COUT);
   const uint32_t hi = umma_desc_hi_sw128();
   const uint32_t a_lo0 = umma_desc_lo(smem_u32(s.ring));
   const uint32_t w_lo0 = umma_desc_lo(smem_u32(s.wsm));
   const uint32_t tmem_base = s.tmem_base;
+  const int nstage = s.nstage;
+  const uint32_t dx_lo = nchunk * (Cfg::kWBoxBytes >> 4);  // weight boxes are ordered [dx][chunk]
   constexpr uint32_t kSlabLo = kSlabBytes >> 4, kBoxLo = Cfg::kWBoxBytes >> 4;
   mbar_wait(s.wbar, wphase);
   tc_fence_after();
@@ -228,7 +264,7 @@ __device__ __forceinline__ void mma_bands(const ConvParams& p, const Pipe& s, Ri
   [[maybe_unused]] const long long prof_start = PROF_NOW();
   [[maybe_unused]] int prof_rows = 0;
   for (int bi = band_begin; bi < band_end; ++bi) {
-    const int rows = p.bands[bi].rows;
+    const int rows = bands[bi].rows;
     prof_rows += rows + 2;
     for (int j = 0; j < 2; ++j) {                          // slots of the first two (virtual) output rows
       const uint32_t v = u + j;
@@ -241,6 +277,15 @@ __device__ __forceinline__ void mma_bands(const ConvParams& p, const Pipe& s, Ri
         mbar_wait(&s.tempty[v % Cfg::kSlots], ((v / Cfg::kSlots) & 1) ^ 1);
       }
       PROF_END(0);
+      {                                                    // every slab of this input row has landed
+        int st = rp.stage;
+        uint32_t ph = rp.phase;
+        for (int c = 0; c < nchunk; ++c) {
+          mbar_wait(&s.full[st], ph);
+          if (++st == nstage) { st = 0; ph ^= 1; }
+        }
+      }
+      PROF_END(1);
       tc_fence_after();
       const uint32_t q = (u + i) % Cfg::kSlots;
       // accumulator = row slots (q, q+1, q+2); at the ring end it splits into two narrower MMAs
@@ -248,57 +293,58 @@ __device__ __forceinline__ void mma_bands(const ConvParams& p, const Pipe& s, Ri
       uint32_t id0 = idesc3, id1 = 0, b1 = 0;
       if (q + 2 == Cfg::kSlots) { id0 = idesc2; id1 = idesc1; b1 = (2 * COUT * 128) >> 4; }
       else if (q + 1 == Cfg::kSlots) { id0 = idesc1; id1 = idesc2; b1 = (COUT * 128) >> 4; }
-      for (int c = 0; c < nchunk; ++c) {
-        const int rem = (p.cin - c * kChunkChannels) >> 4;
-        const int ksteps = rem < 4 ? rem : 4;
-        PROF_BEGIN();
-        mbar_wait(&s.full[rp.stage], rp.phase);
-        PROF_END(1);
-        tc_fence_after();
-        const uint32_t a_lo = a_lo0 + rp.stage * kSlabLo;
-        const uint32_t b_lo = w_lo0 + c * kBoxLo;
-        if (!(p.debug_flags & 2) && elect_one()) {
-          if (ksteps == 4) {
+      if (elect_one()) {
+        int st = rp.stage;
+        for (int c = 0; c < nchunk; ++c) {
+          const uint32_t a_lo = a_lo0 + st * kSlabLo;
+          const uint32_t b_lo = w_lo0 + c * kBoxLo;
+          if (!(dbg & 2)) {
+            if (c + 1 < nchunk || last_ks == 4) {
 #pragma unroll
-            for (int dxi = 0; dxi < 3; ++dxi) {
-              umma_f16_ksteps<4>(d0, a_lo + dxi * 8, b_lo + dxi * nchunk * kBoxLo, hi, id0);
-              if (id1) umma_f16_ksteps<4>(tmem_base, a_lo + dxi * 8, b_lo + dxi * nchunk * kBoxLo + b1, hi, id1);
-            }
-          } else {
+              for (int dxi = 0; dxi < 3; ++dxi) {
+                umma_f16_ksteps<4>(d0, a_lo + dxi * 8, b_lo + dxi * dx_lo, hi, id0);
+                if (id1) umma_f16_ksteps<4>(tmem_base, a_lo + dxi * 8, b_lo + dxi * dx_lo + b1, hi, id1);
+              }
+            } else {
 #pragma unroll
-            for (int dxi = 0; dxi < 3; ++dxi) {
-              umma_f16_ksteps_rt(ksteps, d0, a_lo + dxi * 8, b_lo + dxi * nchunk * kBoxLo, hi, id0);
-              if (id1) umma_f16_ksteps_rt(ksteps, tmem_base, a_lo + dxi * 8, b_lo + dxi * nchunk * kBoxLo + b1, hi, id1);
+              for (int dxi = 0; dxi < 3; ++dxi) {
+                umma_f16_ksteps_rt(last_ks, d0, a_lo + dxi * 8, b_lo + dxi * dx_lo, hi, id0);
+                if (id1) umma_f16_ksteps_rt(last_ks, tmem_base, a_lo + dxi * 8, b_lo + dxi * dx_lo + b1, hi, id1);
+              }
             }
           }
+          umma_commit(&s.empty[st]);                         // slab may be overwritten once these MMAs have read it
+          if (++st == nstage) st = 0;
         }
-        PROF_END(2);
-        if (elect_one()) umma_commit(&s.empty[rp.stage]);
-        PROF_END(3);
-        if (++rp.stage == s.nstage) { rp.stage = 0; rp.phase ^= 1; }
-      }
-      PROF_BEGIN();
-      if (elect_one()) {
         umma_commit(&s.tfull[q]);                            // output row i has all its contributions
         if (i == rows + 1) {
           umma_commit(&s.tfull[(u + i + 1) % Cfg::kSlots]);
           umma_commit(&s.tfull[(u + i + 2) % Cfg::kSlots]);
         }
       }
-      PROF_END(3);
+      __syncwarp();
+      PROF_END(2);
+      rp.stage += nchunk;
+      if (rp.stage >= nstage) { rp.stage -= nstage; rp.phase ^= 1; }
     }
     u += rows + 4;
   }
   if ((threadIdx.x & 31) == 0)
-    PROF_PRINT("[fold cin=%d cout=%d] mma: input rows %d total %lld  wait_tempty %lld  wait_full %lld  issue %lld  commit %lld\n", p.cin, COUT,
-               prof_rows, PROF_NOW() - prof_start, prof_acc[0], prof_acc[1], prof_acc[2], prof_acc[3]);
+    PROF_PRINT("[fold cin=%d cout=%d] mma: input rows %d total %lld  wait_tempty %lld  wait_full %lld  issue+commit %lld\n", cin, COUT,
+               prof_rows, PROF_NOW() - prof_start, prof_acc[0], prof_acc[1], prof_acc[2]);
 }
 
 // ------------------------------ epilogue (warps 2..9) ---------------------------------------------
-template <int COUT>
+// kTrunk: a residual-dense-block pass (see EpiRegs).
+template <int COUT, bool kTrunk>
 __device__ __forceinline__ void epilogue_bands(const ConvParams& p, const Pipe& s, uint32_t& u, int warp, int lane,
                                                int band_begin, int band_end) {
   using Cfg = FoldCfg<COUT>;
+  const EpiRegs e = make_epi_regs<kTrunk>(p);
+  const FoldBand* const bands = p.bands;
+  const FoldSeg* const segs = p.segs;
+  const TileGeom* const tiles = p.tiles;
+  const int level = e.level, dbg = p.debug_flags;
   const int quarter = warp & 3;
   const int group = (warp - 2) >> 2;                         // rows alternate between the epilogue groups
   const int m = quarter * 32 + lane;                         // A row == TMEM lane == pixel x0 + m
@@ -306,34 +352,35 @@ __device__ __forceinline__ void epilogue_bands(const ConvParams& p, const Pipe& 
   PROF_DECL;
   [[maybe_unused]] const long long prof_start = PROF_NOW();
   for (int bi = band_begin; bi < band_end; ++bi) {
-    const FoldBand band = p.bands[bi];
+    const FoldBand band = bands[bi];
     int my_tile = 0, x = 1 << 20;                            // this lane's pixel column (none: masked lane)
     for (int sgi = 0; sgi < band.nseg; ++sgi) {
-      const FoldSeg sg = p.segs[band.seg0 + sgi];
+      const FoldSeg sg = segs[band.seg0 + sgi];
       if (m >= sg.lane0 && m < sg.lane0 + sg.width) { my_tile = sg.tile; x = sg.x0 + (m - sg.lane0); }
     }
-    const TileGeom& tg = p.tiles[my_tile];
-    const LevelGeom g = tg.lv[p.level];
+    const TileGeom& tg = tiles[my_tile];
+    const LevelGeom g = tg.lv[level];
+    const bool lane_on = x < g.w && !(dbg & 1);
     for (int j = 0; j < band.rows + 4; ++j) {
       const uint32_t v = u + j;
       if (static_cast<int>(v % kEpiGroups) != group) continue;
       const uint32_t slot = v % Cfg::kSlots;
       const int y = band.r0 - 2 + j;
-      const bool active = j >= 2 && j < band.rows + 2 && x < g.w && !(p.debug_flags & 1);
+      const bool active = j >= 2 && j < band.rows + 2 && lane_on;
       PixelRef px;
       px.P = g.base + y * g.pitch + x;
       px.y = y; px.x = x; px.valid = true;
       // residual rows are fetched BEFORE waiting for the accumulator: their latency hides behind the MMAs
       constexpr bool kPrefetchR2 = COUT <= 32;                // 64-wide layers never carry a second residual
       float r1[COUT], r2[kPrefetchR2 ? COUT : 1];
-      if (active && p.res1) {
+      if (active && e.res1) {
 #pragma unroll
-        for (int c = 0; c < COUT / 16; ++c) load_trunk16(p.res1, px.P, p.c_off + c * 16, &r1[c * 16]);
+        for (int c = 0; c < COUT / 16; ++c) load_trunk16(e.res1, px.P, e.c_off + c * 16, &r1[c * 16]);
       }
       if constexpr (kPrefetchR2) {
-        if (active && p.res2) {
+        if (active && e.res2) {
 #pragma unroll
-          for (int c = 0; c < COUT / 16; ++c) load_trunk16(p.res2, px.P, p.c_off + c * 16, &r2[c * 16]);
+          for (int c = 0; c < COUT / 16; ++c) load_trunk16(e.res2, px.P, e.c_off + c * 16, &r2[c * 16]);
         }
       }
       PROF_BEGIN();
@@ -346,7 +393,7 @@ __device__ __forceinline__ void epilogue_bands(const ConvParams& p, const Pipe& 
 #pragma unroll
       for (int c = 0; c < COUT / 16; ++c) tmem_ld16(taddr + c * 16, r[c]);
       tmem_ld_wait();
-      if (!(p.debug_flags & 8)) {
+      if (!(dbg & 8)) {
 #pragma unroll
         for (int c = 0; c < COUT / 16; ++c) tmem_st16_zero(taddr + c * 16);
         tmem_st_wait();
@@ -357,12 +404,12 @@ __device__ __forceinline__ void epilogue_bands(const ConvParams& p, const Pipe& 
       if (active) {
 #pragma unroll
         for (int c = 0; c < COUT / 16; ++c) {
-          if (c * 16 < p.cout) {
+          if (c * 16 < e.cout) {
             float vals[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) vals[e] = __uint_as_float(r[c][e]);
-            epilogue16(p, tg, px, c * 16, vals, p.res1 ? &r1[c * 16] : nullptr,
-                       (kPrefetchR2 && p.res2) ? &r2[kPrefetchR2 ? c * 16 : 0] : nullptr);
+            for (int k = 0; k < 16; ++k) vals[k] = __uint_as_float(r[c][k]);
+            epilogue16(e, tg, px, c * 16, vals, e.res1 ? &r1[c * 16] : nullptr,
+                       (kPrefetchR2 && e.res2) ? &r2[kPrefetchR2 ? c * 16 : 0] : nullptr);
           }
         }
       }

@@ -25,6 +25,20 @@ cudaError_t launch_conv3x3_body(const CUtensorMap& d0_136, const CUtensorMap& d1
                                 const CUtensorMap& d1_8, const CUtensorMap& wmap96, const ConvParams* d_passes, int npass,
                                 unsigned* d_gbar, int grid, cudaStream_t stream);
 
+// --- conv3x3_trunk.cu : all RDB layer passes of an L2-resident tile group; TMEM-resident bands, chunk-major sweeps,
+//     streamed weights, pass transitions overlapped (needs <= kTrunkMaxRows rows and <= kTrunkMaxBands bands per CTA)
+// Tensor maps of the trunk kernel: the two dense-block buffers with a 136-pixel box (full strips) and with boxes of
+// 8 / 16 / 32 / 64 pixels (segments of packed remainder strips are loaded with as few TMA operations as possible --
+// with 8-pixel boxes only, the CTAs that own packed strips were producer-bound and set the pace of all their neighbours).
+struct TrunkMaps {
+  CUtensorMap full[2];
+  CUtensorMap box[2][4];
+  CUtensorMap w;               // folded weights, box 96 rows
+};
+cudaError_t conv3x3_trunk_configure();
+cudaError_t launch_conv3x3_trunk(const TrunkMaps& maps, const ConvParams* d_passes, int npass, unsigned* d_prog, int grid,
+                                 cudaStream_t stream);
+
 // --- conv3x3_simt.cu : plain CUDA-core conv over the same buffers (test-only cross-check) -------
 cudaError_t launch_conv3x3_simt(const ConvParams& p, cudaStream_t stream);
 

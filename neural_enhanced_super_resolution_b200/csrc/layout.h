@@ -107,6 +107,15 @@ struct ConvParams {
   int32_t src_sel;             // which of the two dense-block buffers (tensor maps) this pass reads
   int32_t sync_passes;         // passes [0, sync_passes) of every CTA must be complete before this pass loads activations
   int32_t debug_flags;         // NESR_B200_DEBUG_FLAGS (timing experiments only): 1 no epilogue stores, 2 no MMA, 4 no TMA, 8 no TMEM re-zero
+  // L2-resident trunk kernel (conv3x3_trunk.cu): input chunk c may be loaded once every CTA has completed passes [0, need[c])
+  int32_t need[3];
+  int32_t l2_pin_chunks;       // row-folded kernels: loads of input chunks [0, l2_pin_chunks) ask L2 to keep them (0: no hints)
+  const int32_t* trunk_deps;   // [grid][kTrunkMaxDeps] CTAs (incl. itself) whose bands overlap this CTA's input halo; padded with itself
 };
+
+// conv3x3_trunk.cu keeps every output row of a CTA in TMEM for a whole pass: 16 row slots of 32 fp32 columns.
+constexpr int kTrunkMaxRows = 16;
+constexpr int kTrunkMaxBands = 4;
+constexpr int kTrunkMaxDeps = 32;            // one polling lane per dependency
 
 }  // namespace nesr
