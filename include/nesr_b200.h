@@ -67,13 +67,16 @@ typedef struct nesr_b200_config {
   int32_t num_grow_ch;
   int32_t body_format;        /* residual-dense-block convs: NESR_FMT_BF16 (default) | NESR_FMT_FP16 */
   int32_t edge_format;        /* conv_first/body/up1/up2/hr/last:  NESR_FMT_FP16 (default) | NESR_FMT_BF16 */
-  int32_t conv_impl;          /* 0 = row-folded tcgen05/TMEM/TMA kernels (product): one persistent launch for
-                                 the 69 residual dense blocks, one launch per edge layer.  Test-only
+  int32_t conv_impl;          /* 0 = row-folded tcgen05/TMEM/TMA kernels (product): tiles are processed in
+                                 L2-resident groups, each with ONE persistent launch for the 69 residual dense
+                                 blocks (conv3x3_trunk.cu) and one launch per edge layer.  Test-only
                                  cross-checks, never selected implicitly: 1 = SIMT validation kernel,
                                  2 = first-generation per-tap tcgen05 kernel, 3 = row-folded kernel with one
-                                 launch per layer pass */
+                                 launch per layer pass, 4 = whole-frame persistent trunk kernel with a
+                                 grid-wide arrival counter (conv3x3_body.cu, the previous product path) */
   int32_t reserved0;
-  int64_t max_batch_pixels;   /* cap on feature-grid pixels resident per batch; 0 = default */
+  int64_t max_batch_pixels;   /* cap on feature-grid pixels per tile group (batch); 0 = default (150k for
+                                 conv_impl 0: the group's dense-block activations stay in the 126 MB L2) */
 } nesr_b200_config;
 
 typedef struct nesr_b200_stats {
@@ -83,6 +86,8 @@ typedef struct nesr_b200_stats {
   double  last_device_ms;     /* CUDA-event time of the last enhance/forward call (device part only) */
   double  last_conv_ms;       /* ... conv kernels only (first to last conv of the call) */
   int64_t arena_bytes;        /* activation arena currently allocated */
+  double  last_trunk_ms;      /* ... persistent trunk kernel(s) of the last call only (the dominant kernel; sum over tile groups) */
+  int64_t last_trunk_launches;/* trunk kernel launches of the last call (= tile groups) */
 } nesr_b200_stats;
 
 /* Fills *cfg with the x2plus defaults for `device`. */

@@ -36,7 +36,8 @@ class Config(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("conv_launches", C.c_int64), ("tiles_processed", C.c_int64),
-                ("last_device_ms", C.c_double), ("last_conv_ms", C.c_double), ("arena_bytes", C.c_int64)]
+                ("last_device_ms", C.c_double), ("last_conv_ms", C.c_double), ("arena_bytes", C.c_int64),
+                ("last_trunk_ms", C.c_double), ("last_trunk_launches", C.c_int64)]
 
 
 _lib = None

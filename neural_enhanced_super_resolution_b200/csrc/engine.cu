@@ -110,6 +110,8 @@ struct nesr_b200_handle {
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evc0 = nullptr, evc1 = nullptr;
+  std::vector<cudaEvent_t> ev_trunk;                   // begin/end pairs around each trunk kernel launch of the last call
+  int n_trunk_timed = 0;
   EncodeTiledFn encode = nullptr;
   std::string error;
 
@@ -726,7 +728,7 @@ struct Sink {
 };
 
 int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in, const Sink& sink, cudaStream_t s,
-                  bool time_begin, bool time_end) {
+                  bool time_begin, bool time_end, bool time_trunk = false) {
   Arena& a = h->arena;
   const nesr_b200_config& c = h->cfg;
   int rc;
@@ -761,11 +763,20 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
       }
       tm.w = fold_weight_map(h, 32);
     }
+    if (time_trunk) {                  // events on the launching stream around the dominant kernel
+      while ((int)h->ev_trunk.size() < 2 * (h->n_trunk_timed + 1)) {
+        cudaEvent_t ev = nullptr;
+        if (cudaEventCreate(&ev) != cudaSuccess) return fail(h, NESR_E_CUDA, "cudaEventCreate failed");
+        h->ev_trunk.push_back(ev);
+      }
+      cudaEventRecord(h->ev_trunk[2 * h->n_trunk_timed], s);
+    }
     cudaError_t eb = b.trunk_fits
         ? launch_conv3x3_trunk(tm, b.d_body_passes, b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s)
         : launch_conv3x3_body(a.f_d[0], a.f_d[1], a.e_d[0], a.e_d[1], fold_weight_map(h, 32), b.d_body_passes,
                               b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s);
     if (eb != cudaSuccess) return fail(h, NESR_E_CUDA, "trunk kernel launch failed: %s", cudaGetErrorString(eb));
+    if (time_trunk) { cudaEventRecord(h->ev_trunk[2 * h->n_trunk_timed + 1], s); ++h->n_trunk_timed; }
     h->stats.kernel_launches++;
     h->stats.conv_launches++;
     li += (size_t)nrdb * 5;
@@ -861,11 +872,12 @@ int enhance_impl(nesr_b200_handle* h, const uint8_t* in, int n_frames, int H, in
                                       cudaMemcpyHostToDevice, h->stream));
   }
   cudaEventRecord(h->ev0, h->stream);
+  h->n_trunk_timed = 0;
   PackParams pk{};
   pk.in_u8 = d_in; pk.in_stride = d_in_stride; pk.in_frame_stride = d_in_fs; pk.H = H; pk.W = W; pk.pre_pad = pre_pad;
   Sink sink; sink.out_u8 = d_out; sink.out_stride = d_out_stride; sink.out_frame_stride = d_out_fs;
   for (size_t bi = 0; bi < h->batches.size(); ++bi)
-    if ((rc = forward_batch(h, h->batches[bi], pk, sink, h->stream, bi == 0, bi + 1 == h->batches.size()))) return rc;
+    if ((rc = forward_batch(h, h->batches[bi], pk, sink, h->stream, bi == 0, bi + 1 == h->batches.size(), true))) return rc;
   cudaEventRecord(h->ev1, h->stream);
   if (!(flags & NESR_PTR_OUT_DEVICE))
     for (int f = 0; f < n_frames; ++f)
@@ -875,6 +887,11 @@ int enhance_impl(nesr_b200_handle* h, const uint8_t* in, int n_frames, int H, in
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->stats.last_device_ms = ms;
   if (cudaEventElapsedTime(&ms, h->evc0, h->evc1) == cudaSuccess) h->stats.last_conv_ms = ms;
+  double trunk_ms = 0;
+  for (int t = 0; t < h->n_trunk_timed; ++t)
+    if (cudaEventElapsedTime(&ms, h->ev_trunk[2 * t], h->ev_trunk[2 * t + 1]) == cudaSuccess) trunk_ms += ms;
+  h->stats.last_trunk_ms = trunk_ms;
+  h->stats.last_trunk_launches = h->n_trunk_timed;
   return NESR_OK;
 }
 
@@ -963,6 +980,7 @@ int nesr_b200_destroy(nesr_b200_handle* h) {
   if (h->d_tmp) cudaFree(h->d_tmp);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (cudaEvent_t ev : h->ev_trunk) cudaEventDestroy(ev);
   if (h->evc0) cudaEventDestroy(h->evc0);
   if (h->evc1) cudaEventDestroy(h->evc1);
   if (h->stream) cudaStreamDestroy(h->stream);
