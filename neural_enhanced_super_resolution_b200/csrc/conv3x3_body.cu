@@ -41,6 +41,11 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* ptr) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* ptr) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void red_release_gpu_add(unsigned* ptr, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
 }
@@ -87,12 +92,15 @@ conv3x3_body_kernel(const __grid_constant__ CUtensorMap amap_d0, const __grid_co
       if (p.sync_passes > 0) {                                 // every CTA has finished the first sync_passes passes
         if (lane == 0) {
           const unsigned target = static_cast<unsigned>(p.sync_passes) * gridDim.x;
-          if (ld_acquire_gpu(gbar) < target) {
+          // relaxed spin, one acquire at the end: ld.acquire.gpu is LDG.STRONG + CCTL.IVALL, and an L1 invalidation per
+          // poll makes every L1-cached load of the epilogue warps miss
+          if (ld_relaxed_gpu(gbar) < target) {
             const long long t0 = clock64();
-            while (ld_acquire_gpu(gbar) < target) {
+            while (ld_relaxed_gpu(gbar) < target) {
               if (clock64() - t0 > NESR_HANG_GUARD_CYCLES) __trap();
             }
           }
+          (void)ld_acquire_gpu(gbar);
         }
         __syncwarp();
         fence_proxy_async_all();

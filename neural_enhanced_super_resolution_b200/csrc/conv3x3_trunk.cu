@@ -53,8 +53,12 @@ constexpr int kMaxBands = kTrunkMaxBands;
 #if NESR_PROF
 constexpr int kTracePasses = 48;
 #define TS(k, pass) do { if ((pass) < kTracePasses) sh.ts[k][pass] = clock64(); } while (0)
+#define EPI_T(var) const long long var = clock64()
+#define EPI_ACC(k, pass, dt) do { if (threadIdx.x == 64 && (pass) < kTracePasses) sh.epi_acc[k][pass] += (dt); } while (0)
 #else
 #define TS(k, pass) do {} while (0)
+#define EPI_T(var) do {} while (0)
+#define EPI_ACC(k, pass, dt) do {} while (0)
 #endif
 
 constexpr int kMaxOps = 20;                            // TMA operations per slab row of a packed strip
@@ -76,8 +80,10 @@ struct Shared {
   BandInfo band[kMaxBands];
   int32_t lane_px[kMaxBands][128];                     // flat pixel of (r0, x) of each MMA lane, or -1 (masked lane)
   int32_t lane_pitch[kMaxBands][128];
+  int32_t lane_rows[kMaxBands][128];                   // band rows [0, lane_rows) belong to the lane's piece
 #if NESR_PROF
   long long ts[6][kTracePasses];                       // per-pass time stamps of the dependency chain (debug_flags & 1024)
+  long long epi_acc[4][kTracePasses];                  // epilogue warp 2: cycles in wait_tfull / tmem ld+zero+arrive / math+stores / rows
 #endif
 };
 
@@ -88,6 +94,11 @@ static_assert(kSmemBytes <= 232448, "trunk kernel: shared memory budget");
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* ptr) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* ptr) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_release_gpu(unsigned* ptr, unsigned v) {
@@ -154,7 +165,7 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
         for (int sgi = 0; sgi < band.nseg; ++sgi) {
           const FoldSeg sg = p0.segs[band.seg0 + sgi];
           const LevelGeom g = p0.tiles[sg.tile].lv[0];
-          const int px = g.base + (band.r0 - 1) * g.pitch + sg.x0 - 1;
+          const int px = g.base + (band.r0 - 1 + sg.y0) * g.pitch + sg.x0 - 1;
           if (sg.width == kBlockPixels) {                        // a 128-pixel segment is always alone: one 136-pixel box
             bi.full_strip = 1;
             bi.op_px[0] = px; bi.op_pitch[0] = g.pitch; bi.op_off[0] = 0; bi.op_box[0] = 0; bi.nop = 1;
@@ -177,17 +188,18 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
       const int m = threadIdx.x;
       for (int b = 0; b < nband; ++b) {
         const FoldBand band = p0.bands[band_begin + b];
-        int px = -1, pitch = 0;
+        int px = -1, pitch = 0, nrow = 0;
         for (int sgi = 0; sgi < band.nseg; ++sgi) {
           const FoldSeg sg = p0.segs[band.seg0 + sgi];
           if (m >= sg.lane0 && m < sg.lane0 + sg.width) {
             const LevelGeom g = p0.tiles[sg.tile].lv[0];
             const int x = sg.x0 + (m - sg.lane0);
-            if (x < g.w) { px = g.base + band.r0 * g.pitch + x; pitch = g.pitch; }
+            if (x < g.w) { px = g.base + (band.r0 + sg.y0) * g.pitch + x; pitch = g.pitch; nrow = min(max(sg.h - band.r0, 0), band.rows); }
           }
         }
         sh.lane_px[b][m] = px;
         sh.lane_pitch[b][m] = pitch;
+        sh.lane_rows[b][m] = nrow;
       }
     }
   }
@@ -195,6 +207,9 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sh.tmem_slot;
+#if NESR_PROF
+  for (int i = threadIdx.x; i < 4 * kTracePasses; i += kThreads) (&sh.epi_acc[0][0])[i] = 0;
+#endif
   if (warp >= 2 && warp < 6) {                                  // every MMA accumulates: start from zero
     const uint32_t t0 = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     for (int c = 0; c < 512; c += 16) tmem_st16_zero(t0 + c);
@@ -233,12 +248,16 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
         // activations of this chunk: every CTA must have published the passes that wrote them
         const unsigned need = static_cast<unsigned>(c == 0 ? h.need0 : (c == 1 ? h.need1 : h.need2));
         if (need > known) {
-          if (ld_acquire_gpu(my_dep) < need) {                  // every lane polls one neighbour (padding lanes: this CTA)
+          // every lane polls one neighbour (padding lanes: this CTA).  The spin is RELAXED: ld.acquire.gpu compiles to
+          // LDG.STRONG + CCTL.IVALL, and an L1 invalidation per poll made every L1-cached load of the epilogue warps
+          // (bias) miss -- ~700 cycles per row.  One acquire after the last poll orders the TMA loads that follow.
+          if (ld_relaxed_gpu(my_dep) < need) {
             const long long t0 = clock64();
-            while (ld_acquire_gpu(my_dep) < need) {
+            while (ld_relaxed_gpu(my_dep) < need) {
               if (clock64() - t0 > NESR_HANG_GUARD_CYCLES) __trap();
             }
           }
+          (void)ld_acquire_gpu(my_dep);
           __syncwarp();
           fence_proxy_async_all();
           known = need;
@@ -355,31 +374,56 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
     const int group = (warp - 2) >> 2;                          // rows alternate between the two epilogue groups
     const int m = quarter * 32 + lane;                          // TMEM lane == MMA row == pixel
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const TileGeom& tg0 = passes[0].tiles[0];                   // never dereferenced: trunk passes do not upsample / paste
     for (int pass = 0; pass < npass; ++pass) {
-      const EpiRegs e = make_epi_regs<true>(passes[pass]);
-      const int dbg = __ldg(&passes[pass].debug_flags);
+      // The epilogue warps are instruction-latency bound (one or two warps per scheduler, ~4 cycles per dependent
+      // instruction): the generic epilogue16() path cost ~300 instructions = 1200 cycles per row.  A trunk pass is one of
+      // two kinds, fixed for the whole pass, so the row loop below is straight-line code specialised at pass level:
+      //   conv1..4 : v = lrelu(acc + bias)                               -> 16-bit, channels [coff, coff+32) of this buffer
+      //   conv5    : v = (acc + bias)*0.2 + trunk [; v = v*0.2 + rrdb_in] -> fp32 trunk [+ rrdb], 16-bit x of the next block
+      const ConvParams* pp = passes + pass;
+      const int dbg = __ldg(&pp->debug_flags);
+      const float* res1 = pp->res1;
+      const float* res2 = pp->res2;
+      float* dst32a = pp->dst32a;
+      float* dst32b = pp->dst32b;
+      const float s1 = pp->s1, s2 = pp->s2;
+      const int c_off = pp->c_off, fmt16 = pp->dst16_fmt, lrelu = pp->lrelu;
+      const int coff16 = pp->dst16_coff;
+      uint16_t* const base16 = reinterpret_cast<uint16_t*>(pp->dst16) + static_cast<size_t>(coff16 >> 6) * pp->dst16_plane_px * 64 + (coff16 & 63);
+      float bias_r[COUT];                                       // once per pass, in registers
+      {
+        const float4* b4 = reinterpret_cast<const float4*>(pp->bias);
+#pragma unroll
+        for (int k = 0; k < COUT / 4; ++k) {
+          const float4 bv = __ldg(b4 + k);
+          bias_r[4 * k] = bv.x; bias_r[4 * k + 1] = bv.y; bias_r[4 * k + 2] = bv.z; bias_r[4 * k + 3] = bv.w;
+        }
+      }
       const uint32_t tparity = static_cast<uint32_t>(pass & 1);
       for (int b = 0; b < nband; ++b) {
         const int rows = sh.band[b].rows, slot0 = sh.band[b].slot0;
-        const int px0 = sh.lane_px[b][m], pitch = sh.lane_pitch[b][m];
-        const bool lane_on = px0 >= 0 && !(dbg & 1);
+        const int px0 = sh.lane_px[b][m], pitch = sh.lane_pitch[b][m], my_rows = sh.lane_rows[b][m];
+        const bool band_on = px0 >= 0 && !(dbg & 1);
         for (int j = 0; j < rows; ++j) {
           const int slot = slot0 + j;
           if ((slot & 1) != group) continue;
-          PixelRef px;
-          px.P = px0 + j * pitch; px.y = 0; px.x = 0; px.valid = true;
+          const bool lane_on = band_on && j < my_rows;
+          const int P = px0 + j * pitch;
+          // blocked fp32 trunk layout: [pixel/32][ch/8][pixel%32][ch%8]; this lane's 32 channels are 4 runs of 8 floats
+          const size_t toff = (static_cast<size_t>(P >> 5) * 8 + (c_off >> 3)) * 256 + (static_cast<size_t>(P & 31) << 3);
           // residual rows are fetched BEFORE waiting for the accumulator: their latency hides behind the MMAs
           float r1[COUT], r2[COUT];
-          if (lane_on && e.res1) {
+          if (lane_on && res1) {
 #pragma unroll
-            for (int c = 0; c < COUT / 16; ++c) load_trunk16(e.res1, px.P, e.c_off + c * 16, &r1[c * 16]);
+            for (int q = 0; q < COUT / 8; ++q) ldg256_stream(res1 + toff + q * 256, &r1[q * 8]);
           }
-          if (lane_on && e.res2) {
+          if (lane_on && res2) {
 #pragma unroll
-            for (int c = 0; c < COUT / 16; ++c) load_trunk16(e.res2, px.P, e.c_off + c * 16, &r2[c * 16]);
+            for (int q = 0; q < COUT / 8; ++q) ldg256_stream(res2 + toff + q * 256, &r2[q * 8]);
           }
+          EPI_T(et0);
           mbar_wait(&sh.tfull[slot], tparity);
+          EPI_T(et1);
           tc_fence_after();
           __syncwarp();
           const uint32_t taddr = lane_base + static_cast<uint32_t>(slot) * COUT;
@@ -392,15 +436,49 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&sh.tempty[slot]);
+          EPI_T(et2);
           if (lane_on) {
+            float v[COUT];
 #pragma unroll
-            for (int c = 0; c < COUT / 16; ++c) {
-              float vals[16];
+            for (int k = 0; k < COUT; ++k) v[k] = __uint_as_float(r[k >> 4][k & 15]) + bias_r[k];
+            if (!res1) {
+              if (lrelu) {
 #pragma unroll
-              for (int k = 0; k < 16; ++k) vals[k] = __uint_as_float(r[c][k]);
-              epilogue16(e, tg0, px, c * 16, vals, e.res1 ? &r1[c * 16] : nullptr, e.res2 ? &r2[c * 16] : nullptr);
+                for (int k = 0; k < COUT; ++k) v[k] = fmaxf(v[k], 0.2f * v[k]);     // LeakyReLU(0.2): slope < 1
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < COUT; ++k) v[k] = fmaf(v[k], s1, r1[k]);
+              if (res2) {
+#pragma unroll
+                for (int k = 0; k < COUT; ++k) v[k] = fmaf(v[k], s2, r2[k]);
+              }
+              if (!(dbg & 4096)) {
+#pragma unroll
+                for (int q = 0; q < COUT / 8; ++q) stg256f_stream(dst32a + toff + q * 256, &v[q * 8]);
+                if (dst32b) {
+#pragma unroll
+                  for (int q = 0; q < COUT / 8; ++q) stg256f_stream(dst32b + toff + q * 256, &v[q * 8]);
+                }
+              }
+            }
+            if (!(dbg & 16)) {
+              uint32_t w[COUT / 2];
+              if (fmt16) {
+#pragma unroll
+                for (int k = 0; k < COUT / 2; ++k) w[k] = pack2(v[2 * k], v[2 * k + 1], 1);
+              } else {
+#pragma unroll
+                for (int k = 0; k < COUT / 2; ++k) w[k] = pack2(v[2 * k], v[2 * k + 1], 0);
+              }
+              uint16_t* dst = base16 + static_cast<size_t>(P) * 64;
+              stg256(dst, reinterpret_cast<const uint32_t(&)[8]>(w[0]));
+              stg256(dst + 16, reinterpret_cast<const uint32_t(&)[8]>(w[8]));
             }
           }
+#if NESR_PROF
+          { const long long et3 = clock64(); EPI_ACC(0, pass, et1 - et0); EPI_ACC(1, pass, et2 - et1); EPI_ACC(2, pass, et3 - et2); EPI_ACC(3, pass, 1); }
+#endif
         }
       }
       // publish the pass: generic-proxy stores -> TMA (async proxy) reads of any CTA
@@ -425,6 +503,9 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
     for (int q = 0; q < kTracePasses && q < npass; ++q)
       printf("[trunk blk %d pass %d cin=%d] acquired %lld  first_full_last_chunk %lld  mma_issued %lld  epi_rows_done %lld  epi_synced %lld  published %lld\n",
              (int)blockIdx.x, q, passes[q].cin, sh.ts[4][q] - t0, sh.ts[5][q] - t0, sh.ts[0][q] - t0, sh.ts[1][q] - t0, sh.ts[2][q] - t0, sh.ts[3][q] - t0);
+    for (int q = 0; q < kTracePasses && q < npass; ++q)
+      printf("[trunk epi blk %d pass %d cin=%d] rows %lld  wait_tfull %lld  tmem_ld_zero_arrive %lld  math_stores %lld\n", (int)blockIdx.x, q,
+             passes[q].cin, sh.epi_acc[3][q], sh.epi_acc[0][q], sh.epi_acc[1][q], sh.epi_acc[2][q]);
   }
 #endif
 }

@@ -346,28 +346,64 @@ void build_fold_schedule(Batch& b, int level, int num_sms) {
     const LevelGeom& g = b.tiles[ti].lv[level];
     for (int x0 = 0; x0 + kBlockPixels <= g.w; x0 += kBlockPixels) {
       strips.push_back(Strip{(int32_t)lp.segs.size(), 1, g.h});
-      lp.segs.push_back(FoldSeg{(int32_t)ti, x0, kBlockPixels, 0});
+      lp.segs.push_back(FoldSeg{(int32_t)ti, x0, kBlockPixels, 0, 0, g.h});
     }
   }
-  // right-hand remainders: packed side by side (with their halo pixels) among tiles of equal height
-  std::vector<bool> done(b.tiles.size(), false);
+  // right-hand remainder columns: cut into pieces of at most T rows and packed side by side (with their halo
+  // pixels) into combined strips; T is chosen to minimise the number of strip rows (+2 halo rows per strip)
+  struct Piece { int32_t tile, x0, rem, span, y0, h; };
+  std::vector<Piece> cols;
   for (size_t ti = 0; ti < b.tiles.size(); ++ti) {
     const LevelGeom& g = b.tiles[ti].lv[level];
-    if (done[ti] || g.w % kBlockPixels == 0) continue;
-    Strip st{(int32_t)lp.segs.size(), 0, g.h};
-    int lane = 0;
-    for (size_t tj = ti; tj < b.tiles.size() && st.nseg < kMaxFoldSegs; ++tj) {
-      const LevelGeom& gj = b.tiles[tj].lv[level];
-      const int rem = gj.w % kBlockPixels;
-      if (done[tj] || rem == 0 || gj.h != g.h) continue;
-      const int span = (rem + 2 + 7) / 8 * 8;                  // slab rows incl. halo, in 8-pixel TMA boxes
-      if (lane + span > 136 || lane + rem > kBlockPixels) continue;   // slab rows and MMA lanes available
-      lp.segs.push_back(FoldSeg{(int32_t)tj, gj.w - rem, rem, lane});
-      lane += span;
-      ++st.nseg;
-      done[tj] = true;
+    const int rem = g.w % kBlockPixels;
+    if (rem) cols.push_back(Piece{(int32_t)ti, g.w - rem, rem, (rem + 2 + 7) / 8 * 8, 0, g.h});
+  }
+  if (!cols.empty()) {
+    // every piece costs the TMA producer at least one more operation per slab row; with 8 pieces a packed strip's
+    // CTAs were producer-bound and paced the whole group (9.3 instead of 6.7 ms), with 11 one-box operations likewise
+    static const int kMaxPieces = getenv("NESR_B200_MAX_PIECES") ? atoi(getenv("NESR_B200_MAX_PIECES")) : 3;
+    struct Packed { std::vector<Piece> pcs; int lanes = 0, h = 0; };
+    auto plan = [&](int T, std::vector<Packed>* out) -> int64_t {
+      std::vector<Piece> pcs;
+      for (const Piece& c : cols) {
+        const int n = (c.h + T - 1) / T, hp = (c.h + n - 1) / n;
+        for (int y = 0; y < c.h; y += hp) pcs.push_back(Piece{c.tile, c.x0, c.rem, c.span, y, std::min(hp, c.h - y)});
+      }
+      std::stable_sort(pcs.begin(), pcs.end(), [](const Piece& a, const Piece& o) { return a.h > o.h; });
+      std::vector<Packed> packed;
+      for (const Piece& pc : pcs) {
+        Packed* dst = nullptr;
+        for (Packed& pk : packed)
+          if ((int)pk.pcs.size() < kMaxPieces && pk.lanes + pc.span <= 136 && pk.lanes + pc.rem <= kBlockPixels) { dst = &pk; break; }
+        if (!dst) { packed.emplace_back(); dst = &packed.back(); }
+        dst->pcs.push_back(pc); dst->lanes += pc.span; dst->h = std::max(dst->h, pc.h);
+      }
+      int64_t cost = 0;
+      for (const Packed& pk : packed) cost += pk.h + 2;
+      if (out) *out = std::move(packed);
+      return cost;
+    };
+    int best_T = 1 << 30;
+    int64_t best = plan(best_T, nullptr);                       // no cutting
+    for (const Piece& c : cols)
+      for (int n = 2; n <= 16; ++n) {
+        const int T = (c.h + n - 1) / n;
+        if (T < 8) break;
+        const int64_t cost = plan(T, nullptr);
+        if (cost < best) { best = cost; best_T = T; }
+      }
+    std::vector<Packed> packed;
+    plan(best_T, &packed);
+    for (const Packed& pk : packed) {
+      Strip st{(int32_t)lp.segs.size(), 0, pk.h};
+      int lane = 0;
+      for (const Piece& pc : pk.pcs) {
+        lp.segs.push_back(FoldSeg{pc.tile, pc.x0, pc.rem, lane, pc.y0, pc.h});
+        lane += pc.span;
+        ++st.nseg;
+      }
+      strips.push_back(st);
     }
-    strips.push_back(st);
   }
   int64_t total_rows = 0;
   for (const Strip& st : strips) total_rows += st.h;
@@ -415,7 +451,8 @@ void build_trunk_deps(LevelPlan& lp) {
       const FoldBand& band = lp.bands[b];
       for (int sgi = 0; sgi < band.nseg; ++sgi) {
         const FoldSeg& sg = lp.segs[band.seg0 + sgi];
-        rects.push_back(Rect{sg.tile, sg.x0, sg.x0 + sg.width - 1, band.r0, band.r0 + band.rows - 1, c});
+        if (band.r0 >= sg.h) continue;                            // this piece has no rows in the band
+        rects.push_back(Rect{sg.tile, sg.x0, sg.x0 + sg.width - 1, sg.y0 + band.r0, sg.y0 + std::min(band.r0 + band.rows, sg.h) - 1, c});
       }
     }
   lp.deps.assign((size_t)grid * kTrunkMaxDeps, 0);

@@ -142,11 +142,13 @@ __device__ __forceinline__ EpiRegs make_epi_regs(const ConvParams& p) {
 template <class Params>
 __device__ __forceinline__ void epilogue16(const Params& p, const TileGeom& tg, const PixelRef& px, int n0,
                                            float (&v)[16], const float* r1pre = nullptr, const float* r2pre = nullptr) {
-  const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+  if (p.bias) {                                              // null: the caller has added the bias already
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float4 b = __ldg(b4 + i);
-    v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    for (int i = 0; i < 4; ++i) {
+      const float4 b = __ldg(b4 + i);
+      v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    }
   }
   if (p.lrelu) {
 #pragma unroll

@@ -181,7 +181,7 @@ __device__ __forceinline__ void producer_bands(const ConvParams& p, const CUtens
       if (sgi < band.nseg) {
         const FoldSeg sg = segs[band.seg0 + sgi];
         const LevelGeom g = tiles[sg.tile].lv[level];
-        seg_px[sgi] = g.base + (band.r0 - 1) * g.pitch + sg.x0 - 1;
+        seg_px[sgi] = g.base + (band.r0 - 1 + sg.y0) * g.pitch + sg.x0 - 1;
         seg_pitch[sgi] = g.pitch;
         seg_off[sgi] = sg.lane0 * 128;
         seg_n8[sgi] = (sg.width + 2 + 7) >> 3;
@@ -353,10 +353,10 @@ __device__ __forceinline__ void epilogue_bands(const ConvParams& p, const Pipe& 
   [[maybe_unused]] const long long prof_start = PROF_NOW();
   for (int bi = band_begin; bi < band_end; ++bi) {
     const FoldBand band = bands[bi];
-    int my_tile = 0, x = 1 << 20;                            // this lane's pixel column (none: masked lane)
+    int my_tile = 0, x = 1 << 20, y_off = 0, y_end = 0;      // this lane's pixel column (none: masked lane), piece rows
     for (int sgi = 0; sgi < band.nseg; ++sgi) {
       const FoldSeg sg = segs[band.seg0 + sgi];
-      if (m >= sg.lane0 && m < sg.lane0 + sg.width) { my_tile = sg.tile; x = sg.x0 + (m - sg.lane0); }
+      if (m >= sg.lane0 && m < sg.lane0 + sg.width) { my_tile = sg.tile; x = sg.x0 + (m - sg.lane0); y_off = sg.y0; y_end = sg.h; }
     }
     const TileGeom& tg = tiles[my_tile];
     const LevelGeom g = tg.lv[level];
@@ -365,8 +365,9 @@ __device__ __forceinline__ void epilogue_bands(const ConvParams& p, const Pipe& 
       const uint32_t v = u + j;
       if (static_cast<int>(v % kEpiGroups) != group) continue;
       const uint32_t slot = v % Cfg::kSlots;
-      const int y = band.r0 - 2 + j;
-      const bool active = j >= 2 && j < band.rows + 2 && lane_on;
+      const int ys = band.r0 - 2 + j;                          // strip row; the lane's piece holds strip rows [0, y_end)
+      const int y = ys + y_off;
+      const bool active = j >= 2 && j < band.rows + 2 && lane_on && ys < y_end;
       PixelRef px;
       px.P = g.base + y * g.pitch + x;
       px.y = y; px.x = x; px.valid = true;

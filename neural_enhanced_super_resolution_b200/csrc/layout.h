@@ -48,14 +48,17 @@ struct BlockRef {
 };
 
 // Row-folded conv kernel work units.  A strip is 128 MMA lanes wide.  A full strip is one segment of
-// 128 pixels of one tile; the narrow right-hand remainders of several tiles that share a height
-// (the tiles of one tile-row) are PACKED side by side into one combined strip, each with its own
-// halo pixels, so ragged tile widths cost neither MMA lanes nor memory traffic.
+// 128 pixels of one tile.  The narrow right-hand remainder columns of the tiles are cut into vertical
+// PIECES and the pieces -- of one tile or of several -- are PACKED side by side into combined strips, each
+// with its own halo pixels, so ragged tile widths cost neither MMA lanes nor memory traffic: a 10-pixel
+// remainder of a 266-row tile becomes 8 pieces of 34 rows in one 34-row strip instead of a 266-row strip.
 struct FoldSeg {
   int32_t tile;    // tile the pixels belong to
   int32_t x0;      // first pixel column
   int32_t width;   // pixels (<= 128)
   int32_t lane0;   // MMA lane of pixel x0 (multiple of 8).  Slab rows [lane0, lane0+width+2) hold pixels x0-1 .. x0+width
+  int32_t y0;      // tile row of the segment's strip-row 0 (0 unless the segment is a piece of a cut column)
+  int32_t h;       // rows of the segment: strip rows >= h belong to nobody and are dropped
 };
 constexpr int kMaxFoldSegs = 8;
 // One band: output rows [r0, r0+rows) of a strip made of segments segs[seg0 .. seg0+nseg).
