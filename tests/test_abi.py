@@ -39,7 +39,7 @@ def test_config_struct_matches_header_defaults():
     assert (cfg.abi_version, cfg.num_in_ch, cfg.num_out_ch, cfg.scale) == (_ffi.ABI_VERSION, 3, 3, 2)
     assert (cfg.num_feat, cfg.num_block, cfg.num_grow_ch) == (64, 23, 32)
     assert (cfg.body_format, cfg.edge_format, cfg.conv_impl) == (_ffi.FMT_BF16, _ffi.FMT_FP16, 0)
-    assert ctypes.sizeof(_ffi.Config) == 56 and ctypes.sizeof(_ffi.Stats) == 48
+    assert ctypes.sizeof(_ffi.Config) == 56 and ctypes.sizeof(_ffi.Stats) == 64
 
 
 def test_tile_count_follows_upstream_grid():
