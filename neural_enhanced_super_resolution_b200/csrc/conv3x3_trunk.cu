@@ -123,6 +123,53 @@ __device__ __forceinline__ PassHead load_head(const ConvParams* passes, int pass
   return h;
 }
 
+// One chunk sweep over one band, executed by the single MMA-issuing thread.  KS k-steps per (row, dx); FIRST: first
+// sweep of the pass (wait until the epilogue has drained + zeroed a slot before its first MMA); LAST: last sweep (commit
+// each output row's completion).  The thread is the bottleneck of a sweep (~120 instructions per row at one instruction
+// per ~4-5 cycles against 684 cycles of MMA work), so everything that can be is a template parameter and interior rows
+// (all three output rows inside the band) take a path without clamps.
+template <int KS, bool FIRST, bool LAST>
+__device__ __forceinline__ void sweep_band(Shared& sh, const int rows, const int slot0, const uint32_t tmem_base, const uint32_t hw,
+                                           const uint32_t hi, const uint32_t a_lo0, const uint32_t w_lo, const uint32_t tparity,
+                                           int& stage, uint32_t& phase, const bool mma_on) {
+  constexpr uint32_t kSlabLo = kSlabBytes >> 4, kWBoxLo = kWBoxBytes >> 4;
+  constexpr uint32_t kBlkLo = (COUT * 128) >> 4;                // one dy block of 32 weight rows
+  const uint32_t id96 = umma_idesc_f16(hw, 3 * COUT);
+  // input row -1: its slab, and (first sweep of the pass) output slot 0 drained + zeroed by the epilogue
+  if (FIRST) mbar_wait(&sh.tempty[slot0], tparity ^ 1);
+  mbar_wait(&sh.full[stage], phase);
+  tc_fence_after();
+  for (int i = -1; i <= rows; ++i) {
+    uint32_t d, id, b_lo;
+    if (i >= 1 && i + 1 <= rows - 1) {                          // interior: output rows i-1, i, i+1
+      d = tmem_base + static_cast<uint32_t>(slot0 + i - 1) * COUT; id = id96; b_lo = w_lo;
+    } else {
+      const int lo = i - 1 < 0 ? 0 : i - 1;
+      const int hi_row = i + 1 > rows - 1 ? rows - 1 : i + 1;
+      d = tmem_base + static_cast<uint32_t>(slot0 + lo) * COUT;
+      id = umma_idesc_f16(hw, static_cast<uint32_t>(COUT * (hi_row - lo + 1)));
+      b_lo = w_lo + static_cast<uint32_t>(lo - (i - 1)) * kBlkLo;
+    }
+    const uint32_t a_lo = a_lo0 + stage * kSlabLo;
+    if (mma_on) umma_f16_ksteps<KS>(d, a_lo, b_lo, hi, id);
+    // while those run: is the next input row ready?  (slot i+2 is first touched by input row i+1)
+    const int nstage = stage + 1 == kStages ? 0 : stage + 1;
+    if (i < rows) {
+      if (FIRST && i + 2 <= rows - 1) mbar_wait(&sh.tempty[slot0 + i + 2], tparity ^ 1);
+      mbar_wait(&sh.full[nstage], nstage == 0 ? phase ^ 1 : phase);
+      tc_fence_after();
+    }
+    if (mma_on) {
+      umma_f16_ksteps<KS>(d, a_lo + 8, b_lo + kWBoxLo, hi, id);
+      umma_f16_ksteps<KS>(d, a_lo + 16, b_lo + 2 * kWBoxLo, hi, id);
+    }
+    umma_commit(&sh.empty[stage]);                              // slab may be overwritten once these MMAs have read it
+    if (LAST && i >= 1) umma_commit(&sh.tfull[slot0 + i - 1]);  // output row i-1 has all its contributions
+    stage = nstage;
+    if (stage == 0) phase ^= 1;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* __restrict__ passes, const int npass,
                      unsigned* __restrict__ prog) {
@@ -305,8 +352,7 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
       const uint32_t hi = umma_desc_hi_sw128();
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(ring));
       const uint32_t w_lo0 = umma_desc_lo(smem_u32(wring));
-      constexpr uint32_t kSlabLo = kSlabBytes >> 4, kWChunkLo = kWChunkBytes >> 4, kWBoxLo = kWBoxBytes >> 4;
-      constexpr uint32_t kBlkLo = (COUT * 128) >> 4;            // one dy block of 32 weight rows
+      constexpr uint32_t kWChunkLo = kWChunkBytes >> 4;
       PassHead h = load_head(passes, 0, npass);
       for (int pass = 0; pass < npass; ++pass) {
         const PassHead nh = load_head(passes, pass + 1, npass);
@@ -319,46 +365,21 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
           const bool first_chunk = c == 0;
           mbar_wait(&sh.wfull[ws], wphase);
           const uint32_t w_lo = w_lo0 + ws * kWChunkLo;
+          const bool mma_on = !(h.dbg & 2);
+          const int variant = (ks == 4 ? 0 : 4) + (first_chunk ? 2 : 0) + (last_chunk ? 1 : 0);
           for (int b = 0; b < nband; ++b) {
             const int rows = sh.band[b].rows, slot0 = sh.band[b].slot0;
-            // input row -1: its slab, and (first sweep of the pass) output slot 0 drained + zeroed by the epilogue
-            if (first_chunk) mbar_wait(&sh.tempty[slot0], tparity ^ 1);
-            mbar_wait(&sh.full[stage], phase);
-            if (last_chunk && b == 0) TS(5, pass);
-            tc_fence_after();
-            for (int i = -1; i <= rows; ++i) {
-              const int lo = i - 1 < 0 ? 0 : i - 1;
-              const int hi_row = i + 1 > rows - 1 ? rows - 1 : i + 1;
-              const uint32_t d = tmem_base + static_cast<uint32_t>(slot0 + lo) * COUT;
-              const uint32_t id = umma_idesc_f16(hw, static_cast<uint32_t>(COUT * (hi_row - lo + 1)));
-              const uint32_t a_lo = a_lo0 + stage * kSlabLo;
-              const uint32_t b_lo = w_lo + static_cast<uint32_t>(lo - (i - 1)) * kBlkLo;
-              const bool mma_on = !(h.dbg & 2);
-              if (mma_on) {
-                if (ks == 4) umma_f16_ksteps<4>(d, a_lo, b_lo, hi, id);
-                else umma_f16_ksteps_rt(ks, d, a_lo, b_lo, hi, id);
-              }
-              // while those run: is the next input row ready?  (slot i+2 is first touched by input row i+1)
-              const int nstage = stage + 1 == kStages ? 0 : stage + 1;
-              if (i < rows) {
-                if (first_chunk && i + 2 <= rows - 1) mbar_wait(&sh.tempty[slot0 + i + 2], tparity ^ 1);
-                mbar_wait(&sh.full[nstage], nstage == 0 ? phase ^ 1 : phase);
-                tc_fence_after();
-              }
-              if (mma_on) {
-                if (ks == 4) {
-                  umma_f16_ksteps<4>(d, a_lo + 8, b_lo + kWBoxLo, hi, id);
-                  umma_f16_ksteps<4>(d, a_lo + 16, b_lo + 2 * kWBoxLo, hi, id);
-                } else {
-                  umma_f16_ksteps_rt(ks, d, a_lo + 8, b_lo + kWBoxLo, hi, id);
-                  umma_f16_ksteps_rt(ks, d, a_lo + 16, b_lo + 2 * kWBoxLo, hi, id);
-                }
-              }
-              umma_commit(&sh.empty[stage]);                     // slab may be overwritten once these MMAs have read it
-              if (last_chunk && i >= 1) umma_commit(&sh.tfull[slot0 + i - 1]);   // output row i-1 has all its contributions
-              stage = nstage;
-              if (stage == 0) phase ^= 1;
+            switch (variant) {                                  // trunk passes only have 4- and 2-k-step chunks
+              case 0: sweep_band<4, false, false>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
+              case 1: sweep_band<4, false, true>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
+              case 2: sweep_band<4, true, false>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
+              case 3: sweep_band<4, true, true>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
+              case 4: sweep_band<2, false, false>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
+              case 5: sweep_band<2, false, true>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
+              case 6: sweep_band<2, true, false>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
+              default: sweep_band<2, true, true>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
             }
+            if (last_chunk && b == 0) TS(5, pass);
           }
           umma_commit(&sh.wempty[ws]);
           if (++ws == kWStages) { ws = 0; wphase ^= 1; }
