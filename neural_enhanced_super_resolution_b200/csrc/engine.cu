@@ -59,6 +59,7 @@ struct LevelPlan {
   FoldSeg* d_segs = nullptr;
   int32_t* d_cta_off = nullptr;
   int fold_grid = 0;
+  bool paired = false;         // level 0: CTAs 2p / 2p+1 have bands of identical shape (CTA-pair trunk kernel)
   std::vector<int32_t> deps;   // level 0 only: [grid][kTrunkMaxDeps] halo dependencies of the trunk kernel (empty: too many)
   int32_t* d_deps = nullptr;
 };
@@ -77,7 +78,8 @@ struct Batch {
   LevelPlan lv[3];
   ConvParams* d_body_passes = nullptr;   // persistent trunk kernel: one ConvParams per RDB layer pass
   int n_body_passes = 0;
-  bool trunk_fits = false;               // level-0 schedule fits the TMEM-resident trunk kernel (conv3x3_trunk.cu)
+  bool trunk_fits = false;               // level-0 schedule fits a TMEM-resident trunk kernel (conv3x3_trunk.cu / conv3x3_trunk2.cu)
+  bool trunk_pairs = false;              // ... the CTA-pair one
 };
 
 struct Arena {
@@ -139,6 +141,7 @@ struct nesr_b200_handle {
 
   nesr_b200_stats stats{};
   int debug_flags = 0;        // NESR_B200_DEBUG_FLAGS: timing experiments (results are wrong when set)
+  int use_pairs = 1;          // NESR_B200_PAIRS: CTA-pair trunk kernel (conv3x3_trunk2.cu) when the schedule allows
   int l2_pin_chunks = 1;      // NESR_B200_L2_PIN: dense-block planes whose loads are tagged evict_last in the trunk passes
 };
 
@@ -336,7 +339,7 @@ void layout_level(Batch& b, int level) {
 // CTA gets the same number of rows +-1 and at most a few bands, so no SM waits for a straggler
 // (a longest-first deal of fixed-size bands left 12 of 148 CTAs with 35 % more work), and the two
 // halo rows a band costs are paid as rarely as possible.
-void build_fold_schedule(Batch& b, int level, int num_sms) {
+void build_fold_schedule(Batch& b, int level, int num_sms, bool pairs = false) {
   LevelPlan& lp = b.lv[level];
   struct Strip { int32_t seg0, nseg, h; };
   std::vector<Strip> strips;
@@ -405,6 +408,67 @@ void build_fold_schedule(Batch& b, int level, int num_sms) {
       strips.push_back(st);
     }
   }
+  lp.paired = false;
+  if (pairs && num_sms >= 2) {
+    // CTA-pair schedule (conv3x3_trunk2.cu): CTAs 2p and 2p+1 get bands of IDENTICAL shape.  Strips are paired by height
+    // (an odd one out is cut into its upper and lower half); a pair-strip has the length of its longer member and the
+    // shorter one's missing rows are dropped by the segments' row counts.  The pair-strip sequence is cut into
+    // contiguous runs of equal cost exactly like the single-CTA schedule below.
+    struct Half { int32_t strip, off, len; };
+    struct PairStrip { Half a, b; int32_t len; };
+    std::vector<int> order(strips.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return strips[x].h > strips[y].h; });
+    std::vector<PairStrip> ps;
+    for (size_t i = 0; i + 1 < order.size(); i += 2) {
+      const Strip &sa = strips[order[i]], &sb = strips[order[i + 1]];
+      ps.push_back(PairStrip{Half{order[i], 0, sa.h}, Half{order[i + 1], 0, sb.h}, std::max(sa.h, sb.h)});
+    }
+    if (order.size() & 1) {
+      const int si = order.back(), hh = strips[si].h, up = (hh + 1) / 2;
+      ps.push_back(PairStrip{Half{si, 0, up}, Half{si, up, hh - up}, up});
+    }
+    int64_t total = 0;
+    for (const PairStrip& q : ps) total += q.len;
+    const int npair = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms / 2, total / 4));
+    std::vector<std::vector<FoldBand>> per_cta(2 * npair);
+    auto deal2 = [&](int64_t budget, bool emit) -> bool {
+      size_t pi = 0;
+      int r = 0;
+      if (emit) for (auto& v : per_cta) v.clear();
+      for (int c = 0; c < npair; ++c) {
+        int64_t left = budget;
+        while (pi < ps.size() && left >= 3) {
+          const PairStrip& q = ps[pi];
+          const int n = (int)std::min<int64_t>(left - 2, q.len - r);
+          if (emit) {
+            const Strip &sa = strips[q.a.strip], &sb = strips[q.b.strip];
+            per_cta[2 * c].push_back(FoldBand{sa.seg0, sa.nseg, q.a.off + r, n});
+            per_cta[2 * c + 1].push_back(FoldBand{sb.seg0, sb.nseg, q.b.off + r, n});
+          }
+          left -= n + 2;
+          r += n;
+          if (r == q.len) { ++pi; r = 0; }
+        }
+      }
+      return pi == ps.size();
+    };
+    int64_t lo2 = 3, hi2 = total + 2 * (int64_t)ps.size() + 3;
+    while (lo2 < hi2) {
+      const int64_t mid = (lo2 + hi2) / 2;
+      if (deal2(mid, false)) hi2 = mid; else lo2 = mid + 1;
+    }
+    deal2(lo2, true);
+    lp.bands.clear();
+    lp.cta_off.assign(1, 0);
+    for (const auto& v : per_cta) {
+      lp.bands.insert(lp.bands.end(), v.begin(), v.end());
+      lp.cta_off.push_back((int32_t)lp.bands.size());
+    }
+    lp.fold_grid = 2 * npair;
+    lp.paired = true;
+    return;
+  }
   int64_t total_rows = 0;
   for (const Strip& st : strips) total_rows += st.h;
   const int min_rows = 4;                                      // do not spread tiny work over every SM
@@ -469,6 +533,19 @@ void build_trunk_deps(LevelPlan& lp) {
   }
 }
 
+// conv3x3_trunk2.cu: every band needs two junk row slots on either side (shared between consecutive bands).
+bool trunk2_schedule_fits(const LevelPlan& lp) {
+  if (!lp.paired || (lp.fold_grid & 1)) return false;
+  for (int c = 0; c < lp.fold_grid; ++c) {
+    const int b0 = lp.cta_off[c], b1 = lp.cta_off[c + 1];
+    if (b1 - b0 > kTrunkMaxBands) return false;
+    int slots = 2;
+    for (int b = b0; b < b1; ++b) slots += lp.bands[b].rows + 2;
+    if (slots > kTrunkMaxRows) return false;
+  }
+  return true;
+}
+
 bool trunk_schedule_fits(const LevelPlan& lp) {
   for (int c = 0; c < lp.fold_grid; ++c) {
     const int b0 = lp.cta_off[c], b1 = lp.cta_off[c + 1];
@@ -522,6 +599,10 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
   // level-0 schedule must fit the TMEM-resident trunk kernel; other paths keep the whole frame in one batch.
   const bool l2_groups = h->cfg.conv_impl == 0;
   const int64_t cap = h->cfg.max_batch_pixels > 0 ? h->cfg.max_batch_pixels : (l2_groups ? (int64_t)150000 : (int64_t)3 << 20);
+  const bool pairs = l2_groups && h->use_pairs && h->num_sms >= 2;
+  // level-0 schedule of a group and whether a TMEM-resident trunk kernel can run it
+  auto sched0 = [&](Batch& bb) { layout_level(bb, 0); build_fold_schedule(bb, 0, h->num_sms, pairs); };
+  auto fits0 = [&](const Batch& bb) { return bb.lv[0].paired ? trunk2_schedule_fits(bb.lv[0]) : trunk_schedule_fits(bb.lv[0]); };
   size_t i = 0;
   while (i < all.size()) {
     Batch b;
@@ -531,26 +612,31 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
       if (!b.tiles.empty() && px + n > cap) break;
       b.tiles.push_back(all[i]);
       if (l2_groups && b.tiles.size() > 1) {                    // would the group still fit the trunk kernel?
-        layout_level(b, 0); build_fold_schedule(b, 0, h->num_sms);
-        if (!trunk_schedule_fits(b.lv[0])) { b.tiles.pop_back(); break; }
+        sched0(b);
+        if (!fits0(b)) { b.tiles.pop_back(); break; }
       }
       px += n;
       ++i;
     }
-    for (int l = 0; l < 3; ++l) { layout_level(b, l); build_fold_schedule(b, l, h->num_sms); }
     if (l2_groups && i == all.size() && !h->batches.empty() && px * 5 < cap * 2) {
       // A small tail group pays the trunk's per-pass latency (414 dependent passes) for almost no work: fold it into the
       // previous group when the combined schedule still fits the trunk kernel.
       Batch m = h->batches.back();
       m.tiles.insert(m.tiles.end(), b.tiles.begin(), b.tiles.end());
-      layout_level(m, 0); build_fold_schedule(m, 0, h->num_sms);
-      if (trunk_schedule_fits(m.lv[0])) {
+      sched0(m);
+      if (fits0(m)) {
         h->batches.pop_back();
         b = std::move(m);
-        for (int l = 0; l < 3; ++l) { layout_level(b, l); build_fold_schedule(b, l, h->num_sms); }
       }
     }
-    b.trunk_fits = l2_groups && trunk_schedule_fits(b.lv[0]);
+    for (int l = 1; l < 3; ++l) { layout_level(b, l); build_fold_schedule(b, l, h->num_sms); }
+    sched0(b);
+    b.trunk_fits = l2_groups && fits0(b);
+    if (l2_groups && !b.trunk_fits && b.lv[0].paired) {          // pairs do not fit: try the single-CTA kernel's schedule
+      layout_level(b, 0); build_fold_schedule(b, 0, h->num_sms, false);
+      b.trunk_fits = trunk_schedule_fits(b.lv[0]);
+    }
+    b.trunk_pairs = b.trunk_fits && b.lv[0].paired;
     if (b.trunk_fits) {
       build_trunk_deps(b.lv[0]);
       b.trunk_fits = !b.lv[0].deps.empty();
@@ -798,7 +884,7 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
         tm.full[i2] = a.f_d[i2];
         for (int k = 0; k < 4; ++k) tm.box[i2][k] = a.b_d[i2][k];
       }
-      tm.w = fold_weight_map(h, 32);
+      tm.w = b.trunk_pairs ? h->m_wf[0] : fold_weight_map(h, 32);   // pairs: 48-row boxes = one CTA's half of a 96-row folded box
     }
     if (time_trunk) {                  // events on the launching stream around the dominant kernel
       while ((int)h->ev_trunk.size() < 2 * (h->n_trunk_timed + 1)) {
@@ -808,7 +894,9 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
       }
       cudaEventRecord(h->ev_trunk[2 * h->n_trunk_timed], s);
     }
-    cudaError_t eb = b.trunk_fits
+    cudaError_t eb = b.trunk_pairs
+        ? launch_conv3x3_trunk2(tm, b.d_body_passes, b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s)
+        : b.trunk_fits
         ? launch_conv3x3_trunk(tm, b.d_body_passes, b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s)
         : launch_conv3x3_body(a.f_d[0], a.f_d[1], a.e_d[0], a.e_d[1], fold_weight_map(h, 32), b.d_body_passes,
                               b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s);
@@ -990,7 +1078,7 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
       (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
       (e = cudaEventCreate(&h->evc0)) != cudaSuccess || (e = cudaEventCreate(&h->evc1)) != cudaSuccess ||
       (e = conv3x3_tc_configure()) != cudaSuccess || (e = conv3x3_fold_configure()) != cudaSuccess ||
-      (e = conv3x3_body_configure()) != cudaSuccess || (e = conv3x3_trunk_configure()) != cudaSuccess || (e = cudaMalloc(&h->d_gbar, 1024 * 128)) != cudaSuccess) {
+      (e = conv3x3_body_configure()) != cudaSuccess || (e = conv3x3_trunk_configure()) != cudaSuccess || (e = conv3x3_trunk2_configure()) != cudaSuccess || (e = cudaMalloc(&h->d_gbar, 1024 * 128)) != cudaSuccess) {
     std::string msg = cudaGetErrorString(e);
     nesr_b200_destroy(h);
     return fail(nullptr, NESR_E_CUDA, "device setup failed: %s", msg.c_str());
@@ -998,6 +1086,7 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
   build_layers(h);
   if (const char* dbg = getenv("NESR_B200_DEBUG_FLAGS")) h->debug_flags = atoi(dbg);
   if (const char* pin = getenv("NESR_B200_L2_PIN")) h->l2_pin_chunks = atoi(pin);
+  if (const char* pr = getenv("NESR_B200_PAIRS")) h->use_pairs = atoi(pr);
   *out = h;
   return NESR_OK;
 }

@@ -39,6 +39,12 @@ cudaError_t conv3x3_trunk_configure();
 cudaError_t launch_conv3x3_trunk(const TrunkMaps& maps, const ConvParams* d_passes, int npass, unsigned* d_prog, int grid,
                                  cudaStream_t stream);
 
+// --- conv3x3_trunk2.cu : the same trunk kernel on CTA pairs (cta_group::2, M = 256): CTAs 2p / 2p+1 own bands of identical
+//     shape, the leader issues the MMAs of both SMs; `maps.w` must be the 48-row weight box map; grid must be even
+cudaError_t conv3x3_trunk2_configure();
+cudaError_t launch_conv3x3_trunk2(const TrunkMaps& maps, const ConvParams* d_passes, int npass, unsigned* d_prog, int grid,
+                                  cudaStream_t stream);
+
 // --- conv3x3_simt.cu : plain CUDA-core conv over the same buffers (test-only cross-check) -------
 cudaError_t launch_conv3x3_simt(const ConvParams& p, cudaStream_t stream);
 

@@ -230,6 +230,80 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// ------------------------------------------------------------------------------------------
+// CTA pairs (cta_group::2): two CTAs of one cluster drive both SMs' tensor cores with ONE tcgen05.mma (M = 256: each
+// CTA supplies 128 rows of A and half of B's N rows from the same shared-memory offsets, and receives its 128 rows of D
+// at the same TMEM address).  Only the leader (cluster rank 0) issues MMAs; barriers it waits on collect arrivals and TMA
+// bytes from both CTAs through shared::cluster addresses; its commits are multicast to both CTAs' barriers.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+// RELAXED on purpose: a .release.cluster arrive compiles to MEMBAR.ALL.GPU + arrive (measured: +4 ms per tile group when
+// every slab's arrive carried one).  The producers publish nothing through these arrives (the data arrives with the TMA's
+// own complete_tx), and the epilogue's TMEM accesses are ordered by tcgen05.wait + tcgen05.fence::before_thread_sync.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose completion bytes are signalled on a barrier of either CTA of the pair
+__device__ __forceinline__ void tma_load_2d_hint_2sm(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int32_t c0,
+                                                     int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t ncols) {   // whole warp, in both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// commit of cta_group::2 MMAs, multicast to the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+#define NESR_UMMA2_STEP(K)                                             \
+  "add.u32 ta, %1, " #K ";\n\t"                                        \
+  "add.u32 tb, %2, " #K ";\n\t"                                        \
+  "mov.b64 da, {ta, %3};\n\t"                                          \
+  "mov.b64 db, {tb, %3};\n\t"                                          \
+  "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t"
+template <int KS>
+__device__ __forceinline__ void umma2_f16_ksteps(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+  static_assert(KS == 2 || KS == 4, "trunk chunks have 2 or 4 k-steps");
+  if constexpr (KS == 2) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 ta, tb;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 NESR_UMMA2_STEP(0) NESR_UMMA2_STEP(2) "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 ta, tb;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 NESR_UMMA2_STEP(0) NESR_UMMA2_STEP(2) NESR_UMMA2_STEP(4) NESR_UMMA2_STEP(6) "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc) : "memory");
+  }
+}
+// M = 256 instruction descriptor (cta_group::2), kind::f16, fp32 accumulate, K-major A and B
+__host__ __device__ __forceinline__ uint32_t umma_idesc_f16_m256(uint32_t hw_fmt, uint32_t n) {
+  return (1u << 4) | (hw_fmt << 7) | (hw_fmt << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24);
+}
+
 // TMEM -> registers: each thread of the warp reads 16 consecutive 32-bit columns of its own lane
 // (warp w of the CTA may only touch lanes 32*(w%4) .. 32*(w%4)+31).
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
