@@ -37,8 +37,10 @@
 //   Here the two CTAs of a cluster own bands of IDENTICAL shape (engine.cu build_pair_schedule) and the leader issues
 //   M = 256 MMAs that drive both SMs' tensor cores: the same instruction stream now feeds twice the pixels.  Each CTA
 //   loads its own row slabs and HALF of the weights (48 of the 96 folded rows of every [dx] box); slab and weight
-//   barriers live in the leader and collect both CTAs' TMA bytes through shared::cluster addresses; commits are
-//   multicast to both CTAs; the follower's epilogue warps return TMEM slots with remote arrives.
+//   barriers live in the leader; commits are multicast to both CTAs; the follower's epilogue warps return TMEM slots
+//   with remote arrives.  The follower's TMA loads complete on LOCAL barriers and its (otherwise idle) MMA warp relays
+//   each completion to the leader with one remote arrive: letting the follower's TMA signal the leader's barrier directly
+//   (cta_group::2 TMA, complete_tx across the pair) made every slab take ~1.6k cycles to land.
 //   N is always 96 (a narrower MMA would need a different half of B in each CTA), so every band carries two junk
 //   row slots above and below its output rows; they are never read or zeroed.
 #include <stdio.h>
@@ -52,7 +54,9 @@ namespace nesr {
 namespace {
 
 constexpr int COUT = 32;
-constexpr int kThreads = 320;
+constexpr int kEpiWarps = 16;                          // 2 row groups x 2 channel halves x 4 TMEM lane quarters
+constexpr int kEC = COUT / 2;                          // channels per epilogue thread
+constexpr int kThreads = 64 + 32 * kEpiWarps;          // 576
 constexpr int kSlabPx = 136;
 constexpr int kSlabBytes = kSlabPx * 128;              // 17408
 constexpr int kStages = 8;                             // activation slab ring
@@ -85,7 +89,8 @@ struct BandInfo {                                      // one band of this CTA, 
 struct Shared {
   uint64_t wfull[kWStages], wempty[kWStages];
   uint64_t full[kStages], empty[kStages];
-  uint64_t tfull[kSlots], tempty[kSlots];       // tempty: 8 arrivals (one per epilogue warp of the group, both CTAs)
+  uint64_t lfull[kStages], lwfull[kWStages];            // follower only: its own TMA completions, relayed to the leader's full / wfull
+  uint64_t tfull[kSlots], tempty[kSlots];       // tempty: 16 arrivals (the 8 epilogue warps that share a row, in both CTAs)
   uint32_t tmem_slot;
   int32_t nband;
   BandInfo band[kMaxBands];
@@ -117,7 +122,7 @@ __device__ __forceinline__ void st_release_gpu(unsigned* ptr, unsigned v) {
 }
 constexpr int kProgStride = 32;                        // one 128-byte line per CTA
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // The fields of a pass the TMA producer / MMA issuer need, fetched one pass ahead.
 struct PassHead {
@@ -141,10 +146,16 @@ __device__ __forceinline__ PassHead load_head(const ConvParams* passes, int pass
 template <int KS, bool FIRST, bool LAST>
 __device__ __forceinline__ void sweep_band2(Shared& sh, const int rows, const int slot0, const uint32_t tmem_base, const uint32_t id96,
                                             const uint32_t hi, const uint32_t a_lo0, const uint32_t w_lo, const uint32_t tparity,
-                                            int& stage, uint32_t& phase, const bool mma_on) {
+                                            int& stage, uint32_t& phase, const bool mma_on, const int prof_pass = -1) {
   constexpr uint32_t kSlabLo = kSlabBytes >> 4, kWBoxLo = kWBoxBytes >> 4;
-  if (FIRST) mbar_wait(&sh.tempty[slot0 + 2], tparity ^ 1);
-  mbar_wait(&sh.full[stage], phase);
+#if NESR_PROF
+  long long w_te = 0, w_fu = 0, tq;
+#define WAITP(acc, stmt) do { tq = clock64(); stmt; acc += clock64() - tq; } while (0)
+#else
+#define WAITP(acc, stmt) do { stmt; } while (0)
+#endif
+  if (FIRST) WAITP(w_te, mbar_wait(&sh.tempty[slot0 + 2], tparity ^ 1));
+  WAITP(w_fu, mbar_wait(&sh.full[stage], phase));
   tc_fence_after();
   for (int i = -1; i <= rows; ++i) {
     const uint32_t d = tmem_base + static_cast<uint32_t>(slot0 + i + 1) * COUT;
@@ -153,8 +164,8 @@ __device__ __forceinline__ void sweep_band2(Shared& sh, const int rows, const in
     // while those run: is the next input row ready?  (output row i+2 is first touched by input row i+1)
     const int nstage = stage + 1 == kStages ? 0 : stage + 1;
     if (i < rows) {
-      if (FIRST && i + 2 <= rows - 1) mbar_wait(&sh.tempty[slot0 + 2 + i + 2], tparity ^ 1);
-      mbar_wait(&sh.full[nstage], nstage == 0 ? phase ^ 1 : phase);
+      if (FIRST && i + 2 <= rows - 1) WAITP(w_te, mbar_wait(&sh.tempty[slot0 + 2 + i + 2], tparity ^ 1));
+      WAITP(w_fu, mbar_wait(&sh.full[nstage], nstage == 0 ? phase ^ 1 : phase));
       tc_fence_after();
     }
     if (mma_on) {
@@ -166,6 +177,9 @@ __device__ __forceinline__ void sweep_band2(Shared& sh, const int rows, const in
     stage = nstage;
     if (stage == 0) phase ^= 1;
   }
+#if NESR_PROF
+  if (prof_pass >= 0 && prof_pass < kTracePasses) { sh.epi_acc[0][prof_pass] += w_te; sh.epi_acc[1][prof_pass] += w_fu; }
+#endif
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -186,8 +200,9 @@ conv3x3_trunk2_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* 
     tma_prefetch_desc(&maps.w);
     // full / wfull / tempty are waited on in the leader only and collect arrivals from both CTAs
     for (int i = 0; i < kWStages; ++i) { mbar_init(&sh.wfull[i], 2); mbar_init(&sh.wempty[i], 1); }
-    for (int i = 0; i < kStages; ++i) { mbar_init(&sh.full[i], 2); mbar_init(&sh.empty[i], 1); }
-    for (int i = 0; i < kSlots; ++i) { mbar_init(&sh.tfull[i], 1); mbar_init(&sh.tempty[i], 8); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sh.full[i], 2); mbar_init(&sh.empty[i], 1); mbar_init(&sh.lfull[i], 1); }
+    for (int i = 0; i < kWStages; ++i) mbar_init(&sh.lwfull[i], 1);
+    for (int i = 0; i < kSlots; ++i) { mbar_init(&sh.tfull[i], 1); mbar_init(&sh.tempty[i], 16); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -275,9 +290,6 @@ conv3x3_trunk2_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* 
     const int plane_px = __ldg(&passes[0].src_plane_px);
     const uint64_t keep = l2_policy_evict_last();               // dense-block activations and weights: stay in L2
     const unsigned* my_dep = prog + static_cast<size_t>(__ldg(passes[0].trunk_deps + blockIdx.x * kTrunkMaxDeps + lane)) * kProgStride;
-    // the slab and weight barriers the MMA issuer waits on live in the leader: shared::cluster addresses of rank 0
-    const uint32_t full0 = mapa_cluster(smem_u32(&sh.full[0]), 0);
-    const uint32_t wfull0 = mapa_cluster(smem_u32(&sh.wfull[0]), 0);
     PassHead h = load_head(passes, 0, npass);
     for (int pass = 0; pass < npass; ++pass) {
       const PassHead nh = load_head(passes, pass + 1, npass);   // next pass, fetched early
@@ -288,11 +300,12 @@ conv3x3_trunk2_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* 
         // weights of (pass, chunk): depend on nobody
         mbar_wait(&sh.wempty[ws], wphase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx_cluster(wfull0 + ws * 8, kWChunkBytes);
+          uint64_t* wbar = cta_rank == 0 ? &sh.wfull[ws] : &sh.lwfull[ws];
+          mbar_arrive_expect_tx(wbar, kWChunkBytes);
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx)                          // this CTA's half of the 96 folded rows of every [dx] box
-            tma_load_2d_hint_2sm(wring + ws * kWChunkBytes + dx * kWBoxBytes, &maps.w, wfull0 + ws * 8, 0,
-                                 h.w_row0 + (dx * nchunk + c) * 3 * COUT + static_cast<int>(cta_rank) * (3 * COUT / 2), keep);
+            tma_load_2d_hint(wring + ws * kWChunkBytes + dx * kWBoxBytes, &maps.w, wbar, 0,
+                             h.w_row0 + (dx * nchunk + c) * 3 * COUT + static_cast<int>(cta_rank) * (3 * COUT / 2), keep);
         }
         __syncwarp();
         if (++ws == kWStages) { ws = 0; wphase ^= 1; }
@@ -323,18 +336,18 @@ conv3x3_trunk2_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* 
           for (int i = 0; i < nrow; ++i) {
             mbar_wait(&sh.empty[stage], phase ^ 1);
             if (elect_one()) {
-              const uint32_t fbar = full0 + stage * 8;
+              uint64_t* fbar = cta_rank == 0 ? &sh.full[stage] : &sh.lfull[stage];
               if (h.dbg & 4) {
-                mbar_arrive_cluster(fbar);
+                mbar_arrive(fbar);
               } else {
-                mbar_arrive_expect_tx_cluster(fbar, row_bytes);
+                mbar_arrive_expect_tx(fbar, row_bytes);
                 uint8_t* slab = ring + stage * kSlabBytes;
                 if (full_strip) {
-                  tma_load_2d_hint_2sm(slab, amap, fbar, 0, plane + bi.op_px[0] + i * bi.op_pitch[0], keep);
+                  tma_load_2d_hint(slab, amap, fbar, 0, plane + bi.op_px[0] + i * bi.op_pitch[0], keep);
                 } else {
                   for (int k = 0; k < bi.nop; ++k)
-                    tma_load_2d_hint_2sm(slab + bi.op_off[k], bmap + bi.op_box[k], fbar, 0,
-                                         plane + bi.op_px[k] + i * bi.op_pitch[k], keep);
+                    tma_load_2d_hint(slab + bi.op_off[k], bmap + bi.op_box[k], fbar, 0,
+                                     plane + bi.op_px[k] + i * bi.op_pitch[k], keep);
                 }
               }
             }
@@ -376,14 +389,14 @@ conv3x3_trunk2_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* 
           for (int b = 0; b < nband; ++b) {
             const int rows = sh.band[b].rows, slot0 = sh.band[b].slot0;
             switch (variant) {                                  // trunk passes only have 4- and 2-k-step chunks
-              case 0: sweep_band2<4, false, false>(sh, rows, slot0, tmem_base, id96, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
-              case 1: sweep_band2<4, false, true>(sh, rows, slot0, tmem_base, id96, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
-              case 2: sweep_band2<4, true, false>(sh, rows, slot0, tmem_base, id96, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
-              case 3: sweep_band2<4, true, true>(sh, rows, slot0, tmem_base, id96, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
-              case 4: sweep_band2<2, false, false>(sh, rows, slot0, tmem_base, id96, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
-              case 5: sweep_band2<2, false, true>(sh, rows, slot0, tmem_base, id96, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
-              case 6: sweep_band2<2, true, false>(sh, rows, slot0, tmem_base, id96, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
-              default: sweep_band2<2, true, true>(sh, rows, slot0, tmem_base, id96, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
+              case 0: sweep_band2<4, false, false>(sh, rows, slot0, tmem_base, id96, hi, a_lo0, w_lo, tparity, stage, phase, mma_on, pass); break;
+              case 1: sweep_band2<4, false, true>(sh, rows, slot0, tmem_base, id96, hi, a_lo0, w_lo, tparity, stage, phase, mma_on, pass); break;
+              case 2: sweep_band2<4, true, false>(sh, rows, slot0, tmem_base, id96, hi, a_lo0, w_lo, tparity, stage, phase, mma_on, pass); break;
+              case 3: sweep_band2<4, true, true>(sh, rows, slot0, tmem_base, id96, hi, a_lo0, w_lo, tparity, stage, phase, mma_on, pass); break;
+              case 4: sweep_band2<2, false, false>(sh, rows, slot0, tmem_base, id96, hi, a_lo0, w_lo, tparity, stage, phase, mma_on, pass); break;
+              case 5: sweep_band2<2, false, true>(sh, rows, slot0, tmem_base, id96, hi, a_lo0, w_lo, tparity, stage, phase, mma_on, pass); break;
+              case 6: sweep_band2<2, true, false>(sh, rows, slot0, tmem_base, id96, hi, a_lo0, w_lo, tparity, stage, phase, mma_on, pass); break;
+              default: sweep_band2<2, true, true>(sh, rows, slot0, tmem_base, id96, hi, a_lo0, w_lo, tparity, stage, phase, mma_on, pass); break;
             }
             if (last_chunk && b == 0) TS(5, pass);
           }
@@ -393,19 +406,48 @@ conv3x3_trunk2_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* 
         }
         h = nh;
       }
+    } else if (cta_rank != 0 && elect_one()) {
+      // =========================== follower: relay of its own TMA completions ===========================
+      const uint32_t full0 = mapa_cluster(smem_u32(&sh.full[0]), 0);
+      const uint32_t wfull0 = mapa_cluster(smem_u32(&sh.wfull[0]), 0);
+      int stage = 0; uint32_t phase = 0;
+      int ws = 0; uint32_t wphase = 0;
+      PassHead h = load_head(passes, 0, npass);
+      for (int pass = 0; pass < npass; ++pass) {
+        const PassHead nh = load_head(passes, pass + 1, npass);
+        const int nchunk = (h.cin + kChunkChannels - 1) / kChunkChannels;
+        for (int c = 0; c < nchunk; ++c) {
+          mbar_wait(&sh.lwfull[ws], wphase);
+          mbar_arrive_cluster(wfull0 + ws * 8);
+          if (++ws == kWStages) { ws = 0; wphase ^= 1; }
+          for (int b = 0; b < nband; ++b) {
+            const int nrow = sh.band[b].rows + 2;
+            for (int i = 0; i < nrow; ++i) {
+              mbar_wait(&sh.lfull[stage], phase);
+              mbar_arrive_cluster(full0 + stage * 8);
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+        h = nh;
+      }
     }
     __syncwarp();
   } else {
-    // =========================== epilogue (warps 2..9) ===========================
-    const int quarter = warp & 3;
-    const int group = (warp - 2) >> 2;                          // rows alternate between the two epilogue groups
+    // =========================== epilogue (warps 2..17) ===========================
+    // With the MMAs of two SMs issued by one thread the epilogue became the bottleneck of the last sweep of a pass (a
+    // lone warp per scheduler issues a dependent instruction every ~4 cycles).  16 warps: each row is shared by two warps
+    // per TMEM lane quarter (16 of the 32 output channels each), rows alternate between two such sets.
+    const int quarter = warp & 3;                               // TMEM lanes this warp may touch: 32*(warp % 4)
+    const int ew = (warp - 2) >> 2;                             // 0..3, distinct for the four warps of a quarter
+    const int half = ew & 1;                                    // channel half
+    const int group = ew >> 1;                                  // row group
+    const int cb = half * kEC;                                  // first of this thread's channels within the pass's 32
     const int m = quarter * 32 + lane;                          // TMEM lane == MMA row == pixel
-    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + cb;
     const uint32_t tempty0 = mapa_cluster(smem_u32(&sh.tempty[0]), 0);      // the issuer (leader) waits on its own copies
     for (int pass = 0; pass < npass; ++pass) {
-      // The epilogue warps are instruction-latency bound (one or two warps per scheduler, ~4 cycles per dependent
-      // instruction): the generic epilogue16() path cost ~300 instructions = 1200 cycles per row.  A trunk pass is one of
-      // two kinds, fixed for the whole pass, so the row loop below is straight-line code specialised at pass level:
+      // A trunk pass is one of two kinds, fixed for the whole pass, so the row loop is straight-line code:
       //   conv1..4 : v = lrelu(acc + bias)                               -> 16-bit, channels [coff, coff+32) of this buffer
       //   conv5    : v = (acc + bias)*0.2 + trunk [; v = v*0.2 + rrdb_in] -> fp32 trunk [+ rrdb], 16-bit x of the next block
       const ConvParams* pp = passes + pass;
@@ -415,14 +457,14 @@ conv3x3_trunk2_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* 
       float* dst32a = pp->dst32a;
       float* dst32b = pp->dst32b;
       const float s1 = pp->s1, s2 = pp->s2;
-      const int c_off = pp->c_off, fmt16 = pp->dst16_fmt, lrelu = pp->lrelu;
-      const int coff16 = pp->dst16_coff;
+      const int c_off = pp->c_off + cb, fmt16 = pp->dst16_fmt, lrelu = pp->lrelu;
+      const int coff16 = pp->dst16_coff + cb;
       uint16_t* const base16 = reinterpret_cast<uint16_t*>(pp->dst16) + static_cast<size_t>(coff16 >> 6) * pp->dst16_plane_px * 64 + (coff16 & 63);
-      float bias_r[COUT];                                       // once per pass, in registers
+      float bias_r[kEC];                                        // once per pass, in registers
       {
-        const float4* b4 = reinterpret_cast<const float4*>(pp->bias);
+        const float4* b4 = reinterpret_cast<const float4*>(pp->bias + cb);
 #pragma unroll
-        for (int k = 0; k < COUT / 4; ++k) {
+        for (int k = 0; k < kEC / 4; ++k) {
           const float4 bv = __ldg(b4 + k);
           bias_r[4 * k] = bv.x; bias_r[4 * k + 1] = bv.y; bias_r[4 * k + 2] = bv.z; bias_r[4 * k + 3] = bv.w;
         }
@@ -437,77 +479,67 @@ conv3x3_trunk2_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* 
           if ((slot & 1) != group) continue;
           const bool lane_on = band_on && j < my_rows;
           const int P = px0 + j * pitch;
-          // blocked fp32 trunk layout: [pixel/32][ch/8][pixel%32][ch%8]; this lane's 32 channels are 4 runs of 8 floats
+          // blocked fp32 trunk layout: [pixel/32][ch/8][pixel%32][ch%8]; this thread's 16 channels are 2 runs of 8 floats
           const size_t toff = (static_cast<size_t>(P >> 5) * 8 + (c_off >> 3)) * 256 + (static_cast<size_t>(P & 31) << 3);
           // residual rows are fetched BEFORE waiting for the accumulator: their latency hides behind the MMAs
-          float r1[COUT], r2[COUT];
+          float r1[kEC], r2[kEC];
           if (lane_on && res1) {
 #pragma unroll
-            for (int q = 0; q < COUT / 8; ++q) ldg256_stream(res1 + toff + q * 256, &r1[q * 8]);
+            for (int q = 0; q < kEC / 8; ++q) ldg256_stream(res1 + toff + q * 256, &r1[q * 8]);
           }
           if (lane_on && res2) {
 #pragma unroll
-            for (int q = 0; q < COUT / 8; ++q) ldg256_stream(res2 + toff + q * 256, &r2[q * 8]);
+            for (int q = 0; q < kEC / 8; ++q) ldg256_stream(res2 + toff + q * 256, &r2[q * 8]);
           }
-          EPI_T(et0);
           mbar_wait(&sh.tfull[slot], tparity);
-          EPI_T(et1);
           tc_fence_after();
           __syncwarp();
           const uint32_t taddr = lane_base + static_cast<uint32_t>(slot) * COUT;
-          uint32_t r[COUT / 16][16];
-#pragma unroll
-          for (int c = 0; c < COUT / 16; ++c) tmem_ld16(taddr + c * 16, r[c]);
+          uint32_t r[16];
+          tmem_ld16(taddr, r);
           tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < COUT / 16; ++c) tmem_st16_zero(taddr + c * 16);
+          tmem_st16_zero(taddr);
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(tempty0 + slot * 8);
-          EPI_T(et2);
           if (lane_on) {
-            float v[COUT];
+            float v[kEC];
 #pragma unroll
-            for (int k = 0; k < COUT; ++k) v[k] = __uint_as_float(r[k >> 4][k & 15]) + bias_r[k];
+            for (int k = 0; k < kEC; ++k) v[k] = __uint_as_float(r[k]) + bias_r[k];
             if (!res1) {
               if (lrelu) {
 #pragma unroll
-                for (int k = 0; k < COUT; ++k) v[k] = fmaxf(v[k], 0.2f * v[k]);     // LeakyReLU(0.2): slope < 1
+                for (int k = 0; k < kEC; ++k) v[k] = fmaxf(v[k], 0.2f * v[k]);      // LeakyReLU(0.2): slope < 1
               }
             } else {
 #pragma unroll
-              for (int k = 0; k < COUT; ++k) v[k] = fmaf(v[k], s1, r1[k]);
+              for (int k = 0; k < kEC; ++k) v[k] = fmaf(v[k], s1, r1[k]);
               if (res2) {
 #pragma unroll
-                for (int k = 0; k < COUT; ++k) v[k] = fmaf(v[k], s2, r2[k]);
+                for (int k = 0; k < kEC; ++k) v[k] = fmaf(v[k], s2, r2[k]);
               }
               if (!(dbg & 4096)) {
 #pragma unroll
-                for (int q = 0; q < COUT / 8; ++q) stg256f_stream(dst32a + toff + q * 256, &v[q * 8]);
+                for (int q = 0; q < kEC / 8; ++q) stg256f_stream(dst32a + toff + q * 256, &v[q * 8]);
                 if (dst32b) {
 #pragma unroll
-                  for (int q = 0; q < COUT / 8; ++q) stg256f_stream(dst32b + toff + q * 256, &v[q * 8]);
+                  for (int q = 0; q < kEC / 8; ++q) stg256f_stream(dst32b + toff + q * 256, &v[q * 8]);
                 }
               }
             }
             if (!(dbg & 16)) {
-              uint32_t w[COUT / 2];
+              uint32_t w[kEC / 2];
               if (fmt16) {
 #pragma unroll
-                for (int k = 0; k < COUT / 2; ++k) w[k] = pack2(v[2 * k], v[2 * k + 1], 1);
+                for (int k = 0; k < kEC / 2; ++k) w[k] = pack2(v[2 * k], v[2 * k + 1], 1);
               } else {
 #pragma unroll
-                for (int k = 0; k < COUT / 2; ++k) w[k] = pack2(v[2 * k], v[2 * k + 1], 0);
+                for (int k = 0; k < kEC / 2; ++k) w[k] = pack2(v[2 * k], v[2 * k + 1], 0);
               }
-              uint16_t* dst = base16 + static_cast<size_t>(P) * 64;
-              stg256(dst, reinterpret_cast<const uint32_t(&)[8]>(w[0]));
-              stg256(dst + 16, reinterpret_cast<const uint32_t(&)[8]>(w[8]));
+              stg256(base16 + static_cast<size_t>(P) * 64, w);
             }
           }
-#if NESR_PROF
-          { const long long et3 = clock64(); EPI_ACC(0, pass, et1 - et0); EPI_ACC(1, pass, et2 - et1); EPI_ACC(2, pass, et3 - et2); EPI_ACC(3, pass, 1); }
-#endif
         }
       }
       // publish the pass: generic-proxy stores -> TMA (async proxy) reads of any CTA
@@ -533,7 +565,7 @@ conv3x3_trunk2_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* 
       printf("[trunk blk %d pass %d cin=%d] acquired %lld  first_full_last_chunk %lld  mma_issued %lld  epi_rows_done %lld  epi_synced %lld  published %lld\n",
              (int)blockIdx.x, q, passes[q].cin, sh.ts[4][q] - t0, sh.ts[5][q] - t0, sh.ts[0][q] - t0, sh.ts[1][q] - t0, sh.ts[2][q] - t0, sh.ts[3][q] - t0);
     for (int q = 0; q < kTracePasses && q < npass; ++q)
-      printf("[trunk epi blk %d pass %d cin=%d] rows %lld  wait_tfull %lld  tmem_ld_zero_arrive %lld  math_stores %lld\n", (int)blockIdx.x, q,
+      printf("[trunk mma blk %d pass %d cin=%d] rows %lld  wait_tempty %lld  wait_full %lld  x %lld\n", (int)blockIdx.x, q,
              passes[q].cin, sh.epi_acc[3][q], sh.epi_acc[0][q], sh.epi_acc[1][q], sh.epi_acc[2][q]);
   }
 #endif
