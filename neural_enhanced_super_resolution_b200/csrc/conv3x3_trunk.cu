@@ -27,6 +27,11 @@
 //   warp polls the words of its halo neighbours (host-built list, one lane each) and of its own CTA.  A
 //   slow CTA delays its neighbours, not all 148 SMs (the grid-wide counter cost 5-22k cycles of skew per pass).
 //   The epilogue warps publish a pass with their own named barrier; TMA and MMA warps never stop.
+//   TWO BAND SETS PER CTA.  Even so, a pass is a dependency chain (last sweep -> epilogue tail -> proxy fence + release
+//   -> neighbours' acquire -> first slab) of ~6 us with NO work in it, and every pass of a group pays it: groups ran
+//   at ~12 us per pass whatever their size.  The schedule therefore gives each CTA two band sets far apart in the strip
+//   sequence (ideally different tiles) and the kernel alternates (pass k, set 0), (pass k, set 1), (pass k+1, set 0) ...:
+//   while one set's chain is in flight the CTA works on the other.  Progress words and halo lists are per (CTA, set).
 //
 // Roles (fold_roles.cuh explains the row fold itself): warp 0 TMA producer (weights + row slabs), warp 1
 // MMA issuer, warps 2..9 epilogue (two groups alternating rows).  Launched cooperatively (grid <= #SMs).
@@ -76,7 +81,7 @@ struct Shared {
   uint64_t full[kStages], empty[kStages];
   uint64_t tfull[kSlots], tempty[kSlots];
   uint32_t tmem_slot;
-  int32_t nband;
+  int32_t nband, nband0;                                // bands of this CTA; the first nband0 are set 0, the rest set 1
   BandInfo band[kMaxBands];
   int32_t lane_px[kMaxBands][128];                     // flat pixel of (r0, x) of each MMA lane, or -1 (masked lane)
   int32_t lane_pitch[kMaxBands][128];
@@ -202,6 +207,7 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
     const int nband = min(band_end - band_begin, kMaxBands);
     if (threadIdx.x == 0) {
       sh.nband = nband;
+      sh.nband0 = min(__ldg(p0.trunk_split + blockIdx.x), nband);
       int slot0 = 0;
       for (int b = 0; b < nband; ++b) {
         const FoldBand band = p0.bands[band_begin + b];
@@ -265,24 +271,29 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const int nband = sh.nband;
+  const int nband = sh.nband, nband0 = sh.nband0;
+  const int nsets = nband0 < nband ? 2 : 1;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
     int stage = 0; uint32_t phase = 0;                          // slab ring
     int ws = 0; uint32_t wphase = 0;                            // weight ring
-    unsigned known = 0;                                         // passes known to be complete on every halo neighbour
+    unsigned known[2] = {0, 0};                                 // passes known to be complete on every halo neighbour, per set
     const int plane_px = __ldg(&passes[0].src_plane_px);
     const uint64_t keep = l2_policy_evict_last();               // dense-block activations and weights: stay in L2
-    const unsigned* my_dep = prog + static_cast<size_t>(__ldg(passes[0].trunk_deps + blockIdx.x * kTrunkMaxDeps + lane)) * kProgStride;
+    const unsigned* my_dep[2];
+    for (int st = 0; st < 2; ++st)
+      my_dep[st] = prog + static_cast<size_t>(__ldg(passes[0].trunk_deps + (blockIdx.x * 2 + st) * kTrunkMaxDeps + lane)) * kProgStride;
     PassHead h = load_head(passes, 0, npass);
     for (int pass = 0; pass < npass; ++pass) {
       const PassHead nh = load_head(passes, pass + 1, npass);   // next pass, fetched early
       const int nchunk = (h.cin + kChunkChannels - 1) / kChunkChannels;
       const CUtensorMap* amap = &maps.full[h.src_sel ? 1 : 0];
       const CUtensorMap* bmap = &maps.box[h.src_sel ? 1 : 0][0];
+      for (int set = 0; set < nsets; ++set) {
+      const int sb0 = set == 0 ? 0 : nband0, sb1 = set == 0 ? nband0 : nband;
       for (int c = 0; c < nchunk; ++c) {
-        // weights of (pass, chunk): depend on nobody
+        // weights of (pass, set, chunk): depend on nobody
         mbar_wait(&sh.wempty[ws], wphase ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&sh.wfull[ws], kWChunkBytes);
@@ -294,24 +305,24 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
         if (++ws == kWStages) { ws = 0; wphase ^= 1; }
         // activations of this chunk: every CTA must have published the passes that wrote them
         const unsigned need = static_cast<unsigned>(c == 0 ? h.need0 : (c == 1 ? h.need1 : h.need2));
-        if (need > known) {
-          // every lane polls one neighbour (padding lanes: this CTA).  The spin is RELAXED: ld.acquire.gpu compiles to
+        if (need > known[set]) {
+          // every lane polls one neighbouring band set (padding lanes: this one).  The spin is RELAXED: ld.acquire.gpu compiles to
           // LDG.STRONG + CCTL.IVALL, and an L1 invalidation per poll made every L1-cached load of the epilogue warps
           // (bias) miss -- ~700 cycles per row.  One acquire after the last poll orders the TMA loads that follow.
-          if (ld_relaxed_gpu(my_dep) < need) {
+          if (ld_relaxed_gpu(my_dep[set]) < need) {
             const long long t0 = clock64();
-            while (ld_relaxed_gpu(my_dep) < need) {
+            while (ld_relaxed_gpu(my_dep[set]) < need) {
               if (clock64() - t0 > NESR_HANG_GUARD_CYCLES) __trap();
             }
           }
-          (void)ld_acquire_gpu(my_dep);
+          (void)ld_acquire_gpu(my_dep[set]);
           __syncwarp();
           fence_proxy_async_all();
-          known = need;
+          known[set] = need;
           if (lane == 0) TS(4, pass);
         }
         const int plane = c * plane_px;
-        for (int b = 0; b < nband; ++b) {
+        for (int b = sb0; b < sb1; ++b) {
           const BandInfo& bi = sh.band[b];
           const int nrow = bi.rows + 2;
           const bool full_strip = bi.full_strip != 0;
@@ -338,6 +349,7 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
           }
         }
       }
+      }
       h = nh;
     }
   } else if (warp == 1) {
@@ -358,6 +370,8 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
         const PassHead nh = load_head(passes, pass + 1, npass);
         const int nchunk = (h.cin + kChunkChannels - 1) / kChunkChannels;
         const uint32_t tparity = static_cast<uint32_t>(pass & 1);
+        for (int set = 0; set < nsets; ++set) {
+        const int sb0 = set == 0 ? 0 : nband0, sb1 = set == 0 ? nband0 : nband;
         for (int c = 0; c < nchunk; ++c) {
           const int rem = (h.cin - c * kChunkChannels) >> 4;
           const int ks = rem < 4 ? rem : 4;
@@ -367,7 +381,7 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
           const uint32_t w_lo = w_lo0 + ws * kWChunkLo;
           const bool mma_on = !(h.dbg & 2);
           const int variant = (ks == 4 ? 0 : 4) + (first_chunk ? 2 : 0) + (last_chunk ? 1 : 0);
-          for (int b = 0; b < nband; ++b) {
+          for (int b = sb0; b < sb1; ++b) {
             const int rows = sh.band[b].rows, slot0 = sh.band[b].slot0;
             switch (variant) {                                  // trunk passes only have 4- and 2-k-step chunks
               case 0: sweep_band<4, false, false>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
@@ -379,11 +393,12 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
               case 6: sweep_band<2, true, false>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
               default: sweep_band<2, true, true>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
             }
-            if (last_chunk && b == 0) TS(5, pass);
+            if (last_chunk && b == sb0) TS(5, pass);
           }
           umma_commit(&sh.wempty[ws]);
           if (++ws == kWStages) { ws = 0; wphase ^= 1; }
           if (last_chunk) TS(0, pass);
+        }
         }
         h = nh;
       }
@@ -421,7 +436,9 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
         }
       }
       const uint32_t tparity = static_cast<uint32_t>(pass & 1);
-      for (int b = 0; b < nband; ++b) {
+      for (int set = 0; set < nsets; ++set) {
+      const int sb0 = set == 0 ? 0 : nband0, sb1 = set == 0 ? nband0 : nband;
+      for (int b = sb0; b < sb1; ++b) {
         const int rows = sh.band[b].rows, slot0 = sh.band[b].slot0;
         const int px0 = sh.lane_px[b][m], pitch = sh.lane_pitch[b][m], my_rows = sh.lane_rows[b][m];
         const bool band_on = px0 >= 0 && !(dbg & 1);
@@ -504,12 +521,14 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
       }
       // publish the pass: generic-proxy stores -> TMA (async proxy) reads of any CTA
       if (threadIdx.x == 64) TS(1, pass);
+      if (__ldg(&pp->trunk_no_publish)) continue;               // (uniform) covered by the next pass's publish
       fence_proxy_async_all();
       epi_bar_sync();
       if (threadIdx.x == 64) {
         TS(2, pass);
-        st_release_gpu(prog + static_cast<size_t>(blockIdx.x) * kProgStride, static_cast<unsigned>(pass + 1));
+        st_release_gpu(prog + static_cast<size_t>(blockIdx.x * 2 + set) * kProgStride, static_cast<unsigned>(pass + 1));
         TS(3, pass);
+      }
       }
     }
   }
@@ -541,7 +560,7 @@ cudaError_t launch_conv3x3_trunk(const TrunkMaps& maps, const ConvParams* d_pass
                                  cudaStream_t stream) {
   if (grid <= 0 || npass <= 0) return cudaSuccess;
   if (grid > 1024) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaMemsetAsync(d_gbar, 0, static_cast<size_t>(grid) * kProgStride * sizeof(unsigned), stream);
+  cudaError_t e = cudaMemsetAsync(d_gbar, 0, static_cast<size_t>(2 * grid) * kProgStride * sizeof(unsigned), stream);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);

@@ -289,7 +289,7 @@ conv3x3_trunk2_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* 
     unsigned known = 0;                                         // passes known to be complete on every halo neighbour
     const int plane_px = __ldg(&passes[0].src_plane_px);
     const uint64_t keep = l2_policy_evict_last();               // dense-block activations and weights: stay in L2
-    const unsigned* my_dep = prog + static_cast<size_t>(__ldg(passes[0].trunk_deps + blockIdx.x * kTrunkMaxDeps + lane)) * kProgStride;
+    const unsigned* my_dep = prog + static_cast<size_t>(__ldg(passes[0].trunk_deps + (blockIdx.x * 2) * kTrunkMaxDeps + lane)) * kProgStride;
     PassHead h = load_head(passes, 0, npass);
     for (int pass = 0; pass < npass; ++pass) {
       const PassHead nh = load_head(passes, pass + 1, npass);   // next pass, fetched early
@@ -544,11 +544,12 @@ conv3x3_trunk2_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* 
       }
       // publish the pass: generic-proxy stores -> TMA (async proxy) reads of any CTA
       if (threadIdx.x == 64) TS(1, pass);
+      if (__ldg(&pp->trunk_no_publish)) continue;               // (uniform) covered by the next pass's publish
       fence_proxy_async_all();
       epi_bar_sync();
       if (threadIdx.x == 64) {
         TS(2, pass);
-        st_release_gpu(prog + static_cast<size_t>(blockIdx.x) * kProgStride, static_cast<unsigned>(pass + 1));
+        st_release_gpu(prog + static_cast<size_t>(blockIdx.x * 2) * kProgStride, static_cast<unsigned>(pass + 1));
         TS(3, pass);
       }
     }
@@ -581,7 +582,7 @@ cudaError_t launch_conv3x3_trunk2(const TrunkMaps& maps, const ConvParams* d_pas
                                  cudaStream_t stream) {
   if (grid <= 0 || npass <= 0) return cudaSuccess;
   if (grid > 1024 || (grid & 1)) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaMemsetAsync(d_gbar, 0, static_cast<size_t>(grid) * kProgStride * sizeof(unsigned), stream);
+  cudaError_t e = cudaMemsetAsync(d_gbar, 0, static_cast<size_t>(2 * grid) * kProgStride * sizeof(unsigned), stream);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);

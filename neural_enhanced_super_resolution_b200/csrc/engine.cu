@@ -60,8 +60,10 @@ struct LevelPlan {
   int32_t* d_cta_off = nullptr;
   int fold_grid = 0;
   bool paired = false;         // level 0: CTAs 2p / 2p+1 have bands of identical shape (CTA-pair trunk kernel)
-  std::vector<int32_t> deps;   // level 0 only: [grid][kTrunkMaxDeps] halo dependencies of the trunk kernel (empty: too many)
+  std::vector<int32_t> deps;   // level 0 only: [grid][2][kTrunkMaxDeps] halo dependencies of the trunk kernel (empty: too many)
   int32_t* d_deps = nullptr;
+  std::vector<int32_t> split;  // level 0 only: [grid] bands of each CTA in set 0 (two-set schedule: rest in set 1)
+  int32_t* d_split = nullptr;
 };
 
 struct PlanKey {
@@ -141,7 +143,8 @@ struct nesr_b200_handle {
 
   nesr_b200_stats stats{};
   int debug_flags = 0;        // NESR_B200_DEBUG_FLAGS: timing experiments (results are wrong when set)
-  int use_pairs = 1;          // NESR_B200_PAIRS: CTA-pair trunk kernel (conv3x3_trunk2.cu) when the schedule allows
+  int use_pairs = 0;          // NESR_B200_PAIRS: CTA-pair trunk kernel (conv3x3_trunk2.cu) when the schedule allows
+  int trunk_sets = 1;         // NESR_B200_SETS: band sets per CTA in the single-CTA trunk kernel (2: alternate two far-apart sets -- measured slower: profiles/r1_trunk_experiments.txt)
   int l2_pin_chunks = 1;      // NESR_B200_L2_PIN: dense-block planes whose loads are tagged evict_last in the trunk passes
 };
 
@@ -309,6 +312,7 @@ void free_batches(nesr_b200_handle* h) {
       if (l.d_segs) cudaFree(l.d_segs);
       if (l.d_cta_off) cudaFree(l.d_cta_off);
       if (l.d_deps) cudaFree(l.d_deps);
+      if (l.d_split) cudaFree(l.d_split);
     }
   }
   h->batches.clear();
@@ -339,7 +343,7 @@ void layout_level(Batch& b, int level) {
 // CTA gets the same number of rows +-1 and at most a few bands, so no SM waits for a straggler
 // (a longest-first deal of fixed-size bands left 12 of 148 CTAs with 35 % more work), and the two
 // halo rows a band costs are paid as rarely as possible.
-void build_fold_schedule(Batch& b, int level, int num_sms, bool pairs = false) {
+void build_fold_schedule(Batch& b, int level, int num_sms, bool pairs = false, int sets = 1) {
   LevelPlan& lp = b.lv[level];
   struct Strip { int32_t seg0, nseg, h; };
   std::vector<Strip> strips;
@@ -461,9 +465,11 @@ void build_fold_schedule(Batch& b, int level, int num_sms, bool pairs = false) {
     deal2(lo2, true);
     lp.bands.clear();
     lp.cta_off.assign(1, 0);
+    lp.split.clear();
     for (const auto& v : per_cta) {
       lp.bands.insert(lp.bands.end(), v.begin(), v.end());
       lp.cta_off.push_back((int32_t)lp.bands.size());
+      lp.split.push_back((int32_t)v.size());
     }
     lp.fold_grid = 2 * npair;
     lp.paired = true;
@@ -474,30 +480,43 @@ void build_fold_schedule(Batch& b, int level, int num_sms, bool pairs = false) {
   const int min_rows = 4;                                      // do not spread tiny work over every SM
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms, total_rows / min_rows));
   // Contiguous runs of equal COST: a band of n rows costs n + 2 slab rows (its halo), so a CTA whose run crosses a
-  // strip boundary gets fewer output rows.  The smallest per-CTA budget that covers everything is found by bisection.
-  auto deal = [&](int64_t budget, std::vector<FoldBand>* bands, std::vector<int32_t>* cta_off) -> bool {
+  // strip boundary gets fewer output rows.  The smallest per-run budget that covers everything is found by bisection.
+  // With sets == 2 (trunk kernel) the sequence is cut into 2*grid runs and CTA c owns run c (set 0) and run grid + c
+  // (set 1): two band sets far apart, processed alternately so that one set's publish -> acquire latency between layer
+  // passes is hidden behind the other set's work.
+  const int nrun = sets * grid;
+  std::vector<std::vector<FoldBand>> runs(nrun);
+  auto deal = [&](int64_t budget, bool emit) -> bool {
     size_t si = 0;
     int r = 0;                                                 // next row of strips[si]
-    if (bands) { bands->clear(); cta_off->assign(1, 0); }
-    for (int c = 0; c < grid; ++c) {
+    for (int c = 0; c < nrun; ++c) {
+      if (emit) runs[c].clear();
       int64_t left = budget;
       while (si < strips.size() && left >= 3) {
         const int n = (int)std::min<int64_t>(left - 2, strips[si].h - r);
-        if (bands) bands->push_back(FoldBand{strips[si].seg0, strips[si].nseg, r, n});
+        if (emit) runs[c].push_back(FoldBand{strips[si].seg0, strips[si].nseg, r, n});
         left -= n + 2;
         r += n;
         if (r == strips[si].h) { ++si; r = 0; }
       }
-      if (cta_off) cta_off->push_back((int32_t)bands->size());
     }
     return si == strips.size();
   };
   int64_t lo = 3, hi = total_rows + 2 * (int64_t)strips.size() + 3;
   while (lo < hi) {
     const int64_t mid = (lo + hi) / 2;
-    if (deal(mid, nullptr, nullptr)) hi = mid; else lo = mid + 1;
+    if (deal(mid, false)) hi = mid; else lo = mid + 1;
   }
-  deal(lo, &lp.bands, &lp.cta_off);
+  deal(lo, true);
+  lp.bands.clear();
+  lp.cta_off.assign(1, 0);
+  lp.split.clear();
+  for (int c = 0; c < grid; ++c) {
+    lp.bands.insert(lp.bands.end(), runs[c].begin(), runs[c].end());
+    lp.split.push_back((int32_t)runs[c].size());
+    if (sets == 2) lp.bands.insert(lp.bands.end(), runs[grid + c].begin(), runs[grid + c].end());
+    lp.cta_off.push_back((int32_t)lp.bands.size());
+  }
   lp.fold_grid = grid;
 }
 
@@ -508,28 +527,30 @@ int build_body_passes(nesr_b200_handle* h, Batch& b);
 // pixel of its bands' input halos (one pixel around each segment, inside the tile) has published that pass.
 void build_trunk_deps(LevelPlan& lp) {
   const int grid = lp.fold_grid;
-  struct Rect { int tile, x0, x1, y0, y1, cta; };              // inclusive pixel rectangle of one segment of one band
+  struct Rect { int tile, x0, x1, y0, y1, word; };             // inclusive pixel rectangle of one segment of one band; word = cta*2 + set
   std::vector<Rect> rects;
   for (int c = 0; c < grid; ++c)
     for (int b = lp.cta_off[c]; b < lp.cta_off[c + 1]; ++b) {
       const FoldBand& band = lp.bands[b];
+      const int set = (b - lp.cta_off[c]) < lp.split[c] ? 0 : 1;
       for (int sgi = 0; sgi < band.nseg; ++sgi) {
         const FoldSeg& sg = lp.segs[band.seg0 + sgi];
         if (band.r0 >= sg.h) continue;                            // this piece has no rows in the band
-        rects.push_back(Rect{sg.tile, sg.x0, sg.x0 + sg.width - 1, sg.y0 + band.r0, sg.y0 + std::min(band.r0 + band.rows, sg.h) - 1, c});
+        rects.push_back(Rect{sg.tile, sg.x0, sg.x0 + sg.width - 1, sg.y0 + band.r0, sg.y0 + std::min(band.r0 + band.rows, sg.h) - 1, 2 * c + set});
       }
     }
-  lp.deps.assign((size_t)grid * kTrunkMaxDeps, 0);
-  std::vector<std::vector<int32_t>> dep(grid);
+  const int nword = 2 * grid;
+  lp.deps.assign((size_t)nword * kTrunkMaxDeps, 0);
+  std::vector<std::vector<int32_t>> dep(nword);
   for (const Rect& a : rects)
     for (const Rect& o : rects) {
-      if (o.tile != a.tile || o.cta == a.cta) continue;
+      if (o.tile != a.tile || o.word == a.word) continue;
       if (o.x1 < a.x0 - 1 || o.x0 > a.x1 + 1 || o.y1 < a.y0 - 1 || o.y0 > a.y1 + 1) continue;
-      if (std::find(dep[a.cta].begin(), dep[a.cta].end(), o.cta) == dep[a.cta].end()) dep[a.cta].push_back(o.cta);
+      if (std::find(dep[a.word].begin(), dep[a.word].end(), o.word) == dep[a.word].end()) dep[a.word].push_back(o.word);
     }
-  for (int c = 0; c < grid; ++c) {
-    if ((int)dep[c].size() + 1 > kTrunkMaxDeps) { lp.deps.clear(); return; }
-    for (int k = 0; k < kTrunkMaxDeps; ++k) lp.deps[(size_t)c * kTrunkMaxDeps + k] = k < (int)dep[c].size() ? dep[c][k] : c;
+  for (int w = 0; w < nword; ++w) {
+    if ((int)dep[w].size() + 1 > kTrunkMaxDeps) { lp.deps.clear(); return; }
+    for (int k = 0; k < kTrunkMaxDeps; ++k) lp.deps[(size_t)w * kTrunkMaxDeps + k] = k < (int)dep[w].size() ? dep[w][k] : w;
   }
 }
 
@@ -601,7 +622,8 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
   const int64_t cap = h->cfg.max_batch_pixels > 0 ? h->cfg.max_batch_pixels : (l2_groups ? (int64_t)150000 : (int64_t)3 << 20);
   const bool pairs = l2_groups && h->use_pairs && h->num_sms >= 2;
   // level-0 schedule of a group and whether a TMEM-resident trunk kernel can run it
-  auto sched0 = [&](Batch& bb) { layout_level(bb, 0); build_fold_schedule(bb, 0, h->num_sms, pairs); };
+  const int sets = (l2_groups && !pairs && h->trunk_sets == 2) ? 2 : 1;
+  auto sched0 = [&](Batch& bb) { layout_level(bb, 0); build_fold_schedule(bb, 0, h->num_sms, pairs, sets); };
   auto fits0 = [&](const Batch& bb) { return bb.lv[0].paired ? trunk2_schedule_fits(bb.lv[0]) : trunk_schedule_fits(bb.lv[0]); };
   size_t i = 0;
   while (i < all.size()) {
@@ -633,7 +655,7 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
     sched0(b);
     b.trunk_fits = l2_groups && fits0(b);
     if (l2_groups && !b.trunk_fits && b.lv[0].paired) {          // pairs do not fit: try the single-CTA kernel's schedule
-      layout_level(b, 0); build_fold_schedule(b, 0, h->num_sms, false);
+      layout_level(b, 0); build_fold_schedule(b, 0, h->num_sms, false, h->trunk_sets == 2 ? 2 : 1);
       b.trunk_fits = trunk_schedule_fits(b.lv[0]);
     }
     b.trunk_pairs = b.trunk_fits && b.lv[0].paired;
@@ -657,6 +679,10 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
       CUDA_TRY(h, cudaMemcpyAsync(lp.d_bands, lp.bands.data(), lp.bands.size() * sizeof(FoldBand), cudaMemcpyHostToDevice, h->stream));
       CUDA_TRY(h, cudaMalloc(&lp.d_segs, std::max<size_t>(1, lp.segs.size()) * sizeof(FoldSeg)));
       CUDA_TRY(h, cudaMemcpyAsync(lp.d_segs, lp.segs.data(), lp.segs.size() * sizeof(FoldSeg), cudaMemcpyHostToDevice, h->stream));
+      if (!lp.split.empty()) {
+        CUDA_TRY(h, cudaMalloc(&lp.d_split, lp.split.size() * sizeof(int32_t)));
+        CUDA_TRY(h, cudaMemcpyAsync(lp.d_split, lp.split.data(), lp.split.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+      }
       if (!lp.deps.empty()) {
         CUDA_TRY(h, cudaMalloc(&lp.d_deps, lp.deps.size() * sizeof(int32_t)));
         CUDA_TRY(h, cudaMemcpyAsync(lp.d_deps, lp.deps.data(), lp.deps.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
@@ -830,6 +856,9 @@ int build_body_passes(nesr_b200_handle* h, Batch& b) {
         q.need[1] = k == 2 ? rb + 1 : rb + 2;
         q.need[2] = k == 4 ? rb + 3 : rb + 4;
         q.trunk_deps = b.lv[0].d_deps;
+        q.trunk_split = b.lv[0].d_split;
+        // the first half of conv5 is needed by nobody before the second half has been published too: skip its publish
+        q.trunk_no_publish = (k == 5 && ps + 1 < L.fold_passes) ? 1 : 0;
         q.l2_pin_chunks = h->l2_pin_chunks;
         passes.push_back(q);
       }
@@ -1078,7 +1107,7 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
       (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
       (e = cudaEventCreate(&h->evc0)) != cudaSuccess || (e = cudaEventCreate(&h->evc1)) != cudaSuccess ||
       (e = conv3x3_tc_configure()) != cudaSuccess || (e = conv3x3_fold_configure()) != cudaSuccess ||
-      (e = conv3x3_body_configure()) != cudaSuccess || (e = conv3x3_trunk_configure()) != cudaSuccess || (e = conv3x3_trunk2_configure()) != cudaSuccess || (e = cudaMalloc(&h->d_gbar, 1024 * 128)) != cudaSuccess) {
+      (e = conv3x3_body_configure()) != cudaSuccess || (e = conv3x3_trunk_configure()) != cudaSuccess || (e = conv3x3_trunk2_configure()) != cudaSuccess || (e = cudaMalloc(&h->d_gbar, 2048 * 128)) != cudaSuccess) {
     std::string msg = cudaGetErrorString(e);
     nesr_b200_destroy(h);
     return fail(nullptr, NESR_E_CUDA, "device setup failed: %s", msg.c_str());
@@ -1087,6 +1116,7 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
   if (const char* dbg = getenv("NESR_B200_DEBUG_FLAGS")) h->debug_flags = atoi(dbg);
   if (const char* pin = getenv("NESR_B200_L2_PIN")) h->l2_pin_chunks = atoi(pin);
   if (const char* pr = getenv("NESR_B200_PAIRS")) h->use_pairs = atoi(pr);
+  if (const char* st = getenv("NESR_B200_SETS")) h->trunk_sets = atoi(st);
   *out = h;
   return NESR_OK;
 }

@@ -113,7 +113,11 @@ struct ConvParams {
   // L2-resident trunk kernel (conv3x3_trunk.cu): input chunk c may be loaded once every CTA has completed passes [0, need[c])
   int32_t need[3];
   int32_t l2_pin_chunks;       // row-folded kernels: loads of input chunks [0, l2_pin_chunks) ask L2 to keep them (0: no hints)
-  const int32_t* trunk_deps;   // [grid][kTrunkMaxDeps] CTAs (incl. itself) whose bands overlap this CTA's input halo; padded with itself
+  // [grid][2][kTrunkMaxDeps] progress words (cta*2 + set, incl. its own) of the band sets that overlap the input halo of
+  // this CTA's band set; padded with its own word
+  const int32_t* trunk_deps;
+  int32_t trunk_no_publish;    // trunk kernels: this pass's completion is implied by the next pass's (conv5 first half)
+  const int32_t* trunk_split;  // [grid] number of bands of a CTA that belong to set 0 (the rest: set 1)
 };
 
 // conv3x3_trunk.cu keeps every output row of a CTA in TMEM for a whole pass: 16 row slots of 32 fp32 columns.
