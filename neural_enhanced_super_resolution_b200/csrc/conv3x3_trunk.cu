@@ -305,7 +305,7 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
         if (++ws == kWStages) { ws = 0; wphase ^= 1; }
         // activations of this chunk: every CTA must have published the passes that wrote them
         const unsigned need = static_cast<unsigned>(c == 0 ? h.need0 : (c == 1 ? h.need1 : h.need2));
-        if (need > known[set]) {
+        if (need > known[set] && !(h.dbg & 16384)) {              // 16384: no dependency polling (timing experiments)
           // every lane polls one neighbouring band set (padding lanes: this one).  The spin is RELAXED: ld.acquire.gpu compiles to
           // LDG.STRONG + CCTL.IVALL, and an L1 invalidation per poll made every L1-cached load of the epilogue warps
           // (bias) miss -- ~700 cycles per row.  One acquire after the last poll orders the TMA loads that follow.
@@ -317,7 +317,7 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
           }
           (void)ld_acquire_gpu(my_dep[set]);
           __syncwarp();
-          fence_proxy_async_all();
+          if (!(h.dbg & 8192)) fence_proxy_async_all();          // 8192: no proxy fences (timing experiments)
           known[set] = need;
           if (lane == 0) TS(4, pass);
         }
@@ -522,11 +522,11 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
       // publish the pass: generic-proxy stores -> TMA (async proxy) reads of any CTA
       if (threadIdx.x == 64) TS(1, pass);
       if (__ldg(&pp->trunk_no_publish)) continue;               // (uniform) covered by the next pass's publish
-      fence_proxy_async_all();
-      epi_bar_sync();
+      if (!(dbg & 8192)) fence_proxy_async_all();
+      if (!(dbg & 32768)) epi_bar_sync();                       // 32768: no named barrier / release (timing experiments)
       if (threadIdx.x == 64) {
         TS(2, pass);
-        st_release_gpu(prog + static_cast<size_t>(blockIdx.x * 2 + set) * kProgStride, static_cast<unsigned>(pass + 1));
+        if (!(dbg & 32768)) st_release_gpu(prog + static_cast<size_t>(blockIdx.x * 2 + set) * kProgStride, static_cast<unsigned>(pass + 1));
         TS(3, pass);
       }
       }
