@@ -74,16 +74,6 @@ struct PlanKey {
   }
 };
 
-struct Batch {
-  std::vector<TileGeom> tiles;
-  TileGeom* d_tiles = nullptr;
-  LevelPlan lv[3];
-  ConvParams* d_body_passes = nullptr;   // persistent trunk kernel: one ConvParams per RDB layer pass
-  int n_body_passes = 0;
-  bool trunk_fits = false;               // level-0 schedule fits a TMEM-resident trunk kernel (conv3x3_trunk.cu / conv3x3_trunk2.cu)
-  bool trunk_pairs = false;              // ... the CTA-pair one
-};
-
 struct Arena {
   uint8_t* base = nullptr;
   size_t bytes = 0;
@@ -102,6 +92,18 @@ struct Arena {
   CUtensorMap e_x0, e_d[2], e_g2, e_g4[2];             // box 8 px (row-folded kernel, packed remainder strips)
   CUtensorMap b_d[2][4];                               // boxes 8 / 16 / 32 / 64 px of the dense-block buffers (trunk kernel)
 };
+
+struct Batch {
+  std::vector<TileGeom> tiles;
+  TileGeom* d_tiles = nullptr;
+  LevelPlan lv[3];
+  ConvParams* d_body_passes = nullptr;   // persistent trunk kernel: one ConvParams per RDB layer pass
+  int n_body_passes = 0;
+  bool trunk_fits = false;               // level-0 schedule fits a TMEM-resident trunk kernel (conv3x3_trunk.cu / conv3x3_trunk2.cu)
+  bool trunk_pairs = false;              // ... the CTA-pair one
+  Arena arena;                           // this group's activation buffers: its own slice of the handle's allocation, or all of it
+};
+
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -133,7 +135,9 @@ struct nesr_b200_handle {
 
   PlanKey key;
   std::vector<Batch> batches;
-  Arena arena;
+  uint8_t* arena_base = nullptr;                       // one allocation; every tile group owns a slice, or all share it
+  size_t arena_bytes = 0;
+  bool arena_shared = false;                           // groups share one slice: its zero pads are re-established per group
 
   uint8_t* d_in = nullptr;  size_t d_in_bytes = 0;
   uint8_t* d_out = nullptr; size_t d_out_bytes = 0;
@@ -693,44 +697,70 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
     }
   }
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));      // host vectors may now be reused
-  // arena (sized for the largest batch)
-  Arena& a = h->arena;
-  const size_t sz_x0 = round_up(P[0] * 64 * 2, 1024), sz_d = round_up(P[0] * kDense * 2, 1024);
-  const size_t sz_f = round_up(P[0] * 64 * 4, 1024), sz_g2 = round_up(P[1] * 64 * 2, 1024), sz_g4 = round_up(P[2] * 64 * 2, 1024);
-  const size_t need = sz_x0 + 2 * sz_d + 3 * sz_f + sz_g2 + 2 * sz_g4;
-  if (need > a.bytes) {
-    if (a.base) cudaFree(a.base);
-    a.base = nullptr; a.bytes = 0;
-    cudaError_t e = cudaMalloc(&a.base, need);
-    if (e != cudaSuccess) return fail(h, NESR_E_NOMEM, "activation arena of %zu bytes: %s", need, cudaGetErrorString(e));
-    a.bytes = need;
+  // Activation arena.  Every tile group gets its own slice (its zero pads -- pad columns, guard rows -- are written once and
+  // never touched again); only when that would need more than 24 GB do all groups share one slice sized for the largest,
+  // whose pads are then re-established by a memset before every group (0.2 ms per group at 1080p).
+  auto slice_bytes = [&](const Batch& bb, size_t* zero) {
+    const int64_t p0 = bb.lv[0].pixels, p1 = bb.lv[1].pixels, p2 = bb.lv[2].pixels;
+    const size_t sz_x0 = round_up(p0 * 64 * 2, 1024), sz_d = round_up(p0 * kDense * 2, 1024);
+    const size_t sz_f = round_up(p0 * 64 * 4, 1024), sz_g2 = round_up(p1 * 64 * 2, 1024), sz_g4 = round_up(p2 * 64 * 2, 1024);
+    if (zero) *zero = sz_x0 + 2 * sz_d + sz_g2 + 2 * sz_g4;
+    return sz_x0 + 2 * sz_d + 3 * sz_f + sz_g2 + 2 * sz_g4;
+  };
+  size_t total = 0, largest = 0;
+  for (const Batch& bb : h->batches) { const size_t n = slice_bytes(bb, nullptr); total += n; largest = std::max(largest, n); }
+  h->arena_shared = h->batches.size() > 1 && total > ((size_t)24 << 30);
+  // a shared slice must hold the largest extent of EVERY level (groups differ in shape)
+  size_t need = total;
+  if (h->arena_shared) {
+    Batch big;
+    for (int l = 0; l < 3; ++l) big.lv[l].pixels = P[l];
+    need = slice_bytes(big, nullptr);
   }
-  uint8_t* p = a.base;
-  a.x0 = p; p += sz_x0;
-  a.d[0] = p; p += sz_d; a.d[1] = p; p += sz_d;
-  a.g2 = p; p += sz_g2;
-  a.g4[0] = p; p += sz_g4; a.g4[1] = p; p += sz_g4;
-  a.zero_bytes = (size_t)(p - a.base);                // every buffer a conv reads: pads must be zero
-  a.trunk = (float*)p; p += sz_f; a.rrdb = (float*)p; p += sz_f; a.feat = (float*)p; p += sz_f;
-  for (int l = 0; l < 3; ++l) a.P[l] = P[l];
-  CUDA_TRY(h, cudaMemsetAsync(a.base, 0, a.zero_bytes, h->stream));
+  if (need > h->arena_bytes) {
+    if (h->arena_base) cudaFree(h->arena_base);
+    h->arena_base = nullptr; h->arena_bytes = 0;
+    cudaError_t e = cudaMalloc(&h->arena_base, need);
+    if (e != cudaSuccess) return fail(h, NESR_E_NOMEM, "activation arena of %zu bytes: %s", need, cudaGetErrorString(e));
+    h->arena_bytes = need;
+  }
   int rc;
-  if ((rc = make_map(h, &a.m_x0, a.x0, 64, P[0], kBlockPixels))) return rc;
-  for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.m_d[i2], a.d[i2], 64, 3 * P[0], kBlockPixels))) return rc;
-  if ((rc = make_map(h, &a.m_g2, a.g2, 64, P[1], kBlockPixels))) return rc;
-  for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.m_g4[i2], a.g4[i2], 64, P[2], kBlockPixels))) return rc;
-  constexpr int kSlab = 136;                                   // row slab of the folded kernel
-  if ((rc = make_map(h, &a.f_x0, a.x0, 64, P[0], kSlab))) return rc;
-  for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.f_d[i2], a.d[i2], 64, 3 * P[0], kSlab))) return rc;
-  if ((rc = make_map(h, &a.f_g2, a.g2, 64, P[1], kSlab))) return rc;
-  for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.f_g4[i2], a.g4[i2], 64, P[2], kSlab))) return rc;
-  if ((rc = make_map(h, &a.e_x0, a.x0, 64, P[0], 8))) return rc;
-  for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.e_d[i2], a.d[i2], 64, 3 * P[0], 8))) return rc;
-  for (int i2 = 0; i2 < 2; ++i2)
-    for (int k = 0; k < 4; ++k) if ((rc = make_map(h, &a.b_d[i2][k], a.d[i2], 64, 3 * P[0], 8 << k))) return rc;
-  if ((rc = make_map(h, &a.e_g2, a.g2, 64, P[1], 8))) return rc;
-  for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.e_g4[i2], a.g4[i2], 64, P[2], 8))) return rc;
-  h->stats.arena_bytes = (int64_t)a.bytes;
+  uint8_t* cursor = h->arena_base;
+  for (Batch& bb : h->batches) {
+    Arena& a = bb.arena;
+    int64_t Pb[3];
+    for (int l = 0; l < 3; ++l) Pb[l] = h->arena_shared ? P[l] : bb.lv[l].pixels;
+    const size_t sz_x0 = round_up(Pb[0] * 64 * 2, 1024), sz_d = round_up(Pb[0] * kDense * 2, 1024);
+    const size_t sz_f = round_up(Pb[0] * 64 * 4, 1024), sz_g2 = round_up(Pb[1] * 64 * 2, 1024), sz_g4 = round_up(Pb[2] * 64 * 2, 1024);
+    uint8_t* p = h->arena_shared ? h->arena_base : cursor;
+    a.base = p;
+    a.x0 = p; p += sz_x0;
+    a.d[0] = p; p += sz_d; a.d[1] = p; p += sz_d;
+    a.g2 = p; p += sz_g2;
+    a.g4[0] = p; p += sz_g4; a.g4[1] = p; p += sz_g4;
+    a.zero_bytes = (size_t)(p - a.base);              // every buffer a conv reads: pads must be zero
+    a.trunk = (float*)p; p += sz_f; a.rrdb = (float*)p; p += sz_f; a.feat = (float*)p; p += sz_f;
+    a.bytes = (size_t)(p - a.base);
+    cursor = p;
+    for (int l = 0; l < 3; ++l) a.P[l] = Pb[l];
+    if (!h->arena_shared || &bb == &h->batches.front()) CUDA_TRY(h, cudaMemsetAsync(a.base, 0, a.zero_bytes, h->stream));
+    if ((rc = make_map(h, &a.m_x0, a.x0, 64, Pb[0], kBlockPixels))) return rc;
+    for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.m_d[i2], a.d[i2], 64, 3 * Pb[0], kBlockPixels))) return rc;
+    if ((rc = make_map(h, &a.m_g2, a.g2, 64, Pb[1], kBlockPixels))) return rc;
+    for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.m_g4[i2], a.g4[i2], 64, Pb[2], kBlockPixels))) return rc;
+    constexpr int kSlab = 136;                                 // row slab of the folded kernel
+    if ((rc = make_map(h, &a.f_x0, a.x0, 64, Pb[0], kSlab))) return rc;
+    for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.f_d[i2], a.d[i2], 64, 3 * Pb[0], kSlab))) return rc;
+    if ((rc = make_map(h, &a.f_g2, a.g2, 64, Pb[1], kSlab))) return rc;
+    for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.f_g4[i2], a.g4[i2], 64, Pb[2], kSlab))) return rc;
+    if ((rc = make_map(h, &a.e_x0, a.x0, 64, Pb[0], 8))) return rc;
+    for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.e_d[i2], a.d[i2], 64, 3 * Pb[0], 8))) return rc;
+    for (int i2 = 0; i2 < 2; ++i2)
+      for (int k = 0; k < 4; ++k) if ((rc = make_map(h, &a.b_d[i2][k], a.d[i2], 64, 3 * Pb[0], 8 << k))) return rc;
+    if ((rc = make_map(h, &a.e_g2, a.g2, 64, Pb[1], 8))) return rc;
+    for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.e_g4[i2], a.g4[i2], 64, Pb[2], 8))) return rc;
+  }
+  h->stats.arena_bytes = (int64_t)h->arena_bytes;
   if (h->cfg.conv_impl == 0 || h->cfg.conv_impl == 4)
     for (Batch& b : h->batches)
       if ((rc = build_body_passes(h, b))) return rc;
@@ -754,7 +784,7 @@ struct ConvIO {
 void bind_layer(nesr_b200_handle* h, const Batch& b, const Layer& L, const ConvIO& io, ConvParams& p) {
   const LevelPlan& lp = b.lv[io.level];
   p.blocks = lp.d_blocks; p.tiles = b.d_tiles; p.nblk = (int)lp.blocks.size(); p.level = io.level;
-  p.src = io.src; p.src_plane_px = (int)h->arena.P[io.level]; p.cin = L.cin16;
+  p.src = io.src; p.src_plane_px = (int)b.arena.P[io.level]; p.cin = L.cin16;
   p.wpack = h->d_wpack; p.w_row0 = L.w_row0; p.npad = L.npad; p.fmt = L.fmt;
   p.idesc = umma_idesc_f16(hw_fmt(L.fmt), (uint32_t)L.npad);
   p.bias = h->d_bias + L.bias_off; p.cout = L.cout;
@@ -806,8 +836,7 @@ int run_conv(nesr_b200_handle* h, const Batch& b, const Layer& L, const ConvIO& 
 // Epilogue wiring of the 5 convs of residual dense block r (0-based over the whole trunk) reading
 // dense buffer `cur`: conv1-4 append 32 channels to the same buffer (torch.cat as addressing), conv5
 // writes 0.2*x5 + x (+ the RRDB skip on every third block) as the next block's channels [0,64).
-ConvParams rdb_conv_params(const nesr_b200_handle* h, int r, int k, int cur) {
-  const Arena& a = h->arena;
+ConvParams rdb_conv_params(const nesr_b200_handle* h, const Arena& a, int r, int k, int cur) {
   const nesr_b200_config& c = h->cfg;
   const int nrdb = c.num_block * 3;
   ConvParams p{};
@@ -830,7 +859,7 @@ ConvParams rdb_conv_params(const nesr_b200_handle* h, int r, int k, int cur) {
 
 // One ConvParams per layer pass of the trunk, in execution order, for the persistent kernel.
 int build_body_passes(nesr_b200_handle* h, Batch& b) {
-  const Arena& a = h->arena;
+  const Arena& a = b.arena;
   const int nrdb = h->cfg.num_block * 3;
   std::vector<ConvParams> passes;
   size_t li = 1;                     // layers[0] is conv_first
@@ -841,7 +870,7 @@ int build_body_passes(nesr_b200_handle* h, Batch& b) {
       const Layer& L = h->layers[li++];
       if (L.fold_npad != 32 || L.fmt != h->cfg.body_format)
         return fail(h, NESR_E_STATE, "persistent trunk kernel: layer %s is not a 32-channel pass", L.name.c_str());
-      ConvParams bound = rdb_conv_params(h, r, k, cur);
+      ConvParams bound = rdb_conv_params(h, b.arena, r, k, cur);
       bind_layer(h, b, L, io, bound);
       const int first = (int)passes.size();
       for (int ps = 0; ps < L.fold_passes; ++ps) {
@@ -881,10 +910,10 @@ struct Sink {
 
 int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in, const Sink& sink, cudaStream_t s,
                   bool time_begin, bool time_end, bool time_trunk = false) {
-  Arena& a = h->arena;
+  const Arena& a = b.arena;
   const nesr_b200_config& c = h->cfg;
   int rc;
-  if (h->batches.size() > 1) {   // batches have different flat layouts: re-establish the zero pads
+  if (h->arena_shared) {         // groups share one slice but have different flat layouts: re-establish the zero pads
     cudaError_t ez = cudaMemsetAsync(a.base, 0, a.zero_bytes, s);
     if (ez != cudaSuccess) return fail(h, NESR_E_CUDA, "arena memset failed: %s", cudaGetErrorString(ez));
   }
@@ -939,7 +968,7 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
     for (int r = 0; r < nrdb; ++r) {
       const ConvIO io{&a.m_d[cur], &a.f_d[cur], &a.e_d[cur], a.d[cur], 3, 0};
       for (int k = 1; k <= 5; ++k)
-        if ((rc = run_conv(h, b, next(), io, rdb_conv_params(h, r, k, cur), s))) return rc;
+        if ((rc = run_conv(h, b, next(), io, rdb_conv_params(h, b.arena, r, k, cur), s))) return rc;
       cur ^= 1;
     }
   }
@@ -1126,7 +1155,7 @@ int nesr_b200_destroy(nesr_b200_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   free_batches(h);
-  if (h->arena.base) cudaFree(h->arena.base);
+  if (h->arena_base) cudaFree(h->arena_base);
   if (h->d_wpack) cudaFree(h->d_wpack);
   if (h->d_bias) cudaFree(h->d_bias);
   if (h->d_wfold) cudaFree(h->d_wfold);
