@@ -452,8 +452,11 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
           // residual rows are fetched BEFORE waiting for the accumulator: their latency hides behind the MMAs
           float r1[COUT], r2[COUT];
           if (lane_on && res1) {
+            // a tile group's fp32 trunk (35 MB) fits in L2 next to its dense-block planes: plain accesses (1 % faster than
+            // evict_first streaming, which is what the whole-frame kernel needs); the RRDB input, read once in three
+            // blocks, keeps streaming
 #pragma unroll
-            for (int q = 0; q < COUT / 8; ++q) ldg256_stream(res1 + toff + q * 256, &r1[q * 8]);
+            for (int q = 0; q < COUT / 8; ++q) ldg256(res1 + toff + q * 256, &r1[q * 8]);
           }
           if (lane_on && res2) {
 #pragma unroll
@@ -493,7 +496,7 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
               }
               if (!(dbg & 4096)) {
 #pragma unroll
-                for (int q = 0; q < COUT / 8; ++q) stg256f_stream(dst32a + toff + q * 256, &v[q * 8]);
+                for (int q = 0; q < COUT / 8; ++q) stg256f(dst32a + toff + q * 256, &v[q * 8]);
                 if (dst32b) {
 #pragma unroll
                   for (int q = 0; q < COUT / 8; ++q) stg256f_stream(dst32b + toff + q * 256, &v[q * 8]);
