@@ -154,6 +154,23 @@ def test_persistent_trunk_kernels_agree_with_per_layer_launches():
         assert np.array_equal(first, again)
 
 
+def test_trunk_kernel_variants_are_bit_identical(monkeypatch):
+    """The CTA-pair trunk kernel (cta_group::2, NESR_B200_PAIRS=1) and the two-band-set schedule (NESR_B200_SETS=2) sum the
+    same products in the same order as the default trunk kernel: bit-identical output, whatever the band schedule."""
+    img = natural_image(300, 420, seed=12)
+    want, _ = gpu_up("calibrated", 160, 10).enhance(img)
+    for var, val in (("NESR_B200_PAIRS", "1"), ("NESR_B200_SETS", "2")):
+        monkeypatch.setenv(var, val)
+        got, _ = gpu_up("calibrated", 160, 10).enhance(img)
+        monkeypatch.delenv(var)
+        assert np.array_equal(got, want), var
+    monkeypatch.setenv("NESR_B200_PAIRS", "1")
+    whole, _ = gpu_up("calibrated", 0, 10).enhance(img)           # one untiled group: several strips, packed remainder
+    monkeypatch.delenv("NESR_B200_PAIRS")
+    ref, _ = gpu_up("calibrated", 0, 10).enhance(img)
+    assert np.array_equal(whole, ref)
+
+
 def test_validation_kernels_agree_with_the_product_kernel():
     img = natural_image(40, 140, seed=3)                      # two column strips
     fold, _ = gpu_up("calibrated").enhance(img)
