@@ -132,6 +132,15 @@ int nesr_b200_enhance_batch_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32
  * into `out_bgr`, which addresses the FULL 2H x 2W output (pixels of other tiles are untouched).
  * nesr_b200_tile_count reports the size of the grid. */
 int nesr_b200_tile_count(int32_t H, int32_t W, int32_t tile, int32_t pre_pad, int32_t scale);
+
+/* (test hook, host only -- no CUDA call, works without a GPU) Builds the tile-group plan that an enhance call with these
+ * arguments would use on a device with `num_sms` SMs and verifies its invariants: every pixel of every tile of every
+ * resolution level owned by exactly one (CTA, band, lane); segment lanes inside the 128-lane MMA / 136-row slab; TMEM row
+ * limits of the trunk kernels; band shapes of CTA pairs identical; halo dependency lists symmetric.
+ * out[8]: groups, tiles, feature pixels, level-0 strip rows, max output rows per CTA, groups run by a TMEM-resident trunk
+ * kernel, of those on CTA pairs, level-0 halo rows.  pairs / sets: the NESR_B200_PAIRS / NESR_B200_SETS switches. */
+int nesr_b200_debug_plan(int32_t n_frames, int32_t H, int32_t W, int32_t tile, int32_t tile_pad, int32_t pre_pad, int32_t num_sms,
+                         int32_t conv_impl, int64_t max_batch_pixels, int32_t pairs, int32_t sets, int64_t* out);
 int nesr_b200_enhance_tiles_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32_t H, int32_t W,
                                int64_t in_stride, int32_t tile, int32_t tile_pad, int32_t pre_pad,
                                int32_t tile_first, int32_t tile_count, uint8_t* out_bgr,

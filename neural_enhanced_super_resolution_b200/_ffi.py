@@ -20,7 +20,7 @@ PTR_IN_DEVICE, PTR_OUT_DEVICE = 1, 2
 EXPORTS = (
     "nesr_b200_default_config", "nesr_b200_create", "nesr_b200_destroy", "nesr_b200_last_error",
     "nesr_b200_load_weight", "nesr_b200_finalize_weights", "nesr_b200_enhance_u8",
-    "nesr_b200_enhance_batch_u8", "nesr_b200_tile_count", "nesr_b200_enhance_tiles_u8",
+    "nesr_b200_enhance_batch_u8", "nesr_b200_tile_count", "nesr_b200_debug_plan", "nesr_b200_enhance_tiles_u8",
     "nesr_b200_forward_nchw_f32", "nesr_b200_blend_u8", "nesr_b200_sharpen_u8", "nesr_b200_get_stats",
     "nesr_b200_synchronize", "nesr_b200_debug_conv",
 )
@@ -75,6 +75,7 @@ def load_library() -> C.CDLL:
                                                    C.c_int32, C.c_int32, C.c_int32, u8p, C.c_int64, C.c_int64,
                                                    C.c_int32]
         lib.nesr_b200_tile_count.argtypes = [C.c_int32] * 5
+        lib.nesr_b200_debug_plan.argtypes = [C.c_int32] * 8 + [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
         lib.nesr_b200_enhance_tiles_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                                    C.c_int32, C.c_int32, C.c_int32, u8p, C.c_int64, C.c_int32]
         lib.nesr_b200_forward_nchw_f32.argtypes = [H, f32p, C.c_int32, C.c_int32, C.c_int32, f32p, C.c_void_p]

@@ -582,9 +582,9 @@ bool trunk_schedule_fits(const LevelPlan& lp) {
   return true;
 }
 
-int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
-  if (h->key == key && !h->batches.empty()) return NESR_OK;
-  free_batches(h);
+// Host half of the plan (no CUDA calls): tiles of the frame(s), split into tile groups, every level's flat layout and
+// row-folded schedule, and the trunk kernel's halo dependency lists.  Fills h->batches.
+int plan_groups(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
   const int scale = h->cfg.scale;
   const Grid g = tile_grid_dims(key.H, key.W, key.tile, key.pre_pad, scale);
   std::vector<TileGeom> all;
@@ -670,6 +670,13 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
     if (b.lv[2].pixels >= ((int64_t)1 << 31) - 4096) return fail(h, NESR_E_INVALID, "batch too large for 32-bit pixel indices");
     h->batches.push_back(std::move(b));
   }
+  return NESR_OK;
+}
+
+int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
+  if (h->key == key && !h->batches.empty()) return NESR_OK;
+  free_batches(h);
+  if (int prc = plan_groups(h, key, out_h, out_w)) return prc;
   // upload
   int64_t P[3] = {0, 0, 0};
   for (Batch& b : h->batches) {
@@ -1240,6 +1247,90 @@ int nesr_b200_tile_count(int32_t H, int32_t W, int32_t tile, int32_t pre_pad, in
   if (H < 1 || W < 1 || tile < 0 || pre_pad < 0) return NESR_E_INVALID;
   const Grid g = tile_grid_dims(H, W, tile, pre_pad, scale);
   return g.tiles_x * g.tiles_y;
+}
+
+// Host-only: builds the tile-group plan a call with these arguments would use (no CUDA calls, works without a GPU) and
+// verifies its invariants.  out[]: 0 groups, 1 tiles, 2 feature pixels, 3 strip rows of level 0 (all groups), 4 largest
+// number of output rows owned by one CTA, 5 groups a TMEM-resident trunk kernel can run, 6 of those on CTA pairs,
+// 7 halo rows (2 per band, level 0).  Returns NESR_OK, or NESR_E_STATE with the violated invariant in last_error(NULL).
+int nesr_b200_debug_plan(int32_t n_frames, int32_t H, int32_t W, int32_t tile, int32_t tile_pad, int32_t pre_pad, int32_t num_sms,
+                         int32_t conv_impl, int64_t max_batch_pixels, int32_t pairs, int32_t sets, int64_t* out) {
+  if (!out || n_frames < 1 || H < 2 || W < 2 || num_sms < 1) return fail(nullptr, NESR_E_INVALID, "bad arguments");
+  nesr_b200_handle hd;
+  nesr_b200_default_config(&hd.cfg, 0);
+  hd.cfg.conv_impl = conv_impl; hd.cfg.max_batch_pixels = max_batch_pixels;
+  hd.num_sms = num_sms; hd.use_pairs = pairs; hd.trunk_sets = sets;
+  PlanKey key; key.n_frames = n_frames; key.H = H; key.W = W; key.tile = tile; key.tile_pad = tile_pad; key.pre_pad = pre_pad;
+  key.first = 0; key.count = 0; key.whole = 1;
+  const int rc = plan_groups(&hd, key, H * hd.cfg.scale, W * hd.cfg.scale);
+  if (rc) return fail(nullptr, rc, "%s", hd.error.c_str());
+  for (int k = 0; k < 8; ++k) out[k] = 0;
+  out[0] = (int64_t)hd.batches.size();
+  for (size_t bi = 0; bi < hd.batches.size(); ++bi) {
+    const Batch& b = hd.batches[bi];
+    out[1] += (int64_t)b.tiles.size();
+    out[5] += b.trunk_fits; out[6] += b.trunk_pairs;
+    for (int level = 0; level < 3; ++level) {
+      const LevelPlan& lp = b.lv[level];
+      // every pixel of every tile is owned by exactly one (band, segment, lane); nothing outside a tile is owned
+      std::vector<std::vector<uint8_t>> cover(b.tiles.size());
+      for (size_t t = 0; t < b.tiles.size(); ++t) cover[t].assign((size_t)b.tiles[t].lv[level].h * b.tiles[t].lv[level].w, 0);
+      if ((int)lp.cta_off.size() != lp.fold_grid + 1 || lp.fold_grid > num_sms)
+        return fail(nullptr, NESR_E_STATE, "group %zu level %d: grid %d, %zu offsets", bi, level, lp.fold_grid, lp.cta_off.size());
+      for (int c = 0; c < lp.fold_grid; ++c) {
+        int rows = 0;
+        for (int q = lp.cta_off[c]; q < lp.cta_off[c + 1]; ++q) {
+          const FoldBand& band = lp.bands[q];
+          if (band.rows < 1 || band.nseg < 1 || band.nseg > kMaxFoldSegs)
+            return fail(nullptr, NESR_E_STATE, "group %zu level %d: band %d has %d rows, %d segments", bi, level, q, band.rows, band.nseg);
+          rows += band.rows;
+          if (level == 0) { out[3] += band.rows; out[7] += 2; }
+          int lanes = 0;
+          for (int sgi = 0; sgi < band.nseg; ++sgi) {
+            const FoldSeg& sg = lp.segs[band.seg0 + sgi];
+            const LevelGeom& g = b.tiles[sg.tile].lv[level];
+            if (sg.lane0 < lanes || (sg.lane0 & 7) || sg.lane0 + sg.width > kBlockPixels || sg.lane0 + sg.width + 2 > 136 ||
+                sg.x0 < 0 || sg.x0 + sg.width > g.w || sg.y0 < 0 || sg.y0 + sg.h > g.h)
+              return fail(nullptr, NESR_E_STATE, "group %zu level %d: segment %d out of range", bi, level, band.seg0 + sgi);
+            lanes = sg.lane0 + (sg.width + 2 + 7) / 8 * 8;
+            for (int r = band.r0; r < band.r0 + band.rows && r < sg.h; ++r)
+              for (int x = sg.x0; x < sg.x0 + sg.width; ++x)
+                if (++cover[sg.tile][(size_t)(sg.y0 + r) * g.w + x] != 1)
+                  return fail(nullptr, NESR_E_STATE, "group %zu level %d: tile %d pixel (%d,%d) owned twice", bi, level, sg.tile, sg.y0 + r, x);
+          }
+        }
+        if (level == 0) out[4] = std::max<int64_t>(out[4], rows);
+      }
+      for (size_t t = 0; t < b.tiles.size(); ++t)
+        for (size_t i2 = 0; i2 < cover[t].size(); ++i2)
+          if (cover[t][i2] != 1) return fail(nullptr, NESR_E_STATE, "group %zu level %d: tile %zu pixel %zu not owned", bi, level, t, i2);
+      if (level == 0) {
+        for (const TileGeom& t : b.tiles) out[2] += (int64_t)t.lv[0].h * t.lv[0].w;
+        if (b.trunk_fits) {
+          if (b.trunk_pairs ? !trunk2_schedule_fits(lp) : !trunk_schedule_fits(lp)) return fail(nullptr, NESR_E_STATE, "group %zu: trunk fit flag wrong", bi);
+          if (b.trunk_pairs)                                   // CTAs 2p / 2p+1: same number of bands, same rows per band
+            for (int c = 0; c < lp.fold_grid; c += 2) {
+              const int n0 = lp.cta_off[c + 1] - lp.cta_off[c], n1 = lp.cta_off[c + 2] - lp.cta_off[c + 1];
+              if (n0 != n1) return fail(nullptr, NESR_E_STATE, "group %zu: pair %d has %d / %d bands", bi, c / 2, n0, n1);
+              for (int q = 0; q < n0; ++q)
+                if (lp.bands[lp.cta_off[c] + q].rows != lp.bands[lp.cta_off[c + 1] + q].rows)
+                  return fail(nullptr, NESR_E_STATE, "group %zu: pair %d band %d row counts differ", bi, c / 2, q);
+            }
+          // halo dependency lists: symmetric (a needs b <=> b needs a), self-padded
+          const int nword = 2 * lp.fold_grid;
+          if ((int)lp.deps.size() != nword * kTrunkMaxDeps) return fail(nullptr, NESR_E_STATE, "group %zu: dependency table size", bi);
+          auto has = [&](int w, int v) { for (int k = 0; k < kTrunkMaxDeps; ++k) if (lp.deps[(size_t)w * kTrunkMaxDeps + k] == v) return true; return false; };
+          for (int w = 0; w < nword; ++w)
+            for (int k = 0; k < kTrunkMaxDeps; ++k) {
+              const int v = lp.deps[(size_t)w * kTrunkMaxDeps + k];
+              if (v < 0 || v >= nword || !has(v, w)) return fail(nullptr, NESR_E_STATE, "group %zu: dependency %d -> %d not symmetric", bi, w, v);
+            }
+        }
+      }
+    }
+  }
+  free_batches(&hd);
+  return NESR_OK;
 }
 
 int nesr_b200_enhance_tiles_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32_t H, int32_t W, int64_t in_stride, int32_t tile,

@@ -1,0 +1,97 @@
+"""Host-side planning logic of libnesr_b200 (no GPU): tile groups, row-folded band schedules, remainder-piece packing,
+CTA-pair schedules and halo dependency lists, checked through the C ABI's host-only test hook ``nesr_b200_debug_plan``
+(``csrc/engine.cu``), which verifies that every pixel of every tile of every level is owned by exactly one (CTA, band,
+lane) and that the trunk kernels' TMEM / pairing / dependency invariants hold.
+
+Geometry being planned: upstream ``RealESRGANer.tile_process`` (tiles of ``tile`` pixels extended by ``tile_pad``, clamped at
+the image edge; reference twin ``nesr/nesr.py:311-475``) on the pixel-unshuffled feature grid (H/2 x W/2)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from neural_enhanced_super_resolution_b200 import _ffi
+
+SMS = 148
+
+
+def plan(H, W, tile, pad, pre=0, n=1, sms=SMS, impl=0, cap=0, pairs=0, sets=1):
+    lib = _ffi.load_library()
+    out = (C.c_int64 * 8)()
+    rc = lib.nesr_b200_debug_plan(n, H, W, tile, pad, pre, sms, impl, cap, pairs, sets, out)
+    msg = lib.nesr_b200_last_error(None).decode()
+    return rc, msg, dict(zip(("groups", "tiles", "pixels", "strip_rows", "max_rows", "trunk_groups", "pair_groups", "halo_rows"),
+                             [int(v) for v in out]))
+
+
+def feature_pixels(H, W, tile, pad, pre=0):
+    """Sum over tiles of the padded tile extent on the feature grid (mod-pad to even, as upstream pre_process does)."""
+    H2, W2 = H + pre, W + pre
+    H2 += H2 % 2
+    W2 += W2 % 2
+    if tile == 0:
+        return (H2 // 2) * (W2 // 2), 1
+    px = nt = 0
+    for y0 in range(0, H2, tile):
+        for x0 in range(0, W2, tile):
+            y1, x1 = min(y0 + tile, H2), min(x0 + tile, W2)
+            th = min(y1 + pad, H2) - max(y0 - pad, 0)
+            tw = min(x1 + pad, W2) - max(x0 - pad, 0)
+            px += (th // 2) * (tw // 2)
+            nt += 1
+    return px, nt
+
+
+SHAPES = [(1080, 1920, 512, 10), (2160, 3840, 512, 10), (512, 512, 0, 10), (522, 1044, 0, 10), (300, 420, 160, 10),
+          (72, 88, 48, 6), (64, 80, 32, 4), (40, 140, 0, 10), (26, 30, 0, 10), (2, 2, 0, 10), (1080, 1920, 256, 16),
+          (720, 1280, 400, 10), (1440, 2560, 1024, 10)]
+
+
+@pytest.mark.parametrize("H,W,tile,pad", SHAPES)
+@pytest.mark.parametrize("pairs,sets", [(0, 1), (1, 1), (0, 2)])
+def test_every_pixel_is_owned_once_and_invariants_hold(H, W, tile, pad, pairs, sets):
+    rc, msg, st = plan(H, W, tile, pad, pairs=pairs, sets=sets)
+    assert rc == 0, msg
+    px, nt = feature_pixels(H, W, tile, pad)
+    assert (st["tiles"], st["pixels"]) == (nt, px)
+    assert 1 <= st["groups"] <= nt
+    assert st["strip_rows"] * 128 >= px                        # 128 lanes per strip row cover all pixels
+    if st["trunk_groups"] == st["groups"]:
+        assert st["max_rows"] <= 16                            # 16 TMEM row slots of 32 fp32 columns
+    assert st["pair_groups"] <= st["trunk_groups"] <= st["groups"]
+    if not pairs:
+        assert st["pair_groups"] == 0
+
+
+def test_1080p_plan_is_the_one_the_benchmark_runs():
+    rc, msg, st = plan(1080, 1920, 512, 10)
+    assert rc == 0, msg
+    assert st["tiles"] == 12 and st["groups"] == 4 and st["trunk_groups"] == 4
+    # ragged tile widths (266 = 2*128 + 10) and the halo rows of 7-9-row bands are the overheads DESIGN.md quotes
+    lanes = st["strip_rows"] * 128
+    assert 1.0 <= lanes / st["pixels"] < 1.12
+    assert 0.15 < st["halo_rows"] / st["strip_rows"] < 0.35
+    # the whole-frame kernels keep one group
+    rc, msg, whole = plan(1080, 1920, 512, 10, impl=4)
+    assert rc == 0 and whole["groups"] == 1 and whole["trunk_groups"] == 0
+    assert whole["strip_rows"] <= st["strip_rows"]             # one packed remainder strip per tile row instead of per group
+
+
+def test_group_cap_and_frames():
+    rc, msg, a = plan(512, 512, 0, 10, n=6)                    # six frames = six independent tiles
+    assert rc == 0 and a["tiles"] == 6 and a["pixels"] == 6 * 256 * 256
+    assert a["groups"] == 3                                    # 150k-pixel groups: two 65k-pixel frames each
+    rc, msg, b = plan(512, 512, 0, 10, n=6, cap=70000)
+    assert rc == 0 and b["groups"] == 6
+    rc, msg, c = plan(300, 420, 160, 10, cap=20000)
+    assert rc == 0 and c["groups"] >= 2
+
+
+def test_small_devices_and_errors():
+    for sms in (1, 2, 7, 32):
+        rc, msg, st = plan(300, 420, 160, 10, sms=sms, pairs=1)
+        assert rc == 0, msg
+    rc, msg, _ = plan(300, 420, 161, 10)                       # odd tile extent: pixel_unshuffle(2) needs even tiles
+    assert rc != 0 and "odd" in msg
+    rc, msg, _ = plan(1, 1, 0, 10)
+    assert rc != 0
