@@ -27,11 +27,11 @@
 //   warp polls the words of its halo neighbours (host-built list, one lane each) and of its own CTA.  A
 //   slow CTA delays its neighbours, not all 148 SMs (the grid-wide counter cost 5-22k cycles of skew per pass).
 //   The epilogue warps publish a pass with their own named barrier; TMA and MMA warps never stop.
-//   TWO BAND SETS PER CTA.  Even so, a pass is a dependency chain (last sweep -> epilogue tail -> proxy fence + release
-//   -> neighbours' acquire -> first slab) of ~6 us with NO work in it, and every pass of a group pays it: groups ran
-//   at ~12 us per pass whatever their size.  The schedule therefore gives each CTA two band sets far apart in the strip
-//   sequence (ideally different tiles) and the kernel alternates (pass k, set 0), (pass k, set 1), (pass k+1, set 0) ...:
-//   while one set's chain is in flight the CTA works on the other.  Progress words and halo lists are per (CTA, set).
+//   TWO BAND SETS PER CTA (optional, NESR_B200_SETS=2; off by default).  The schedule can give each CTA two band sets far
+//   apart in the strip sequence and the kernel then alternates (pass k, set 0), (pass k, set 1), (pass k+1, set 0) ... with
+//   progress words and halo lists per (CTA, set), so that one set's publish -> acquire latency hides behind the other set's
+//   work.  Measured SLOWER (6.7 vs 6.0 ms per group): the cross-CTA machinery costs only ~7 % in total, the three roles of a
+//   CTA are the bound, and the second band costs two more halo rows (profiles/r1_trunk_experiments.txt).
 //
 // Roles (fold_roles.cuh explains the row fold itself): warp 0 TMA producer (weights + row slabs), warp 1
 // MMA issuer, warps 2..9 epilogue (two groups alternating rows).  Launched cooperatively (grid <= #SMs).
