@@ -115,6 +115,8 @@ struct nesr_b200_handle {
   nesr_b200_config cfg{};
   int num_sms = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;                  // device -> host copies of finished tile groups, overlapped with the next group
+  std::vector<cudaEvent_t> ev_group;                   // "group g stitched" events
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evc0 = nullptr, evc1 = nullptr;
   std::vector<cudaEvent_t> ev_trunk;                   // begin/end pairs around each trunk kernel launch of the last call
   int n_trunk_timed = 0;
@@ -1066,13 +1068,36 @@ int enhance_impl(nesr_b200_handle* h, const uint8_t* in, int n_frames, int H, in
   PackParams pk{};
   pk.in_u8 = d_in; pk.in_stride = d_in_stride; pk.in_frame_stride = d_in_fs; pk.H = H; pk.W = W; pk.pre_pad = pre_pad;
   Sink sink; sink.out_u8 = d_out; sink.out_stride = d_out_stride; sink.out_frame_stride = d_out_fs;
-  for (size_t bi = 0; bi < h->batches.size(); ++bi)
+  // Host output of a whole frame: every tile group's stitched rectangles go back on a second stream while the next group
+  // computes (the tiles' crop rectangles partition the frame).  A tile range keeps the single full-frame copy.
+  const bool overlap_d2h = !(flags & NESR_PTR_OUT_DEVICE) && whole && h->batches.size() > 1 && h->copy_stream;
+  for (size_t bi = 0; bi < h->batches.size(); ++bi) {
     if ((rc = forward_batch(h, h->batches[bi], pk, sink, h->stream, bi == 0, bi + 1 == h->batches.size(), true))) return rc;
+    if (overlap_d2h) {
+      while (h->ev_group.size() <= bi) {
+        cudaEvent_t ev = nullptr;
+        CUDA_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        h->ev_group.push_back(ev);
+      }
+      CUDA_TRY(h, cudaEventRecord(h->ev_group[bi], h->stream));
+      CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_group[bi], 0));
+      for (const TileGeom& t : h->batches[bi].tiles) {
+        if (t.crop_w <= 0 || t.crop_h <= 0) continue;
+        const size_t off_d = (size_t)t.frame * d_out_fs + (size_t)t.out_y0 * d_out_stride + (size_t)t.out_x0 * 3;
+        const size_t off_h = (size_t)t.frame * out_frame_stride + (size_t)t.out_y0 * out_stride + (size_t)t.out_x0 * 3;
+        CUDA_TRY(h, cudaMemcpy2DAsync(out + off_h, out_stride, d_out + off_d, d_out_stride, (size_t)t.crop_w * 3, t.crop_h,
+                                      cudaMemcpyDeviceToHost, h->copy_stream));
+      }
+    }
+  }
   cudaEventRecord(h->ev1, h->stream);
-  if (!(flags & NESR_PTR_OUT_DEVICE))
+  if (overlap_d2h) {
+    CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+  } else if (!(flags & NESR_PTR_OUT_DEVICE)) {
     for (int f = 0; f < n_frames; ++f)
       CUDA_TRY(h, cudaMemcpy2DAsync(out + f * out_frame_stride, out_stride, d_out + f * d_out_fs, d_out_stride, (size_t)OW * 3, OH,
                                     cudaMemcpyDeviceToHost, h->stream));
+  }
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->stats.last_device_ms = ms;
@@ -1140,6 +1165,7 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
   }
   h->encode = (EncodeTiledFn)fn;
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
       (e = cudaEventCreate(&h->evc0)) != cudaSuccess || (e = cudaEventCreate(&h->evc1)) != cudaSuccess ||
       (e = conv3x3_tc_configure()) != cudaSuccess || (e = conv3x3_fold_configure()) != cudaSuccess ||
@@ -1175,6 +1201,8 @@ int nesr_b200_destroy(nesr_b200_handle* h) {
   for (cudaEvent_t ev : h->ev_trunk) cudaEventDestroy(ev);
   if (h->evc0) cudaEventDestroy(h->evc0);
   if (h->evc1) cudaEventDestroy(h->evc1);
+  for (cudaEvent_t ev : h->ev_group) cudaEventDestroy(ev);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return NESR_OK;
