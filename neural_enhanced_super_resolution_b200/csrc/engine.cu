@@ -646,7 +646,7 @@ int plan_groups(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
       px += n;
       ++i;
     }
-    if (l2_groups && i == all.size() && !h->batches.empty() && px * 5 < cap * 2) {
+    if (l2_groups && i == all.size() && !h->batches.empty() && px * 5 < cap * 3) {
       // A small tail group pays the trunk's per-pass latency (414 dependent passes) for almost no work: fold it into the
       // previous group when the combined schedule still fits the trunk kernel.
       Batch m = h->batches.back();
