@@ -19,20 +19,25 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 // blend
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint8_t blend_byte(const BlendParams& p, const uint8_t (&b)[kMaxBlendMembers]) {
-  float acc = 0.f;
-  for (int m = 0; m < p.k; ++m)
-    acc = static_cast<float>(__dadd_rn(static_cast<double>(acc), __dmul_rn(static_cast<double>(b[m]), p.weights[m])));
-  return static_cast<uint8_t>(acc);           // astype(uint8): truncation (acc >= 0)
+// acc_f32 = f32( f64(acc_f32) + f64(byte) * w ) per member, in member order (oracle/postprocess.py ensemble_results)
+__device__ __forceinline__ float blend_step(float acc, uint32_t byte, double w) {
+  return static_cast<float>(__dadd_rn(static_cast<double>(acc), __dmul_rn(static_cast<double>(byte), w)));
 }
 
-__global__ void __launch_bounds__(256) blend_kernel(const BlendParams p, const int vec_ok) {
+// K members known at compile time: pointers, weights and the 16-byte vectors live in registers.  (With K a run-time value the
+// per-member arrays were indexed dynamically and lived in local memory: 0.7 TB/s of algorithmic traffic on a B200.)
+// Two independent 16-byte vectors per member are in flight per thread and iteration.
+template <int K>
+__global__ void __launch_bounds__(256) blend_kernel_k(const BlendParams p, const int vec_ok) {
   const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const int64_t nvec = vec_ok ? p.nbytes / 16 : 0;
-  for (int64_t i = tid; i < nvec; i += nthreads) {
-    uint4 in[kMaxBlendMembers];
-    for (int m = 0; m < p.k; ++m) in[m] = __ldg(reinterpret_cast<const uint4*>(p.members[m]) + i);
+  const uint4* src[K];
+  double w[K];
+#pragma unroll
+  for (int m = 0; m < K; ++m) { src[m] = reinterpret_cast<const uint4*>(p.members[m]); w[m] = p.weights[m]; }
+  uint4* dst = reinterpret_cast<uint4*>(p.out);
+  auto blend16 = [&](const uint4 (&in)[K]) {
     uint4 o;
     uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
@@ -40,18 +45,68 @@ __global__ void __launch_bounds__(256) blend_kernel(const BlendParams p, const i
       uint32_t word = 0;
 #pragma unroll
       for (int by = 0; by < 4; ++by) {
-        uint8_t b[kMaxBlendMembers];
-        for (int m = 0; m < p.k; ++m) b[m] = (reinterpret_cast<const uint32_t*>(&in[m])[wd] >> (8 * by)) & 0xFF;
-        word |= static_cast<uint32_t>(blend_byte(p, b)) << (8 * by);
+        float acc = 0.f;
+#pragma unroll
+        for (int m = 0; m < K; ++m) acc = blend_step(acc, (reinterpret_cast<const uint32_t*>(&in[m])[wd] >> (8 * by)) & 0xFF, w[m]);
+        word |= static_cast<uint32_t>(static_cast<uint8_t>(acc)) << (8 * by);   // astype(uint8): truncation (acc >= 0)
       }
+      ow[wd] = word;
+    }
+    return o;
+  };
+  int64_t i = tid;
+  for (; i + nthreads < nvec; i += 2 * nthreads) {
+    uint4 a[K], b[K];
+#pragma unroll
+    for (int m = 0; m < K; ++m) { a[m] = __ldcs(src[m] + i); b[m] = __ldcs(src[m] + i + nthreads); }
+    __stcs(dst + i, blend16(a));
+    __stcs(dst + i + nthreads, blend16(b));
+  }
+  for (; i < nvec; i += nthreads) {
+    uint4 a[K];
+#pragma unroll
+    for (int m = 0; m < K; ++m) a[m] = __ldcs(src[m] + i);
+    __stcs(dst + i, blend16(a));
+  }
+  for (int64_t j = nvec * 16 + tid; j < p.nbytes; j += nthreads) {
+    float acc = 0.f;
+#pragma unroll
+    for (int m = 0; m < K; ++m) acc = blend_step(acc, p.members[m][j], w[m]);
+    p.out[j] = static_cast<uint8_t>(acc);
+  }
+}
+
+// any K up to kMaxBlendMembers (members indexed at run time)
+__global__ void __launch_bounds__(256) blend_kernel(const BlendParams p, const int vec_ok) {
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t nvec = vec_ok ? p.nbytes / 16 : 0;
+  for (int64_t i = tid; i < nvec; i += nthreads) {
+    float acc[16];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) acc[b] = 0.f;
+    for (int m = 0; m < p.k; ++m) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.members[m]) + i);
+      const double w = p.weights[m];
+      const uint32_t* vw = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+      for (int b = 0; b < 16; ++b) acc[b] = blend_step(acc[b], (vw[b >> 2] >> (8 * (b & 3))) & 0xFF, w);
+    }
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int wd = 0; wd < 4; ++wd) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int by = 0; by < 4; ++by) word |= static_cast<uint32_t>(static_cast<uint8_t>(acc[wd * 4 + by])) << (8 * by);
       ow[wd] = word;
     }
     reinterpret_cast<uint4*>(p.out)[i] = o;
   }
   for (int64_t i = nvec * 16 + tid; i < p.nbytes; i += nthreads) {
-    uint8_t b[kMaxBlendMembers];
-    for (int m = 0; m < p.k; ++m) b[m] = p.members[m][i];
-    p.out[i] = blend_byte(p, b);
+    float acc = 0.f;
+    for (int m = 0; m < p.k; ++m) acc = blend_step(acc, p.members[m][i], p.weights[m]);
+    p.out[i] = static_cast<uint8_t>(acc);
   }
 }
 
@@ -62,11 +117,38 @@ constexpr int kTW = 64, kTH = 32;         // output tile
 constexpr int kR3 = 9, kR2 = 6;           // radii of the 19- and 13-tap kernels
 constexpr int kInW = kTW + 2 * kR3;       // 82
 constexpr int kInH = kTH + 2 * kR3;       // 50
-constexpr int kInWp = kInW + 2;           // padded pitch
+constexpr int kInWp = 88;                 // padded pitch in bytes (22 aligned words)
 constexpr int kGrayRows = kTH + 2 * kR2;  // 44
+constexpr int kRuns = kTW / 4;            // runs of four horizontally adjacent outputs per tile row
 
 __constant__ int c_q3[19] = {0, 1, 3, 4, 9, 14, 20, 28, 32, 34, 32, 28, 20, 14, 9, 4, 3, 1, 0};
 __constant__ int c_q2[13] = {1, 2, 7, 16, 31, 45, 52, 45, 31, 16, 7, 2, 1};
+
+// Row pass with dp4a.  Four outputs ox0 .. ox0+3 (ox0 a multiple of 4) read the 24 bytes ox0 .. ox0+23 of a tile row as six
+// ALIGNED words; output j weighs byte i with q[i - j] (zero outside the kernel), so each output is six dp4a with weight words
+// that depend only on (j, word) -- no byte extraction, no unaligned loads.  All weights are < 128 and non-negative.
+struct RowWeights {
+  uint32_t w3[4][6];   // 19-tap kernel (taps 0 and 18 are zero)
+  uint32_t w2[4][6];   // 13-tap kernel, centred in the 19-tap window (offset kR3 - kR2 = 3)
+};
+constexpr RowWeights make_row_weights() {
+  constexpr int q3[19] = {0, 1, 3, 4, 9, 14, 20, 28, 32, 34, 32, 28, 20, 14, 9, 4, 3, 1, 0};
+  constexpr int q2[13] = {1, 2, 7, 16, 31, 45, 52, 45, 31, 16, 7, 2, 1};
+  RowWeights r{};
+  for (int j = 0; j < 4; ++j)
+    for (int k = 0; k < 6; ++k) {
+      uint32_t a = 0, b = 0;
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * k + e;
+        const int t3 = i - j, t2 = i - j - (kR3 - kR2);
+        if (t3 >= 0 && t3 < 19) a |= static_cast<uint32_t>(q3[t3]) << (8 * e);
+        if (t2 >= 0 && t2 < 13) b |= static_cast<uint32_t>(q2[t2]) << (8 * e);
+      }
+      r.w3[j][k] = a; r.w2[j][k] = b;
+    }
+  return r;
+}
+__constant__ RowWeights c_rw = make_row_weights();
 
 __device__ __forceinline__ int reflect101(int i, int n) {
   if (n == 1) return 0;
@@ -74,12 +156,16 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   return i;
 }
 
+// One shared-memory tiled pass: every image byte is read from HBM once (plus halo) and written once.  The arithmetic is the
+// integer restatement of cv2's fixed-point Gaussians (oracle/postprocess.py); sums are exact, so the order is free:
+//   load   : tile + 9-pixel halo -> planar R, G, B and gray bytes (BORDER_REFLECT_101)
+//   rows   : 19-tap (three channels) and 13-tap (gray) horizontal sums as dp4a over aligned words -> 16-bit Q8.8
+//   columns: vertical sums, one rounding, threshold mask, unsharp with round-half-even, saturate
 __global__ void __launch_bounds__(256) sharpen_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                       const int H, const int W, const int bgr) {
-  __shared__ uint8_t s_in[3][kInH][kInWp];          // planar R, G, B
-  __shared__ uint8_t s_gray[kInH][kInWp];
-  __shared__ uint16_t s_h3[3][kInH][kTW];           // row pass of the 19-tap blur (Q8.8, <= 65280)
-  __shared__ uint16_t s_h2[kGrayRows][kTW];         // row pass of the 13-tap blur on gray
+  __shared__ __align__(16) uint8_t s_in[4][kInH][kInWp];     // planar R, G, B, gray
+  __shared__ __align__(16) uint16_t s_h3[3][kInH][kTW];      // row pass of the 19-tap blur (Q8.8, <= 65280)
+  __shared__ __align__(16) uint16_t s_h2[kGrayRows][kTW];    // row pass of the 13-tap blur on gray
 
   const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
   const int tid = threadIdx.x;
@@ -91,25 +177,30 @@ __global__ void __launch_bounds__(256) sharpen_kernel(const uint8_t* __restrict_
     const int c0 = px[0], c1 = px[1], c2 = px[2];
     const int r = bgr ? c2 : c0, b = bgr ? c0 : c2;
     s_in[0][ly][lx] = r; s_in[1][ly][lx] = c1; s_in[2][ly][lx] = b;
-    s_gray[ly][lx] = static_cast<uint8_t>((9798 * r + 19235 * c1 + 3735 * b + 16384) >> 15);
+    s_in[3][ly][lx] = static_cast<uint8_t>((9798 * r + 19235 * c1 + 3735 * b + 16384) >> 15);
   }
   __syncthreads();
 
-  for (int idx = tid; idx < kInH * kTW; idx += 256) {
-    const int ly = idx / kTW, ox = idx - ly * kTW;
+  // rows: item = (plane, tile row, run of four outputs)
+  for (int idx = tid; idx < 4 * kInH * kRuns; idx += 256) {
+    const int plane = idx / (kInH * kRuns);
+    const int rem = idx - plane * (kInH * kRuns);
+    const int ly = rem / kRuns, run = rem - ly * kRuns;
+    if (plane == 3 && (ly < kR3 - kR2 || ly >= kR3 - kR2 + kGrayRows)) continue;
+    const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(&s_in[plane][ly][4 * run]);
+    uint32_t wv[6];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      int acc = 0;
+    for (int k = 0; k < 6; ++k) wv[k] = wsrc[k];
+    uint32_t acc[4];
 #pragma unroll
-      for (int t = 1; t < 18; ++t) acc += c_q3[t] * s_in[c][ly][ox + t];       // taps 0 and 18 are zero
-      s_h3[c][ly][ox] = static_cast<uint16_t>(acc);
+    for (int j = 0; j < 4; ++j) {
+      uint32_t a = 0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) a = __dp4a(wv[k], plane == 3 ? c_rw.w2[j][k] : c_rw.w3[j][k], a);
+      acc[j] = a;
     }
-    if (ly >= kR3 - kR2 && ly < kR3 - kR2 + kGrayRows) {
-      int acc = 0;
-#pragma unroll
-      for (int t = 0; t < 13; ++t) acc += c_q2[t] * s_gray[ly][ox + (kR3 - kR2) + t];
-      s_h2[ly - (kR3 - kR2)][ox] = static_cast<uint16_t>(acc);
-    }
+    uint16_t* dst = plane == 3 ? &s_h2[ly - (kR3 - kR2)][4 * run] : &s_h3[plane][ly][4 * run];
+    *reinterpret_cast<uint2*>(dst) = make_uint2(acc[0] | (acc[1] << 16), acc[2] | (acc[3] << 16));
   }
   __syncthreads();
 
@@ -121,7 +212,7 @@ __global__ void __launch_bounds__(256) sharpen_kernel(const uint8_t* __restrict_
 #pragma unroll
     for (int t = 0; t < 13; ++t) g2 += c_q2[t] * s_h2[oy + t][ox];
     g2 = (g2 + 32768) >> 16;
-    const int gray = s_gray[oy + kR3][ox + kR3];
+    const int gray = s_in[3][oy + kR3][ox + kR3];
     const bool mask = (gray - g2) > 10;                    // saturating subtract then threshold
     int res[3];
 #pragma unroll
@@ -156,7 +247,14 @@ cudaError_t launch_blend(const BlendParams& p, cudaStream_t stream) {
   const int64_t work = vec_ok ? (p.nbytes + 15) / 16 : p.nbytes;
   int64_t blocks = (work + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  blend_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p, vec_ok);
+  const unsigned g = static_cast<unsigned>(blocks);
+  switch (p.k) {
+    case 1: blend_kernel_k<1><<<g, 256, 0, stream>>>(p, vec_ok); break;
+    case 2: blend_kernel_k<2><<<g, 256, 0, stream>>>(p, vec_ok); break;
+    case 3: blend_kernel_k<3><<<g, 256, 0, stream>>>(p, vec_ok); break;
+    case 4: blend_kernel_k<4><<<g, 256, 0, stream>>>(p, vec_ok); break;
+    default: blend_kernel<<<g, 256, 0, stream>>>(p, vec_ok); break;
+  }
   return cudaGetLastError();
 }
 
