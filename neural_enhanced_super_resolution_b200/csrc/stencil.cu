@@ -115,40 +115,43 @@ __global__ void __launch_bounds__(256) blend_kernel(const BlendParams p, const i
 // ---------------------------------------------------------------------------------------------
 constexpr int kTW = 64, kTH = 32;         // output tile
 constexpr int kR3 = 9, kR2 = 6;           // radii of the 19- and 13-tap kernels
-constexpr int kInW = kTW + 2 * kR3;       // 82
 constexpr int kInH = kTH + 2 * kR3;       // 50
 constexpr int kInWp = 88;                 // padded pitch in bytes (22 aligned words)
 constexpr int kGrayRows = kTH + 2 * kR2;  // 44
 constexpr int kRuns = kTW / 4;            // runs of four horizontally adjacent outputs per tile row
+constexpr int kTp = 52;                   // pitch of the transposed row sums: 13 words (odd: conflict-free across columns)
 
-__constant__ int c_q3[19] = {0, 1, 3, 4, 9, 14, 20, 28, 32, 34, 32, 28, 20, 14, 9, 4, 3, 1, 0};
-__constant__ int c_q2[13] = {1, 2, 7, 16, 31, 45, 52, 45, 31, 16, 7, 2, 1};
-
-// Row pass with dp4a.  Four outputs ox0 .. ox0+3 (ox0 a multiple of 4) read the 24 bytes ox0 .. ox0+23 of a tile row as six
-// ALIGNED words; output j weighs byte i with q[i - j] (zero outside the kernel), so each output is six dp4a with weight words
-// that depend only on (j, word) -- no byte extraction, no unaligned loads.  All weights are < 128 and non-negative.
-struct RowWeights {
+// Both passes run on dp4a.  Four outputs o0 .. o0+3 (o0 a multiple of 4) read the 24 bytes o0 .. o0+23 of a line as six ALIGNED
+// words; output j weighs byte i with q[i - j] (zero outside the kernel), so each output is six dp4a with weight words that depend
+// only on (j, word) -- no byte extraction, no unaligned loads.  All weights are < 128 and non-negative.
+//   rows   : lines are tile rows of the planar input bytes; the 16-bit sums are stored as two BYTE planes (high, low), transposed
+//            ([column][row]), so that
+//   columns: lines are tile columns of those byte planes: sum = 256 * dp4a(high bytes) + dp4a(low bytes), exact.
+struct TapWeights {
   uint32_t w3[4][6];   // 19-tap kernel (taps 0 and 18 are zero)
-  uint32_t w2[4][6];   // 13-tap kernel, centred in the 19-tap window (offset kR3 - kR2 = 3)
+  uint32_t w2r[4][6];  // 13-tap kernel inside the 19-tap window of a ROW (offset kR3 - kR2 = 3)
+  uint32_t w2c[4][4];  // 13-tap kernel on the 44 gray row sums of a COLUMN (no offset: 16-byte window)
 };
-constexpr RowWeights make_row_weights() {
+constexpr TapWeights make_tap_weights() {
   constexpr int q3[19] = {0, 1, 3, 4, 9, 14, 20, 28, 32, 34, 32, 28, 20, 14, 9, 4, 3, 1, 0};
   constexpr int q2[13] = {1, 2, 7, 16, 31, 45, 52, 45, 31, 16, 7, 2, 1};
-  RowWeights r{};
+  TapWeights r{};
   for (int j = 0; j < 4; ++j)
     for (int k = 0; k < 6; ++k) {
-      uint32_t a = 0, b = 0;
+      uint32_t a = 0, b = 0, c = 0;
       for (int e = 0; e < 4; ++e) {
         const int i = 4 * k + e;
-        const int t3 = i - j, t2 = i - j - (kR3 - kR2);
+        const int t3 = i - j, t2 = i - j - (kR3 - kR2), tc = i - j;
         if (t3 >= 0 && t3 < 19) a |= static_cast<uint32_t>(q3[t3]) << (8 * e);
         if (t2 >= 0 && t2 < 13) b |= static_cast<uint32_t>(q2[t2]) << (8 * e);
+        if (tc >= 0 && tc < 13) c |= static_cast<uint32_t>(q2[tc]) << (8 * e);
       }
-      r.w3[j][k] = a; r.w2[j][k] = b;
+      r.w3[j][k] = a; r.w2r[j][k] = b;
+      if (k < 4) r.w2c[j][k] = c;
     }
   return r;
 }
-__constant__ RowWeights c_rw = make_row_weights();
+__constant__ TapWeights c_tw = make_tap_weights();
 
 __device__ __forceinline__ int reflect101(int i, int n) {
   if (n == 1) return 0;
@@ -157,84 +160,136 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 }
 
 // One shared-memory tiled pass: every image byte is read from HBM once (plus halo) and written once.  The arithmetic is the
-// integer restatement of cv2's fixed-point Gaussians (oracle/postprocess.py); sums are exact, so the order is free:
+// integer restatement of cv2's fixed-point Gaussians (oracle/postprocess.py); sums are exact, so their order is free:
 //   load   : tile + 9-pixel halo -> planar R, G, B and gray bytes (BORDER_REFLECT_101)
-//   rows   : 19-tap (three channels) and 13-tap (gray) horizontal sums as dp4a over aligned words -> 16-bit Q8.8
+//   rows   : 19-tap (three channels) and 13-tap (gray) horizontal sums, Q8.8 in 16 bits
 //   columns: vertical sums, one rounding, threshold mask, unsharp with round-half-even, saturate
 __global__ void __launch_bounds__(256) sharpen_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                       const int H, const int W, const int bgr) {
   __shared__ __align__(16) uint8_t s_in[4][kInH][kInWp];     // planar R, G, B, gray
-  __shared__ __align__(16) uint16_t s_h3[3][kInH][kTW];      // row pass of the 19-tap blur (Q8.8, <= 65280)
-  __shared__ __align__(16) uint16_t s_h2[kGrayRows][kTW];    // row pass of the 13-tap blur on gray
+  __shared__ __align__(16) uint8_t s_t3[3][2][kTW][kTp];     // row sums of the 19-tap blur: [channel][high | low byte][column][row]
+  __shared__ __align__(16) uint8_t s_t2[2][kTW][kTp];        // row sums of the 13-tap blur on gray: [high | low][column][row - 3]
 
   const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
   const int tid = threadIdx.x;
 
-  for (int idx = tid; idx < kInH * kInW; idx += 256) {
-    const int ly = idx / kInW, lx = idx - ly * kInW;
-    const int gy = reflect101(y0 + ly - kR3, H), gx = reflect101(x0 + lx - kR3, W);
-    const uint8_t* px = in + (static_cast<size_t>(gy) * W + gx) * 3;
-    const int c0 = px[0], c1 = px[1], c2 = px[2];
-    const int r = bgr ? c2 : c0, b = bgr ? c0 : c2;
-    s_in[0][ly][lx] = r; s_in[1][ly][lx] = c1; s_in[2][ly][lx] = b;
-    s_in[3][ly][lx] = static_cast<uint8_t>((9798 * r + 19235 * c1 + 3735 * b + 16384) >> 15);
+  // load: a thread takes four horizontally adjacent pixels of a tile row (one index computation, one 32-bit store per plane;
+  // columns 82, 83 of the 84 loaded are never weighted)
+  for (int idx = tid; idx < kInH * (kInWp / 4 - 1); idx += 256) {
+    const int ly = idx / (kInWp / 4 - 1), lx = 4 * (idx - ly * (kInWp / 4 - 1));
+    const int gy = reflect101(y0 + ly - kR3, H);
+    const uint8_t* row = in + static_cast<size_t>(gy) * W * 3;
+    const int gx0 = x0 + lx - kR3;
+    uint32_t pr = 0, pg = 0, pb = 0, py = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int gx = (gx0 >= 0 && gx0 + 3 < W) ? gx0 + e : reflect101(gx0 + e, W);
+      const uint8_t* px = row + gx * 3;
+      const int c0 = px[0], c1 = px[1], c2 = px[2];
+      const int r = bgr ? c2 : c0, b = bgr ? c0 : c2;
+      pr |= static_cast<uint32_t>(r) << (8 * e); pg |= static_cast<uint32_t>(c1) << (8 * e); pb |= static_cast<uint32_t>(b) << (8 * e);
+      py |= static_cast<uint32_t>((9798 * r + 19235 * c1 + 3735 * b + 16384) >> 15) << (8 * e);
+    }
+    *reinterpret_cast<uint32_t*>(&s_in[0][ly][lx]) = pr;
+    *reinterpret_cast<uint32_t*>(&s_in[1][ly][lx]) = pg;
+    *reinterpret_cast<uint32_t*>(&s_in[2][ly][lx]) = pb;
+    *reinterpret_cast<uint32_t*>(&s_in[3][ly][lx]) = py;
   }
   __syncthreads();
 
-  // rows: item = (plane, tile row, run of four outputs)
-  for (int idx = tid; idx < 4 * kInH * kRuns; idx += 256) {
-    const int plane = idx / (kInH * kRuns);
-    const int rem = idx - plane * (kInH * kRuns);
-    const int ly = rem / kRuns, run = rem - ly * kRuns;
+  // rows: item = (plane, run of four outputs, tile row); consecutive threads take consecutive rows, so the transposed byte
+  // stores of a warp fall into consecutive bytes
+  for (int idx = tid; idx < 4 * kRuns * kInH; idx += 256) {
+    const int plane = idx / (kRuns * kInH);
+    const int rem = idx - plane * (kRuns * kInH);
+    const int run = rem / kInH, ly = rem - run * kInH;
     if (plane == 3 && (ly < kR3 - kR2 || ly >= kR3 - kR2 + kGrayRows)) continue;
     const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(&s_in[plane][ly][4 * run]);
     uint32_t wv[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) wv[k] = wsrc[k];
-    uint32_t acc[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint32_t a = 0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) a = __dp4a(wv[k], plane == 3 ? c_rw.w2[j][k] : c_rw.w3[j][k], a);
-      acc[j] = a;
+      for (int k = 0; k < 6; ++k) a = __dp4a(wv[k], plane == 3 ? c_tw.w2r[j][k] : c_tw.w3[j][k], a);
+      if (plane == 3) {
+        s_t2[0][4 * run + j][ly - (kR3 - kR2)] = static_cast<uint8_t>(a >> 8);
+        s_t2[1][4 * run + j][ly - (kR3 - kR2)] = static_cast<uint8_t>(a);
+      } else {
+        s_t3[plane][0][4 * run + j][ly] = static_cast<uint8_t>(a >> 8);
+        s_t3[plane][1][4 * run + j][ly] = static_cast<uint8_t>(a);
+      }
     }
-    uint16_t* dst = plane == 3 ? &s_h2[ly - (kR3 - kR2)][4 * run] : &s_h3[plane][ly][4 * run];
-    *reinterpret_cast<uint2*>(dst) = make_uint2(acc[0] | (acc[1] << 16), acc[2] | (acc[3] << 16));
   }
   __syncthreads();
 
-  for (int idx = tid; idx < kTH * kTW; idx += 256) {
-    const int oy = idx / kTW, ox = idx - oy * kTW;
-    const int gy = y0 + oy, gx = x0 + ox;
-    if (gy >= H || gx >= W) continue;
-    int g2 = 0;
+  // columns: item = (group of four vertically adjacent outputs, column); consecutive threads take consecutive columns
+  for (int idx = tid; idx < (kTH / 4) * kTW; idx += 256) {
+    const int og = idx / kTW, ox = idx - og * kTW;
+    const int oy0 = 4 * og;
+    const int gx = x0 + ox;
+    if (gx >= W || y0 + oy0 >= H) continue;
+    bool mask[4];
+    bool any = false;
+    {
+      const uint32_t* hi = reinterpret_cast<const uint32_t*>(&s_t2[0][ox][oy0]);
+      const uint32_t* lo = reinterpret_cast<const uint32_t*>(&s_t2[1][ox][oy0]);
+      uint32_t hv[4], lv[4];
 #pragma unroll
-    for (int t = 0; t < 13; ++t) g2 += c_q2[t] * s_h2[oy + t][ox];
-    g2 = (g2 + 32768) >> 16;
-    const int gray = s_in[3][oy + kR3][ox + kR3];
-    const bool mask = (gray - g2) > 10;                    // saturating subtract then threshold
-    int res[3];
+      for (int k = 0; k < 4; ++k) { hv[k] = hi[k]; lv[k] = lo[k]; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t sh = 0, sl = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { sh = __dp4a(hv[k], c_tw.w2c[j][k], sh); sl = __dp4a(lv[k], c_tw.w2c[j][k], sl); }
+        const int g2 = static_cast<int>((sh * 256u + sl + 32768u) >> 16);
+        const int gray = s_in[3][oy0 + j + kR3][ox + kR3];
+        mask[j] = (gray - g2) > 10;                            // saturating subtract then threshold
+        any |= mask[j];
+      }
+    }
+    int res[4][3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const int a = s_in[c][oy + kR3][ox + kR3];
-      int v = a;
-      if (mask) {
-        int b3 = 0;
+      int b3[4] = {0, 0, 0, 0};
+      if (any) {
+        const uint32_t* hi = reinterpret_cast<const uint32_t*>(&s_t3[c][0][ox][oy0]);
+        const uint32_t* lo = reinterpret_cast<const uint32_t*>(&s_t3[c][1][ox][oy0]);
+        uint32_t hv[6], lv[6];
 #pragma unroll
-        for (int t = 1; t < 18; ++t) b3 += c_q3[t] * s_h3[c][oy + t][ox];
-        b3 = (b3 + 32768) >> 16;
-        const int t2 = 3 * a - b3;                         // twice (1.5 a - 0.5 b)
-        const int half = t2 >> 1;                          // floor
-        v = half + ((t2 & 1) & (half & 1));                // ties to even
-        v = v < 0 ? 0 : (v > 255 ? 255 : v);
+        for (int k = 0; k < 6; ++k) { hv[k] = hi[k]; lv[k] = lo[k]; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t sh = 0, sl = 0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) { sh = __dp4a(hv[k], c_tw.w3[j][k], sh); sl = __dp4a(lv[k], c_tw.w3[j][k], sl); }
+          b3[j] = static_cast<int>((sh * 256u + sl + 32768u) >> 16);
+        }
       }
-      res[c] = v;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int a = s_in[c][oy0 + j + kR3][ox + kR3];
+        int v = a;
+        if (mask[j]) {
+          const int t2 = 3 * a - b3[j];                        // twice (1.5 a - 0.5 b)
+          const int half = t2 >> 1;                            // floor
+          v = half + ((t2 & 1) & (half & 1));                  // ties to even
+          v = v < 0 ? 0 : (v > 255 ? 255 : v);
+        }
+        res[j][c] = v;
+      }
     }
-    uint8_t* o = out + (static_cast<size_t>(gy) * W + gx) * 3;
-    o[0] = static_cast<uint8_t>(bgr ? res[2] : res[0]);
-    o[1] = static_cast<uint8_t>(res[1]);
-    o[2] = static_cast<uint8_t>(bgr ? res[0] : res[2]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gy = y0 + oy0 + j;
+      if (gy < H) {
+        uint8_t* o = out + (static_cast<size_t>(gy) * W + gx) * 3;
+        o[0] = static_cast<uint8_t>(bgr ? res[j][2] : res[j][0]);
+        o[1] = static_cast<uint8_t>(res[j][1]);
+        o[2] = static_cast<uint8_t>(bgr ? res[j][0] : res[j][2]);
+      }
+    }
   }
 }
 
