@@ -140,6 +140,7 @@ struct nesr_b200_handle {
   uint8_t* arena_base = nullptr;                       // one allocation; every tile group owns a slice, or all share it
   size_t arena_bytes = 0;
   bool arena_shared = false;                           // groups share one slice: its zero pads are re-established per group
+  size_t arena_limit = (size_t)24 << 30;               // NESR_B200_ARENA_LIMIT_MB: above this, groups share one slice
 
   uint8_t* d_in = nullptr;  size_t d_in_bytes = 0;
   uint8_t* d_out = nullptr; size_t d_out_bytes = 0;
@@ -718,7 +719,7 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
   };
   size_t total = 0, largest = 0;
   for (const Batch& bb : h->batches) { const size_t n = slice_bytes(bb, nullptr); total += n; largest = std::max(largest, n); }
-  h->arena_shared = h->batches.size() > 1 && total > ((size_t)24 << 30);
+  h->arena_shared = h->batches.size() > 1 && total > h->arena_limit;
   // a shared slice must hold the largest extent of EVERY level (groups differ in shape)
   size_t need = total;
   if (h->arena_shared) {
@@ -1179,6 +1180,7 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
   if (const char* pin = getenv("NESR_B200_L2_PIN")) h->l2_pin_chunks = atoi(pin);
   if (const char* pr = getenv("NESR_B200_PAIRS")) h->use_pairs = atoi(pr);
   if (const char* st = getenv("NESR_B200_SETS")) h->trunk_sets = atoi(st);
+  if (const char* al = getenv("NESR_B200_ARENA_LIMIT_MB")) h->arena_limit = (size_t)atoll(al) << 20;
   *out = h;
   return NESR_OK;
 }

@@ -164,6 +164,10 @@ def test_trunk_kernel_variants_are_bit_identical(monkeypatch):
         got, _ = gpu_up("calibrated", 160, 10).enhance(img)
         monkeypatch.delenv(var)
         assert np.array_equal(got, want), var
+    monkeypatch.setenv("NESR_B200_ARENA_LIMIT_MB", "1")          # tile groups share one arena slice (re-zeroed per group)
+    shared, _ = gpu_up("calibrated", 160, 10, max_batch_pixels=20000).enhance(img)
+    monkeypatch.delenv("NESR_B200_ARENA_LIMIT_MB")
+    assert np.array_equal(shared, want)
     monkeypatch.setenv("NESR_B200_PAIRS", "1")
     whole, _ = gpu_up("calibrated", 0, 10).enhance(img)           # one untiled group: several strips, packed remainder
     monkeypatch.delenv("NESR_B200_PAIRS")
