@@ -51,6 +51,24 @@ def test_identity_weights_bit_exact(shape, tile, pad, pre):
         assert np.array_equal(out, identity_expected(img))
 
 
+def test_identity_ragged_shapes_and_group_plans(monkeypatch):
+    """Index work under every planner variant: ragged tile widths (remainder columns cut into pieces and packed), several tile
+    groups, CTA pairs, two band sets -- the identity network must reproduce the nearest-neighbour-doubled input exactly."""
+    rng = np.random.default_rng(5)
+    shapes = [(2 * int(rng.integers(20, 160)), 2 * int(rng.integers(20, 330))) for _ in range(5)] + [(266 * 2, 266 * 2), (66, 522)]
+    for i, (h, w) in enumerate(shapes):
+        img = natural_image(h, w, seed=h + w)
+        tile, pad = [(0, 10), (64, 10), (128, 8), (96, 4)][i % 4]
+        want = identity_expected(img)
+        for env in ({}, {"NESR_B200_PAIRS": "1"}, {"NESR_B200_SETS": "2"}, {"NESR_B200_MAX_PIECES": "8"}):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            out, _ = gpu_up("identity", tile, pad, 0, max_batch_pixels=[0, 9000][i % 2]).enhance(img)
+            for k in env:
+                monkeypatch.delenv(k)
+            assert np.array_equal(out, want), (h, w, tile, pad, env)
+
+
 def test_identity_full_size_1080p_tiled():
     """BASELINE config 2 geometry (1920x1080, tile 512, halo 10): 12 tiles stitched exactly."""
     img = natural_image(1080, 1920, seed=2)
