@@ -79,6 +79,15 @@ def test_identity_full_size_1080p_tiled():
     assert up.model.engine().stats()["tiles_processed"] >= 12
 
 
+def test_identity_untiled_frame_takes_the_whole_frame_kernel():
+    """tile=0 on a 1080p frame is ONE tile of 518k feature pixels = 29 output rows per CTA, more than the 16 TMEM row slots of
+    the trunk kernel: the engine falls back to the whole-frame persistent kernel (conv3x3_body.cu)."""
+    for h, w in ((1080, 1920),):
+        img = natural_image(h, w, seed=3)
+        out, _ = gpu_up("identity", 0, 10, 0).enhance(img)
+        assert np.array_equal(out, identity_expected(img))
+
+
 # ---------------------------------------------------------------------------------------------
 # tolerance of the 16-bit conv chain
 # ---------------------------------------------------------------------------------------------
