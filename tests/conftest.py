@@ -21,6 +21,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "reference: needs /root/reference (authoring container only)")
 
 
+def pytest_sessionstart(session):
+    """The shared library is a build artefact (git-ignored).  If a fresh checkout has none, build it once (nvcc cross-compiles
+    sm_100a without a GPU, ~2 min); a failure here is left for the tests that load it to report."""
+    from neural_enhanced_super_resolution_b200 import _build
+    if not os.path.exists(_build.LIB):
+        try:
+            _build.build()
+        except Exception as exc:                                   # noqa: BLE001
+            print(f"conftest: building {_build.LIB} failed: {exc}", file=sys.stderr)
+
+
 def pytest_collection_modifyitems(config, items):
     have_ref = os.path.isdir(os.path.join(REFERENCE, "nesr"))
     for item in items:
