@@ -9,6 +9,9 @@ What is produced by the reference itself (imported unmodified from ``/root/refer
   * ``postprocess.npz``  -- inputs and outputs of ``SuperResolutionPipeline._postprocess_image``
                             (``nesr/nesr.py:1056-1084``, cv2 4.13) incl. tiny / ragged sizes
   * ``ensemble.npz``     -- inputs and outputs of ``_ensemble_results`` (``nesr/nesr.py:1033-1054``), K = 2, 3, 4
+  * ``preprocess.npz``   -- inputs and outputs of ``_preprocess_image`` (``nesr/nesr.py:668-689``: NLM denoise + LAB CLAHE,
+                            cv2 4.13) at denoise levels 0 / 0.3 / 0.5 / 1.0 incl. ragged and tiny sizes
+                            (``python -m oracle.make_golden preprocess`` regenerates only this file)
   * ``pipeline.npz``     -- the unmodified ``enhance_image`` run end to end (1 iteration, diffusion and
                             segmentation off) with the oracle registered as ``basicsr``/``realesrgan``:
                             HEAD behaviour (12-channel replicate, x4) -- pins shims + glue
@@ -39,9 +42,38 @@ def state_dict_digest(sd) -> str:
     return h.hexdigest()
 
 
+def make_preprocess() -> None:
+    """``preprocess.npz``: the reference's ``_preprocess_image`` run on crops of its own test image and on noise."""
+    from oracle import shims
+    Pipeline = shims.import_reference(REF)
+    photo = cv2.cvtColor(cv2.imread(os.path.join(REF, "images", "test.jpeg")), cv2.COLOR_BGR2RGB)
+    rng = np.random.default_rng(20261019)
+    noisy = np.clip(photo[100:164, 300:396].astype(np.int32) + rng.integers(-25, 26, (64, 96, 3)), 0, 255).astype(np.uint8)
+    cases = {
+        "photo_h5": (np.ascontiguousarray(photo[200:248, 180:240]), 0.5),      # 48 x 60, the GUI default level
+        "noisy_h10": (noisy, 1.0),                                              # 64 x 96 (divisible by the CLAHE grid)
+        "ragged_h3": (np.ascontiguousarray(photo[300:337, 100:145]), 0.3),     # 37 x 45
+        "noise_h5": (rng.integers(0, 256, (33, 29, 3), dtype=np.uint8), 0.5),
+        "tiny_h5": (rng.integers(0, 256, (9, 11, 3), dtype=np.uint8), 0.5),
+        "photo_h0": (cv2.resize(photo, (100, 76), interpolation=cv2.INTER_AREA), 0.0),   # CLAHE only
+    }
+    out = {}
+    for name, (img, level) in cases.items():
+        pipe = Pipeline(device="cpu", config={"denoise_level": level})
+        out[name + "_in"] = img
+        out[name + "_level"] = np.array(level)
+        out[name + "_out"] = pipe._preprocess_image(img.copy())
+    np.savez_compressed(os.path.join(OUT, "preprocess.npz"), **out)
+    print("preprocess.npz", os.path.getsize(os.path.join(OUT, "preprocess.npz")))
+
+
 def main() -> None:
     sys.dont_write_bytecode = True
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["preprocess"]:
+        make_preprocess()
+        return
+    make_preprocess()
     from oracle import shims
     from oracle.realesrganer import RealESRGANer
     from oracle.rrdbnet import RRDBNet, x2plus
