@@ -166,6 +166,22 @@ int nesr_b200_blend_u8(nesr_b200_handle* h, const uint8_t* const* members, int32
 int nesr_b200_sharpen_u8(nesr_b200_handle* h, const uint8_t* in, int32_t H, int32_t W,
                          int32_t bgr, uint8_t* out, int32_t flags);
 
+/* Replaces: SuperResolutionPipeline._preprocess_image (nesr/nesr.py:668-689): RGB H x W x 3 u8 ->
+ * same layout.  denoise_h > 0: cv2.fastNlMeansDenoisingColored(img, None, denoise_h, denoise_h_color, 7, 21) (the reference
+ * passes 10 * config['denoise_level'] for both; denoise_h_color <= 0 means "same as denoise_h"); denoise_h <= 0 skips the
+ * denoiser as the reference does at level 0.  Then CLAHE(clahe_clip, (tiles_x, tiles_y)) on L of cvtColor(RGB2LAB) and
+ * cvtColor(LAB2RGB) -- the reference uses 2.0 and (8, 8).  Bit-exact with cv2 4.13 (integer Lab paths, integer NLM weights,
+ * float32 CLAHE interpolation without contraction). */
+int nesr_b200_preprocess_u8(nesr_b200_handle* h, const uint8_t* rgb, int32_t H, int32_t W, float denoise_h,
+                            float denoise_h_color, float clahe_clip, int32_t tiles_x, int32_t tiles_y,
+                            uint8_t* out, int32_t flags);
+
+/* Test hooks (host only, no GPU): the committed 8-bit Lab tables (which: 0 sRGB gamma u16[256], 1 cube root u16[3072],
+ * 2 L -> (y, fy) u16[512], 3 inverse sRGB gamma u8[4096]) and the NLM weight table for (h, channels); both return the size
+ * (bytes resp. entries; out may be NULL to query) or -1. */
+int nesr_b200_debug_lab_table(int32_t which, void* out, int32_t capacity_bytes);
+int nesr_b200_debug_nlm_weights(float h, int32_t channels, int32_t* out, int32_t capacity);
+
 int nesr_b200_get_stats(const nesr_b200_handle* h, nesr_b200_stats* out);
 int nesr_b200_synchronize(nesr_b200_handle* h);
 

@@ -22,7 +22,8 @@ EXPORTS = (
     "nesr_b200_load_weight", "nesr_b200_finalize_weights", "nesr_b200_enhance_u8",
     "nesr_b200_enhance_batch_u8", "nesr_b200_tile_count", "nesr_b200_debug_plan", "nesr_b200_enhance_tiles_u8",
     "nesr_b200_forward_nchw_f32", "nesr_b200_blend_u8", "nesr_b200_sharpen_u8", "nesr_b200_get_stats",
-    "nesr_b200_synchronize", "nesr_b200_debug_conv",
+    "nesr_b200_synchronize", "nesr_b200_debug_conv", "nesr_b200_preprocess_u8", "nesr_b200_debug_lab_table",
+    "nesr_b200_debug_nlm_weights",
 )
 
 
@@ -82,6 +83,10 @@ def load_library() -> C.CDLL:
         lib.nesr_b200_blend_u8.argtypes = [H, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32,
                                            C.POINTER(C.c_double), u8p, C.c_int32]
         lib.nesr_b200_sharpen_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int32, u8p, C.c_int32]
+        lib.nesr_b200_preprocess_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32,
+                                                C.c_int32, u8p, C.c_int32]
+        lib.nesr_b200_debug_lab_table.argtypes = [C.c_int32, C.c_void_p, C.c_int32]
+        lib.nesr_b200_debug_nlm_weights.argtypes = [C.c_float, C.c_int32, C.c_void_p, C.c_int32]
         lib.nesr_b200_get_stats.argtypes = [H, C.POINTER(Stats)]
         lib.nesr_b200_synchronize.argtypes = [H]
         lib.nesr_b200_debug_conv.argtypes = [H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
@@ -92,6 +97,28 @@ def load_library() -> C.CDLL:
                 fn.restype = C.c_int
         _lib = lib
         return lib
+
+
+def lab_table(which: int) -> np.ndarray:
+    """The library's committed 8-bit Lab table ``which`` (0 sRGB gamma, 1 cube root, 2 L->(y, fy), 3 inverse sRGB gamma)."""
+    lib = load_library()
+    nbytes = lib.nesr_b200_debug_lab_table(which, None, 0)
+    if nbytes < 0:
+        raise ValueError("no such table")
+    buf = np.empty(nbytes, np.uint8)
+    lib.nesr_b200_debug_lab_table(which, buf.ctypes.data, nbytes)
+    return buf if which == 3 else buf.view(np.uint16)
+
+
+def nlm_weights(h: float, channels: int) -> np.ndarray:
+    """The library's NLM weight table (non-zero prefix) for strength ``h`` and 1 or 2 channels."""
+    lib = load_library()
+    n = lib.nesr_b200_debug_nlm_weights(float(h), channels, None, 0)
+    if n < 0:
+        raise ValueError("bad arguments")
+    buf = np.empty(n, np.int32)
+    lib.nesr_b200_debug_nlm_weights(float(h), channels, buf.ctypes.data, n)
+    return buf
 
 
 def _is_torch_cuda(x) -> bool:
@@ -256,6 +283,22 @@ class Engine:
         op, odev = _image_ptr(out)
         flags = (PTR_IN_DEVICE if idev else 0) | (PTR_OUT_DEVICE if odev else 0)
         self._check(self._lib.nesr_b200_sharpen_u8(self._h, ip, h, w, int(bool(bgr)), op, flags), "sharpen_u8")
+        return out
+
+    def preprocess_u8(self, img, denoise_level: float = 0.5, clip: float = 2.0, tiles=(8, 8), out=None):
+        """``SuperResolutionPipeline._preprocess_image`` (``nesr/nesr.py:668-689``): RGB H x W x 3 u8 -> same, bit-exact with
+        cv2 4.13.  ``denoise_level`` is the reference's config value (h = hColor = 10 * level; 0 skips the denoiser)."""
+        h, w = img.shape[:2]
+        if img.ndim != 3 or img.shape[2] != 3:
+            raise ValueError("preprocess_u8 expects H x W x 3")
+        if out is None:
+            out = self._alloc_like(img, (h, w, 3))
+        ip, idev = _image_ptr(img)
+        op, odev = _image_ptr(out)
+        flags = (PTR_IN_DEVICE if idev else 0) | (PTR_OUT_DEVICE if odev else 0)
+        strength = float(denoise_level) * 10
+        self._check(self._lib.nesr_b200_preprocess_u8(self._h, ip, h, w, strength, strength, float(clip), int(tiles[0]),
+                                                      int(tiles[1]), op, flags), "preprocess_u8")
         return out
 
     # -- misc --------------------------------------------------------------------------------

@@ -148,6 +148,11 @@ struct nesr_b200_handle {
 
   unsigned* d_gbar = nullptr;                          // arrival counter of the persistent trunk kernel
 
+  uint8_t* d_pre = nullptr; size_t d_pre_bytes = 0;    // pre-process workspace (Lab planes, CLAHE LUTs)
+  int32_t* d_nlm_w[2] = {nullptr, nullptr};            // NLM weight tables (L, ab) for nlm_h[]
+  int n_nlm_w[2] = {0, 0};
+  float nlm_h[2] = {-1.f, -1.f};
+
   nesr_b200_stats stats{};
   int debug_flags = 0;        // NESR_B200_DEBUG_FLAGS: timing experiments (results are wrong when set)
   int use_pairs = 0;          // NESR_B200_PAIRS: CTA-pair trunk kernel (conv3x3_trunk2.cu) when the schedule allows
@@ -1198,6 +1203,8 @@ int nesr_b200_destroy(nesr_b200_handle* h) {
   if (h->d_in) cudaFree(h->d_in);
   if (h->d_out) cudaFree(h->d_out);
   if (h->d_tmp) cudaFree(h->d_tmp);
+  if (h->d_pre) cudaFree(h->d_pre);
+  for (int i = 0; i < 2; ++i) if (h->d_nlm_w[i]) cudaFree(h->d_nlm_w[i]);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (cudaEvent_t ev : h->ev_trunk) cudaEventDestroy(ev);
@@ -1426,6 +1433,76 @@ int nesr_b200_blend_u8(nesr_b200_handle* h, const uint8_t* const* members, int32
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->stats.last_device_ms = ms;
   return NESR_OK;
+}
+
+int nesr_b200_preprocess_u8(nesr_b200_handle* h, const uint8_t* rgb, int32_t H, int32_t W, float denoise_h, float denoise_h_color,
+                            float clahe_clip, int32_t tiles_x, int32_t tiles_y, uint8_t* out, int32_t flags) {
+  if (!h) return NESR_E_INVALID;
+  if (!rgb || !out || H < 1 || W < 1 || tiles_x < 1 || tiles_y < 1 || tiles_x * tiles_y > 4096)
+    return fail(h, NESR_E_INVALID, "preprocess: bad arguments");
+  if ((int64_t)H * W > (int64_t)1 << 30) return fail(h, NESR_E_INVALID, "preprocess: image too large");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const int64_t n = (int64_t)H * W * 3;
+  const uint8_t* d_in = rgb;
+  uint8_t* d_out = out;
+  int rc;
+  if (!(flags & NESR_PTR_IN_DEVICE)) {
+    if ((rc = ensure(h, &h->d_in, &h->d_in_bytes, (size_t)n))) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_in, rgb, n, cudaMemcpyHostToDevice, h->stream));
+    d_in = h->d_in;
+  }
+  if (!(flags & NESR_PTR_OUT_DEVICE)) {
+    if ((rc = ensure(h, &h->d_out, &h->d_out_bytes, (size_t)n))) return rc;
+    d_out = h->d_out;
+  }
+  if ((rc = ensure(h, &h->d_pre, &h->d_pre_bytes, preprocess_workspace_bytes(H, W, tiles_x, tiles_y)))) return rc;
+  const bool denoise = denoise_h > 0.f;                  // the reference skips the denoiser at level 0 (nesr/nesr.py:671)
+  if (denoise) {
+    const float hs[2] = {denoise_h, denoise_h_color > 0.f ? denoise_h_color : denoise_h};
+    for (int i = 0; i < 2; ++i) {
+      if (h->nlm_h[i] == hs[i] && h->d_nlm_w[i]) continue;
+      const std::vector<int32_t> tab = nlm_weight_table(hs[i], i + 1);
+      if (h->d_nlm_w[i]) { cudaFree(h->d_nlm_w[i]); h->d_nlm_w[i] = nullptr; }
+      CUDA_TRY(h, cudaMalloc(&h->d_nlm_w[i], tab.size() * sizeof(int32_t)));
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_nlm_w[i], tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));     // tab is a local
+      h->n_nlm_w[i] = (int)tab.size();
+      h->nlm_h[i] = hs[i];
+    }
+  }
+  int launches = 0;
+  cudaEventRecord(h->ev0, h->stream);
+  cudaError_t e = launch_preprocess(d_in, d_out, H, W, denoise ? h->d_nlm_w[0] : nullptr, h->n_nlm_w[0], denoise ? h->d_nlm_w[1] : nullptr,
+                                    h->n_nlm_w[1], clahe_clip, tiles_x, tiles_y, h->d_pre, &launches, h->stream);
+  cudaEventRecord(h->ev1, h->stream);
+  h->stats.kernel_launches += launches;
+  if (e != cudaSuccess) return fail(h, NESR_E_CUDA, "preprocess launch failed: %s", cudaGetErrorString(e));
+  if (!(flags & NESR_PTR_OUT_DEVICE)) CUDA_TRY(h, cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->stats.last_device_ms = ms;
+  return NESR_OK;
+}
+
+int nesr_b200_debug_lab_table(int32_t which, void* out, int32_t capacity_bytes) {
+  int count = 0, elem = 0;
+  const void* src = lab_table_host(which, &count, &elem);
+  if (!src) return -1;
+  if (out) {
+    if (capacity_bytes < count * elem) return -1;
+    memcpy(out, src, (size_t)count * elem);
+  }
+  return count * elem;
+}
+
+int nesr_b200_debug_nlm_weights(float h, int32_t channels, int32_t* out, int32_t capacity) {
+  if (channels < 1 || channels > 2) return -1;
+  const std::vector<int32_t> tab = nlm_weight_table(h, channels);
+  if (out) {
+    if (capacity < (int32_t)tab.size()) return -1;
+    memcpy(out, tab.data(), tab.size() * sizeof(int32_t));
+  }
+  return (int32_t)tab.size();
 }
 
 int nesr_b200_sharpen_u8(nesr_b200_handle* h, const uint8_t* in, int32_t H, int32_t W, int32_t bgr, uint8_t* out, int32_t flags) {

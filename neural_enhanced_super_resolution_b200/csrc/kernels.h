@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+
+#include <vector>
 #include <stdint.h>
 
 #include "layout.h"
@@ -74,5 +76,12 @@ struct BlendParams {
 };
 cudaError_t launch_blend(const BlendParams& p, cudaStream_t stream);
 cudaError_t launch_sharpen(const uint8_t* in, uint8_t* out, int32_t H, int32_t W, int32_t bgr, cudaStream_t stream);
+
+// --- preprocess.cu : NLM denoise in Lab + CLAHE, bit-exact with cv2 (reference nesr/nesr.py:668-689) --------------
+std::vector<int32_t> nlm_weight_table(float h, int channels);                    // non-zero prefix of cv2's almost_dist2weight_
+const void* lab_table_host(int which, int* count, int* elem_bytes);              // the committed Lab tables (tests)
+size_t preprocess_workspace_bytes(int H, int W, int tiles_x, int tiles_y);
+cudaError_t launch_preprocess(const uint8_t* rgb, uint8_t* out, int H, int W, const int32_t* wtab_l, int n_wl, const int32_t* wtab_ab, int n_wab,
+                              float clip, int tiles_x, int tiles_y, uint8_t* workspace, int* launches, cudaStream_t stream);
 
 }  // namespace nesr

@@ -1,6 +1,7 @@
 """``SuperResolutionPipeline`` -- the reference's orchestrator surface (``nesr/nesr.py:18``) for the
-ESRGAN path, with its three hot stages on the GPU:
+ESRGAN path, with its four stages on the GPU:
 
+    _preprocess_image   -> nesr_b200_preprocess_u8      (reference nesr/nesr.py:668-689: NLM denoise + LAB CLAHE)
     _apply_esrgan       -> RealESRGANer.enhance        (reference nesr/nesr.py:754-986, the call
                                                          standalone/superres_project.py:277-286 makes)
     _ensemble_results   -> nesr_b200_blend_u8           (reference nesr/nesr.py:1033-1054)
@@ -8,12 +9,11 @@ ESRGAN path, with its three hot stages on the GPU:
 
 ``enhance_image(image_path, prompt=None) -> str`` keeps the reference's loop, config keys, progress /
 image callbacks, intermediate saves and output naming (``nesr/nesr.py:477-659``).  Diffusion and
-segmentation are out of scope (BASELINE north_star) and are reported as disabled; ``_preprocess_image``
-(NLM denoise + CLAHE, ``nesr/nesr.py:668-689``) stays the reference's own cv2 host code.
+segmentation are out of scope (BASELINE north_star) and are reported as disabled.
 
-Within one iteration the image stays in GPU memory between the three stages.
+Within one iteration the image stays in GPU memory between the four stages.
 
-``install(ReferencePipelineClass)`` patches the three stage methods of the UNMODIFIED reference class
+``install(ReferencePipelineClass)`` patches the four stage methods of the UNMODIFIED reference class
 instead.
 """
 from __future__ import annotations
@@ -112,7 +112,11 @@ class SuperResolutionPipeline:
                 self.config[key] = False
 
     def _engine(self) -> "_ffi.Engine":
-        return self.models["esrgan"].model.engine(self.device)
+        if "esrgan" in self.models:
+            return self.models["esrgan"].model.engine(self.device)
+        if getattr(self, "_stencil_engine", None) is None:           # ESRGAN disabled: the stencil stages still run on the GPU
+            self._stencil_engine = _ffi.Engine(device=torch.device(self.device).index or torch.cuda.current_device())
+        return self._stencil_engine
 
     # -- stages --------------------------------------------------------------------------------
     def _load_image(self, image_path):
@@ -122,22 +126,10 @@ class SuperResolutionPipeline:
         return cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
 
     def _preprocess_image(self, image):
-        """Reference ``nesr/nesr.py:668-689`` (host cv2; outside the accelerated path)."""
-        if self.config["denoise_level"] > 0:
-            strength = self.config["denoise_level"] * 10
-            try:
-                image = cv2.fastNlMeansDenoisingColored(image, None, h=strength, hColor=strength,
-                                                        templateWindowSize=7, searchWindowSize=21)
-            except Exception as e:  # noqa: BLE001 - same ladder as the reference
-                logger.warning(f"Denoising failed: {e}, skipping")
-        try:
-            lab = cv2.cvtColor(image, cv2.COLOR_RGB2LAB)
-            l, a, b = cv2.split(lab)
-            clahe = cv2.createCLAHE(clipLimit=2.0, tileGridSize=(8, 8))
-            image = cv2.cvtColor(cv2.merge((clahe.apply(l), a, b)), cv2.COLOR_LAB2RGB)
-        except Exception as e:  # noqa: BLE001
-            logger.warning(f"Contrast enhancement failed: {e}, skipping")
-        return image
+        """Reference ``nesr/nesr.py:668-689``: NLM denoise (h = 10 * denoise_level) + LAB CLAHE(2.0, 8x8), on the GPU and
+        bit-exact with cv2 (``nesr_b200_preprocess_u8``).  ndarray in -> ndarray out, CUDA tensor in -> CUDA tensor out."""
+        src = image if isinstance(image, torch.Tensor) else np.ascontiguousarray(image)
+        return self._engine().preprocess_u8(src, denoise_level=float(self.config["denoise_level"]))
 
     def _apply_esrgan(self, image):
         """RGB HWC u8 (ndarray or CUDA tensor) -> RGB HWC u8 at x2, same container kind."""
@@ -191,9 +183,8 @@ class SuperResolutionPipeline:
             t0 = time.time()
             self._progress("Enhancement", iteration, f"Starting iteration {iteration + 1}/{n_iter}")
             self._progress("Preprocessing", iteration, "Applying denoising and contrast enhancement")
-            current = self._preprocess_image(current)
+            dev_in = self._preprocess_image(torch.from_numpy(np.ascontiguousarray(current)).to(self.device))
             upscaled = []
-            dev_in = torch.from_numpy(np.ascontiguousarray(current)).to(self.device)
             if self.config["use_esrgan"] and "esrgan" in self.models:
                 self._progress("ESRGAN", iteration, "Applying Real-ESRGAN upscaling")
                 res = self._apply_esrgan(dev_in)
@@ -201,13 +192,14 @@ class SuperResolutionPipeline:
                     upscaled.append(res)
             extra = self.config.get("ensemble_members")
             if extra and upscaled:
-                for m in extra(current, upscaled[0]):
+                for m in extra(dev_in.cpu().numpy(), upscaled[0]):
                     upscaled.append(m if isinstance(m, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(m)).to(self.device))
             self._progress("Ensemble", iteration, "Combining results from multiple models")
             if upscaled:
                 dev = self._ensemble_results(upscaled)
             else:
                 logger.warning("All models failed, falling back to bicubic upscaling")
+                current = dev_in.cpu().numpy()
                 h, w = current.shape[:2]
                 f = self.config["upscale_factor"]
                 dev = torch.from_numpy(cv2.resize(current, (int(w * f), int(h * f)), interpolation=cv2.INTER_CUBIC)).to(self.device)
@@ -294,6 +286,10 @@ def install(reference_cls, engine_getter=None) -> None:
             return image
         return _engine(self).sharpen_u8(np.ascontiguousarray(image), bgr=False)
 
+    def _preprocess_image(self, image):
+        return _engine(self).preprocess_u8(np.ascontiguousarray(image), denoise_level=float(self.config["denoise_level"]))
+
+    reference_cls._preprocess_image = _preprocess_image
     reference_cls._apply_esrgan = _apply_esrgan
     reference_cls._ensemble_results = _ensemble_results
     reference_cls._postprocess_image = _postprocess_image

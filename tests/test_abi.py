@@ -101,3 +101,21 @@ def test_image_pointer_validation():
         _ffi._image_ptr(np.zeros((4, 8, 3), np.uint8)[:, ::2])
     addr, dev = _ffi._image_ptr(np.zeros((4, 4, 3), np.uint8))
     assert addr != 0 and dev is False
+
+
+def test_lab_tables_match_oracle():
+    """The Lab tables compiled into the library (csrc/lab_tables.inc) are the oracle's, which equal cv2's on all 2^24 colours."""
+    from oracle import preprocess as P
+    assert np.array_equal(_ffi.lab_table(0), P.gamma_table(True))
+    assert np.array_equal(_ffi.lab_table(1), P.cbrt_table())
+    assert np.array_equal(_ffi.lab_table(2), P.l_to_yf_table().reshape(-1))
+    assert np.array_equal(_ffi.lab_table(3), P.inv_gamma_table())
+
+
+def test_nlm_weight_tables_match_oracle():
+    from oracle import preprocess as P
+    for h in (1.0, 2.5, 3.0, 5.0, 7.0, 10.0):
+        for channels in (1, 2):
+            got = _ffi.nlm_weights(h, channels)
+            want, _ = P.nlm_weight_table(h, channels)
+            assert len(got) == np.count_nonzero(want) and np.array_equal(got, want[:len(got)])

@@ -8,6 +8,7 @@ import pytest
 
 import neural_enhanced_super_resolution_b200 as pkg
 from oracle import postprocess as O
+from oracle import preprocess as P
 from gpu_common import checkpoint, natural_image
 
 pytestmark = pytest.mark.gpu
@@ -24,7 +25,7 @@ def test_enhance_image_chain_and_contract(tmp_path):
     cv2.imwrite(src, cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR))
     stages, images = [], []
     pipe = pkg.SuperResolutionPipeline(device="cuda", config={
-        "iterations": 2, "use_diffusion": False, "segment_enhancement": False, "denoise_level": 0,
+        "iterations": 2, "use_diffusion": False, "segment_enhancement": False, "denoise_level": 0.5,
         "output_dir": str(tmp_path / "out"), "esrgan_model_path": checkpoint("calibrated"),
         "max_tile_size": 32, "tile_pad": 4, "ensemble_members": _bicubic_member, "intermediate_saves": True,
         "progress_callback": lambda stage, it, total, msg: stages.append(stage),
@@ -39,7 +40,7 @@ def test_enhance_image_chain_and_contract(tmp_path):
     # composition: iteration = preprocess -> esrgan -> blend(esrgan, bicubic) -> sharpen, stages exact
     cur = rgb
     for _ in range(2):
-        cur = pipe._preprocess_image(cur)
+        cur = P.preprocess_image(cur, 0.5)
         e = pipe._apply_esrgan(cur)
         cur = O.postprocess_image(O.ensemble_results([e, _bicubic_member(cur, e)[0]]))
     assert np.array_equal(cur, out)
