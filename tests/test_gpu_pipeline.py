@@ -47,9 +47,9 @@ def test_enhance_image_chain_and_contract(tmp_path):
 
 
 def test_install_patches_a_reference_like_class(tmp_path):
-    class RefLike:                                   # the three hooks of nesr/nesr.py, numpy in/out
+    class RefLike:                                   # the four hooks of nesr/nesr.py, numpy in/out
         def __init__(self):
-            self.config = {"use_esrgan": True, "adaptive_sharpening": True}
+            self.config = {"use_esrgan": True, "adaptive_sharpening": True, "denoise_level": 0.4}
             self.models = {"esrgan": pkg.RealESRGANer(2, checkpoint("calibrated"), model=pkg.RRDBNet(3, 3, scale=2),
                                                       tile=0, pre_pad=0, device="cuda")}
     pkg.install(RefLike)
@@ -61,3 +61,4 @@ def test_install_patches_a_reference_like_class(tmp_path):
     assert np.array_equal(r._ensemble_results([up, other]), O.ensemble_results([up, other]))
     assert r._ensemble_results([up]) is up
     assert np.array_equal(r._postprocess_image(up), O.postprocess_image(up))
+    assert np.array_equal(r._preprocess_image(rgb), P.preprocess_image(rgb, 0.4))

@@ -5,7 +5,8 @@
 C1  512x512 -> 1024x1024, untiled                         (enhance_u8)
 C3  3840x2160 -> 7680x4320, tile 512 / halo 10            (enhance_u8, 40 tiles, several L2-resident tile groups)
 C4  32 frames of 512x512 (one GPU's share of 256 frames)  (enhance_batch_u8)
-C5  256 -> 512 -> 1024 -> 2048: ESRGAN + 2-member blend + adaptive sharpen per iteration (device-resident stages)
+C5  256 -> 512 -> 1024 -> 2048: ESRGAN + 2-member blend + adaptive sharpen per iteration (device-resident stages), without and
+    with the NLM + CLAHE pre-process in front of every iteration
 
 Inputs are resident in HBM; times are CUDA events around the calls (median of `steps`), after 3 warm-up calls.
 """
@@ -75,9 +76,11 @@ report("C4 32 x (512x512->1024x1024) batched", 32 * 1024 * 1024, ms, trunk_launc
 cur0 = u8(256, 256, 3)
 
 
-def c5():
+def c5(level=0.0):
     cur = cur0
     for _ in range(3):
+        if level > 0:
+            cur = eng.preprocess_u8(cur, denoise_level=level)
         up = eng.enhance_u8(cur, tile=0)
         other = up.flip(0).contiguous()                          # a second ensemble member of the same size
         ens = eng.blend_u8([up, other])
@@ -86,3 +89,5 @@ def c5():
 
 
 report("C5 256->512->1024->2048 (ESRGAN + blend K=2 + sharpen per iteration)", 512 * 512 + 1024 * 1024 + 2048 * 2048, timed(c5))
+report("C5 with the pre-process stage (NLM h=5 + CLAHE) in front of every iteration, as enhance_image runs it",
+       512 * 512 + 1024 * 1024 + 2048 * 2048, timed(lambda: c5(0.5)))
