@@ -55,6 +55,8 @@ _DEFAULTS = {
     "tile_pad": 10,                  # halo of RealESRGANer.tile_process (standalone/direct_esrgan.py:123)
     "pre_pad": 0,
     "ensemble_members": None,        # callable(rgb_u8_in, rgb_u8_esrgan) -> list of extra RGB u8 members
+    "head_compat": False,            # True: the ESRGAN stage exactly as the reference's HEAD runs it (nesr/nesr.py:845-986):
+                                     # RRDBNet(num_in_ch=12) fed a 12-channel full-resolution tensor, x4 out, truncating u8
 }
 
 
@@ -76,6 +78,21 @@ def _find_checkpoint(explicit=None):
         if os.path.exists(path):
             return path
     return None
+
+
+def gaussian_blur3_u8(chw_u8: torch.Tensor) -> torch.Tensor:
+    """``cv2.GaussianBlur(img, (3, 3), 0)`` for u8 (C x H x W tensor): the fixed 1-2-1 kernel in both directions,
+    BORDER_REFLECT_101, one rounding at the end ``(sum + 8) >> 4``."""
+    x = chw_u8.to(torch.int32)
+    c, h, w = x.shape
+    ys = torch.arange(-1, h + 1, device=x.device).abs()
+    ys = torch.where(ys >= h, 2 * (h - 1) - ys, ys).clamp_(0, h - 1)
+    xs = torch.arange(-1, w + 1, device=x.device).abs()
+    xs = torch.where(xs >= w, 2 * (w - 1) - xs, xs).clamp_(0, w - 1)
+    p = x[:, ys][:, :, xs]
+    hsum = p[:, :, :-2] + 2 * p[:, :, 1:-1] + p[:, :, 2:]
+    vsum = hsum[:, :-2] + 2 * hsum[:, 1:-1] + hsum[:, 2:]
+    return ((vsum + 8) >> 4).to(torch.uint8)
 
 
 class SuperResolutionPipeline:
@@ -100,11 +117,16 @@ class SuperResolutionPipeline:
             if path is None:
                 raise FileNotFoundError("RealESRGAN_x2plus.pth not found (searched the reference's locations); "
                                         "set config['esrgan_model_path']")
-            model = RRDBNet(num_in_ch=3, num_out_ch=3, scale=2, num_feat=64, num_block=23, num_grow_ch=32)
-            tile = int(self.config["max_tile_size"]) if self.config["enable_tiling"] else 0
-            self.models["esrgan"] = RealESRGANer(scale=int(self.config["upscale_factor"]), model_path=path, model=model,
-                                                 tile=tile, tile_pad=int(self.config["tile_pad"]),
-                                                 pre_pad=int(self.config["pre_pad"]), half=False, device=self.device)
+            if self.config["head_compat"]:                           # nesr/nesr.py:216-229 verbatim arguments
+                model = RRDBNet(num_in_ch=12, num_out_ch=3, num_feat=64, num_block=23, num_grow_ch=32)
+                self.models["esrgan"] = RealESRGANer(scale=int(self.config["upscale_factor"]), model_path=path, model=model,
+                                                     tile=0, tile_pad=0, pre_pad=0, half=False, device=self.device)
+            else:
+                model = RRDBNet(num_in_ch=3, num_out_ch=3, scale=2, num_feat=64, num_block=23, num_grow_ch=32)
+                tile = int(self.config["max_tile_size"]) if self.config["enable_tiling"] else 0
+                self.models["esrgan"] = RealESRGANer(scale=int(self.config["upscale_factor"]), model_path=path, model=model,
+                                                     tile=tile, tile_pad=int(self.config["tile_pad"]),
+                                                     pre_pad=int(self.config["pre_pad"]), half=False, device=self.device)
             logger.info("Real-ESRGAN model loaded on %s (libnesr_b200)", self.device)
         for key, what in (("use_diffusion", "diffusion"), ("segment_enhancement", "segmentation")):
             if self.config.get(key):
@@ -135,11 +157,32 @@ class SuperResolutionPipeline:
         """RGB HWC u8 (ndarray or CUDA tensor) -> RGB HWC u8 at x2, same container kind."""
         if not self.config["use_esrgan"] or "esrgan" not in self.models:
             return None
+        if self.config["head_compat"]:
+            return self._apply_esrgan_head(image)
         if isinstance(image, torch.Tensor):
             out, _ = self.models["esrgan"].enhance(image.flip(-1).contiguous())
             return out.flip(-1).contiguous()
         out, _ = self.models["esrgan"].enhance(cv2.cvtColor(image, cv2.COLOR_RGB2BGR))
         return cv2.cvtColor(out, cv2.COLOR_BGR2RGB)
+
+    def _apply_esrgan_head(self, image):
+        """The reference HEAD's ESRGAN stage (``_apply_esrgan_12channel`` / ``_apply_esrgan_3channel``, ``nesr/nesr.py:845-986``),
+        untiled: BGR / 255 -> 12 channels (image, x1.1, x0.9 clamped, 3x3 Gaussian blur -- or four copies with
+        ``force_3channel``) -> ``model(x12)`` -> ``clip(out * 255, 0, 255)`` TRUNCATED to u8 -> RGB.  x4 per call (the 12-channel
+        network is the x2plus network without its un-shuffle).  The reference tiles images above ``cuda_megapixel_threshold`` with
+        ``_process_with_tiling`` (``:311-475``); that host loop is not restated -- larger images run untiled here."""
+        host = not isinstance(image, torch.Tensor)
+        rgb = torch.from_numpy(np.ascontiguousarray(image)).to(self.device) if host else image
+        bgr = rgb.flip(-1).permute(2, 0, 1).contiguous()                                     # 3 x H x W u8
+        t = bgr.float() / 255.0
+        if self.config["force_3channel"]:
+            x12 = torch.cat([t, t, t, t], 0)
+        else:
+            x12 = torch.cat([t, torch.clamp(t * 1.1, 0, 1), torch.clamp(t * 0.9, 0, 1), gaussian_blur3_u8(bgr).float() / 255.0], 0)
+        out = self.models["esrgan"].model(x12.unsqueeze(0)).squeeze(0)                       # 3 x 4H x 4W float
+        out = torch.clamp(out.permute(1, 2, 0) * 255.0, 0, 255).to(torch.uint8)              # truncation, as astype(np.uint8)
+        out = out.flip(-1).contiguous()
+        return out.cpu().numpy() if host else out
 
     def _ensemble_results(self, upscaled_images):
         if len(upscaled_images) == 1:
@@ -271,6 +314,25 @@ def install(reference_cls, engine_getter=None) -> None:
             return None
         out, _ = self.models["esrgan"].enhance(cv2.cvtColor(image, cv2.COLOR_RGB2BGR))
         return cv2.cvtColor(out, cv2.COLOR_BGR2RGB)
+
+    def _apply_esrgan_head(self, image):
+        """The reference HEAD's ESRGAN stage (``_apply_esrgan_12channel`` / ``_apply_esrgan_3channel``, ``nesr/nesr.py:845-986``),
+        untiled: BGR / 255 -> 12 channels (image, x1.1, x0.9 clamped, 3x3 Gaussian blur -- or four copies with
+        ``force_3channel``) -> ``model(x12)`` -> ``clip(out * 255, 0, 255)`` TRUNCATED to u8 -> RGB.  x4 per call (the 12-channel
+        network is the x2plus network without its un-shuffle).  The reference tiles images above ``cuda_megapixel_threshold`` with
+        ``_process_with_tiling`` (``:311-475``); that host loop is not restated -- larger images run untiled here."""
+        host = not isinstance(image, torch.Tensor)
+        rgb = torch.from_numpy(np.ascontiguousarray(image)).to(self.device) if host else image
+        bgr = rgb.flip(-1).permute(2, 0, 1).contiguous()                                     # 3 x H x W u8
+        t = bgr.float() / 255.0
+        if self.config["force_3channel"]:
+            x12 = torch.cat([t, t, t, t], 0)
+        else:
+            x12 = torch.cat([t, torch.clamp(t * 1.1, 0, 1), torch.clamp(t * 0.9, 0, 1), gaussian_blur3_u8(bgr).float() / 255.0], 0)
+        out = self.models["esrgan"].model(x12.unsqueeze(0)).squeeze(0)                       # 3 x 4H x 4W float
+        out = torch.clamp(out.permute(1, 2, 0) * 255.0, 0, 255).to(torch.uint8)              # truncation, as astype(np.uint8)
+        out = out.flip(-1).contiguous()
+        return out.cpu().numpy() if host else out
 
     def _ensemble_results(self, upscaled_images):
         if len(upscaled_images) == 1:

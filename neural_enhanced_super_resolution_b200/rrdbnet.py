@@ -48,6 +48,12 @@ class RRDB(nn.Module):
 class RRDBNet(nn.Module):
     """Drop-in for ``basicsr.archs.rrdbnet_arch.RRDBNet`` (x2plus: ``num_in_ch=3, scale=2``).
 
+    The reference's HEAD builds the SAME weights as ``RRDBNet(num_in_ch=12, num_out_ch=3, ...)`` with the default ``scale=4``
+    (``nesr/nesr.py:216``) and calls ``model(x12)`` on a 12-channel full-resolution tensor (``nesr/nesr.py:845-986``): that
+    architecture is the x2plus network AFTER its pixel-unshuffle (feature grid = input grid, x4 out).  It is accepted here too:
+    ``forward`` pixel-shuffles the 12 channels into the 3 x 2H x 2W image whose un-shuffle they are (an index permutation, exact)
+    and runs the same engine.
+
     Extra keyword-only knobs (not in upstream): ``body_format`` / ``edge_format`` select the 16-bit
     operand format of the dense-block / edge convolutions ("bf16" | "fp16").
     """
@@ -59,6 +65,7 @@ class RRDBNet(nn.Module):
         self.num_in_ch, self.num_out_ch = num_in_ch, num_out_ch
         self.num_feat, self.num_block, self.num_grow_ch = num_feat, num_block, num_grow_ch
         in_ch = num_in_ch * (4 if scale == 2 else 16 if scale == 1 else 1)
+        self._head_layout = (scale == 4 and num_in_ch == 12)       # the reference HEAD's constructor call
         self.conv_first = _conv(in_ch, num_feat)
         self.body = nn.Sequential(*[RRDB(num_feat, num_grow_ch) for _ in range(num_block)])
         self.conv_body = _conv(num_feat, num_feat)
@@ -87,14 +94,15 @@ class RRDBNet(nn.Module):
         index = device.index if device.index is not None else torch.cuda.current_device()
         version = (index,) + self._params_version()
         if self._engine is None or self._engine_version != version:
-            if self.scale != 2:
-                raise RuntimeError("this build implements the x2plus network: RRDBNet(num_in_ch=3, num_out_ch=3, scale=2, ...)")
+            if self.scale != 2 and not self._head_layout:
+                raise RuntimeError("this build implements the x2plus network: RRDBNet(num_in_ch=3, num_out_ch=3, scale=2, ...) "
+                                   "or its un-shuffled form RRDBNet(num_in_ch=12, num_out_ch=3) as the reference's HEAD builds it")
             if self._engine is not None:
                 self._engine.close()
             eng = _ffi.Engine(device=index, num_block=self.num_block, body_format=self._formats[0],
                               edge_format=self._formats[1], conv_impl=self._conv_impl,
-                              max_batch_pixels=self._max_batch_pixels, num_in_ch=self.num_in_ch,
-                              num_out_ch=self.num_out_ch, scale=self.scale, num_feat=self.num_feat,
+                              max_batch_pixels=self._max_batch_pixels, num_in_ch=3 if self._head_layout else self.num_in_ch,
+                              num_out_ch=self.num_out_ch, scale=2 if self._head_layout else self.scale, num_feat=self.num_feat,
                               num_grow_ch=self.num_grow_ch)
             eng.load_state_dict(self.state_dict())
             self._engine, self._engine_version = eng, version
@@ -103,6 +111,10 @@ class RRDBNet(nn.Module):
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("RRDBNet.forward: input must be a CUDA tensor (no CPU fallback)")
+        if self._head_layout:
+            if x.dim() != 4 or x.shape[1] != 12:
+                raise RuntimeError(f"expected a N x 12 x H x W tensor, got {tuple(x.shape)}")
+            x = torch.nn.functional.pixel_shuffle(x, 2)            # exact inverse of the x2plus network's pixel_unshuffle(2)
         return self.engine(x.device).forward_nchw(x.float()).to(x.dtype)
 
 
