@@ -154,6 +154,13 @@ int nesr_b200_enhance_tiles_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32
 int nesr_b200_forward_nchw_f32(nesr_b200_handle* h, const float* x, int32_t n, int32_t H,
                                int32_t W, float* y, void* stream);
 
+/* Replaces: `self.models['esrgan'].model(img_12ch)` of the reference HEAD (nesr/nesr.py:887-891, 930-935), whose model is
+ * RRDBNet(num_in_ch=12, num_out_ch=3) with the default scale=4 (nesr/nesr.py:216): the x2plus weights applied to a 12-channel
+ * tensor at full resolution, no un-shuffle, x4 out.  Device fp32 NCHW [n, 12, H, W] -> device fp32 NCHW [n, num_out_ch, 4H, 4W],
+ * unclamped; stream semantics as nesr_b200_forward_nchw_f32. */
+int nesr_b200_forward_nchw12_f32(nesr_b200_handle* h, const float* x12, int32_t n, int32_t H,
+                                 int32_t W, float* y, void* stream);
+
 /* Replaces: SuperResolutionPipeline._ensemble_results (nesr/nesr.py:1033-1054) for K >= 2
  * equally sized H x W x 3 u8 members: acc(f32) += f64(img) * w[i] rounded to f32 per member,
  * truncated to u8.  weights == NULL means the reference's uniform 1/K. */

@@ -23,7 +23,7 @@ EXPORTS = (
     "nesr_b200_enhance_batch_u8", "nesr_b200_tile_count", "nesr_b200_debug_plan", "nesr_b200_enhance_tiles_u8",
     "nesr_b200_forward_nchw_f32", "nesr_b200_blend_u8", "nesr_b200_sharpen_u8", "nesr_b200_get_stats",
     "nesr_b200_synchronize", "nesr_b200_debug_conv", "nesr_b200_preprocess_u8", "nesr_b200_debug_lab_table",
-    "nesr_b200_debug_nlm_weights",
+    "nesr_b200_debug_nlm_weights", "nesr_b200_forward_nchw12_f32",
 )
 
 
@@ -80,6 +80,7 @@ def load_library() -> C.CDLL:
         lib.nesr_b200_enhance_tiles_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                                    C.c_int32, C.c_int32, C.c_int32, u8p, C.c_int64, C.c_int32]
         lib.nesr_b200_forward_nchw_f32.argtypes = [H, f32p, C.c_int32, C.c_int32, C.c_int32, f32p, C.c_void_p]
+        lib.nesr_b200_forward_nchw12_f32.argtypes = [H, f32p, C.c_int32, C.c_int32, C.c_int32, f32p, C.c_void_p]
         lib.nesr_b200_blend_u8.argtypes = [H, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32,
                                            C.POINTER(C.c_double), u8p, C.c_int32]
         lib.nesr_b200_sharpen_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int32, u8p, C.c_int32]
@@ -251,6 +252,19 @@ class Engine:
         stream = torch.cuda.current_stream(x.device).cuda_stream
         self._check(self._lib.nesr_b200_forward_nchw_f32(self._h, x.data_ptr(), n, h, w, y.data_ptr(),
                                                          C.c_void_p(stream)), "forward_nchw_f32")
+        return y
+
+    def forward_nchw12(self, x12):
+        """The reference HEAD's ``model(x12)``: CUDA float32 [n, 12, H, W] -> [n, num_out_ch, 4H, 4W]."""
+        import torch
+        if not (x12.is_cuda and x12.dtype == torch.float32 and x12.dim() == 4 and x12.shape[1] == 12):
+            raise ValueError("forward_nchw12 expects a CUDA float32 N x 12 x H x W tensor")
+        x12 = x12.contiguous()
+        n, _, h, w = x12.shape
+        y = torch.empty((n, self.config.num_out_ch, 4 * h, 4 * w), dtype=torch.float32, device=x12.device)
+        stream = torch.cuda.current_stream(x12.device).cuda_stream
+        self._check(self._lib.nesr_b200_forward_nchw12_f32(self._h, x12.data_ptr(), n, h, w, y.data_ptr(),
+                                                           C.c_void_p(stream)), "forward_nchw12_f32")
         return y
 
     # -- post-process ------------------------------------------------------------------------

@@ -1377,7 +1377,8 @@ int nesr_b200_enhance_tiles_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32
   return enhance_impl(h, in_bgr, 1, H, W, in_stride, 0, tile, tile_pad, pre_pad, tile_first, tile_count, 0, out_bgr, out_stride, 0, flags);
 }
 
-int nesr_b200_forward_nchw_f32(nesr_b200_handle* h, const float* x, int32_t n, int32_t H, int32_t W, float* y, void* stream) {
+namespace {
+int forward_nchw(nesr_b200_handle* h, const float* x, bool unshuffled, int32_t n, int32_t H, int32_t W, float* y, void* stream) {
   if (!h) return NESR_E_INVALID;
   if (!h->finalized) return fail(h, NESR_E_STATE, "weights not finalized");
   if (!x || !y || n < 1 || H < 2 || W < 2) return fail(h, NESR_E_INVALID, "bad tensor arguments");
@@ -1390,11 +1391,22 @@ int nesr_b200_forward_nchw_f32(nesr_b200_handle* h, const float* x, int32_t n, i
   if (rc) return rc;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // plan uploads / memset ran on our own stream
   PackParams pk{};
-  pk.in_f32 = x; pk.H = H; pk.W = W; pk.pre_pad = 0;
+  if (unshuffled) pk.in_f32_12 = x; else pk.in_f32 = x;
+  pk.H = H; pk.W = W; pk.pre_pad = 0;
   Sink sink; sink.out_f32 = y; sink.out_h = H * sc; sink.out_w = W * sc;
   for (const Batch& b : h->batches)
     if ((rc = forward_batch(h, b, pk, sink, s, false, false))) return rc;
   return NESR_OK;
+}
+}  // namespace
+
+int nesr_b200_forward_nchw_f32(nesr_b200_handle* h, const float* x, int32_t n, int32_t H, int32_t W, float* y, void* stream) {
+  return forward_nchw(h, x, false, n, H, W, y, stream);
+}
+
+int nesr_b200_forward_nchw12_f32(nesr_b200_handle* h, const float* x12, int32_t n, int32_t H, int32_t W, float* y, void* stream) {
+  if (H < 1 || W < 1) return fail(h, NESR_E_INVALID, "bad tensor arguments");
+  return forward_nchw(h, x12, true, n, 2 * H, 2 * W, y, stream);        // the 12 channels are the un-shuffle of a 2H x 2W image
 }
 
 int nesr_b200_blend_u8(nesr_b200_handle* h, const uint8_t* const* members, int32_t K, int32_t H, int32_t W, const double* weights,

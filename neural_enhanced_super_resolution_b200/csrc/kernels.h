@@ -58,6 +58,7 @@ struct PackParams {
   const uint8_t* in_u8;        // BGR HWC frames, or null
   int64_t in_stride, in_frame_stride;
   const float* in_f32;         // RGB NCHW frames, or null
+  const float* in_f32_12;      // already un-shuffled frames [frame][12][H/2][W/2] (the reference HEAD's 12-channel tensor), or null
   int32_t H, W;                // un-padded frame size
   int32_t pre_pad;             // reflect pad (right/bottom) applied before the mod pad
   void* x0;                    // [pixels][64] 16-bit, channels 0..11 written

@@ -34,7 +34,10 @@ __global__ void __launch_bounds__(kBlockPixels) pack_kernel(const PackParams p) 
         const int sy = unreflect(tg.src_y0 + 2 * px.y + i, p.H, p.pre_pad);
         const int sx = unreflect(tg.src_x0 + 2 * px.x + j, p.W, p.pre_pad);
         float f;
-        if (p.in_u8) {
+        if (p.in_f32_12) {                                   // channel c*4 + i*2 + j of the feature grid (H/2 x W/2), no padding
+          f = p.in_f32_12[((static_cast<size_t>(tg.frame) * 12 + c * 4 + i * 2 + j) * (p.H >> 1) + (tg.src_y0 >> 1) + px.y) * (p.W >> 1) +
+                          (tg.src_x0 >> 1) + px.x];
+        } else if (p.in_u8) {
           const uint8_t u = p.in_u8[tg.frame * p.in_frame_stride + sy * p.in_stride + static_cast<int64_t>(sx) * 3 + (2 - c)];
           f = __fdiv_rn(static_cast<float>(u), 255.f);
         } else {

@@ -51,8 +51,8 @@ class RRDBNet(nn.Module):
     The reference's HEAD builds the SAME weights as ``RRDBNet(num_in_ch=12, num_out_ch=3, ...)`` with the default ``scale=4``
     (``nesr/nesr.py:216``) and calls ``model(x12)`` on a 12-channel full-resolution tensor (``nesr/nesr.py:845-986``): that
     architecture is the x2plus network AFTER its pixel-unshuffle (feature grid = input grid, x4 out).  It is accepted here too:
-    ``forward`` pixel-shuffles the 12 channels into the 3 x 2H x 2W image whose un-shuffle they are (an index permutation, exact)
-    and runs the same engine.
+    ``forward`` hands the 12 channels to ``nesr_b200_forward_nchw12_f32``, whose pack kernel reads them as the un-shuffle of a
+    3 x 2H x 2W image (an index permutation, exact) and runs the same engine.
 
     Extra keyword-only knobs (not in upstream): ``body_format`` / ``edge_format`` select the 16-bit
     operand format of the dense-block / edge convolutions ("bf16" | "fp16").
@@ -114,7 +114,7 @@ class RRDBNet(nn.Module):
         if self._head_layout:
             if x.dim() != 4 or x.shape[1] != 12:
                 raise RuntimeError(f"expected a N x 12 x H x W tensor, got {tuple(x.shape)}")
-            x = torch.nn.functional.pixel_shuffle(x, 2)            # exact inverse of the x2plus network's pixel_unshuffle(2)
+            return self.engine(x.device).forward_nchw12(x.float()).to(x.dtype)   # the pack kernel reads the 12 channels in place
         return self.engine(x.device).forward_nchw(x.float()).to(x.dtype)
 
 

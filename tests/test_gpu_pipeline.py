@@ -87,7 +87,12 @@ def test_head_layout_forward_matches_oracle():
         want = oracle_net(x12)[0]
     net = pkg.RRDBNet(num_in_ch=12, num_out_ch=3, num_feat=64, num_block=23, num_grow_ch=32)
     net.load_state_dict(oracle_net.state_dict(), strict=True)
-    got = net.cuda()(x12.cuda())[0].cpu()
+    net = net.cuda()
+    got = net(x12.cuda())[0].cpu()
+    # the 12-channel entry point is the 3-channel one behind an exact pixel shuffle (same kernels, same bits); batch of 2
+    xb = torch.cat([x12, x12.flip(-1)], 0).cuda()
+    eng = net.engine()
+    assert torch.equal(eng.forward_nchw12(xb), eng.forward_nchw(torch.nn.functional.pixel_shuffle(xb, 2)))
     assert got.shape == want.shape == (3, 144, 176)
     a = np.clip(got.numpy() * 255.0, 0, 255).astype(np.uint8).astype(np.int32)        # the reference's truncating u8
     b = np.clip(want.numpy() * 255.0, 0, 255).astype(np.uint8).astype(np.int32)
