@@ -64,6 +64,13 @@ def test_preprocess_full_size_is_cv2(engine, shape, level):
     assert np.array_equal(engine.preprocess_u8(img, denoise_level=level), cv2_preprocess(img, level))
 
 
+def test_preprocess_large_strength_uses_the_long_weight_table(engine):
+    """h = 16: the (a, b) weight table (2700 entries) no longer fits the packed kernel's shared-memory copy -> per-column kernels."""
+    assert len(_ffi.nlm_weights(16.0, 2)) > 2048
+    img = noisy(50, 61, seed=4, amp=40)
+    assert np.array_equal(engine.preprocess_u8(img, denoise_level=1.6), P.preprocess_image(img, 1.6))
+
+
 def test_preprocess_device_tensors_and_strength_change(engine):
     img = noisy(90, 110, seed=8)
     dev = torch.from_numpy(img).cuda()
