@@ -175,6 +175,10 @@ __device__ __forceinline__ void sweep_band(Shared& sh, const int rows, const int
   }
 }
 
+// WMC (weight multicast): launched as clusters of two CTAs; each loads HALF of every weight chunk (48 of the 96 rows of each dx
+// box) and multicasts it into both CTAs' weight rings, halving the weight bytes read from L2 (weights are ~18 % of the TMA
+// bytes).  A ring slot is refilled once BOTH CTAs' MMAs have released it (multicast commit, barrier count 2).
+template <bool WMC>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* __restrict__ passes, const int npass,
                      unsigned* __restrict__ prog) {
@@ -191,7 +195,7 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.full[0]); tma_prefetch_desc(&maps.full[1]);
     tma_prefetch_desc(&maps.w);
-    for (int i = 0; i < kWStages; ++i) { mbar_init(&sh.wfull[i], 1); mbar_init(&sh.wempty[i], 1); }
+    for (int i = 0; i < kWStages; ++i) { mbar_init(&sh.wfull[i], 1); mbar_init(&sh.wempty[i], WMC ? 2 : 1); }
     for (int i = 0; i < kStages; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 1); }
     for (int i = 0; i < kSlots; ++i) { mbar_init(&sh.tfull[i], 1); mbar_init(&sh.tempty[i], 128); }
     fence_barrier_init();
@@ -259,6 +263,7 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (WMC) cluster_sync_all();                                  // the peer's barriers exist before anything is multicast into them
   const uint32_t tmem_base = sh.tmem_slot;
 #if NESR_PROF
   for (int i = threadIdx.x; i < 4 * kTracePasses; i += kThreads) (&sh.epi_acc[0][0])[i] = 0;
@@ -296,10 +301,18 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
         // weights of (pass, set, chunk): depend on nobody
         mbar_wait(&sh.wempty[ws], wphase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&sh.wfull[ws], kWChunkBytes);
+          mbar_arrive_expect_tx(&sh.wfull[ws], kWChunkBytes);   // both halves land here: this CTA's and the peer's multicast
+          if (WMC) {
+            const int half = static_cast<int>(cluster_ctarank());
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx)
-            tma_load_2d_hint(wring + ws * kWChunkBytes + dx * kWBoxBytes, &maps.w, &sh.wfull[ws], 0, h.w_row0 + (dx * nchunk + c) * 3 * COUT, keep);
+            for (int dx = 0; dx < 3; ++dx)
+              tma_load_2d_hint_mc(wring + ws * kWChunkBytes + dx * kWBoxBytes + half * (kWBoxBytes / 2), &maps.wh, &sh.wfull[ws], 0,
+                                  h.w_row0 + (dx * nchunk + c) * 3 * COUT + half * (3 * COUT / 2), 3, keep);
+          } else {
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+              tma_load_2d_hint(wring + ws * kWChunkBytes + dx * kWBoxBytes, &maps.w, &sh.wfull[ws], 0, h.w_row0 + (dx * nchunk + c) * 3 * COUT, keep);
+          }
         }
         __syncwarp();
         if (++ws == kWStages) { ws = 0; wphase ^= 1; }
@@ -395,7 +408,7 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
             }
             if (last_chunk && b == sb0) TS(5, pass);
           }
-          umma_commit(&sh.wempty[ws]);
+          if (WMC) umma_commit_mc(&sh.wempty[ws], 3); else umma_commit(&sh.wempty[ws]);
           if (++ws == kWStages) { ws = 0; wphase ^= 1; }
           if (last_chunk) TS(0, pass);
         }
@@ -539,6 +552,7 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (WMC) cluster_sync_all();                                  // no CTA leaves while its peer may still multicast into it
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 #if NESR_PROF
   if ((passes[0].debug_flags & 1024) && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 40)) {
@@ -556,11 +570,13 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
 }  // namespace
 
 cudaError_t conv3x3_trunk_configure() {
-  return cudaFuncSetAttribute(conv3x3_trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_trunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(conv3x3_trunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
 }
 
 cudaError_t launch_conv3x3_trunk(const TrunkMaps& maps, const ConvParams* d_passes, int npass, unsigned* d_gbar, int grid,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, bool weight_multicast) {
   if (grid <= 0 || npass <= 0) return cudaSuccess;
   if (grid > 1024) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaMemsetAsync(d_gbar, 0, static_cast<size_t>(2 * grid) * kProgStride * sizeof(unsigned), stream);
@@ -570,12 +586,18 @@ cudaError_t launch_conv3x3_trunk(const TrunkMaps& maps, const ConvParams* d_pass
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeCooperative;                 // co-residency guarantee for the arrival counter
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv3x3_trunk_kernel, maps, d_passes, npass, d_gbar);
+  if (weight_multicast && (grid & 1) == 0) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+    return cudaLaunchKernelEx(&cfg, conv3x3_trunk_kernel<true>, maps, d_passes, npass, d_gbar);
+  }
+  return cudaLaunchKernelEx(&cfg, conv3x3_trunk_kernel<false>, maps, d_passes, npass, d_gbar);
 }
 
 }  // namespace nesr

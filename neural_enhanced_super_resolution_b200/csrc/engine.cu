@@ -157,6 +157,7 @@ struct nesr_b200_handle {
   int debug_flags = 0;        // NESR_B200_DEBUG_FLAGS: timing experiments (results are wrong when set)
   int use_pairs = 0;          // NESR_B200_PAIRS: CTA-pair trunk kernel (conv3x3_trunk2.cu) when the schedule allows
   int trunk_sets = 1;         // NESR_B200_SETS: band sets per CTA in the single-CTA trunk kernel (2: alternate two far-apart sets -- measured slower: profiles/r1_trunk_experiments.txt)
+  int weight_multicast = 0;   // NESR_B200_WMC: trunk kernel as clusters of two CTAs that share every weight chunk load (multicast)
   int l2_pin_chunks = 1;      // NESR_B200_L2_PIN: dense-block planes whose loads are tagged evict_last in the trunk passes
 };
 
@@ -958,6 +959,7 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
         for (int k = 0; k < 4; ++k) tm.box[i2][k] = a.b_d[i2][k];
       }
       tm.w = b.trunk_pairs ? h->m_wf[0] : fold_weight_map(h, 32);   // pairs: 48-row boxes = one CTA's half of a 96-row folded box
+      tm.wh = h->m_wf[0];
     }
     if (time_trunk) {                  // events on the launching stream around the dominant kernel
       while ((int)h->ev_trunk.size() < 2 * (h->n_trunk_timed + 1)) {
@@ -970,7 +972,8 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
     cudaError_t eb = b.trunk_pairs
         ? launch_conv3x3_trunk2(tm, b.d_body_passes, b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s)
         : b.trunk_fits
-        ? launch_conv3x3_trunk(tm, b.d_body_passes, b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s)
+        ? launch_conv3x3_trunk(tm, b.d_body_passes, b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s,
+                               h->weight_multicast && h->trunk_sets != 2)
         : launch_conv3x3_body(a.f_d[0], a.f_d[1], a.e_d[0], a.e_d[1], fold_weight_map(h, 32), b.d_body_passes,
                               b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s);
     if (eb != cudaSuccess) return fail(h, NESR_E_CUDA, "trunk kernel launch failed: %s", cudaGetErrorString(eb));
@@ -1184,6 +1187,7 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
   if (const char* dbg = getenv("NESR_B200_DEBUG_FLAGS")) h->debug_flags = atoi(dbg);
   if (const char* pin = getenv("NESR_B200_L2_PIN")) h->l2_pin_chunks = atoi(pin);
   if (const char* pr = getenv("NESR_B200_PAIRS")) h->use_pairs = atoi(pr);
+  if (const char* wm = getenv("NESR_B200_WMC")) h->weight_multicast = atoi(wm);
   if (const char* st = getenv("NESR_B200_SETS")) h->trunk_sets = atoi(st);
   if (const char* al = getenv("NESR_B200_ARENA_LIMIT_MB")) h->arena_limit = (size_t)atoll(al) << 20;
   *out = h;

@@ -36,10 +36,11 @@ struct TrunkMaps {
   CUtensorMap full[2];
   CUtensorMap box[2][4];
   CUtensorMap w;               // folded weights, box 96 rows
+  CUtensorMap wh;              // folded weights, box 48 rows (half a box: weight multicast between two CTAs)
 };
 cudaError_t conv3x3_trunk_configure();
 cudaError_t launch_conv3x3_trunk(const TrunkMaps& maps, const ConvParams* d_passes, int npass, unsigned* d_prog, int grid,
-                                 cudaStream_t stream);
+                                 cudaStream_t stream, bool weight_multicast = false);
 
 // --- conv3x3_trunk2.cu : the same trunk kernel on CTA pairs (cta_group::2, M = 256): CTAs 2p / 2p+1 own bands of identical
 //     shape, the leader issues the MMAs of both SMs; `maps.w` must be the 48-row weight box map; grid must be even
