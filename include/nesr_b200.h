@@ -75,7 +75,7 @@ typedef struct nesr_b200_config {
                                  launch per layer pass, 4 = whole-frame persistent trunk kernel with a
                                  grid-wide arrival counter (conv3x3_body.cu, the previous product path) */
   int32_t reserved0;
-  int64_t max_batch_pixels;   /* cap on feature-grid pixels per tile group (batch); 0 = default (150k for
+  int64_t max_batch_pixels;   /* cap on feature-grid pixels per tile group (batch); 0 = default (200k for
                                  conv_impl 0: the group's dense-block activations stay in the 126 MB L2) */
 } nesr_b200_config;
 

@@ -293,8 +293,9 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
     for (int pass = 0; pass < npass; ++pass) {
       const PassHead nh = load_head(passes, pass + 1, npass);   // next pass, fetched early
       const int nchunk = (h.cin + kChunkChannels - 1) / kChunkChannels;
-      const CUtensorMap* amap = &maps.full[h.src_sel ? 1 : 0];
-      const CUtensorMap* bmap = &maps.box[h.src_sel ? 1 : 0][0];
+      const CUtensorMap* amap = &maps.full[h.src_sel & 1];
+      const CUtensorMap* bmap = &maps.box[h.src_sel & 1][0];
+      const int plane_skip = h.src_sel == 3 ? 1 : 0;            // shared-growth layout, buffer B: planes xB | (xA) | x1x2 | x3x4
       for (int set = 0; set < nsets; ++set) {
       const int sb0 = set == 0 ? 0 : nband0, sb1 = set == 0 ? nband0 : nband;
       for (int c = 0; c < nchunk; ++c) {
@@ -334,7 +335,7 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
           known[set] = need;
           if (lane == 0) TS(4, pass);
         }
-        const int plane = c * plane_px;
+        const int plane = (c + (c > 0 ? plane_skip : 0)) * plane_px;
         for (int b = sb0; b < sb1; ++b) {
           const BandInfo& bi = sh.band[b];
           const int nrow = bi.rows + 2;

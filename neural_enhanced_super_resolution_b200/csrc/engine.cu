@@ -91,6 +91,7 @@ struct Arena {
   CUtensorMap f_x0, f_d[2], f_g2, f_g4[2];             // box 136 px (row-folded kernel, full strips)
   CUtensorMap e_x0, e_d[2], e_g2, e_g4[2];             // box 8 px (row-folded kernel, packed remainder strips)
   CUtensorMap b_d[2][4];                               // boxes 8 / 16 / 32 / 64 px of the dense-block buffers (trunk kernel)
+  bool shared_g = false;                               // growth planes shared by both dense buffers (see build_plan)
 };
 
 struct Batch {
@@ -157,6 +158,7 @@ struct nesr_b200_handle {
   int debug_flags = 0;        // NESR_B200_DEBUG_FLAGS: timing experiments (results are wrong when set)
   int use_pairs = 0;          // NESR_B200_PAIRS: CTA-pair trunk kernel (conv3x3_trunk2.cu) when the schedule allows
   int trunk_sets = 1;         // NESR_B200_SETS: band sets per CTA in the single-CTA trunk kernel (2: alternate two far-apart sets -- measured slower: profiles/r1_trunk_experiments.txt)
+  int shared_g = 1;           // NESR_B200_SHARED_G: growth planes of the dense-block buffers single-buffered (trunk kernel path; 0: classic ping-pong of all three planes)
   int weight_multicast = 0;   // NESR_B200_WMC: trunk kernel as clusters of two CTAs that share every weight chunk load (multicast)
   int l2_pin_chunks = 1;      // NESR_B200_L2_PIN: dense-block planes whose loads are tagged evict_last in the trunk passes
 };
@@ -632,7 +634,7 @@ int plan_groups(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
   // working set (~512 B per feature pixel) should stay in the 126 MB L2 across all 414 trunk passes, and its
   // level-0 schedule must fit the TMEM-resident trunk kernel; other paths keep the whole frame in one batch.
   const bool l2_groups = h->cfg.conv_impl == 0;
-  const int64_t cap = h->cfg.max_batch_pixels > 0 ? h->cfg.max_batch_pixels : (l2_groups ? (int64_t)150000 : (int64_t)3 << 20);
+  const int64_t cap = h->cfg.max_batch_pixels > 0 ? h->cfg.max_batch_pixels : (l2_groups ? (int64_t)200000 : (int64_t)3 << 20);
   const bool pairs = l2_groups && h->use_pairs && h->num_sms >= 2;
   // level-0 schedule of a group and whether a TMEM-resident trunk kernel can run it
   const int sets = (l2_groups && !pairs && h->trunk_sets == 2) ? 2 : 1;
@@ -751,7 +753,18 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
     uint8_t* p = h->arena_shared ? h->arena_base : cursor;
     a.base = p;
     a.x0 = p; p += sz_x0;
-    a.d[0] = p; p += sz_d; a.d[1] = p; p += sz_d;
+    // Dense-block buffers.  Classic layout: two [3][P0][64] buffers that ping-pong between blocks.  Shared-growth layout (trunk
+    // kernel only, NESR_B200_SHARED_G): only x needs the ping-pong -- a block's conv1 overwrites the previous block's growth
+    // channels only after every halo neighbour has published that block's conv5, i.e. has finished reading them -- so the planes
+    // are [xB][xA][x1|x2][x3|x4]: buffer A = planes 1..3 (contiguous, as before), buffer B = planes 0, 2, 3 (the kernel skips one
+    // plane after chunk 0).  20 % fewer live bytes per pixel in L2.
+    a.shared_g = h->shared_g && h->cfg.conv_impl == 0 && bb.trunk_fits && !bb.trunk_pairs;
+    if (a.shared_g) {
+      const size_t plane = (size_t)Pb[0] * 64 * 2;
+      a.d[1] = p; a.d[0] = p + plane; p += round_up((int64_t)(4 * plane), 1024);
+    } else {
+      a.d[0] = p; p += sz_d; a.d[1] = p; p += sz_d;
+    }
     a.g2 = p; p += sz_g2;
     a.g4[0] = p; p += sz_g4; a.g4[1] = p; p += sz_g4;
     a.zero_bytes = (size_t)(p - a.base);              // every buffer a conv reads: pads must be zero
@@ -761,18 +774,19 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
     for (int l = 0; l < 3; ++l) a.P[l] = Pb[l];
     if (!h->arena_shared || &bb == &h->batches.front()) CUDA_TRY(h, cudaMemsetAsync(a.base, 0, a.zero_bytes, h->stream));
     if ((rc = make_map(h, &a.m_x0, a.x0, 64, Pb[0], kBlockPixels))) return rc;
-    for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.m_d[i2], a.d[i2], 64, 3 * Pb[0], kBlockPixels))) return rc;
+    const int64_t dpx[2] = {3 * Pb[0], (a.shared_g ? 4 : 3) * Pb[0]};     // buffer B spans four planes in the shared-growth layout
+    for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.m_d[i2], a.d[i2], 64, dpx[i2], kBlockPixels))) return rc;
     if ((rc = make_map(h, &a.m_g2, a.g2, 64, Pb[1], kBlockPixels))) return rc;
     for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.m_g4[i2], a.g4[i2], 64, Pb[2], kBlockPixels))) return rc;
     constexpr int kSlab = 136;                                 // row slab of the folded kernel
     if ((rc = make_map(h, &a.f_x0, a.x0, 64, Pb[0], kSlab))) return rc;
-    for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.f_d[i2], a.d[i2], 64, 3 * Pb[0], kSlab))) return rc;
+    for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.f_d[i2], a.d[i2], 64, dpx[i2], kSlab))) return rc;
     if ((rc = make_map(h, &a.f_g2, a.g2, 64, Pb[1], kSlab))) return rc;
     for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.f_g4[i2], a.g4[i2], 64, Pb[2], kSlab))) return rc;
     if ((rc = make_map(h, &a.e_x0, a.x0, 64, Pb[0], 8))) return rc;
-    for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.e_d[i2], a.d[i2], 64, 3 * Pb[0], 8))) return rc;
+    for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.e_d[i2], a.d[i2], 64, dpx[i2], 8))) return rc;
     for (int i2 = 0; i2 < 2; ++i2)
-      for (int k = 0; k < 4; ++k) if ((rc = make_map(h, &a.b_d[i2][k], a.d[i2], 64, 3 * Pb[0], 8 << k))) return rc;
+      for (int k = 0; k < 4; ++k) if ((rc = make_map(h, &a.b_d[i2][k], a.d[i2], 64, dpx[i2], 8 << k))) return rc;
     if ((rc = make_map(h, &a.e_g2, a.g2, 64, Pb[1], 8))) return rc;
     for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.e_g4[i2], a.g4[i2], 64, Pb[2], 8))) return rc;
   }
@@ -859,7 +873,7 @@ ConvParams rdb_conv_params(const nesr_b200_handle* h, const Arena& a, int r, int
   p.dst16_plane_px = (int)a.P[0];
   if (k <= 4) {                      // x_k = lrelu(conv_k(cat(x, x1..x_{k-1})))  -> channels [64+32(k-1), +32)
     p.lrelu = 1;
-    p.dst16 = a.d[cur]; p.dst16_coff = kFeat + (k - 1) * kGrow; p.dst16_fmt = c.body_format;
+    p.dst16 = a.d[a.shared_g ? 0 : cur]; p.dst16_coff = kFeat + (k - 1) * kGrow; p.dst16_fmt = c.body_format;   // shared growth planes sit behind xA
   } else {                           // x5*0.2 + x  (+ RRDB skip on every third block)
     p.res1 = a.trunk; p.s1 = 0.2f;
     p.dst32a = a.trunk;
@@ -892,7 +906,7 @@ int build_body_passes(nesr_b200_handle* h, Batch& b) {
       for (int ps = 0; ps < L.fold_passes; ++ps) {
         ConvParams q;
         select_fold_pass(L, ps, bound, q);
-        q.src_sel = cur;
+        q.src_sel = cur | (a.shared_g ? 2 : 0);      // bit 1: buffer B's chunks 1, 2 are one plane further (shared-growth layout)
         q.sync_passes = first;       // passes of one layer read the same input and write disjoint channels
         // trunk kernel: which passes must be complete everywhere before input chunk c may be loaded.  Chunk 0 is x
         // (previous block's conv5, both halves), chunk 1 holds x1|x2 (conv1, conv2), chunk 2 holds x3|x4 (conv3, conv4).
@@ -1188,6 +1202,7 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
   if (const char* pin = getenv("NESR_B200_L2_PIN")) h->l2_pin_chunks = atoi(pin);
   if (const char* pr = getenv("NESR_B200_PAIRS")) h->use_pairs = atoi(pr);
   if (const char* wm = getenv("NESR_B200_WMC")) h->weight_multicast = atoi(wm);
+  if (const char* sg = getenv("NESR_B200_SHARED_G")) h->shared_g = atoi(sg);
   if (const char* st = getenv("NESR_B200_SETS")) h->trunk_sets = atoi(st);
   if (const char* al = getenv("NESR_B200_ARENA_LIMIT_MB")) h->arena_limit = (size_t)atoll(al) << 20;
   *out = h;

@@ -60,7 +60,7 @@ def test_identity_ragged_shapes_and_group_plans(monkeypatch):
         img = natural_image(h, w, seed=h + w)
         tile, pad = [(0, 10), (64, 10), (128, 8), (96, 4)][i % 4]
         want = identity_expected(img)
-        for env in ({}, {"NESR_B200_PAIRS": "1"}, {"NESR_B200_SETS": "2"}, {"NESR_B200_MAX_PIECES": "8"}, {"NESR_B200_WMC": "1"}):
+        for env in ({}, {"NESR_B200_PAIRS": "1"}, {"NESR_B200_SETS": "2"}, {"NESR_B200_MAX_PIECES": "8"}, {"NESR_B200_WMC": "1"}, {"NESR_B200_SHARED_G": "1"}):
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             out, _ = gpu_up("identity", tile, pad, 0, max_batch_pixels=[0, 9000][i % 2]).enhance(img)
@@ -186,7 +186,7 @@ def test_trunk_kernel_variants_are_bit_identical(monkeypatch):
     same products in the same order as the default trunk kernel: bit-identical output, whatever the band schedule."""
     img = natural_image(300, 420, seed=12)
     want, _ = gpu_up("calibrated", 160, 10).enhance(img)
-    for var, val in (("NESR_B200_PAIRS", "1"), ("NESR_B200_SETS", "2"), ("NESR_B200_WMC", "1")):
+    for var, val in (("NESR_B200_PAIRS", "1"), ("NESR_B200_SETS", "2"), ("NESR_B200_WMC", "1"), ("NESR_B200_SHARED_G", "1")):
         monkeypatch.setenv(var, val)
         got, _ = gpu_up("calibrated", 160, 10).enhance(img)
         monkeypatch.delenv(var)

@@ -23,7 +23,7 @@ import neural_enhanced_super_resolution_b200 as pkg  # noqa: E402
 FLOP_PER_OUT_PX = 2241504
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 torch.manual_seed(0)
-net = pkg.RRDBNet(3, 3, scale=2).cuda().eval()
+net = pkg.RRDBNet(3, 3, scale=2, max_batch_pixels=int(os.environ.get("NESR_MAX_BATCH_PX", "0"))).cuda().eval()
 eng = net.engine()
 rng = np.random.default_rng(0)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
