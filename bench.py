@@ -140,7 +140,7 @@ def run_reference(args):
     ms = 1e3 * float(np.mean(times))
     val = (2 * sample.shape[0]) * (2 * sample.shape[1]) / (ms / 1e3) / 1e6
     desc = f"1 of 12 tiles ({sample.shape[1]}x{sample.shape[0]} incl. halo) of the 1920x1080 frame per step"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -148,7 +148,7 @@ def run_reference(args):
                    "sample": desc},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def preprocess_stage(eng, img, d_in, level=0.5, reps=5):
@@ -298,7 +298,7 @@ def run_ours(args):
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"top-left {sample.shape[1]}x{sample.shape[0]} of the frame (4 of 12 tiles, tile {TILE} halo {HALO}), fp32 torch-CPU oracle, {dt:.1f} s"}
         pre = preprocess_stage(eng, img, d_in) if world == 1 else None
-        print(json.dumps({
+        emit({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
@@ -326,12 +326,34 @@ def run_ours(args):
             "clocks": clocks,
             "c3": c3,
             "preprocess": pre,
-        }), flush=True)
+        })
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def capture_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries write to fd 1 too (NCCL prints its version banner there when
+    NCCL_DEBUG is set in the environment): point fd 1 at stderr for the whole run and keep the real stdout for emit()."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        os.write(1, line)
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
+    capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
