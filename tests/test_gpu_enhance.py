@@ -60,7 +60,7 @@ def test_identity_ragged_shapes_and_group_plans(monkeypatch):
         img = natural_image(h, w, seed=h + w)
         tile, pad = [(0, 10), (64, 10), (128, 8), (96, 4)][i % 4]
         want = identity_expected(img)
-        for env in ({}, {"NESR_B200_PAIRS": "1"}, {"NESR_B200_SETS": "2"}, {"NESR_B200_MAX_PIECES": "8"}, {"NESR_B200_WMC": "1"}, {"NESR_B200_SHARED_G": "1"}):
+        for env in ({}, {"NESR_B200_PAIRS": "1"}, {"NESR_B200_SETS": "2"}, {"NESR_B200_MAX_PIECES": "8"}, {"NESR_B200_WMC": "1"}, {"NESR_B200_SHARED_G": "0"}):
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             out, _ = gpu_up("identity", tile, pad, 0, max_batch_pixels=[0, 9000][i % 2]).enhance(img)
@@ -186,11 +186,20 @@ def test_trunk_kernel_variants_are_bit_identical(monkeypatch):
     same products in the same order as the default trunk kernel: bit-identical output, whatever the band schedule."""
     img = natural_image(300, 420, seed=12)
     want, _ = gpu_up("calibrated", 160, 10).enhance(img)
-    for var, val in (("NESR_B200_PAIRS", "1"), ("NESR_B200_SETS", "2"), ("NESR_B200_WMC", "1"), ("NESR_B200_SHARED_G", "1")):
+    for var, val in (("NESR_B200_PAIRS", "1"), ("NESR_B200_SETS", "2"), ("NESR_B200_WMC", "1"), ("NESR_B200_SHARED_G", "0")):
         monkeypatch.setenv(var, val)
         got, _ = gpu_up("calibrated", 160, 10).enhance(img)
         monkeypatch.delenv(var)
         assert np.array_equal(got, want), var
+    # the single-buffered growth planes rely on the halo progress words: full-size frame, every CTA with neighbours, twice
+    big = natural_image(1080, 1920, seed=2)
+    want_big, _ = gpu_up("calibrated", 512, 10).enhance(big)
+    again, _ = gpu_up("calibrated", 512, 10).enhance(big)
+    assert np.array_equal(again, want_big)
+    monkeypatch.setenv("NESR_B200_SHARED_G", "0")
+    classic, _ = gpu_up("calibrated", 512, 10).enhance(big)
+    monkeypatch.delenv("NESR_B200_SHARED_G")
+    assert np.array_equal(classic, want_big)
     monkeypatch.setenv("NESR_B200_ARENA_LIMIT_MB", "1")          # tile groups share one arena slice (re-zeroed per group)
     shared, _ = gpu_up("calibrated", 160, 10, max_batch_pixels=20000).enhance(img)
     monkeypatch.delenv("NESR_B200_ARENA_LIMIT_MB")
