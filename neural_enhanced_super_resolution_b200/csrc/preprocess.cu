@@ -331,41 +331,57 @@ void launch_nlm4(const uint8_t* src, uint8_t* dst, int H, int W, const int* wtab
 // ------------------------------------------------------------------------------------------------------------------
 // CLAHE (cv2 clahe.cpp)
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restrict__ L, int H, int W, int tiles_x, int tw, int th, int clip_limit,
-                                                        float lut_scale, uint8_t* __restrict__ luts) {
+constexpr int kClaheThreads = 1024;                                 // four 256-thread groups, one private histogram each
+
+__global__ void __launch_bounds__(kClaheThreads) clahe_lut_kernel(const uint8_t* __restrict__ L, int H, int W, int tiles_x, int tw, int th,
+                                                                  int clip_limit, float lut_scale, uint8_t* __restrict__ luts) {
+  __shared__ int part[kClaheThreads / 256][256];
   __shared__ int hist[256];
   __shared__ int s_clipped;
   const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
-  hist[threadIdx.x] = 0;
-  if (threadIdx.x == 0) s_clipped = 0;
+  const int t = threadIdx.x, grp = t >> 8;
+  part[grp][t & 255] = 0;
+  if (t == 0) s_clipped = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < tw * th; i += 256) {
+  for (int i = t; i < tw * th; i += kClaheThreads) {
     const int yy = i / tw, xx = i - yy * tw;
     const int sy = tile_y * th + yy, sx = tile_x * tw + xx;         // coordinates in the padded plane
     const int py = sy < H ? sy : reflect101(sy, H), px = sx < W ? sx : reflect101(sx, W);
-    atomicAdd(&hist[L[(int64_t)py * W + px]], 1);
+    atomicAdd(&part[grp][L[(int64_t)py * W + px]], 1);
+  }
+  __syncthreads();
+  const bool bin = t < 256;                                          // one thread per histogram bin from here on
+  if (bin) {
+    int v = 0;
+#pragma unroll
+    for (int g = 0; g < kClaheThreads / 256; ++g) v += part[g][t];
+    hist[t] = v;
   }
   __syncthreads();
   if (clip_limit > 0) {
-    const int hv = hist[threadIdx.x];
-    if (hv > clip_limit) {
-      atomicAdd(&s_clipped, hv - clip_limit);
-      hist[threadIdx.x] = clip_limit;
+    if (bin) {
+      const int hv = hist[t];
+      if (hv > clip_limit) {
+        atomicAdd(&s_clipped, hv - clip_limit);
+        hist[t] = clip_limit;
+      }
     }
     __syncthreads();
     const int clipped = s_clipped;
     const int batch = clipped / 256;
-    int residual = clipped - batch * 256;
-    hist[threadIdx.x] += batch;
-    __syncthreads();
-    if (residual != 0) {
-      const int step = 256 / residual > 1 ? 256 / residual : 1;
-      // entries 0, step, 2*step, ... get one more, `residual` of them at most
-      if (threadIdx.x % step == 0 && threadIdx.x / step < residual) hist[threadIdx.x] += 1;
+    const int residual = clipped - batch * 256;
+    if (bin) {
+      int v = hist[t] + batch;
+      if (residual != 0) {
+        const int step = 256 / residual > 1 ? 256 / residual : 1;
+        // entries 0, step, 2*step, ... get one more, `residual` of them at most
+        if (t % step == 0 && t / step < residual) v += 1;
+      }
+      hist[t] = v;
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
+  if (t == 0) {
     int sum = 0;
     uint8_t* lut = luts + (int64_t)blockIdx.x * 256;
     for (int i = 0; i < 256; ++i) {
@@ -493,7 +509,7 @@ cudaError_t launch_preprocess(const uint8_t* rgb, uint8_t* out, int H, int W, co
     if (clip_limit < 1) clip_limit = 1;
   }
   const float lut_scale = 255.0f / (float)area;
-  clahe_lut_kernel<<<tiles_x * tiles_y, 256, 0, stream>>>(L0, H, W, tiles_x, tw, th, clip_limit, lut_scale, luts);
+  clahe_lut_kernel<<<tiles_x * tiles_y, kClaheThreads, 0, stream>>>(L0, H, W, tiles_x, tw, th, clip_limit, lut_scale, luts);
   const dim3 ablock(32, 8), agrid((W + 31) / 32, (H + 7) / 8);
   clahe_apply_kernel<<<agrid, ablock, 0, stream>>>(L0, ab0, H, W, tiles_x, tiles_y, 1.0f / (float)tw, 1.0f / (float)th, luts, out);
   nl += 2;
