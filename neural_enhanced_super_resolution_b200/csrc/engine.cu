@@ -595,7 +595,27 @@ bool trunk_schedule_fits(const LevelPlan& lp) {
 
 // Host half of the plan (no CUDA calls): tiles of the frame(s), split into tile groups, every level's flat layout and
 // row-folded schedule, and the trunk kernel's halo dependency lists.  Fills h->batches.
+int plan_groups_with_cap(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w, int64_t default_cap);
+
+// Default cap of the product path: 200k feature pixels per tile group.  Tiles are atomic, so a slightly larger cap sometimes packs
+// a frame into fewer groups (the 71k-pixel tiles of a 4K frame: three instead of two per group, 1.5-2 % faster;
+// profiles/r1_config_sweep.txt): the plan under a 15 % larger cap is taken when it has strictly fewer groups and every group still
+// fits the trunk kernel.  An explicit max_batch_pixels is taken as is.
 int plan_groups(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
+  constexpr int64_t kCap = 200000;
+  int rc = plan_groups_with_cap(h, key, out_h, out_w, kCap);
+  if (rc != NESR_OK || h->cfg.conv_impl != 0 || h->cfg.max_batch_pixels > 0 || h->batches.size() < 3) return rc;
+  const size_t ngroups = h->batches.size();
+  std::vector<Batch> first = std::move(h->batches);
+  h->batches.clear();
+  rc = plan_groups_with_cap(h, key, out_h, out_w, kCap * 23 / 20);
+  bool better = rc == NESR_OK && h->batches.size() < ngroups;
+  for (const Batch& b : h->batches) better = better && b.trunk_fits;
+  if (!better) h->batches = std::move(first);
+  return NESR_OK;
+}
+
+int plan_groups_with_cap(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w, int64_t default_cap) {
   const int scale = h->cfg.scale;
   const Grid g = tile_grid_dims(key.H, key.W, key.tile, key.pre_pad, scale);
   std::vector<TileGeom> all;
@@ -634,7 +654,7 @@ int plan_groups(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
   // working set (~512 B per feature pixel) should stay in the 126 MB L2 across all 414 trunk passes, and its
   // level-0 schedule must fit the TMEM-resident trunk kernel; other paths keep the whole frame in one batch.
   const bool l2_groups = h->cfg.conv_impl == 0;
-  const int64_t cap = h->cfg.max_batch_pixels > 0 ? h->cfg.max_batch_pixels : (l2_groups ? (int64_t)200000 : (int64_t)3 << 20);
+  const int64_t cap = h->cfg.max_batch_pixels > 0 ? h->cfg.max_batch_pixels : (l2_groups ? default_cap : (int64_t)3 << 20);
   const bool pairs = l2_groups && h->use_pairs && h->num_sms >= 2;
   // level-0 schedule of a group and whether a TMEM-resident trunk kernel can run it
   const int sets = (l2_groups && !pairs && h->trunk_sets == 2) ? 2 : 1;
