@@ -95,3 +95,16 @@ def test_small_devices_and_errors():
     assert rc != 0 and "odd" in msg
     rc, msg, _ = plan(1, 1, 0, 10)
     assert rc != 0
+
+
+def test_larger_cap_is_taken_only_when_it_saves_groups():
+    """Default plan: 200k-pixel groups, or the plan under a 15 % larger cap when that has strictly fewer groups."""
+    rc, msg, dflt = plan(2160, 3840, 512, 10)                  # 4K: 71k-pixel tiles go in threes under 230k, in twos under 200k
+    assert rc == 0, msg
+    rc, msg, fixed = plan(2160, 3840, 512, 10, cap=200000)
+    assert rc == 0, msg
+    assert dflt["groups"] < fixed["groups"] and dflt["trunk_groups"] == dflt["groups"] and dflt["max_rows"] <= 16
+    assert dflt["pixels"] == fixed["pixels"]
+    rc, msg, a = plan(1080, 1920, 512, 10)
+    rc2, msg2, b = plan(1080, 1920, 512, 10, cap=200000)
+    assert rc == 0 and rc2 == 0 and a == b                     # same group count either way: the default cap's plan is kept
