@@ -126,11 +126,14 @@ def _is_torch_cuda(x) -> bool:
     return hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
 
 
-def _image_ptr(img):
-    """(address, is_device) of a contiguous u8 image held in numpy or in a torch CUDA tensor."""
+def _image_ptr(img, device=None):
+    """(address, is_device) of a contiguous u8 image held in numpy or in a torch CUDA tensor.  ``device``: the engine's
+    device ordinal -- a tensor on another GPU is an error, not a peer access."""
     if _is_torch_cuda(img):
         if not img.is_contiguous() or str(img.dtype) != "torch.uint8":
             raise ValueError("device images must be contiguous torch.uint8")
+        if device is not None and img.device.index != device:
+            raise ValueError(f"image is on cuda:{img.device.index} but this engine runs on cuda:{device}")
         import torch
         torch.cuda.current_stream(img.device).synchronize()   # the library works on its own stream
         return img.data_ptr(), True
@@ -203,8 +206,8 @@ class Engine:
             raise ValueError("enhance_u8 expects H x W x 3")
         if out is None:
             out = self._alloc_like(img, (h * self.scale, w * self.scale, 3))
-        ip, idev = _image_ptr(img)
-        op, odev = _image_ptr(out)
+        ip, idev = _image_ptr(img, self.device)
+        op, odev = _image_ptr(out, self.device)
         flags = (PTR_IN_DEVICE if idev else 0) | (PTR_OUT_DEVICE if odev else 0)
         self._check(self._lib.nesr_b200_enhance_u8(self._h, ip, h, w, w * 3, tile, tile_pad, pre_pad, op,
                                                    w * self.scale * 3, flags), "enhance_u8")
@@ -214,8 +217,8 @@ class Engine:
         n, h, w = frames.shape[:3]
         if out is None:
             out = self._alloc_like(frames, (n, h * self.scale, w * self.scale, 3))
-        ip, idev = _image_ptr(frames)
-        op, odev = _image_ptr(out)
+        ip, idev = _image_ptr(frames, self.device)
+        op, odev = _image_ptr(out, self.device)
         flags = (PTR_IN_DEVICE if idev else 0) | (PTR_OUT_DEVICE if odev else 0)
         s = self.scale
         self._check(self._lib.nesr_b200_enhance_batch_u8(self._h, ip, n, h, w, w * 3, h * w * 3, tile, tile_pad,
@@ -232,8 +235,8 @@ class Engine:
     def enhance_tiles_u8(self, img, out, tile: int, tile_pad: int, pre_pad: int, first: int, count: int):
         """Process tiles [first, first+count) of the tile grid into ``out`` (full-size output)."""
         h, w = img.shape[:2]
-        ip, idev = _image_ptr(img)
-        op, odev = _image_ptr(out)
+        ip, idev = _image_ptr(img, self.device)
+        op, odev = _image_ptr(out, self.device)
         flags = (PTR_IN_DEVICE if idev else 0) | (PTR_OUT_DEVICE if odev else 0)
         self._check(self._lib.nesr_b200_enhance_tiles_u8(self._h, ip, h, w, w * 3, tile, tile_pad, pre_pad, first,
                                                          count, op, w * self.scale * 3, flags), "enhance_tiles_u8")
@@ -275,14 +278,14 @@ class Engine:
         for m in members:
             if tuple(m.shape) != (h, w, 3):
                 raise ValueError("blend members must share one H x W x 3 shape")
-            p, d = _image_ptr(m)
+            p, d = _image_ptr(m, self.device)
             if dev is not None and d != dev:
                 raise ValueError("blend members must all be host or all be device images")
             dev = d
             ptrs.append(p)
         if out is None:
             out = self._alloc_like(members[0], (h, w, 3))
-        op, odev = _image_ptr(out)
+        op, odev = _image_ptr(out, self.device)
         arr = (C.c_void_p * k)(*ptrs)
         wts = None if weights is None else (C.c_double * k)(*[float(v) for v in weights])
         flags = (PTR_IN_DEVICE if dev else 0) | (PTR_OUT_DEVICE if odev else 0)
@@ -293,8 +296,8 @@ class Engine:
         h, w = img.shape[:2]
         if out is None:
             out = self._alloc_like(img, (h, w, 3))
-        ip, idev = _image_ptr(img)
-        op, odev = _image_ptr(out)
+        ip, idev = _image_ptr(img, self.device)
+        op, odev = _image_ptr(out, self.device)
         flags = (PTR_IN_DEVICE if idev else 0) | (PTR_OUT_DEVICE if odev else 0)
         self._check(self._lib.nesr_b200_sharpen_u8(self._h, ip, h, w, int(bool(bgr)), op, flags), "sharpen_u8")
         return out
@@ -307,8 +310,8 @@ class Engine:
             raise ValueError("preprocess_u8 expects H x W x 3")
         if out is None:
             out = self._alloc_like(img, (h, w, 3))
-        ip, idev = _image_ptr(img)
-        op, odev = _image_ptr(out)
+        ip, idev = _image_ptr(img, self.device)
+        op, odev = _image_ptr(out, self.device)
         flags = (PTR_IN_DEVICE if idev else 0) | (PTR_OUT_DEVICE if odev else 0)
         strength = float(denoise_level) * 10
         self._check(self._lib.nesr_b200_preprocess_u8(self._h, ip, h, w, strength, strength, float(clip), int(tiles[0]),

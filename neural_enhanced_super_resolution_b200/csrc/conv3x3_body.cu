@@ -125,7 +125,7 @@ conv3x3_body_kernel(const __grid_constant__ CUtensorMap amap_d0, const __grid_co
       red_release_gpu_add(gbar, 1u);
     }
 #if NESR_PROF
-    if ((sp.debug_flags & 1024) && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 77) && pass < 48) {
+    if ((dbg_flags(sp) & 1024) && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 77) && pass < 48) {
       prof_t3 = PROF_NOW();
       printf("[body blk %d pass %d cin=%d] params+wload+spin %lld  producer %lld  drain+sync %lld  total %lld\n", (int)blockIdx.x, pass,
              sp.cin, prof_t1 - prof_t0, prof_t2 - prof_t1, prof_t3 - prof_t2, prof_t3 - prof_t0);

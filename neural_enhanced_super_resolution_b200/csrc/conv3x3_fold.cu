@@ -36,7 +36,7 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
     tma_prefetch_desc(&amap8);
     tma_prefetch_desc(&wmap);
   }
-  pipe_setup<COUT>(s, warp, lane, !(p.debug_flags & 128));
+  pipe_setup<COUT>(s, warp, lane, !(dbg_flags(p) & 128));
 
   const int band_begin = p.cta_band_off[blockIdx.x];
   const int band_end = p.cta_band_off[blockIdx.x + 1];
@@ -61,7 +61,7 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
 
   pipe_teardown(s, warp);
 #if NESR_PROF
-  if ((p.debug_flags & 256) && threadIdx.x == 0) {       // per-CTA lifetime: who are the stragglers?
+  if ((dbg_flags(p) & 256) && threadIdx.x == 0) {       // per-CTA lifetime: who are the stragglers?
     unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
     int nrows = 0;
@@ -95,7 +95,7 @@ cudaError_t launch_c(const CUtensorMap& amap, const CUtensorMap& amap8, const CU
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (p.debug_flags & 512) ? 0 : 1;      // 512: no programmatic dependent launch (timing experiments)
+  cfg.numAttrs = (dbg_flags(p) & 512) ? 0 : 1;      // 512: no programmatic dependent launch (timing experiments)
   return cudaLaunchKernelEx(&cfg, conv3x3_fold_kernel<COUT>, amap, amap8, wmap, p);
 }
 

@@ -119,6 +119,10 @@ struct nesr_b200_handle {
   cudaStream_t copy_stream = nullptr;                  // device -> host copies of finished tile groups, overlapped with the next group
   std::vector<cudaEvent_t> ev_group;                   // "group g stitched" events
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evc0 = nullptr, evc1 = nullptr;
+  // forward_nchw runs on the CALLER's stream but shares the arena, progress words and plan with the entries that run on
+  // h->stream: ev_own orders the caller's stream behind our plan uploads, ev_ext orders our next h->stream entry behind the forward
+  cudaEvent_t ev_own = nullptr, ev_ext = nullptr;
+  bool ext_pending = false;
   std::vector<cudaEvent_t> ev_trunk;                   // begin/end pairs around each trunk kernel launch of the last call
   int n_trunk_timed = 0;
   EncodeTiledFn encode = nullptr;
@@ -181,6 +185,23 @@ int fail(nesr_b200_handle* h, int code, const char* fmt, ...) {
     if (e__ != cudaSuccess)                                                                      \
       return fail(h, NESR_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
+
+// Every C-ABI entry makes the handle's device current for the duration of the call and restores the caller's device on
+// every return path (an Engine on cuda:1 must not silently move a torch thread that was on cuda:0).
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define DEVICE_SCOPE(h)                                                                          \
+  DeviceGuard device_guard__((h)->cfg.device);                                                   \
+  if (!device_guard__.ok) return fail(h, NESR_E_CUDA, "cudaSetDevice(%d) failed", (h)->cfg.device)
 
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
@@ -1059,6 +1080,15 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
   return NESR_OK;
 }
 
+// Called at the start of every entry that works on h->stream: a forward_nchw still running on the caller's stream uses the
+// same arena and progress words.
+int wait_external(nesr_b200_handle* h) {
+  if (!h->ext_pending) return NESR_OK;
+  CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_ext, 0));
+  h->ext_pending = false;
+  return NESR_OK;
+}
+
 int ensure(nesr_b200_handle* h, uint8_t** buf, size_t* cap, size_t need) {
   if (need <= *cap) return NESR_OK;
   if (*buf) cudaFree(*buf);
@@ -1078,7 +1108,8 @@ int enhance_impl(nesr_b200_handle* h, const uint8_t* in, int n_frames, int H, in
   if (tile < 0 || tile_pad < 0 || pre_pad < 0 || pre_pad >= H || pre_pad >= W)
     return fail(h, NESR_E_INVALID, "bad tile/pad arguments (tile=%d tile_pad=%d pre_pad=%d)", tile, tile_pad, pre_pad);
   if (in_stride < (int64_t)W * 3 || out_stride < (int64_t)W * h->cfg.scale * 3) return fail(h, NESR_E_INVALID, "row stride smaller than a row");
-  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
+  if (int wrc = wait_external(h)) return wrc;
   const int s = h->cfg.scale, OH = H * s, OW = W * s;
   PlanKey key; key.n_frames = n_frames; key.H = H; key.W = W; key.tile = tile; key.tile_pad = tile_pad;
   key.pre_pad = pre_pad; key.first = first; key.count = count; key.whole = whole;
@@ -1183,7 +1214,8 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
   if (e != cudaSuccess || ndev == 0)
     return fail(nullptr, NESR_E_CUDA, "no CUDA device (%s): libnesr_b200 has no CPU fallback", cudaGetErrorString(e));
   if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, NESR_E_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
-  if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail(nullptr, NESR_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  DeviceGuard device_guard(cfg->device);
+  if (!device_guard.ok) return fail(nullptr, NESR_E_CUDA, "cudaSetDevice(%d) failed", cfg->device);
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) return fail(nullptr, NESR_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
   if (prop.major != 10)
@@ -1211,6 +1243,8 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
       (e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
       (e = cudaEventCreate(&h->evc0)) != cudaSuccess || (e = cudaEventCreate(&h->evc1)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_own, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_ext, cudaEventDisableTiming)) != cudaSuccess ||
       (e = conv3x3_tc_configure()) != cudaSuccess || (e = conv3x3_fold_configure()) != cudaSuccess ||
       (e = conv3x3_body_configure()) != cudaSuccess || (e = conv3x3_trunk_configure()) != cudaSuccess || (e = conv3x3_trunk2_configure()) != cudaSuccess || (e = cudaMalloc(&h->d_gbar, 2048 * 128)) != cudaSuccess) {
     std::string msg = cudaGetErrorString(e);
@@ -1218,7 +1252,9 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
     return fail(nullptr, NESR_E_CUDA, "device setup failed: %s", msg.c_str());
   }
   build_layers(h);
-  if (const char* dbg = getenv("NESR_B200_DEBUG_FLAGS")) h->debug_flags = atoi(dbg);
+#if NESR_PROF
+  if (const char* dbg = getenv("NESR_B200_DEBUG_FLAGS")) h->debug_flags = atoi(dbg);   // timing experiments: -DNESR_PROF=1 builds only
+#endif
   if (const char* pin = getenv("NESR_B200_L2_PIN")) h->l2_pin_chunks = atoi(pin);
   if (const char* pr = getenv("NESR_B200_PAIRS")) h->use_pairs = atoi(pr);
   if (const char* wm = getenv("NESR_B200_WMC")) h->weight_multicast = atoi(wm);
@@ -1231,7 +1267,7 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
 
 int nesr_b200_destroy(nesr_b200_handle* h) {
   if (!h) return NESR_OK;
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard device_guard(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   free_batches(h);
   if (h->arena_base) cudaFree(h->arena_base);
@@ -1249,6 +1285,8 @@ int nesr_b200_destroy(nesr_b200_handle* h) {
   for (cudaEvent_t ev : h->ev_trunk) cudaEventDestroy(ev);
   if (h->evc0) cudaEventDestroy(h->evc0);
   if (h->evc1) cudaEventDestroy(h->evc1);
+  if (h->ev_own) cudaEventDestroy(h->ev_own);
+  if (h->ev_ext) cudaEventDestroy(h->ev_ext);
   for (cudaEvent_t ev : h->ev_group) cudaEventDestroy(ev);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1276,7 +1314,7 @@ int nesr_b200_finalize_weights(nesr_b200_handle* h) {
   if (!h) return NESR_E_INVALID;
   for (const auto& kv : h->expect)
     if (!h->staged.count(kv.first)) return fail(h, NESR_E_WEIGHTS, "missing key in state_dict: %s", kv.first.c_str());
-  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
   std::vector<uint16_t> arena((size_t)h->w_rows * 64, 0);
   std::vector<float> bias(h->layers.size() * 64, 0.f);
   for (const Layer& L : h->layers) {
@@ -1303,6 +1341,9 @@ int nesr_b200_finalize_weights(nesr_b200_handle* h) {
     int rc = make_map(h, &h->m_w[i], h->d_wpack, 64, h->w_rows, box[i]);
     if (rc) return rc;
   }
+  // pageable synchronous copies may return before their DMA has landed, and the kernels run on non-blocking streams that
+  // have no implicit ordering with the legacy stream: make the uploads globally complete here
+  CUDA_TRY(h, cudaDeviceSynchronize());
   h->finalized = true;
   return NESR_OK;
 }
@@ -1422,19 +1463,22 @@ int forward_nchw(nesr_b200_handle* h, const float* x, bool unshuffled, int32_t n
   if (!h->finalized) return fail(h, NESR_E_STATE, "weights not finalized");
   if (!x || !y || n < 1 || H < 2 || W < 2) return fail(h, NESR_E_INVALID, "bad tensor arguments");
   if ((H | W) & 1) return fail(h, NESR_E_INVALID, "pixel_unshuffle(2): H and W must be even (got %dx%d)", H, W);
-  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
   cudaStream_t s = (cudaStream_t)stream;      // literally the caller's stream; NULL is the legacy default stream
   const int sc = h->cfg.scale;
   PlanKey key; key.n_frames = n; key.H = H; key.W = W; key.tile = 0; key.whole = 1;
   int rc = build_plan(h, key, H * sc, W * sc);
   if (rc) return rc;
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // plan uploads / memset ran on our own stream
+  CUDA_TRY(h, cudaEventRecord(h->ev_own, h->stream));          // plan uploads / memset (and any earlier u8 call) ran on our own stream
+  CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_own, 0));
   PackParams pk{};
   if (unshuffled) pk.in_f32_12 = x; else pk.in_f32 = x;
   pk.H = H; pk.W = W; pk.pre_pad = 0;
   Sink sink; sink.out_f32 = y; sink.out_h = H * sc; sink.out_w = W * sc;
   for (const Batch& b : h->batches)
     if ((rc = forward_batch(h, b, pk, sink, s, false, false))) return rc;
+  CUDA_TRY(h, cudaEventRecord(h->ev_ext, s));
+  h->ext_pending = true;
   return NESR_OK;
 }
 }  // namespace
@@ -1452,7 +1496,8 @@ int nesr_b200_blend_u8(nesr_b200_handle* h, const uint8_t* const* members, int32
                        uint8_t* out, int32_t flags) {
   if (!h) return NESR_E_INVALID;
   if (!members || !out || K < 2 || K > kMaxBlendMembers || H < 1 || W < 1) return fail(h, NESR_E_INVALID, "blend: need 2..%d members", kMaxBlendMembers);
-  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
+  if (int wrc = wait_external(h)) return wrc;
   const int64_t n = (int64_t)H * W * 3;
   BlendParams p{};
   p.k = K; p.nbytes = n;
@@ -1492,7 +1537,8 @@ int nesr_b200_preprocess_u8(nesr_b200_handle* h, const uint8_t* rgb, int32_t H, 
   if (!rgb || !out || H < 1 || W < 1 || tiles_x < 1 || tiles_y < 1 || tiles_x * tiles_y > 4096)
     return fail(h, NESR_E_INVALID, "preprocess: bad arguments");
   if ((int64_t)H * W > (int64_t)1 << 30) return fail(h, NESR_E_INVALID, "preprocess: image too large");
-  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
+  if (int wrc = wait_external(h)) return wrc;
   const int64_t n = (int64_t)H * W * 3;
   const uint8_t* d_in = rgb;
   uint8_t* d_out = out;
@@ -1559,7 +1605,8 @@ int nesr_b200_debug_nlm_weights(float h, int32_t channels, int32_t* out, int32_t
 int nesr_b200_sharpen_u8(nesr_b200_handle* h, const uint8_t* in, int32_t H, int32_t W, int32_t bgr, uint8_t* out, int32_t flags) {
   if (!h) return NESR_E_INVALID;
   if (!in || !out || H < 1 || W < 1) return fail(h, NESR_E_INVALID, "sharpen: bad arguments");
-  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
+  if (int wrc = wait_external(h)) return wrc;
   const int64_t n = (int64_t)H * W * 3;
   const uint8_t* d_in = in;
   uint8_t* d_out = out;
@@ -1594,7 +1641,7 @@ int nesr_b200_get_stats(const nesr_b200_handle* h, nesr_b200_stats* out) {
 
 int nesr_b200_synchronize(nesr_b200_handle* h) {
   if (!h) return NESR_E_INVALID;
-  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return NESR_OK;
 }
@@ -1606,7 +1653,7 @@ int nesr_b200_debug_conv(nesr_b200_handle* h, int32_t impl, int32_t fmt, int32_t
   if (!h) return NESR_E_INVALID;
   if (!weight_oihw || !bias || !x_nchw || !y_nchw || H < 1 || W < 1 || cin < 1 || cin > kDense || cout < 1 || cout > 64 || (fmt & ~1))
     return fail(h, NESR_E_INVALID, "debug_conv: bad arguments");
-  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_SCOPE(h);
   Layer L;
   L.name = "debug"; L.cin = cin; L.cout = cout; L.fmt = fmt;
   L.cin16 = (int)round_up(cin, 16); L.nchunk = (L.cin16 + 63) / 64; L.npad = cout <= 16 ? 16 : (cout <= 32 ? 32 : 64);

@@ -132,7 +132,7 @@ __device__ __forceinline__ EpiRegs make_epi_regs(const ConvParams& p) {
   e.dst16_up = kTrunk ? 0 : p.dst16_up;
   e.out_u8 = kTrunk ? nullptr : p.out_u8; e.out_stride = p.out_stride; e.out_frame_stride = p.out_frame_stride;
   e.out_f32 = kTrunk ? nullptr : p.out_f32; e.out_h = p.out_h; e.out_w = p.out_w;
-  e.debug_flags = p.debug_flags;
+  e.debug_flags = dbg_flags(p);
   return e;
 }
 
@@ -167,7 +167,7 @@ __device__ __forceinline__ void epilogue16(const Params& p, const TileGeom& tg, 
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], p.s2, r2pre[i]);
   }
-  if (p.dst32a && !(p.debug_flags & 4096)) {                 // 4096: no fp32 trunk stores (timing experiments)
+  if (p.dst32a && !((NESR_PROF ? p.debug_flags : 0) & 4096)) {                 // 4096: no fp32 trunk stores (timing experiments)
     stg256f_stream(p.dst32a + trunk_offset(px.P, ch0), v);
     stg256f_stream(p.dst32a + trunk_offset(px.P, ch0 + 8), v + 8);
   }
@@ -175,7 +175,7 @@ __device__ __forceinline__ void epilogue16(const Params& p, const TileGeom& tg, 
     stg256f_stream(p.dst32b + trunk_offset(px.P, ch0), v);
     stg256f_stream(p.dst32b + trunk_offset(px.P, ch0 + 8), v + 8);
   }
-  if (p.dst16 && !(p.debug_flags & 16)) {                    // 16: no 16-bit activation stores (timing experiments)
+  if (p.dst16 && !((NESR_PROF ? p.debug_flags : 0) & 16)) {                    // 16: no 16-bit activation stores (timing experiments)
     uint32_t w[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) w[i] = pack2(v[2 * i], v[2 * i + 1], p.dst16_fmt);

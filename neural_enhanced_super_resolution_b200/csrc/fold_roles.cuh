@@ -36,7 +36,7 @@ namespace fold {
 
 // NESR_PROF build + debug_flags & 32: block 0 prints where each role spent its cycles (timing experiments only)
 #if NESR_PROF
-#define PROF_DECL long long prof_t = 0, prof_acc[4] = {0, 0, 0, 0}; const bool prof_on = (p.debug_flags & 32) && blockIdx.x == 0
+#define PROF_DECL long long prof_t = 0, prof_acc[4] = {0, 0, 0, 0}; const bool prof_on = (dbg_flags(p) & 32) && blockIdx.x == 0
 #define PROF_BEGIN() do { if (prof_on) prof_t = clock64(); } while (0)
 #define PROF_END(k) do { if (prof_on) { const long long t__ = clock64(); prof_acc[k] += t__ - prof_t; prof_t = t__; } } while (0)
 #define PROF_PRINT(...) do { if (prof_on) printf(__VA_ARGS__); } while (0)
@@ -137,7 +137,7 @@ template <int COUT>
 __device__ __forceinline__ void load_weights(const ConvParams& p, const CUtensorMap* wmap, const Pipe& s) {
   const int nchunk = (p.cin + kChunkChannels - 1) / kChunkChannels;
   if (elect_one()) {
-    if (p.debug_flags & 64) {
+    if (dbg_flags(p) & 64) {
       mbar_arrive(s.wbar);
     } else {
       mbar_arrive_expect_tx(s.wbar, 3 * nchunk * FoldCfg<COUT>::kWBoxBytes);
@@ -156,7 +156,7 @@ __device__ __forceinline__ void load_weights(const ConvParams& p, const CUtensor
 __device__ __forceinline__ void producer_bands(const ConvParams& p, const CUtensorMap* amap, const CUtensorMap* amap8,
                                                const Pipe& s, RingPos& rp, int band_begin, int band_end) {
   const int nchunk = (p.cin + kChunkChannels - 1) / kChunkChannels;
-  const int plane_px = p.src_plane_px, level = p.level, dbg = p.debug_flags;
+  const int plane_px = p.src_plane_px, level = p.level, dbg = dbg_flags(p);
   const FoldBand* const bands = p.bands;
   const FoldSeg* const segs = p.segs;
   const TileGeom* const tiles = p.tiles;
@@ -245,7 +245,7 @@ template <int COUT>
 __device__ __forceinline__ void mma_bands(const ConvParams& p, const Pipe& s, RingPos& rp, uint32_t& u, uint32_t wphase,
                                           int band_begin, int band_end) {
   using Cfg = FoldCfg<COUT>;
-  const int cin = p.cin, dbg = p.debug_flags;
+  const int cin = p.cin, dbg = dbg_flags(p);
   const FoldBand* const bands = p.bands;
   const int nchunk = (cin + kChunkChannels - 1) / kChunkChannels;
   const int last_ks = (cin - (nchunk - 1) * kChunkChannels) >> 4;   // k-steps of the last chunk (1..4)
@@ -344,7 +344,7 @@ __device__ __forceinline__ void epilogue_bands(const ConvParams& p, const Pipe& 
   const FoldBand* const bands = p.bands;
   const FoldSeg* const segs = p.segs;
   const TileGeom* const tiles = p.tiles;
-  const int level = e.level, dbg = p.debug_flags;
+  const int level = e.level, dbg = dbg_flags(p);
   const int quarter = warp & 3;
   const int group = (warp - 2) >> 2;                         // rows alternate between the epilogue groups
   const int m = quarter * 32 + lane;                         // A row == TMEM lane == pixel x0 + m

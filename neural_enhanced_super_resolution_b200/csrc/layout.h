@@ -120,6 +120,16 @@ struct ConvParams {
   const int32_t* trunk_split;  // [grid] number of bands of a CTA that belong to set 0 (the rest: set 1)
 };
 
+// Timing-experiment switches (NESR_B200_DEBUG_FLAGS: results are WRONG when one is set) exist only in a -DNESR_PROF=1 build:
+// in the shipped library this folds to 0 and every `dbg & bit` branch in the kernels compiles away.
+#ifndef NESR_PROF
+#define NESR_PROF 0
+#endif
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int dbg_flags(const ConvParams& p) { return NESR_PROF ? p.debug_flags : 0; }
+
 // conv3x3_trunk.cu keeps every output row of a CTA in TMEM for a whole pass: 16 row slots of 32 fp32 columns.
 constexpr int kTrunkMaxRows = 16;
 constexpr int kTrunkMaxBands = 4;

@@ -23,6 +23,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 #include "kernels.h"
@@ -419,16 +420,21 @@ __global__ void clahe_apply_kernel(const uint8_t* __restrict__ Lp, const uint8_t
 }
 
 bool g_tables_uploaded[64] = {};
+std::mutex g_tables_mutex;                                     // engines on several threads may race to the first upload
 
+// The consuming kernels run on non-blocking streams, which have no implicit ordering with the legacy stream these pageable
+// copies use (and a pageable copy may return before its DMA has landed): the device is synchronised before the flag is set.
 cudaError_t upload_tables() {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(g_tables_mutex);
   if (dev < 64 && g_tables_uploaded[dev]) return cudaSuccess;
   if ((e = cudaMemcpyToSymbol(d_gamma_srgb, kGammaSrgb, sizeof(kGammaSrgb))) != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbol(d_lab_cbrt, kLabCbrt, sizeof(kLabCbrt))) != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbol(d_lab_to_yf, kLabToYF, sizeof(kLabToYF))) != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbol(d_inv_gamma_srgb, kInvGammaSrgb, sizeof(kInvGammaSrgb))) != cudaSuccess) return e;
+  if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
   if (dev < 64) g_tables_uploaded[dev] = true;
   return cudaSuccess;
 }

@@ -62,13 +62,16 @@ def enhance_frames_sharded(engine, frames_bgr, tile: int = 0, tile_pad: int = 10
     world, rank = _world(group)
     n = frames_bgr.shape[0]
     first, count = partition(n, world, rank)
-    local = engine.enhance_batch_u8(frames_bgr[first:first + count], tile=tile, tile_pad=tile_pad, pre_pad=pre_pad) \
-        if count else frames_bgr[:0]
-    if not gather or world == 1:
-        return first, local
     s = engine.scale
     h, w = frames_bgr.shape[1:3]
     on_device = isinstance(frames_bgr, torch.Tensor)
+    if count:
+        local = engine.enhance_batch_u8(frames_bgr[first:first + count], tile=tile, tile_pad=tile_pad, pre_pad=pre_pad)
+    else:                      # fewer frames than ranks: an empty batch of the OUTPUT shape, same container kind
+        local = (torch.empty((0, h * s, w * s, 3), dtype=torch.uint8, device=frames_bgr.device) if on_device
+                 else np.empty((0, h * s, w * s, 3), np.uint8))
+    if not gather or world == 1:
+        return first, local
     full = (torch.zeros((n, h * s, w * s, 3), dtype=torch.uint8, device=frames_bgr.device) if on_device
             else torch.zeros((n, h * s, w * s, 3), dtype=torch.uint8))
     if count:

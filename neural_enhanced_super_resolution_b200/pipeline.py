@@ -137,7 +137,8 @@ class SuperResolutionPipeline:
         if "esrgan" in self.models:
             return self.models["esrgan"].model.engine(self.device)
         if getattr(self, "_stencil_engine", None) is None:           # ESRGAN disabled: the stencil stages still run on the GPU
-            self._stencil_engine = _ffi.Engine(device=torch.device(self.device).index or torch.cuda.current_device())
+            idx = torch.device(self.device).index                    # index 0 is a valid answer, not "unset"
+            self._stencil_engine = _ffi.Engine(device=torch.cuda.current_device() if idx is None else idx)
         return self._stencil_engine
 
     # -- stages --------------------------------------------------------------------------------
@@ -314,25 +315,6 @@ def install(reference_cls, engine_getter=None) -> None:
             return None
         out, _ = self.models["esrgan"].enhance(cv2.cvtColor(image, cv2.COLOR_RGB2BGR))
         return cv2.cvtColor(out, cv2.COLOR_BGR2RGB)
-
-    def _apply_esrgan_head(self, image):
-        """The reference HEAD's ESRGAN stage (``_apply_esrgan_12channel`` / ``_apply_esrgan_3channel``, ``nesr/nesr.py:845-986``),
-        untiled: BGR / 255 -> 12 channels (image, x1.1, x0.9 clamped, 3x3 Gaussian blur -- or four copies with
-        ``force_3channel``) -> ``model(x12)`` -> ``clip(out * 255, 0, 255)`` TRUNCATED to u8 -> RGB.  x4 per call (the 12-channel
-        network is the x2plus network without its un-shuffle).  The reference tiles images above ``cuda_megapixel_threshold`` with
-        ``_process_with_tiling`` (``:311-475``); that host loop is not restated -- larger images run untiled here."""
-        host = not isinstance(image, torch.Tensor)
-        rgb = torch.from_numpy(np.ascontiguousarray(image)).to(self.device) if host else image
-        bgr = rgb.flip(-1).permute(2, 0, 1).contiguous()                                     # 3 x H x W u8
-        t = bgr.float() / 255.0
-        if self.config["force_3channel"]:
-            x12 = torch.cat([t, t, t, t], 0)
-        else:
-            x12 = torch.cat([t, torch.clamp(t * 1.1, 0, 1), torch.clamp(t * 0.9, 0, 1), gaussian_blur3_u8(bgr).float() / 255.0], 0)
-        out = self.models["esrgan"].model(x12.unsqueeze(0)).squeeze(0)                       # 3 x 4H x 4W float
-        out = torch.clamp(out.permute(1, 2, 0) * 255.0, 0, 255).to(torch.uint8)              # truncation, as astype(np.uint8)
-        out = out.flip(-1).contiguous()
-        return out.cpu().numpy() if host else out
 
     def _ensemble_results(self, upscaled_images):
         if len(upscaled_images) == 1:

@@ -72,7 +72,8 @@ class RealESRGANer:
                                                                pre_pad=int(self.pre_pad))
             img_mode = "RGB"
         else:
-            output, img_mode = self._enhance_float(np.asarray(img), alpha_upsampler)
+            host = img.cpu().numpy() if isinstance(img, torch.Tensor) else np.asarray(img)     # gray / RGBA / 16-bit glue is host code
+            output, img_mode = self._enhance_float(host, alpha_upsampler)
         if outscale is not None and outscale != float(self.scale):
             host = output.cpu().numpy() if isinstance(output, torch.Tensor) else output
             output = cv2.resize(host, (int(w_input * outscale), int(h_input * outscale)), interpolation=cv2.INTER_LANCZOS4)

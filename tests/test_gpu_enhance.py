@@ -129,6 +129,52 @@ def test_odd_size_with_pre_pad_within_tolerance():
 
 
 # ---------------------------------------------------------------------------------------------
+# tolerance at the BASELINE configuration sizes (the benchmarked geometry, real weights)
+# ---------------------------------------------------------------------------------------------
+def _check_tolerance(out, want, what, emu=None):
+    d = np.abs(out.astype(np.int32) - want.astype(np.int32))
+    print(f"{what}: max|d|={d.max()} frac(d>0)={(d > 0).mean():.4f} psnr={psnr(out, want):.1f} dB")
+    assert out.shape == want.shape
+    assert d.max() <= TOL_ABS and psnr(out, want) >= TOL_PSNR, what
+    if emu is not None:
+        de = np.abs(out.astype(np.int32) - emu.astype(np.int32))
+        print(f"{what} vs emulation: max|d|={de.max()} frac(d>0)={(de > 0).mean():.5f}")
+        assert de.max() <= 1 and (de > 0).mean() < 5e-2, what
+
+
+def test_c1_512_untiled_within_tolerance():
+    """BASELINE configs[0]: 512x512 RGB, tile=0 (one L2-resident group, full strips, every CTA with halo neighbours),
+    calibrated random-init weights, against the fp32 oracle (+-2 / 45 dB) and the rounding-point emulation (<= 1)."""
+    img = natural_image(512, 512, seed=21)
+    out, _ = gpu_up("calibrated", 0, 10).enhance(img)
+    want, _ = cpu_up("calibrated", 0, 10).enhance(img)
+    emu, _ = cpu_up("calibrated", 0, 10, emulate=True).enhance(img)
+    _check_tolerance(out, want, "C1 512x512 tile=0", emu)
+
+
+def test_c2_crop_1024_tile512_within_tolerance():
+    """BASELINE configs[1] geometry on the top-left 1024x1024 of the 1080p frame: tile 512, halo 10 -> four tiles of
+    522x522 (261-pixel feature rows: two full strips + a packed 5-pixel remainder), the cross-CTA progress-word machinery
+    of the trunk kernel with real weights, against the fp32 oracle."""
+    img = natural_image(1080, 1920, seed=2)[:1024, :1024].copy()
+    out, _ = gpu_up("calibrated", 512, 10).enhance(img)
+    want, _ = cpu_up("calibrated", 512, 10).enhance(img)
+    _check_tolerance(out, want, "C2 crop 1024x1024 tile=512 halo=10")
+
+
+def test_c2_full_frame_product_kernel_vs_per_layer_launches():
+    """1920x1080, tile 512, halo 10 (12 tiles, three tile groups): the product trunk kernel (conv_impl 0: neighbour
+    progress words, TMEM-resident bands) against one launch per layer pass (conv_impl 3: stream order is the only
+    synchronisation) -- an independent mechanism on the benchmarked geometry; fp32 summation order is the only difference."""
+    img = natural_image(1080, 1920, seed=2)
+    a, _ = gpu_up("calibrated", 512, 10).enhance(img)
+    b, _ = gpu_up("calibrated", 512, 10, conv_impl=3).enhance(img)
+    d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+    print(f"1080p conv_impl 0 vs 3: max|d|={d.max()} frac(d>0)={(d > 0).mean():.5f}")
+    assert d.max() <= 1 and (d > 0).mean() < 5e-2
+
+
+# ---------------------------------------------------------------------------------------------
 # invariants of the engine (bit-identical by construction)
 # ---------------------------------------------------------------------------------------------
 def test_batch_tiles_and_multibatch_are_bit_identical(up_random):
