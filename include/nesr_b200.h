@@ -70,10 +70,12 @@ typedef struct nesr_b200_config {
   int32_t conv_impl;          /* 0 = row-folded tcgen05/TMEM/TMA kernels (product): tiles are processed in
                                  L2-resident groups, each with ONE persistent launch for the 69 residual dense
                                  blocks (conv3x3_trunk.cu) and one launch per edge layer.  Test-only
-                                 cross-checks, never selected implicitly: 1 = SIMT validation kernel,
-                                 2 = first-generation per-tap tcgen05 kernel, 3 = row-folded kernel with one
-                                 launch per layer pass, 4 = whole-frame persistent trunk kernel with a
-                                 grid-wide arrival counter (conv3x3_body.cu, the previous product path) */
+                                 cross-checks, never selected implicitly: 1 = SIMT validation kernel (CUDA
+                                 cores, no TMA / tcgen05), 3 = row-folded kernel with one launch per layer
+                                 pass (stream order is the only synchronisation), 4 = whole-frame persistent
+                                 trunk kernel with a grid-wide arrival counter (conv3x3_body.cu; also what a
+                                 tile too large for the trunk kernel's TMEM row budget runs on).  2 is
+                                 rejected (the first-generation per-tap kernel was removed in round 2) */
   int32_t reserved0;
   int64_t max_batch_pixels;   /* cap on feature-grid pixels per tile group (batch); 0 = default (200k for
                                  conv_impl 0: the group's dense-block activations stay in the 126 MB L2) */
@@ -136,9 +138,10 @@ int nesr_b200_tile_count(int32_t H, int32_t W, int32_t tile, int32_t pre_pad, in
 /* (test hook, host only -- no CUDA call, works without a GPU) Builds the tile-group plan that an enhance call with these
  * arguments would use on a device with `num_sms` SMs and verifies its invariants: every pixel of every tile of every
  * resolution level owned by exactly one (CTA, band, lane); segment lanes inside the 128-lane MMA / 136-row slab; TMEM row
- * limits of the trunk kernels; band shapes of CTA pairs identical; halo dependency lists symmetric.
- * out[8]: groups, tiles, feature pixels, level-0 strip rows, max output rows per CTA, groups run by a TMEM-resident trunk
- * kernel, of those on CTA pairs, level-0 halo rows.  pairs / sets: the NESR_B200_PAIRS / NESR_B200_SETS switches. */
+ * limit of the trunk kernel; and, pixel by pixel against an independently built owner map, that the trunk kernel's
+ * row-dependency table makes every input slab row of every CTA wait for the rows of every CTA owning one of its pixels.
+ * out[8]: groups, tiles, feature pixels, level-0 strip rows, max output rows per CTA, groups run by the TMEM-resident trunk
+ * kernel, reserved (0), level-0 halo rows.  pairs / sets: reserved (planner variants removed in round 2), ignored. */
 int nesr_b200_debug_plan(int32_t n_frames, int32_t H, int32_t W, int32_t tile, int32_t tile_pad, int32_t pre_pad, int32_t num_sms,
                          int32_t conv_impl, int64_t max_batch_pixels, int32_t pairs, int32_t sets, int64_t* out);
 int nesr_b200_enhance_tiles_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32_t H, int32_t W,

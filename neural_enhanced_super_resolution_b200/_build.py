@@ -15,12 +15,13 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libnesr_b200.so")
-SOURCES = ["conv3x3_fold.cu", "conv3x3_body.cu", "conv3x3_trunk.cu", "conv3x3_trunk2.cu", "conv3x3_tc.cu", "conv3x3_simt.cu", "pixel_io.cu", "stencil.cu", "preprocess.cu", "engine.cu"]
+SOURCES = ["conv3x3_fold.cu", "conv3x3_body.cu", "conv3x3_trunk.cu", "conv3x3_simt.cu", "pixel_io.cu", "stencil.cu", "preprocess.cu", "engine.cu"]
 HEADERS = ["ptx.cuh", "layout.h", "epilogue.cuh", "fold_roles.cuh", "kernels.h", "lab_tables.inc", os.path.join("..", "..", "include", "nesr_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
-if os.environ.get("NESR_B200_PROF") == "1":          # device printf + per-role cycle accounting (timing experiments)
-    FLAGS.append("-DNESR_PROF=1")
+# Timing-experiment variant (device printf, per-role cycle accounting, the NESR_B200_DEBUG_FLAGS switches): built as a
+# SEPARATE library, libnesr_b200_prof.so, selected at run time with NESR_B200_LIB=<path>; the product library never contains it.
+PROF_LIB = os.path.join(PKG, "libnesr_b200_prof.so")
 
 
 def _nvcc() -> str:
@@ -37,11 +38,14 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, prof: bool = False) -> str:
     nvcc = _nvcc()
+    OBJ = os.path.join(PKG, "build_prof" if prof else "build")
+    LIB = PROF_LIB if prof else globals()["LIB"]
+    FLAGS = globals()["FLAGS"] + (["-DNESR_PROF=1"] if prof else [])
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, h) for h in HEADERS]
-    stamp = os.path.join(OBJ, "flags.txt")                    # a different flag set (e.g. NESR_B200_PROF) rebuilds everything
+    stamp = os.path.join(OBJ, "flags.txt")                    # a different flag set rebuilds everything
     flags_now = " ".join(ARCH + FLAGS)
     if not os.path.exists(stamp) or open(stamp).read() != flags_now:
         force = True
@@ -67,4 +71,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, prof="--prof" in sys.argv))

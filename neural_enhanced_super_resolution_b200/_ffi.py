@@ -12,7 +12,8 @@ import threading
 
 import numpy as np
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libnesr_b200.so")
+# NESR_B200_LIB: another build of the same library (the timing-experiment variant libnesr_b200_prof.so, tools/ only)
+_LIB_PATH = os.environ.get("NESR_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libnesr_b200.so")
 ABI_VERSION = 1
 FMT_BF16, FMT_FP16 = 0, 1
 PTR_IN_DEVICE, PTR_OUT_DEVICE = 1, 2

@@ -59,11 +59,10 @@ struct LevelPlan {
   FoldSeg* d_segs = nullptr;
   int32_t* d_cta_off = nullptr;
   int fold_grid = 0;
-  bool paired = false;         // level 0: CTAs 2p / 2p+1 have bands of identical shape (CTA-pair trunk kernel)
-  std::vector<int32_t> deps;   // level 0 only: [grid][2][kTrunkMaxDeps] halo dependencies of the trunk kernel (empty: too many)
+  std::vector<int32_t> deps;   // level 0 only: [grid][kTrunkMaxDeps] CTAs owning pixels of a CTA's input slab rows (empty: too many)
   int32_t* d_deps = nullptr;
-  std::vector<int32_t> split;  // level 0 only: [grid] bands of each CTA in set 0 (two-set schedule: rest in set 1)
-  int32_t* d_split = nullptr;
+  std::vector<uint8_t> need;   // level 0 only: [grid][kTrunkMaxSlabRows][kTrunkMaxDeps] rows each dependency must have stored per slab row
+  uint8_t* d_need = nullptr;
 };
 
 struct PlanKey {
@@ -100,8 +99,7 @@ struct Batch {
   LevelPlan lv[3];
   ConvParams* d_body_passes = nullptr;   // persistent trunk kernel: one ConvParams per RDB layer pass
   int n_body_passes = 0;
-  bool trunk_fits = false;               // level-0 schedule fits a TMEM-resident trunk kernel (conv3x3_trunk.cu / conv3x3_trunk2.cu)
-  bool trunk_pairs = false;              // ... the CTA-pair one
+  bool trunk_fits = false;               // level-0 schedule fits the TMEM-resident trunk kernel (conv3x3_trunk.cu)
   Arena arena;                           // this group's activation buffers: its own slice of the handle's allocation, or all of it
 };
 
@@ -160,10 +158,7 @@ struct nesr_b200_handle {
 
   nesr_b200_stats stats{};
   int debug_flags = 0;        // NESR_B200_DEBUG_FLAGS: timing experiments (results are wrong when set)
-  int use_pairs = 0;          // NESR_B200_PAIRS: CTA-pair trunk kernel (conv3x3_trunk2.cu) when the schedule allows
-  int trunk_sets = 1;         // NESR_B200_SETS: band sets per CTA in the single-CTA trunk kernel (2: alternate two far-apart sets -- measured slower: profiles/r1_trunk_experiments.txt)
   int shared_g = 1;           // NESR_B200_SHARED_G: growth planes of the dense-block buffers single-buffered (trunk kernel path; 0: classic ping-pong of all three planes)
-  int weight_multicast = 0;   // NESR_B200_WMC: trunk kernel as clusters of two CTAs that share every weight chunk load (multicast)
   int l2_pin_chunks = 1;      // NESR_B200_L2_PIN: dense-block planes whose loads are tagged evict_last in the trunk passes
 };
 
@@ -348,7 +343,7 @@ void free_batches(nesr_b200_handle* h) {
       if (l.d_segs) cudaFree(l.d_segs);
       if (l.d_cta_off) cudaFree(l.d_cta_off);
       if (l.d_deps) cudaFree(l.d_deps);
-      if (l.d_split) cudaFree(l.d_split);
+      if (l.d_need) cudaFree(l.d_need);
     }
   }
   h->batches.clear();
@@ -379,7 +374,7 @@ void layout_level(Batch& b, int level) {
 // CTA gets the same number of rows +-1 and at most a few bands, so no SM waits for a straggler
 // (a longest-first deal of fixed-size bands left 12 of 148 CTAs with 35 % more work), and the two
 // halo rows a band costs are paid as rarely as possible.
-void build_fold_schedule(Batch& b, int level, int num_sms, bool pairs = false, int sets = 1) {
+void build_fold_schedule(Batch& b, int level, int num_sms) {
   LevelPlan& lp = b.lv[level];
   struct Strip { int32_t seg0, nseg, h; };
   std::vector<Strip> strips;
@@ -448,79 +443,13 @@ void build_fold_schedule(Batch& b, int level, int num_sms, bool pairs = false, i
       strips.push_back(st);
     }
   }
-  lp.paired = false;
-  if (pairs && num_sms >= 2) {
-    // CTA-pair schedule (conv3x3_trunk2.cu): CTAs 2p and 2p+1 get bands of IDENTICAL shape.  Strips are paired by height
-    // (an odd one out is cut into its upper and lower half); a pair-strip has the length of its longer member and the
-    // shorter one's missing rows are dropped by the segments' row counts.  The pair-strip sequence is cut into
-    // contiguous runs of equal cost exactly like the single-CTA schedule below.
-    struct Half { int32_t strip, off, len; };
-    struct PairStrip { Half a, b; int32_t len; };
-    std::vector<int> order(strips.size());
-    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return strips[x].h > strips[y].h; });
-    std::vector<PairStrip> ps;
-    for (size_t i = 0; i + 1 < order.size(); i += 2) {
-      const Strip &sa = strips[order[i]], &sb = strips[order[i + 1]];
-      ps.push_back(PairStrip{Half{order[i], 0, sa.h}, Half{order[i + 1], 0, sb.h}, std::max(sa.h, sb.h)});
-    }
-    if (order.size() & 1) {
-      const int si = order.back(), hh = strips[si].h, up = (hh + 1) / 2;
-      ps.push_back(PairStrip{Half{si, 0, up}, Half{si, up, hh - up}, up});
-    }
-    int64_t total = 0;
-    for (const PairStrip& q : ps) total += q.len;
-    const int npair = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms / 2, total / 4));
-    std::vector<std::vector<FoldBand>> per_cta(2 * npair);
-    auto deal2 = [&](int64_t budget, bool emit) -> bool {
-      size_t pi = 0;
-      int r = 0;
-      if (emit) for (auto& v : per_cta) v.clear();
-      for (int c = 0; c < npair; ++c) {
-        int64_t left = budget;
-        while (pi < ps.size() && left >= 3) {
-          const PairStrip& q = ps[pi];
-          const int n = (int)std::min<int64_t>(left - 2, q.len - r);
-          if (emit) {
-            const Strip &sa = strips[q.a.strip], &sb = strips[q.b.strip];
-            per_cta[2 * c].push_back(FoldBand{sa.seg0, sa.nseg, q.a.off + r, n});
-            per_cta[2 * c + 1].push_back(FoldBand{sb.seg0, sb.nseg, q.b.off + r, n});
-          }
-          left -= n + 2;
-          r += n;
-          if (r == q.len) { ++pi; r = 0; }
-        }
-      }
-      return pi == ps.size();
-    };
-    int64_t lo2 = 3, hi2 = total + 2 * (int64_t)ps.size() + 3;
-    while (lo2 < hi2) {
-      const int64_t mid = (lo2 + hi2) / 2;
-      if (deal2(mid, false)) hi2 = mid; else lo2 = mid + 1;
-    }
-    deal2(lo2, true);
-    lp.bands.clear();
-    lp.cta_off.assign(1, 0);
-    lp.split.clear();
-    for (const auto& v : per_cta) {
-      lp.bands.insert(lp.bands.end(), v.begin(), v.end());
-      lp.cta_off.push_back((int32_t)lp.bands.size());
-      lp.split.push_back((int32_t)v.size());
-    }
-    lp.fold_grid = 2 * npair;
-    lp.paired = true;
-    return;
-  }
   int64_t total_rows = 0;
   for (const Strip& st : strips) total_rows += st.h;
   const int min_rows = 4;                                      // do not spread tiny work over every SM
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms, total_rows / min_rows));
   // Contiguous runs of equal COST: a band of n rows costs n + 2 slab rows (its halo), so a CTA whose run crosses a
   // strip boundary gets fewer output rows.  The smallest per-run budget that covers everything is found by bisection.
-  // With sets == 2 (trunk kernel) the sequence is cut into 2*grid runs and CTA c owns run c (set 0) and run grid + c
-  // (set 1): two band sets far apart, processed alternately so that one set's publish -> acquire latency between layer
-  // passes is hidden behind the other set's work.
-  const int nrun = sets * grid;
+  const int nrun = grid;
   std::vector<std::vector<FoldBand>> runs(nrun);
   auto deal = [&](int64_t budget, bool emit) -> bool {
     size_t si = 0;
@@ -546,11 +475,8 @@ void build_fold_schedule(Batch& b, int level, int num_sms, bool pairs = false, i
   deal(lo, true);
   lp.bands.clear();
   lp.cta_off.assign(1, 0);
-  lp.split.clear();
   for (int c = 0; c < grid; ++c) {
     lp.bands.insert(lp.bands.end(), runs[c].begin(), runs[c].end());
-    lp.split.push_back((int32_t)runs[c].size());
-    if (sets == 2) lp.bands.insert(lp.bands.end(), runs[grid + c].begin(), runs[grid + c].end());
     lp.cta_off.push_back((int32_t)lp.bands.size());
   }
   lp.fold_grid = grid;
@@ -559,48 +485,60 @@ void build_fold_schedule(Batch& b, int level, int num_sms, bool pairs = false, i
 int build_body_passes(nesr_b200_handle* h, Batch& b);
 
 // conv3x3_trunk.cu keeps all output rows of a CTA in TMEM: at most kTrunkMaxRows rows in kTrunkMaxBands bands.
-// Halo dependencies of the trunk kernel: CTA c must not load activations another pass wrote before every CTA owning a
-// pixel of its bands' input halos (one pixel around each segment, inside the tile) has published that pass.
-void build_trunk_deps(LevelPlan& lp) {
+// Row dependencies of the trunk kernel.  CTA c streams, per chunk sweep, the input rows -1 .. rows of each of its bands
+// ("slab rows", pixels x0-1 .. x0+width of every segment).  A slab row of the chunk that another layer pass has just
+// written may be loaded once every CTA owning one of its pixels has stored that tile row.  Output: lp.deps[c][d] = the
+// CTAs (c itself first) that own such pixels, lp.need[c][t][d] = how many of its output rows (slot order: bands in order)
+// CTA deps[c][d] must have stored before c loads its slab row t.  Strip rows of a packed piece beyond the piece's height
+// + 1 feed masked lanes only and carry no dependency; rows outside the tile are zero guard rows.
+void build_trunk_deps(const std::vector<TileGeom>& tiles, LevelPlan& lp) {
   const int grid = lp.fold_grid;
-  struct Rect { int tile, x0, x1, y0, y1, word; };             // inclusive pixel rectangle of one segment of one band; word = cta*2 + set
+  struct Rect { int tile, x0, x1, y0, y1, cta, q0; };          // inclusive pixel rectangle of one segment of one band; q0 = slot of tile row y0
   std::vector<Rect> rects;
-  for (int c = 0; c < grid; ++c)
+  for (int c = 0; c < grid; ++c) {
+    int slot0 = 0;
     for (int b = lp.cta_off[c]; b < lp.cta_off[c + 1]; ++b) {
       const FoldBand& band = lp.bands[b];
-      const int set = (b - lp.cta_off[c]) < lp.split[c] ? 0 : 1;
       for (int sgi = 0; sgi < band.nseg; ++sgi) {
         const FoldSeg& sg = lp.segs[band.seg0 + sgi];
         if (band.r0 >= sg.h) continue;                            // this piece has no rows in the band
-        rects.push_back(Rect{sg.tile, sg.x0, sg.x0 + sg.width - 1, sg.y0 + band.r0, sg.y0 + std::min(band.r0 + band.rows, sg.h) - 1, 2 * c + set});
+        rects.push_back(Rect{sg.tile, sg.x0, sg.x0 + sg.width - 1, sg.y0 + band.r0, sg.y0 + std::min(band.r0 + band.rows, sg.h) - 1, c, slot0});
+      }
+      slot0 += band.rows;
+    }
+  }
+  lp.deps.assign((size_t)grid * kTrunkMaxDeps, 0);
+  lp.need.assign((size_t)grid * kTrunkMaxSlabRows * kTrunkMaxDeps, 0);
+  for (int c = 0; c < grid; ++c) {
+    std::vector<int32_t> dep(1, c);
+    int t = 0;
+    for (int b = lp.cta_off[c]; b < lp.cta_off[c + 1]; ++b) {
+      const FoldBand& band = lp.bands[b];
+      for (int i = -1; i <= band.rows; ++i, ++t) {
+        if (t >= kTrunkMaxSlabRows) { lp.deps.clear(); lp.need.clear(); return; }
+        for (int sgi = 0; sgi < band.nseg; ++sgi) {
+          const FoldSeg& sg = lp.segs[band.seg0 + sgi];
+          const int s = band.r0 + i;                              // strip row of this slab row
+          if (band.r0 >= sg.h || s > std::min(band.r0 + band.rows, sg.h)) continue;   // feeds no output row of this piece
+          const LevelGeom& g = tiles[sg.tile].lv[0];
+          const int y = sg.y0 + s;
+          if (y < 0 || y >= g.h) continue;                        // zero guard row
+          const int xa = std::max(sg.x0 - 1, 0), xb = std::min(sg.x0 + sg.width, g.w - 1);
+          for (const Rect& o : rects) {
+            if (o.tile != sg.tile || y < o.y0 || y > o.y1 || o.x1 < xa || o.x0 > xb) continue;
+            size_t d = std::find(dep.begin(), dep.end(), o.cta) - dep.begin();
+            if (d == dep.size()) {
+              if ((int)dep.size() == kTrunkMaxDeps) { lp.deps.clear(); lp.need.clear(); return; }
+              dep.push_back(o.cta);
+            }
+            uint8_t& n = lp.need[((size_t)c * kTrunkMaxSlabRows + t) * kTrunkMaxDeps + d];
+            n = std::max<uint8_t>(n, (uint8_t)(o.q0 + (y - o.y0) + 1));
+          }
+        }
       }
     }
-  const int nword = 2 * grid;
-  lp.deps.assign((size_t)nword * kTrunkMaxDeps, 0);
-  std::vector<std::vector<int32_t>> dep(nword);
-  for (const Rect& a : rects)
-    for (const Rect& o : rects) {
-      if (o.tile != a.tile || o.word == a.word) continue;
-      if (o.x1 < a.x0 - 1 || o.x0 > a.x1 + 1 || o.y1 < a.y0 - 1 || o.y0 > a.y1 + 1) continue;
-      if (std::find(dep[a.word].begin(), dep[a.word].end(), o.word) == dep[a.word].end()) dep[a.word].push_back(o.word);
-    }
-  for (int w = 0; w < nword; ++w) {
-    if ((int)dep[w].size() + 1 > kTrunkMaxDeps) { lp.deps.clear(); return; }
-    for (int k = 0; k < kTrunkMaxDeps; ++k) lp.deps[(size_t)w * kTrunkMaxDeps + k] = k < (int)dep[w].size() ? dep[w][k] : w;
+    for (int k = 0; k < kTrunkMaxDeps; ++k) lp.deps[(size_t)c * kTrunkMaxDeps + k] = k < (int)dep.size() ? dep[k] : c;
   }
-}
-
-// conv3x3_trunk2.cu: every band needs two junk row slots on either side (shared between consecutive bands).
-bool trunk2_schedule_fits(const LevelPlan& lp) {
-  if (!lp.paired || (lp.fold_grid & 1)) return false;
-  for (int c = 0; c < lp.fold_grid; ++c) {
-    const int b0 = lp.cta_off[c], b1 = lp.cta_off[c + 1];
-    if (b1 - b0 > kTrunkMaxBands) return false;
-    int slots = 2;
-    for (int b = b0; b < b1; ++b) slots += lp.bands[b].rows + 2;
-    if (slots > kTrunkMaxRows) return false;
-  }
-  return true;
 }
 
 bool trunk_schedule_fits(const LevelPlan& lp) {
@@ -676,11 +614,9 @@ int plan_groups_with_cap(nesr_b200_handle* h, const PlanKey& key, int out_h, int
   // level-0 schedule must fit the TMEM-resident trunk kernel; other paths keep the whole frame in one batch.
   const bool l2_groups = h->cfg.conv_impl == 0;
   const int64_t cap = h->cfg.max_batch_pixels > 0 ? h->cfg.max_batch_pixels : (l2_groups ? default_cap : (int64_t)3 << 20);
-  const bool pairs = l2_groups && h->use_pairs && h->num_sms >= 2;
-  // level-0 schedule of a group and whether a TMEM-resident trunk kernel can run it
-  const int sets = (l2_groups && !pairs && h->trunk_sets == 2) ? 2 : 1;
-  auto sched0 = [&](Batch& bb) { layout_level(bb, 0); build_fold_schedule(bb, 0, h->num_sms, pairs, sets); };
-  auto fits0 = [&](const Batch& bb) { return bb.lv[0].paired ? trunk2_schedule_fits(bb.lv[0]) : trunk_schedule_fits(bb.lv[0]); };
+  // level-0 schedule of a group and whether the TMEM-resident trunk kernel can run it
+  auto sched0 = [&](Batch& bb) { layout_level(bb, 0); build_fold_schedule(bb, 0, h->num_sms); };
+  auto fits0 = [&](const Batch& bb) { return trunk_schedule_fits(bb.lv[0]); };
   size_t i = 0;
   while (i < all.size()) {
     Batch b;
@@ -710,13 +646,8 @@ int plan_groups_with_cap(nesr_b200_handle* h, const PlanKey& key, int out_h, int
     for (int l = 1; l < 3; ++l) { layout_level(b, l); build_fold_schedule(b, l, h->num_sms); }
     sched0(b);
     b.trunk_fits = l2_groups && fits0(b);
-    if (l2_groups && !b.trunk_fits && b.lv[0].paired) {          // pairs do not fit: try the single-CTA kernel's schedule
-      layout_level(b, 0); build_fold_schedule(b, 0, h->num_sms, false, h->trunk_sets == 2 ? 2 : 1);
-      b.trunk_fits = trunk_schedule_fits(b.lv[0]);
-    }
-    b.trunk_pairs = b.trunk_fits && b.lv[0].paired;
     if (b.trunk_fits) {
-      build_trunk_deps(b.lv[0]);
+      build_trunk_deps(b.tiles, b.lv[0]);
       b.trunk_fits = !b.lv[0].deps.empty();
     }
     if (b.lv[2].pixels >= ((int64_t)1 << 31) - 4096) return fail(h, NESR_E_INVALID, "batch too large for 32-bit pixel indices");
@@ -742,9 +673,9 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
       CUDA_TRY(h, cudaMemcpyAsync(lp.d_bands, lp.bands.data(), lp.bands.size() * sizeof(FoldBand), cudaMemcpyHostToDevice, h->stream));
       CUDA_TRY(h, cudaMalloc(&lp.d_segs, std::max<size_t>(1, lp.segs.size()) * sizeof(FoldSeg)));
       CUDA_TRY(h, cudaMemcpyAsync(lp.d_segs, lp.segs.data(), lp.segs.size() * sizeof(FoldSeg), cudaMemcpyHostToDevice, h->stream));
-      if (!lp.split.empty()) {
-        CUDA_TRY(h, cudaMalloc(&lp.d_split, lp.split.size() * sizeof(int32_t)));
-        CUDA_TRY(h, cudaMemcpyAsync(lp.d_split, lp.split.data(), lp.split.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+      if (!lp.need.empty()) {
+        CUDA_TRY(h, cudaMalloc(&lp.d_need, lp.need.size()));
+        CUDA_TRY(h, cudaMemcpyAsync(lp.d_need, lp.need.data(), lp.need.size(), cudaMemcpyHostToDevice, h->stream));
       }
       if (!lp.deps.empty()) {
         CUDA_TRY(h, cudaMalloc(&lp.d_deps, lp.deps.size() * sizeof(int32_t)));
@@ -799,7 +730,7 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
     // channels only after every halo neighbour has published that block's conv5, i.e. has finished reading them -- so the planes
     // are [xB][xA][x1|x2][x3|x4]: buffer A = planes 1..3 (contiguous, as before), buffer B = planes 0, 2, 3 (the kernel skips one
     // plane after chunk 0).  20 % fewer live bytes per pixel in L2.
-    a.shared_g = h->shared_g && h->cfg.conv_impl == 0 && bb.trunk_fits && !bb.trunk_pairs;
+    a.shared_g = h->shared_g && h->cfg.conv_impl == 0 && bb.trunk_fits;
     if (a.shared_g) {
       const size_t plane = (size_t)Pb[0] * 64 * 2;
       a.d[1] = p; a.d[0] = p + plane; p += round_up((int64_t)(4 * plane), 1024);
@@ -886,10 +817,6 @@ int run_conv(nesr_b200_handle* h, const Batch& b, const Layer& L, const ConvIO& 
   cudaError_t e = cudaSuccess;
   if (h->cfg.conv_impl == 1) {
     e = launch_conv3x3_simt(p, s);
-  } else if (h->cfg.conv_impl == 2) {
-    const CUtensorMap& wm = h->m_w[L.npad == 16 ? 0 : (L.npad == 32 ? 1 : 2)];
-    e = launch_conv3x3_tc(*io.amap, wm, p, h->num_sms, s);
-    h->stats.conv_launches++;
   } else {
     for (int ps = 0; ps < L.fold_passes && e == cudaSuccess; ++ps) {
       ConvParams q;
@@ -956,7 +883,7 @@ int build_body_passes(nesr_b200_handle* h, Batch& b) {
         q.need[1] = k == 2 ? rb + 1 : rb + 2;
         q.need[2] = k == 4 ? rb + 3 : rb + 4;
         q.trunk_deps = b.lv[0].d_deps;
-        q.trunk_split = b.lv[0].d_split;
+        q.trunk_need = b.lv[0].d_need;
         // the first half of conv5 is needed by nobody before the second half has been published too: skip its publish
         q.trunk_no_publish = (k == 5 && ps + 1 < L.fold_passes) ? 1 : 0;
         q.l2_pin_chunks = h->l2_pin_chunks;
@@ -1013,8 +940,7 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
         tm.full[i2] = a.f_d[i2];
         for (int k = 0; k < 4; ++k) tm.box[i2][k] = a.b_d[i2][k];
       }
-      tm.w = b.trunk_pairs ? h->m_wf[0] : fold_weight_map(h, 32);   // pairs: 48-row boxes = one CTA's half of a 96-row folded box
-      tm.wh = h->m_wf[0];
+      tm.w = fold_weight_map(h, 32);
     }
     if (time_trunk) {                  // events on the launching stream around the dominant kernel
       while ((int)h->ev_trunk.size() < 2 * (h->n_trunk_timed + 1)) {
@@ -1024,11 +950,8 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
       }
       cudaEventRecord(h->ev_trunk[2 * h->n_trunk_timed], s);
     }
-    cudaError_t eb = b.trunk_pairs
-        ? launch_conv3x3_trunk2(tm, b.d_body_passes, b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s)
-        : b.trunk_fits
-        ? launch_conv3x3_trunk(tm, b.d_body_passes, b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s,
-                               h->weight_multicast && h->trunk_sets != 2)
+    cudaError_t eb = b.trunk_fits
+        ? launch_conv3x3_trunk(tm, b.d_body_passes, b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s)
         : launch_conv3x3_body(a.f_d[0], a.f_d[1], a.e_d[0], a.e_d[1], fold_weight_map(h, 32), b.d_body_passes,
                               b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s);
     if (eb != cudaSuccess) return fail(h, NESR_E_CUDA, "trunk kernel launch failed: %s", cudaGetErrorString(eb));
@@ -1209,6 +1132,9 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
   if (cfg->scale != 2 || cfg->num_feat != 64 || cfg->num_grow_ch != 32 || cfg->num_in_ch != 3 || cfg->num_out_ch != 3 || cfg->num_block < 1)
     return fail(nullptr, NESR_E_INVALID, "unsupported architecture: this build implements RRDBNet(3,3,scale=2,num_feat=64,num_grow_ch=32)");
   if ((cfg->body_format | cfg->edge_format) & ~1) return fail(nullptr, NESR_E_INVALID, "bad operand format");
+  if (cfg->conv_impl != 0 && cfg->conv_impl != 1 && cfg->conv_impl != 3 && cfg->conv_impl != 4)
+    return fail(nullptr, NESR_E_INVALID, "conv_impl %d: 0 product (L2-resident trunk kernel), 1 SIMT validation kernel, 3 one launch per layer pass, "
+                "4 whole-frame persistent trunk kernel", cfg->conv_impl);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -1245,8 +1171,8 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
       (e = cudaEventCreate(&h->evc0)) != cudaSuccess || (e = cudaEventCreate(&h->evc1)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&h->ev_own, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&h->ev_ext, cudaEventDisableTiming)) != cudaSuccess ||
-      (e = conv3x3_tc_configure()) != cudaSuccess || (e = conv3x3_fold_configure()) != cudaSuccess ||
-      (e = conv3x3_body_configure()) != cudaSuccess || (e = conv3x3_trunk_configure()) != cudaSuccess || (e = conv3x3_trunk2_configure()) != cudaSuccess || (e = cudaMalloc(&h->d_gbar, 2048 * 128)) != cudaSuccess) {
+      (e = conv3x3_fold_configure()) != cudaSuccess ||
+      (e = conv3x3_body_configure()) != cudaSuccess || (e = conv3x3_trunk_configure()) != cudaSuccess || (e = cudaMalloc(&h->d_gbar, 2048 * 128)) != cudaSuccess) {
     std::string msg = cudaGetErrorString(e);
     nesr_b200_destroy(h);
     return fail(nullptr, NESR_E_CUDA, "device setup failed: %s", msg.c_str());
@@ -1256,10 +1182,7 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
   if (const char* dbg = getenv("NESR_B200_DEBUG_FLAGS")) h->debug_flags = atoi(dbg);   // timing experiments: -DNESR_PROF=1 builds only
 #endif
   if (const char* pin = getenv("NESR_B200_L2_PIN")) h->l2_pin_chunks = atoi(pin);
-  if (const char* pr = getenv("NESR_B200_PAIRS")) h->use_pairs = atoi(pr);
-  if (const char* wm = getenv("NESR_B200_WMC")) h->weight_multicast = atoi(wm);
   if (const char* sg = getenv("NESR_B200_SHARED_G")) h->shared_g = atoi(sg);
-  if (const char* st = getenv("NESR_B200_SETS")) h->trunk_sets = atoi(st);
   if (const char* al = getenv("NESR_B200_ARENA_LIMIT_MB")) h->arena_limit = (size_t)atoll(al) << 20;
   *out = h;
   return NESR_OK;
@@ -1368,7 +1291,7 @@ int nesr_b200_tile_count(int32_t H, int32_t W, int32_t tile, int32_t pre_pad, in
 
 // Host-only: builds the tile-group plan a call with these arguments would use (no CUDA calls, works without a GPU) and
 // verifies its invariants.  out[]: 0 groups, 1 tiles, 2 feature pixels, 3 strip rows of level 0 (all groups), 4 largest
-// number of output rows owned by one CTA, 5 groups a TMEM-resident trunk kernel can run, 6 of those on CTA pairs,
+// number of output rows owned by one CTA, 5 groups the TMEM-resident trunk kernel can run, 6 reserved (0),
 // 7 halo rows (2 per band, level 0).  Returns NESR_OK, or NESR_E_STATE with the violated invariant in last_error(NULL).
 int nesr_b200_debug_plan(int32_t n_frames, int32_t H, int32_t W, int32_t tile, int32_t tile_pad, int32_t pre_pad, int32_t num_sms,
                          int32_t conv_impl, int64_t max_batch_pixels, int32_t pairs, int32_t sets, int64_t* out) {
@@ -1376,7 +1299,8 @@ int nesr_b200_debug_plan(int32_t n_frames, int32_t H, int32_t W, int32_t tile, i
   nesr_b200_handle hd;
   nesr_b200_default_config(&hd.cfg, 0);
   hd.cfg.conv_impl = conv_impl; hd.cfg.max_batch_pixels = max_batch_pixels;
-  hd.num_sms = num_sms; hd.use_pairs = pairs; hd.trunk_sets = sets;
+  hd.num_sms = num_sms;
+  (void)pairs; (void)sets;                                     // reserved (round-1 planner variants, removed): ignored
   PlanKey key; key.n_frames = n_frames; key.H = H; key.W = W; key.tile = tile; key.tile_pad = tile_pad; key.pre_pad = pre_pad;
   key.first = 0; key.count = 0; key.whole = 1;
   const int rc = plan_groups(&hd, key, H * hd.cfg.scale, W * hd.cfg.scale);
@@ -1386,7 +1310,7 @@ int nesr_b200_debug_plan(int32_t n_frames, int32_t H, int32_t W, int32_t tile, i
   for (size_t bi = 0; bi < hd.batches.size(); ++bi) {
     const Batch& b = hd.batches[bi];
     out[1] += (int64_t)b.tiles.size();
-    out[5] += b.trunk_fits; out[6] += b.trunk_pairs;
+    out[5] += b.trunk_fits;
     for (int level = 0; level < 3; ++level) {
       const LevelPlan& lp = b.lv[level];
       // every pixel of every tile is owned by exactly one (band, segment, lane); nothing outside a tile is owned
@@ -1424,24 +1348,56 @@ int nesr_b200_debug_plan(int32_t n_frames, int32_t H, int32_t W, int32_t tile, i
       if (level == 0) {
         for (const TileGeom& t : b.tiles) out[2] += (int64_t)t.lv[0].h * t.lv[0].w;
         if (b.trunk_fits) {
-          if (b.trunk_pairs ? !trunk2_schedule_fits(lp) : !trunk_schedule_fits(lp)) return fail(nullptr, NESR_E_STATE, "group %zu: trunk fit flag wrong", bi);
-          if (b.trunk_pairs)                                   // CTAs 2p / 2p+1: same number of bands, same rows per band
-            for (int c = 0; c < lp.fold_grid; c += 2) {
-              const int n0 = lp.cta_off[c + 1] - lp.cta_off[c], n1 = lp.cta_off[c + 2] - lp.cta_off[c + 1];
-              if (n0 != n1) return fail(nullptr, NESR_E_STATE, "group %zu: pair %d has %d / %d bands", bi, c / 2, n0, n1);
-              for (int q = 0; q < n0; ++q)
-                if (lp.bands[lp.cta_off[c] + q].rows != lp.bands[lp.cta_off[c + 1] + q].rows)
-                  return fail(nullptr, NESR_E_STATE, "group %zu: pair %d band %d row counts differ", bi, c / 2, q);
+          if (!trunk_schedule_fits(lp)) return fail(nullptr, NESR_E_STATE, "group %zu: trunk fit flag wrong", bi);
+          // Row-dependency table, checked pixel by pixel against an owner map built independently of build_trunk_deps:
+          // every pixel of every slab row that feeds an output row must be covered by need[c][t][lane of its owner] > its slot.
+          if ((int)lp.deps.size() != lp.fold_grid * kTrunkMaxDeps || (int)lp.need.size() != lp.fold_grid * kTrunkMaxSlabRows * kTrunkMaxDeps)
+            return fail(nullptr, NESR_E_STATE, "group %zu: dependency table size", bi);
+          std::vector<std::vector<int32_t>> owner(b.tiles.size());                  // cta * 32 + slot per pixel
+          for (size_t t = 0; t < b.tiles.size(); ++t) owner[t].assign((size_t)b.tiles[t].lv[0].h * b.tiles[t].lv[0].w, -1);
+          for (int c = 0; c < lp.fold_grid; ++c) {
+            int slot0 = 0;
+            for (int q = lp.cta_off[c]; q < lp.cta_off[c + 1]; ++q) {
+              const FoldBand& band = lp.bands[q];
+              for (int sgi = 0; sgi < band.nseg; ++sgi) {
+                const FoldSeg& sg = lp.segs[band.seg0 + sgi];
+                const LevelGeom& g = b.tiles[sg.tile].lv[0];
+                for (int r = band.r0; r < band.r0 + band.rows && r < sg.h; ++r)
+                  for (int x = sg.x0; x < sg.x0 + sg.width; ++x) owner[sg.tile][(size_t)(sg.y0 + r) * g.w + x] = c * 32 + slot0 + (r - band.r0);
+              }
+              slot0 += band.rows;
             }
-          // halo dependency lists: symmetric (a needs b <=> b needs a), self-padded
-          const int nword = 2 * lp.fold_grid;
-          if ((int)lp.deps.size() != nword * kTrunkMaxDeps) return fail(nullptr, NESR_E_STATE, "group %zu: dependency table size", bi);
-          auto has = [&](int w, int v) { for (int k = 0; k < kTrunkMaxDeps; ++k) if (lp.deps[(size_t)w * kTrunkMaxDeps + k] == v) return true; return false; };
-          for (int w = 0; w < nword; ++w)
-            for (int k = 0; k < kTrunkMaxDeps; ++k) {
-              const int v = lp.deps[(size_t)w * kTrunkMaxDeps + k];
-              if (v < 0 || v >= nword || !has(v, w)) return fail(nullptr, NESR_E_STATE, "group %zu: dependency %d -> %d not symmetric", bi, w, v);
+          }
+          for (int c = 0; c < lp.fold_grid; ++c) {
+            const int32_t* dep = &lp.deps[(size_t)c * kTrunkMaxDeps];
+            if (dep[0] != c) return fail(nullptr, NESR_E_STATE, "group %zu: CTA %d is not its own first dependency", bi, c);
+            int t = 0;
+            for (int q = lp.cta_off[c]; q < lp.cta_off[c + 1]; ++q) {
+              const FoldBand& band = lp.bands[q];
+              for (int i = -1; i <= band.rows; ++i, ++t) {
+                for (int sgi = 0; sgi < band.nseg; ++sgi) {
+                  const FoldSeg& sg = lp.segs[band.seg0 + sgi];
+                  const LevelGeom& g = b.tiles[sg.tile].lv[0];
+                  const int last_out = std::min(band.r0 + band.rows, sg.h) - 1;        // last output strip row of this piece in the band
+                  if (last_out < band.r0) continue;
+                  const int srow = band.r0 + i, y = sg.y0 + srow;
+                  if (srow > last_out + 1 || y < 0 || y >= g.h) continue;
+                  for (int x = std::max(sg.x0 - 1, 0); x <= std::min(sg.x0 + sg.width, g.w - 1); ++x) {
+                    const int32_t o = owner[sg.tile][(size_t)y * g.w + x];
+                    if (o < 0) return fail(nullptr, NESR_E_STATE, "group %zu: unowned pixel in a slab row", bi);
+                    int lane = -1;
+                    for (int k = 0; k < kTrunkMaxDeps; ++k) if (dep[k] == o / 32) { lane = k; break; }
+                    if (lane < 0 || lp.need[((size_t)c * kTrunkMaxSlabRows + t) * kTrunkMaxDeps + lane] < (o % 32) + 1)
+                      return fail(nullptr, NESR_E_STATE, "group %zu: CTA %d slab row %d does not wait for CTA %d row %d", bi, c, t, o / 32, o % 32);
+                  }
+                }
+              }
             }
+            for (int tt = 0; tt < kTrunkMaxSlabRows; ++tt)
+              for (int k = 0; k < kTrunkMaxDeps; ++k)
+                if (lp.need[((size_t)c * kTrunkMaxSlabRows + tt) * kTrunkMaxDeps + k] > kTrunkMaxRows)
+                  return fail(nullptr, NESR_E_STATE, "group %zu: row requirement out of range", bi);
+          }
         }
       }
     }
@@ -1651,7 +1607,7 @@ int nesr_b200_synchronize(nesr_b200_handle* h) {
 int nesr_b200_debug_conv(nesr_b200_handle* h, int32_t impl, int32_t fmt, int32_t H, int32_t W, int32_t cin, int32_t cout,
                          const float* weight_oihw, const float* bias, const float* x_nchw, int32_t lrelu, float* y_nchw) {
   if (!h) return NESR_E_INVALID;
-  if (!weight_oihw || !bias || !x_nchw || !y_nchw || H < 1 || W < 1 || cin < 1 || cin > kDense || cout < 1 || cout > 64 || (fmt & ~1))
+  if (!weight_oihw || !bias || !x_nchw || !y_nchw || H < 1 || W < 1 || cin < 1 || cin > kDense || cout < 1 || cout > 64 || (fmt & ~1) || (impl != 0 && impl != 1))
     return fail(h, NESR_E_INVALID, "debug_conv: bad arguments");
   DEVICE_SCOPE(h);
   Layer L;
@@ -1721,10 +1677,6 @@ int nesr_b200_debug_conv(nesr_b200_handle* h, int32_t impl, int32_t fmt, int32_t
   cudaError_t e = cudaSuccess;
   if (impl == 1) {
     e = launch_conv3x3_simt(p, h->stream);
-  } else if (impl == 2) {
-    CUtensorMap am, wm;
-    if ((rc = make_map(h, &am, d_x, 64, (int64_t)L.nchunk * P, kBlockPixels)) || (rc = make_map(h, &wm, d_w, 64, rows, L.npad))) { cleanup(); return rc; }
-    e = launch_conv3x3_tc(am, wm, p, h->num_sms, h->stream);
   } else {
     CUtensorMap am, am8, wm;
     if ((rc = make_map(h, &am, d_x, 64, (int64_t)L.nchunk * P, 136)) || (rc = make_map(h, &am8, d_x, 64, (int64_t)L.nchunk * P, 8)) ||

@@ -10,11 +10,6 @@
 
 namespace nesr {
 
-// --- conv3x3_tc.cu : per-tap tcgen05 implicit-GEMM conv (first-generation kernel, conv_impl = 2) --
-cudaError_t conv3x3_tc_configure();
-cudaError_t launch_conv3x3_tc(const CUtensorMap& amap, const CUtensorMap& wmap, const ConvParams& p, int num_sms,
-                              cudaStream_t stream);
-
 // --- conv3x3_fold.cu : row-folded tcgen05 conv, N = 3*Cout, one layer pass per launch ------------
 cudaError_t conv3x3_fold_configure();
 bool conv3x3_fold_fits(int cin16, int npad);
@@ -36,17 +31,10 @@ struct TrunkMaps {
   CUtensorMap full[2];
   CUtensorMap box[2][4];
   CUtensorMap w;               // folded weights, box 96 rows
-  CUtensorMap wh;              // folded weights, box 48 rows (half a box: weight multicast between two CTAs)
 };
 cudaError_t conv3x3_trunk_configure();
 cudaError_t launch_conv3x3_trunk(const TrunkMaps& maps, const ConvParams* d_passes, int npass, unsigned* d_prog, int grid,
-                                 cudaStream_t stream, bool weight_multicast = false);
-
-// --- conv3x3_trunk2.cu : the same trunk kernel on CTA pairs (cta_group::2, M = 256): CTAs 2p / 2p+1 own bands of identical
-//     shape, the leader issues the MMAs of both SMs; `maps.w` must be the 48-row weight box map; grid must be even
-cudaError_t conv3x3_trunk2_configure();
-cudaError_t launch_conv3x3_trunk2(const TrunkMaps& maps, const ConvParams* d_passes, int npass, unsigned* d_prog, int grid,
-                                  cudaStream_t stream);
+                                 cudaStream_t stream);
 
 // --- conv3x3_simt.cu : plain CUDA-core conv over the same buffers (test-only cross-check) -------
 cudaError_t launch_conv3x3_simt(const ConvParams& p, cudaStream_t stream);

@@ -113,11 +113,13 @@ struct ConvParams {
   // L2-resident trunk kernel (conv3x3_trunk.cu): input chunk c may be loaded once every CTA has completed passes [0, need[c])
   int32_t need[3];
   int32_t l2_pin_chunks;       // row-folded kernels: loads of input chunks [0, l2_pin_chunks) ask L2 to keep them (0: no hints)
-  // [grid][2][kTrunkMaxDeps] progress words (cta*2 + set, incl. its own) of the band sets that overlap the input halo of
-  // this CTA's band set; padded with its own word
+  // [grid][kTrunkMaxDeps] CTAs (its own first) that own a pixel of this CTA's input slab rows; padded with its own index
   const int32_t* trunk_deps;
-  int32_t trunk_no_publish;    // trunk kernels: this pass's completion is implied by the next pass's (conv5 first half)
-  const int32_t* trunk_split;  // [grid] number of bands of a CTA that belong to set 0 (the rest: set 1)
+  // [grid][kTrunkMaxSlabRows][kTrunkMaxDeps] for slab row t of the CTA (its bands in order, input rows -1 .. rows of each) and
+  // dependency lane d: how many of its output rows (in slot order) CTA trunk_deps[d] must have stored before the slab row of
+  // the newest chunk may be loaded; 0: the slab row holds no pixel of that CTA
+  const uint8_t* trunk_need;
+  int32_t trunk_no_publish;    // trunk kernel: this pass's rows are not published (conv5 first half: implied by the second half's)
 };
 
 // Timing-experiment switches (NESR_B200_DEBUG_FLAGS: results are WRONG when one is set) exist only in a -DNESR_PROF=1 build:
@@ -134,5 +136,6 @@ inline int dbg_flags(const ConvParams& p) { return NESR_PROF ? p.debug_flags : 0
 constexpr int kTrunkMaxRows = 16;
 constexpr int kTrunkMaxBands = 4;
 constexpr int kTrunkMaxDeps = 32;            // one polling lane per dependency
+constexpr int kTrunkMaxSlabRows = kTrunkMaxRows + 2 * kTrunkMaxBands;   // input rows a CTA streams per chunk sweep
 
 }  // namespace nesr

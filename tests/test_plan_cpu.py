@@ -1,7 +1,8 @@
-"""Host-side planning logic of libnesr_b200 (no GPU): tile groups, row-folded band schedules, remainder-piece packing,
-CTA-pair schedules and halo dependency lists, checked through the C ABI's host-only test hook ``nesr_b200_debug_plan``
+"""Host-side planning logic of libnesr_b200 (no GPU): tile groups, row-folded band schedules, remainder-piece packing
+and the trunk kernel's row-dependency tables, checked through the C ABI's host-only test hook ``nesr_b200_debug_plan``
 (``csrc/engine.cu``), which verifies that every pixel of every tile of every level is owned by exactly one (CTA, band,
-lane) and that the trunk kernels' TMEM / pairing / dependency invariants hold.
+lane), that the TMEM row budget holds and -- pixel by pixel, against an owner map built independently of the table
+builder -- that every input slab row of every CTA waits for the rows of every CTA that owns one of its pixels.
 
 Geometry being planned: upstream ``RealESRGANer.tile_process`` (tiles of ``tile`` pixels extended by ``tile_pad``, clamped at
 the image edge; reference twin ``nesr/nesr.py:311-475``) on the pixel-unshuffled feature grid (H/2 x W/2)."""
@@ -15,12 +16,12 @@ from neural_enhanced_super_resolution_b200 import _ffi
 SMS = 148
 
 
-def plan(H, W, tile, pad, pre=0, n=1, sms=SMS, impl=0, cap=0, pairs=0, sets=1):
+def plan(H, W, tile, pad, pre=0, n=1, sms=SMS, impl=0, cap=0):
     lib = _ffi.load_library()
     out = (C.c_int64 * 8)()
-    rc = lib.nesr_b200_debug_plan(n, H, W, tile, pad, pre, sms, impl, cap, pairs, sets, out)
+    rc = lib.nesr_b200_debug_plan(n, H, W, tile, pad, pre, sms, impl, cap, 0, 1, out)
     msg = lib.nesr_b200_last_error(None).decode()
-    return rc, msg, dict(zip(("groups", "tiles", "pixels", "strip_rows", "max_rows", "trunk_groups", "pair_groups", "halo_rows"),
+    return rc, msg, dict(zip(("groups", "tiles", "pixels", "strip_rows", "max_rows", "trunk_groups", "reserved", "halo_rows"),
                              [int(v) for v in out]))
 
 
@@ -48,9 +49,8 @@ SHAPES = [(1080, 1920, 512, 10), (2160, 3840, 512, 10), (512, 512, 0, 10), (522,
 
 
 @pytest.mark.parametrize("H,W,tile,pad", SHAPES)
-@pytest.mark.parametrize("pairs,sets", [(0, 1), (1, 1), (0, 2)])
-def test_every_pixel_is_owned_once_and_invariants_hold(H, W, tile, pad, pairs, sets):
-    rc, msg, st = plan(H, W, tile, pad, pairs=pairs, sets=sets)
+def test_every_pixel_is_owned_once_and_invariants_hold(H, W, tile, pad):
+    rc, msg, st = plan(H, W, tile, pad)
     assert rc == 0, msg
     px, nt = feature_pixels(H, W, tile, pad)
     assert (st["tiles"], st["pixels"]) == (nt, px)
@@ -58,9 +58,7 @@ def test_every_pixel_is_owned_once_and_invariants_hold(H, W, tile, pad, pairs, s
     assert st["strip_rows"] * 128 >= px                        # 128 lanes per strip row cover all pixels
     if st["trunk_groups"] == st["groups"]:
         assert st["max_rows"] <= 16                            # 16 TMEM row slots of 32 fp32 columns
-    assert st["pair_groups"] <= st["trunk_groups"] <= st["groups"]
-    if not pairs:
-        assert st["pair_groups"] == 0
+    assert st["trunk_groups"] <= st["groups"]
 
 
 def test_1080p_plan_is_the_one_the_benchmark_runs():
@@ -89,7 +87,7 @@ def test_group_cap_and_frames():
 
 def test_small_devices_and_errors():
     for sms in (1, 2, 7, 32):
-        rc, msg, st = plan(300, 420, 160, 10, sms=sms, pairs=1)
+        rc, msg, st = plan(300, 420, 160, 10, sms=sms)
         assert rc == 0, msg
     rc, msg, _ = plan(300, 420, 161, 10)                       # odd tile extent: pixel_unshuffle(2) needs even tiles
     assert rc != 0 and "odd" in msg
