@@ -8,13 +8,21 @@
 //     counter, reload up to 110 KB of weights, refill the ring) and small batches have short passes.
 // This kernel removes the fixed cost, so that tile groups small enough for L2 pay off:
 //
-//   TMEM-RESIDENT BANDS.  A CTA owns at most 16 output rows (a few bands of 128-pixel strips); the fp32
-//   accumulators of ALL of them (16 row slots x 32 channels = 512 TMEM columns) stay in TMEM for the whole pass.
-//   CHUNK-MAJOR SWEEPS.  Because the band is TMEM resident, the contraction is ordered chunk by chunk: for each
-//   64-channel input chunk, stream the band's input rows once and accumulate.  The weights stream too -- one
-//   [3 dx][96][64] box set (36 KB) per chunk through a 3-deep ring.
-//   DEPENDENCIES ARRIVE LAST.  Within a dense block conv_k+1 differs from conv_k only by the 32 newest input
-//   channels, and those sit in the LAST chunk: pass k+1 sweeps its older chunks while pass k is still drained.
+//   TMEM-RESIDENT BANDS.  A CTA owns at most 8 output rows (a few bands of 128-pixel strips); a row's TMEM slot is 64
+//   fp32 columns -- half A | half B -- and all 8 x 64 = 512 columns stay resident while a dense block is computed.
+//   CHUNK-MAJOR, MERGED SWEEPS (round 2).  A sweep streams the band's input rows of ONE 64-channel plane once and
+//   accumulates into everything that plane feeds next: the kernel is bound by the bytes it pulls through L2 (TMA alone
+//   needed 75 % of the round-1 kernel's time; profiles/r1_trunk_experiments.txt) and by N = 96 MMAs running at 85 % of the
+//   tensor rate, and merging attacks both.  Round 1 ran conv1..conv5 as six passes = 14 plane sweeps of N = 96 per dense
+//   block; now a block is EIGHT sweeps (layout.h TrunkSweep), six of them N = 192 (99 % of the tensor rate):
+//       S1 x -> conv1|conv2   S2 x1 -> conv2   S3 x -> conv3|conv4   S4 x1,x2 -> conv3|conv4   S5 x3 -> conv4
+//       S6 x -> conv5         S7 x1,x2 -> conv5                      S8 x3,x4 -> conv5
+//   conv1/conv3/conv5[0:32] accumulate in half A of a slot, conv2/conv4/conv5[32:64] in half B; the two single-layer
+//   sweeps (S2, S5) run as N = 160 MMAs whose weight rows over half A are zero (three N = 32 MMAs would cost 162 cycles
+//   against 80).  The epilogue still drains 32 columns at a time, in six passes per block, each as soon as its half is complete.
+//   The weights stream too: one [3 dx][192|160][64] box set (72 KB) per sweep through a 2-deep ring.
+//   DEPENDENCIES ARRIVE LAST.  The sweep that needs the newest channels (S2, S4, S5, S8 and the next block's S1) is the one
+//   that completes an accumulator; the sweeps between them (S3, S6, S7) need nothing new and hide the hand-over.
 //   ROW-GRANULAR HAND-OVER (round 2).  The round-1 kernel published "pass complete" once per pass and CTA, so every pass
 //   was a serial chain  acquire -> first slab -> dependent sweep -> epilogue tail -> fence + barrier + publish  (22k cycles
 //   per conv1-4 pass against 9-22k cycles of MMA work: profiles/r1_trunk_chain_trace.txt).  Now every CTA publishes a
@@ -48,22 +56,23 @@ namespace nesr {
 
 namespace {
 
-constexpr int COUT = 32;
+constexpr int COUT = 32;                               // channels one epilogue pass drains (half a TMEM row slot)
+constexpr int kSlotCols = 64;                          // fp32 columns of a TMEM row slot: half A | half B
 constexpr int kThreads = 352;
 constexpr int kSlabPx = 136;
 constexpr int kSlabBytes = kSlabPx * 128;              // 17408
-constexpr int kStages = 6;                             // activation slab ring
-constexpr int kWStages = 3;                            // weight chunk ring
-constexpr int kWBoxBytes = 3 * COUT * 128;             // one dx: [96 rows][64 ch] = 12288
-constexpr int kWChunkBytes = 3 * kWBoxBytes;           // three dx boxes = 36864
-constexpr int kSlots = 16;                             // TMEM row slots (512 / 32)
+constexpr int kStages = 4;                             // activation slab ring
+constexpr int kWStages = 2;                            // sweep weight ring
+constexpr int kWBoxRows = 192;                         // rows of one dx box (160 for half-B single sweeps)
+constexpr int kWStageBytes = 3 * kWBoxRows * 128;      // three dx boxes = 73728
+constexpr int kSlots = kTrunkMaxRows;                  // TMEM row slots (512 / 64)
 constexpr int kMaxBands = kTrunkMaxBands;
-constexpr int kProgUnit = 32;                          // progress value = pass * kProgUnit + rows stored (rows <= 16)
+constexpr int kProgUnit = 32;                          // progress value = pass * kProgUnit + rows stored (rows <= 8)
 #if NESR_PROF
-constexpr int kTracePasses = 48;
-#define TS(k, pass) do { if ((pass) < kTracePasses) sh.ts[k][pass] = clock64(); } while (0)
+constexpr int kTrace = 48;
+#define TS(k, idx) do { if ((idx) < kTrace) sh.ts[k][idx] = clock64(); } while (0)
 #else
-#define TS(k, pass) do {} while (0)
+#define TS(k, idx) do {} while (0)
 #endif
 
 constexpr int kMaxOps = 20;                            // TMA operations per slab row of a packed strip
@@ -79,7 +88,7 @@ struct BandInfo {                                      // one band of this CTA, 
 struct Shared {
   uint64_t wfull[kWStages], wempty[kWStages];
   uint64_t full[kStages], empty[kStages];
-  uint64_t tfull[kSlots], tempty[kSlots];
+  uint64_t tfull[2][kSlots], tempty[2][kSlots];        // per TMEM half (A, B) and row slot
   uint64_t stored[kSlots];                             // epilogue -> publisher: this row's stores are done (one arrive per warp)
   uint32_t tmem_slot;
   int32_t nband, nrows;                                // bands / output rows of this CTA
@@ -88,12 +97,13 @@ struct Shared {
   int32_t lane_pitch[kMaxBands][128];
   int32_t lane_rows[kMaxBands][128];                   // band rows [0, lane_rows) belong to the lane's piece
   uint8_t need_rows[kTrunkMaxSlabRows][kTrunkMaxDeps]; // [slab row of the CTA][dependency lane]: rows that CTA must have stored
+  alignas(16) float bias[8][2 * COUT];                             // per epilogue warp: bias of the pass (both halves of a paired conv5 pass)
 #if NESR_PROF
-  long long ts[6][kTracePasses];                       // per-pass time stamps of the dependency chain (debug_flags & 1024)
+  long long ts[5][kTrace];                             // time stamps of the dependency chain (debug_flags & 1024)
 #endif
 };
 
-constexpr int kRingBytes = kWStages * kWChunkBytes + kStages * kSlabBytes;      // 110592 + 104448
+constexpr int kRingBytes = kWStages * kWStageBytes + kStages * kSlabBytes;      // 147456 + 69632
 constexpr int kSmemBytes = kRingBytes + static_cast<int>(sizeof(Shared)) + 1024;
 static_assert(kSmemBytes <= 232448, "trunk kernel: shared memory budget");
 
@@ -102,57 +112,49 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* ptr) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
   return v;
 }
-__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* ptr) {
-  unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
-  return v;
-}
 __device__ __forceinline__ void st_release_gpu(unsigned* ptr, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
 }
 constexpr int kProgStride = 32;                        // one 128-byte line per CTA
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// The fields of a pass the TMA producer / MMA issuer need, fetched one pass ahead.
-struct PassHead {
-  int32_t cin, w_row0, src_sel, need0, need1, need2, dbg;
-};
-__device__ __forceinline__ PassHead load_head(const ConvParams* passes, int pass, int npass) {
-  PassHead h{};
-  if (pass < npass) {
-    const ConvParams* p = passes + pass;
-    h.cin = __ldg(&p->cin); h.w_row0 = __ldg(&p->w_row0); h.src_sel = __ldg(&p->src_sel);
-    h.need0 = __ldg(&p->need[0]); h.need1 = __ldg(&p->need[1]); h.need2 = __ldg(&p->need[2]);
-    h.dbg = NESR_PROF ? __ldg(&p->debug_flags) : 0;
+__device__ __forceinline__ TrunkSweep load_sweep(const TrunkSweep* sweeps, int i, int n) {
+  TrunkSweep s{};
+  if (i < n) {
+    const int4* p = reinterpret_cast<const int4*>(sweeps + i);
+    const int4 a = __ldg(p), b = __ldg(p + 1);
+    s.src_sel = a.x; s.plane = a.y; s.w_row0 = a.z; s.nb = a.w; s.ks = b.x; s.need = b.y; s.flags = b.z;
   }
-  return h;
+  return s;
 }
 
-// One chunk sweep over one band, executed by the single MMA-issuing thread.  KS k-steps per (row, dx); FIRST: first
-// sweep of the pass (wait until the epilogue has drained + zeroed a slot before its first MMA); LAST: last sweep (commit
-// each output row's completion).  The thread is the bottleneck of a sweep (~100 instructions per row against 684 cycles
-// of MMA work), so everything that can be is a template parameter and interior rows (all three output rows inside the
-// band) take a path without clamps.
-template <int KS, bool FIRST, bool LAST>
+// One sweep over one band, executed by the single MMA-issuing thread.  KS k-steps per (row, dx).  SINGLE: an N = 160 sweep
+// into half B whose weight rows over half A are zero (D starts at column 32 of the first slot); otherwise both halves of
+// every slot, N = 192.  Input row i feeds output rows i-1, i, i+1 = three consecutive slots; at the band's ends the MMA is
+// clamped to the rows that exist (N and the first weight row shrink).  wait[X]: this sweep is the first toucher of half X
+// after its drain: every slot is waited for (drained + re-zeroed) before the first MMA that touches it; commit[X]: this sweep
+// completes half X: every output row is committed to the epilogue as soon as its last contribution is issued.
+template <int KS, bool SINGLE>
 __device__ __forceinline__ void sweep_band(Shared& sh, const int rows, const int slot0, const uint32_t tmem_base, const uint32_t hw,
-                                           const uint32_t hi, const uint32_t a_lo0, const uint32_t w_lo, const uint32_t tparity,
-                                           int& stage, uint32_t& phase, const bool mma_on) {
-  constexpr uint32_t kSlabLo = kSlabBytes >> 4, kWBoxLo = kWBoxBytes >> 4;
-  constexpr uint32_t kBlkLo = (COUT * 128) >> 4;                // one dy block of 32 weight rows
-  const uint32_t id96 = umma_idesc_f16(hw, 3 * COUT);
-  // input row -1: its slab, and (first sweep of the pass) output slot 0 drained + zeroed by the epilogue
-  if (FIRST) mbar_wait(&sh.tempty[slot0], tparity ^ 1);
+                                           const uint32_t hi, const uint32_t a_lo0, const uint32_t w_lo, const uint32_t box_lo,
+                                           const bool wait_a, const uint32_t par_a, const bool wait_b, const uint32_t par_b,
+                                           const bool commit_a, const bool commit_b, int& stage, uint32_t& phase, const bool mma_on) {
+  constexpr uint32_t kSlabLo = kSlabBytes >> 4;
+  constexpr uint32_t kBlkLo = (kSlotCols * 128) >> 4;           // weight rows of one output row (64 rows of 128 bytes)
+  const uint32_t id_full = umma_idesc_f16(hw, SINGLE ? 160u : 192u);
+  if (wait_a) mbar_wait(&sh.tempty[0][slot0], par_a);
+  if (wait_b) mbar_wait(&sh.tempty[1][slot0], par_b);
   mbar_wait(&sh.full[stage], phase);
   tc_fence_after();
   for (int i = -1; i <= rows; ++i) {
     uint32_t d, id, b_lo;
     if (i >= 1 && i + 1 <= rows - 1) {                          // interior: output rows i-1, i, i+1
-      d = tmem_base + static_cast<uint32_t>(slot0 + i - 1) * COUT; id = id96; b_lo = w_lo;
+      d = tmem_base + static_cast<uint32_t>(slot0 + i - 1) * kSlotCols + (SINGLE ? 32u : 0u); id = id_full; b_lo = w_lo;
     } else {
       const int lo = i - 1 < 0 ? 0 : i - 1;
       const int hi_row = i + 1 > rows - 1 ? rows - 1 : i + 1;
-      d = tmem_base + static_cast<uint32_t>(slot0 + lo) * COUT;
-      id = umma_idesc_f16(hw, static_cast<uint32_t>(COUT * (hi_row - lo + 1)));
+      d = tmem_base + static_cast<uint32_t>(slot0 + lo) * kSlotCols + (SINGLE ? 32u : 0u);
+      id = umma_idesc_f16(hw, static_cast<uint32_t>(SINGLE ? (hi_row - lo) * kSlotCols + 32 : (hi_row - lo + 1) * kSlotCols));
       b_lo = w_lo + static_cast<uint32_t>(lo - (i - 1)) * kBlkLo;
     }
     const uint32_t a_lo = a_lo0 + stage * kSlabLo;
@@ -160,16 +162,22 @@ __device__ __forceinline__ void sweep_band(Shared& sh, const int rows, const int
     // while those run: is the next input row ready?  (slot i+2 is first touched by input row i+1)
     const int nstage = stage + 1 == kStages ? 0 : stage + 1;
     if (i < rows) {
-      if (FIRST && i + 2 <= rows - 1) mbar_wait(&sh.tempty[slot0 + i + 2], tparity ^ 1);
+      if (i + 2 <= rows - 1) {
+        if (wait_a) mbar_wait(&sh.tempty[0][slot0 + i + 2], par_a);
+        if (wait_b) mbar_wait(&sh.tempty[1][slot0 + i + 2], par_b);
+      }
       mbar_wait(&sh.full[nstage], nstage == 0 ? phase ^ 1 : phase);
       tc_fence_after();
     }
     if (mma_on) {
-      umma_f16_ksteps<KS>(d, a_lo + 8, b_lo + kWBoxLo, hi, id);
-      umma_f16_ksteps<KS>(d, a_lo + 16, b_lo + 2 * kWBoxLo, hi, id);
+      umma_f16_ksteps<KS>(d, a_lo + 8, b_lo + box_lo, hi, id);
+      umma_f16_ksteps<KS>(d, a_lo + 16, b_lo + 2 * box_lo, hi, id);
     }
     umma_commit(&sh.empty[stage]);                              // slab may be overwritten once these MMAs have read it
-    if (LAST && i >= 1) umma_commit(&sh.tfull[slot0 + i - 1]);  // output row i-1 has all its contributions
+    if (i >= 1) {                                               // output row i-1 has all its contributions
+      if (commit_a) umma_commit(&sh.tfull[0][slot0 + i - 1]);
+      if (commit_b) umma_commit(&sh.tfull[1][slot0 + i - 1]);
+    }
     stage = nstage;
     if (stage == 0) phase ^= 1;
   }
@@ -177,11 +185,11 @@ __device__ __forceinline__ void sweep_band(Shared& sh, const int rows, const int
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* __restrict__ passes, const int npass,
-                     unsigned* __restrict__ prog) {
+                     const TrunkSweep* __restrict__ sweeps, const int nsweep, unsigned* __restrict__ prog) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* wring = smem;
-  uint8_t* ring = smem + kWStages * kWChunkBytes;
+  uint8_t* ring = smem + kWStages * kWStageBytes;
   Shared& sh = *reinterpret_cast<Shared*>(smem + kRingBytes);
 
   const int warp = threadIdx.x >> 5;
@@ -190,10 +198,14 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
   // ---- one-time setup: barriers, TMEM, band geometry (identical for every pass of the trunk) ----
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.full[0]); tma_prefetch_desc(&maps.full[1]);
-    tma_prefetch_desc(&maps.w);
+    tma_prefetch_desc(&maps.w192); tma_prefetch_desc(&maps.w160);
     for (int i = 0; i < kWStages; ++i) { mbar_init(&sh.wfull[i], 1); mbar_init(&sh.wempty[i], 1); }
     for (int i = 0; i < kStages; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 1); }
-    for (int i = 0; i < kSlots; ++i) { mbar_init(&sh.tfull[i], 1); mbar_init(&sh.tempty[i], 128); mbar_init(&sh.stored[i], 4); }
+    for (int i = 0; i < kSlots; ++i) {
+      mbar_init(&sh.tfull[0][i], 1); mbar_init(&sh.tfull[1][i], 1);
+      mbar_init(&sh.tempty[0][i], 128); mbar_init(&sh.tempty[1][i], 128);
+      mbar_init(&sh.stored[i], 4);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -273,6 +285,7 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
   __syncthreads();
   tc_fence_after();
   const int nband = sh.nband;
+  [[maybe_unused]] const int dbg0 = NESR_PROF ? __ldg(&passes[0].debug_flags) : 0;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -284,97 +297,78 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
     const uint64_t keep = l2_policy_evict_last();               // dense-block activations and weights: stay in L2
     // one lane per dependency: the progress word of a CTA owning pixels of this CTA's slab rows (lane 0: its own; padding: its own)
     const unsigned* my_dep = prog + static_cast<size_t>(__ldg(passes[0].trunk_deps + blockIdx.x * kTrunkMaxDeps + lane)) * kProgStride;
-    PassHead h = load_head(passes, 0, npass);
-    for (int pass = 0; pass < npass; ++pass) {
-      const PassHead nh = load_head(passes, pass + 1, npass);   // next pass, fetched early
-      const int nchunk = (h.cin + kChunkChannels - 1) / kChunkChannels;
-      const CUtensorMap* amap = &maps.full[h.src_sel & 1];
-      const CUtensorMap* bmap = &maps.box[h.src_sel & 1][0];
-      const int plane_skip = h.src_sel == 3 ? 1 : 0;            // shared-growth layout, buffer B: planes xB | (xA) | x1x2 | x3x4
-      for (int c = 0; c < nchunk; ++c) {
-        // weights of (pass, chunk): depend on nobody
-        mbar_wait(&sh.wempty[ws], wphase ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&sh.wfull[ws], kWChunkBytes);
+    TrunkSweep sw = load_sweep(sweeps, 0, nsweep);
+    for (int si = 0; si < nsweep; ++si) {
+      const TrunkSweep nsw = load_sweep(sweeps, si + 1, nsweep);  // next sweep, fetched early
+      // weights of the sweep: depend on nobody
+      mbar_wait(&sh.wempty[ws], wphase ^ 1);
+      if (elect_one()) {
+        const uint32_t box_bytes = static_cast<uint32_t>(sw.nb) * 128u;
+        mbar_arrive_expect_tx(&sh.wfull[ws], 3u * box_bytes);
+        const CUtensorMap* wmap = sw.nb == kWBoxRows ? &maps.w192 : &maps.w160;
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx)
-            tma_load_2d_hint(wring + ws * kWChunkBytes + dx * kWBoxBytes, &maps.w, &sh.wfull[ws], 0, h.w_row0 + (dx * nchunk + c) * 3 * COUT, keep);
-        }
-        __syncwarp();
-        if (++ws == kWStages) { ws = 0; wphase ^= 1; }
-        // activations of this chunk.  The chunk holding the newest channels (always the last one) is written by the pass
-        // need-1: its slab rows are requested one by one, each as soon as the rows it covers have been stored everywhere.
-        const unsigned need = static_cast<unsigned>(c == 0 ? h.need0 : (c == 1 ? h.need1 : h.need2));
-        bool rowwise = false;
-        if (need > known && !(h.dbg & 16384)) {                   // 16384: no dependency waits (timing experiments)
-          if (c + 1 == nchunk) {
-            rowwise = true;
-          } else {                                              // (not a trunk pass shape) an older chunk is not known complete: wait for whole passes
-            const unsigned target = need * kProgUnit;
-            const long long t0 = clock64();
-            while ((seen = ld_acquire_gpu(my_dep)) < target) {
-              if (clock64() - t0 > NESR_HANG_GUARD_CYCLES) __trap();
-            }
-            __syncwarp();
-            known = need;
-          }
-        }
-        const unsigned row_base = (need - 1) * kProgUnit;
-        const int plane = (c + (c > 0 ? plane_skip : 0)) * plane_px;
-        int t = 0;                                              // slab row of the CTA (bands in order, input rows -1 .. rows)
-        for (int b = 0; b < nband; ++b) {
-          const BandInfo& bi = sh.band[b];
-          const int nrow = bi.rows + 2;
-          const bool full_strip = bi.full_strip != 0;
-          const uint32_t row_bytes = bi.row_bytes;
-          for (int i = 0; i < nrow; ++i, ++t) {
-            if (rowwise) {
-              // The spin is RELAXED (ld.acquire.gpu compiles to LDG.STRONG + CCTL.IVALL: an L1 invalidation per poll); one
-              // acquire after the last poll orders the TMA loads that follow.  `seen` only grows, so in the steady state
-              // (neighbours a pass ahead of what is asked) no lane touches memory here.
-              const unsigned req = sh.need_rows[t][lane];
-              unsigned target = req ? row_base + req : 0u;
-              if ((h.dbg & 262144) && req) target = need * kProgUnit;   // 262144: wait for whole passes (timing experiments)
-              if (__any_sync(0xffffffffu, seen < target)) {
-                // Somebody has to look: EVERY lane refreshes its word (one L2 round trip for the warp either way), so that rows
-                // further down -- which usually depend on CTAs this row does not -- find their requirement already seen.
-                // Every poll is an acquire (LDG.STRONG + CCTL.IVALL): nothing in this kernel lives in L1 any more (bias is in
-                // registers, the trunk rows stream), and a separate acquire after a relaxed spin costs one more round trip.
-                // The generic -> async proxy fence of the chain is executed by the PUBLISHER before its release (a proxy fence
-                // in this thread waits for the TMA loads in flight: measured ~1k cycles each, 8 % of the kernel).
-                const long long t0 = clock64();
-                do {
-                  seen = ld_acquire_gpu(my_dep);
-                  if (clock64() - t0 > NESR_HANG_GUARD_CYCLES) __trap();
-                } while (seen < target);
-                __syncwarp();
-                if (h.dbg & 524288) fence_proxy_async_all();     // 524288: consumer-side proxy fence as well (timing experiments)
-              }
-              if (lane == 0 && t == 0) TS(4, pass);
-            }
-            mbar_wait(&sh.empty[stage], phase ^ 1);
-            if (elect_one()) {
-              if (h.dbg & 4) {
-                mbar_arrive(&sh.full[stage]);
-              } else {
-                mbar_arrive_expect_tx(&sh.full[stage], row_bytes);
-                uint8_t* slab = ring + stage * kSlabBytes;
-                if (full_strip) {
-                  tma_load_2d_hint(slab, amap, &sh.full[stage], 0, plane + bi.op_px[0] + i * bi.op_pitch[0], keep);
-                } else {
-                  for (int k = 0; k < bi.nop; ++k)
-                    tma_load_2d_hint(slab + bi.op_off[k], bmap + bi.op_box[k], &sh.full[stage], 0,
-                                     plane + bi.op_px[k] + i * bi.op_pitch[k], keep);
-                }
-              }
-            }
-            __syncwarp();
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
-          }
-        }
-        if (rowwise) known = need;
+        for (int dx = 0; dx < 3; ++dx)
+          tma_load_2d_hint(wring + ws * kWStageBytes + dx * box_bytes, wmap, &sh.wfull[ws], 0, sw.w_row0 + dx * sw.nb, keep);
       }
-      h = nh;
+      __syncwarp();
+      if (++ws == kWStages) { ws = 0; wphase ^= 1; }
+      // activations.  A plane whose newest channels were written by epilogue pass need-1 is requested slab row by slab row,
+      // each as soon as the rows it covers have been stored everywhere (host-built table need_rows).
+      const unsigned need = static_cast<unsigned>(sw.need);
+      const bool rowwise = need > known && !(dbg0 & 16384);     // 16384: no dependency waits (timing experiments)
+      const unsigned row_base = (need - 1) * kProgUnit;
+      const CUtensorMap* amap = &maps.full[sw.src_sel & 1];
+      const CUtensorMap* bmap = &maps.box[sw.src_sel & 1][0];
+      const int plane = sw.plane * plane_px;
+      int t = 0;                                                // slab row of the CTA (bands in order, input rows -1 .. rows)
+      for (int b = 0; b < nband; ++b) {
+        const BandInfo& bi = sh.band[b];
+        const int nrow = bi.rows + 2;
+        const bool full_strip = bi.full_strip != 0;
+        const uint32_t row_bytes = bi.row_bytes;
+        for (int i = 0; i < nrow; ++i, ++t) {
+          if (rowwise) {
+            const unsigned req = sh.need_rows[t][lane];
+            unsigned target = req ? row_base + req : 0u;
+            if ((dbg0 & 262144) && req) target = need * kProgUnit;   // 262144: wait for whole passes (timing experiments)
+            if (__any_sync(0xffffffffu, seen < target)) {
+              // Somebody has to look: EVERY lane refreshes its word (one L2 round trip for the warp either way), so that rows
+              // further down -- which usually depend on CTAs this row does not -- find their requirement already seen.
+              // Every poll is an acquire (LDG.STRONG + CCTL.IVALL): nothing in this kernel lives in L1 (bias is in registers,
+              // the trunk rows stream), and a separate acquire after a relaxed spin costs one more round trip.  The generic ->
+              // async proxy fence of the chain is executed by the PUBLISHER before its release (a proxy fence in this thread
+              // waits for the TMA loads in flight: measured ~1k cycles each, 8 % of the kernel).
+              const long long t0 = clock64();
+              do {
+                seen = ld_acquire_gpu(my_dep);
+                if (clock64() - t0 > NESR_HANG_GUARD_CYCLES) __trap();
+              } while (seen < target);
+              __syncwarp();
+            }
+          }
+          if (lane == 0 && t == 0) TS(4, si);
+          mbar_wait(&sh.empty[stage], phase ^ 1);
+          if (elect_one()) {
+            if (dbg0 & 4) {
+              mbar_arrive(&sh.full[stage]);
+            } else {
+              mbar_arrive_expect_tx(&sh.full[stage], row_bytes);
+              uint8_t* slab = ring + stage * kSlabBytes;
+              if (full_strip) {
+                tma_load_2d_hint(slab, amap, &sh.full[stage], 0, plane + bi.op_px[0] + i * bi.op_pitch[0], keep);
+              } else {
+                for (int k = 0; k < bi.nop; ++k)
+                  tma_load_2d_hint(slab + bi.op_off[k], bmap + bi.op_box[k], &sh.full[stage], 0,
+                                   plane + bi.op_px[k] + i * bi.op_pitch[k], keep);
+              }
+            }
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (rowwise) known = need;
+      sw = nsw;
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
@@ -384,44 +378,37 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       int ws = 0; uint32_t wphase = 0;
+      uint32_t nwait_a = 0, nwait_b = 0;                        // waits done so far on the drained-slot barriers of each half
       const uint32_t hw = (__ldg(&passes[0].idesc) >> 7) & 7u;
       const uint32_t hi = umma_desc_hi_sw128();
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(ring));
       const uint32_t w_lo0 = umma_desc_lo(smem_u32(wring));
-      constexpr uint32_t kWChunkLo = kWChunkBytes >> 4;
-      PassHead h = load_head(passes, 0, npass);
-      for (int pass = 0; pass < npass; ++pass) {
-        const PassHead nh = load_head(passes, pass + 1, npass);
-        const int nchunk = (h.cin + kChunkChannels - 1) / kChunkChannels;
-        const uint32_t tparity = static_cast<uint32_t>(pass & 1);
-        for (int c = 0; c < nchunk; ++c) {
-          const int rem = (h.cin - c * kChunkChannels) >> 4;
-          const int ks = rem < 4 ? rem : 4;
-          const bool last_chunk = c + 1 == nchunk;
-          const bool first_chunk = c == 0;
-          mbar_wait(&sh.wfull[ws], wphase);
-          const uint32_t w_lo = w_lo0 + ws * kWChunkLo;
-          const bool mma_on = !(h.dbg & 2);
-          const int variant = (ks == 4 ? 0 : 4) + (first_chunk ? 2 : 0) + (last_chunk ? 1 : 0);
-          for (int b = 0; b < nband; ++b) {
-            const int rows = sh.band[b].rows, slot0 = sh.band[b].slot0;
-            switch (variant) {                                  // trunk passes only have 4- and 2-k-step chunks
-              case 0: sweep_band<4, false, false>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
-              case 1: sweep_band<4, false, true>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
-              case 2: sweep_band<4, true, false>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
-              case 3: sweep_band<4, true, true>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
-              case 4: sweep_band<2, false, false>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
-              case 5: sweep_band<2, false, true>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
-              case 6: sweep_band<2, true, false>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
-              default: sweep_band<2, true, true>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, tparity, stage, phase, mma_on); break;
-            }
-            if (last_chunk && b == 0) TS(5, pass);
+      constexpr uint32_t kWStageLo = kWStageBytes >> 4;
+      const bool mma_on = !(dbg0 & 2);
+      TrunkSweep sw = load_sweep(sweeps, 0, nsweep);
+      for (int si = 0; si < nsweep; ++si) {
+        const TrunkSweep nsw = load_sweep(sweeps, si + 1, nsweep);
+        const bool wait_a = sw.flags & kSweepWaitA, wait_b = sw.flags & kSweepWaitB;
+        const bool commit_a = sw.flags & kSweepCommitA, commit_b = sw.flags & kSweepCommitB;
+        const uint32_t par_a = (nwait_a & 1u) ^ 1u, par_b = (nwait_b & 1u) ^ 1u;   // the k-th wait passes once k drains have happened
+        const uint32_t box_lo = (static_cast<uint32_t>(sw.nb) * 128u) >> 4;
+        mbar_wait(&sh.wfull[ws], wphase);
+        const uint32_t w_lo = w_lo0 + ws * kWStageLo;
+        const int variant = ((sw.flags & kSweepSingleB) ? 2 : 0) + (sw.ks == 4 ? 0 : 1);
+        for (int b = 0; b < nband; ++b) {
+          const int rows = sh.band[b].rows, slot0 = sh.band[b].slot0;
+          switch (variant) {
+            case 0: sweep_band<4, false>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, box_lo, wait_a, par_a, wait_b, par_b, commit_a, commit_b, stage, phase, mma_on); break;
+            case 1: sweep_band<2, false>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, box_lo, wait_a, par_a, wait_b, par_b, commit_a, commit_b, stage, phase, mma_on); break;
+            case 2: sweep_band<4, true>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, box_lo, wait_a, par_a, wait_b, par_b, commit_a, commit_b, stage, phase, mma_on); break;
+            default: sweep_band<2, true>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, box_lo, wait_a, par_a, wait_b, par_b, commit_a, commit_b, stage, phase, mma_on); break;
           }
-          umma_commit(&sh.wempty[ws]);
-          if (++ws == kWStages) { ws = 0; wphase ^= 1; }
-          if (last_chunk) TS(0, pass);
         }
-        h = nh;
+        umma_commit(&sh.wempty[ws]);
+        if (++ws == kWStages) { ws = 0; wphase ^= 1; }
+        nwait_a += wait_a; nwait_b += wait_b;
+        TS(0, si);
+        sw = nsw;
       }
     }
     __syncwarp();
@@ -431,12 +418,17 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
     const int group = (warp - 2) >> 2;                          // rows alternate between the two epilogue groups
     const int m = quarter * 32 + lane;                          // TMEM lane == MMA row == pixel
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    uint32_t ndrain[2] = {0, 0};                                // passes drained so far from each TMEM half
+    float* const my_bias = sh.bias[warp - 2];
     for (int pass = 0; pass < npass; ++pass) {
       // The epilogue warps are instruction-latency bound (one or two warps per scheduler, ~4 cycles per dependent
       // instruction).  A trunk pass is one of two kinds, fixed for the whole pass, so the row loop below is straight-line
       // code specialised at pass level:
       //   conv1..4 : v = lrelu(acc + bias)                               -> 16-bit, channels [coff, coff+32) of this buffer
       //   conv5    : v = (acc + bias)*0.2 + trunk [; v = v*0.2 + rrdb_in] -> fp32 trunk [+ rrdb], 16-bit x of the next block
+      // conv5's two 32-channel passes complete together (sweep S8 commits both halves of a row at once) and are drained
+      // TOGETHER, row by row (nsub = 2): drained one after the other, the second pass's rows all waited behind the first's and
+      // the block's last sweep was followed by a 20k-cycle epilogue tail before the next block could start.
       const ConvParams* pp = passes + pass;
       const int dbg = NESR_PROF ? __ldg(&pp->debug_flags) : 0;
       const float* res1 = pp->res1;
@@ -444,20 +436,17 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
       float* dst32a = pp->dst32a;
       float* dst32b = pp->dst32b;
       const float s1 = pp->s1, s2 = pp->s2;
-      const int c_off = pp->c_off, fmt16 = pp->dst16_fmt, lrelu = pp->lrelu;
+      const int c_off0 = pp->c_off, fmt16 = pp->dst16_fmt, lrelu = pp->lrelu;
       const int coff16 = pp->dst16_coff;
-      const bool publish = __ldg(&pp->trunk_no_publish) == 0;   // (uniform) conv5's first half is covered by the second half's rows
+      const int half0 = __ldg(&pp->trunk_half) & 1;             // which 32 columns of a row slot this pass drains
+      const int nsub = __ldg(&pp->trunk_no_publish) ? 2 : 1;    // (uniform) conv5's first half: drained with the second (the next pass)
       uint16_t* const base16 = reinterpret_cast<uint16_t*>(pp->dst16) + static_cast<size_t>(coff16 >> 6) * pp->dst16_plane_px * 64 + (coff16 & 63);
-      float bias_r[COUT];                                       // once per pass, in registers
-      {
-        const float4* b4 = reinterpret_cast<const float4*>(pp->bias);
-#pragma unroll
-        for (int k = 0; k < COUT / 4; ++k) {
-          const float4 bv = __ldg(b4 + k);
-          bias_r[4 * k] = bv.x; bias_r[4 * k + 1] = bv.y; bias_r[4 * k + 2] = bv.z; bias_r[4 * k + 3] = bv.w;
-        }
-      }
-      const uint32_t tparity = static_cast<uint32_t>(pass & 1);
+      __syncwarp();                                             // every lane is done with the previous pass's bias
+      for (int k = lane; k < nsub * COUT; k += 32) my_bias[k] = __ldg(pp->bias + k);   // conv5's halves: consecutive channels of one layer
+      __syncwarp();
+      const uint32_t tpar0 = ndrain[half0] & 1u, tpar1 = ndrain[half0 ^ 1] & 1u;
+      ++ndrain[half0];
+      if (nsub == 2) ++ndrain[half0 ^ 1];
       for (int b = 0; b < nband; ++b) {
         const int rows = sh.band[b].rows, slot0 = sh.band[b].slot0;
         const int px0 = sh.lane_px[b][m], pitch = sh.lane_pitch[b][m], my_rows = sh.lane_rows[b][m];
@@ -467,76 +456,85 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
           if ((slot & 1) != group) continue;
           const bool lane_on = band_on && j < my_rows;
           const int P = px0 + j * pitch;
-          // blocked fp32 trunk layout: [pixel/32][ch/8][pixel%32][ch%8]; this lane's 32 channels are 4 runs of 8 floats
-          const size_t toff = (static_cast<size_t>(P >> 5) * 8 + (c_off >> 3)) * 256 + (static_cast<size_t>(P & 31) << 3);
-          // residual rows are fetched BEFORE waiting for the accumulator: their latency hides behind the MMAs
-          float r1[COUT], r2[COUT];
-          if (lane_on && res1) {
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int half = half0 ^ sub;
+            const int c_off = c_off0 + sub * COUT;
+            // blocked fp32 trunk layout: [pixel/32][ch/8][pixel%32][ch%8]; this lane's 32 channels are 4 runs of 8 floats
+            const size_t toff = (static_cast<size_t>(P >> 5) * 8 + (c_off >> 3)) * 256 + (static_cast<size_t>(P & 31) << 3);
+            // residual rows are fetched BEFORE waiting for the accumulator: their latency hides behind the MMAs
+            float r1[COUT], r2[COUT];
+            if (lane_on && res1) {
 #pragma unroll
-            for (int q = 0; q < COUT / 8; ++q) ldg256(res1 + toff + q * 256, &r1[q * 8]);
-          }
-          if (lane_on && res2) {
-#pragma unroll
-            for (int q = 0; q < COUT / 8; ++q) ldg256_stream(res2 + toff + q * 256, &r2[q * 8]);
-          }
-          mbar_wait(&sh.tfull[slot], tparity);
-          tc_fence_after();
-          __syncwarp();
-          const uint32_t taddr = lane_base + static_cast<uint32_t>(slot) * COUT;
-          uint32_t r[COUT / 16][16];
-#pragma unroll
-          for (int c = 0; c < COUT / 16; ++c) tmem_ld16(taddr + c * 16, r[c]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < COUT / 16; ++c) tmem_st16_zero(taddr + c * 16);
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&sh.tempty[slot]);
-          if (lane_on) {
-            float v[COUT];
-#pragma unroll
-            for (int k = 0; k < COUT; ++k) v[k] = __uint_as_float(r[k >> 4][k & 15]) + bias_r[k];
-            if (!res1) {
-              if (lrelu) {
-#pragma unroll
-                for (int k = 0; k < COUT; ++k) v[k] = fmaxf(v[k], 0.2f * v[k]);     // LeakyReLU(0.2): slope < 1
-              }
-            } else {
-#pragma unroll
-              for (int k = 0; k < COUT; ++k) v[k] = fmaf(v[k], s1, r1[k]);
-              if (res2) {
-#pragma unroll
-                for (int k = 0; k < COUT; ++k) v[k] = fmaf(v[k], s2, r2[k]);
-              }
-#pragma unroll
-              for (int q = 0; q < COUT / 8; ++q) stg256f(dst32a + toff + q * 256, &v[q * 8]);
-              if (dst32b) {
-#pragma unroll
-                for (int q = 0; q < COUT / 8; ++q) stg256f_stream(dst32b + toff + q * 256, &v[q * 8]);
-              }
+              for (int q = 0; q < COUT / 8; ++q) ldg256(res1 + toff + q * 256, &r1[q * 8]);
             }
-            uint32_t w[COUT / 2];
-            if (fmt16) {
+            if (lane_on && res2) {
 #pragma unroll
-              for (int k = 0; k < COUT / 2; ++k) w[k] = pack2(v[2 * k], v[2 * k + 1], 1);
-            } else {
-#pragma unroll
-              for (int k = 0; k < COUT / 2; ++k) w[k] = pack2(v[2 * k], v[2 * k + 1], 0);
+              for (int q = 0; q < COUT / 8; ++q) ldg256_stream(res2 + toff + q * 256, &r2[q * 8]);
             }
-            uint16_t* dst = base16 + static_cast<size_t>(P) * 64;
-            stg256(dst, reinterpret_cast<const uint32_t(&)[8]>(w[0]));
-            stg256(dst + 16, reinterpret_cast<const uint32_t(&)[8]>(w[8]));
-          }
-          if (publish) {
-            // this warp's 32 pixels of the row are stored: generic-proxy stores -> async-proxy (TMA) reads of any CTA that are
-            // ordered behind the publisher's release of the row count
-            if (dbg & 65536) fence_proxy_async_all();            // 65536: a proxy fence in every writer too (timing experiments)
+            mbar_wait(&sh.tfull[half][slot], sub ? tpar1 : tpar0);
+            tc_fence_after();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sh.stored[slot]);
+            const uint32_t taddr = lane_base + static_cast<uint32_t>(slot * kSlotCols + half * COUT);
+            uint32_t r[COUT / 16][16];
+#pragma unroll
+            for (int c = 0; c < COUT / 16; ++c) tmem_ld16(taddr + c * 16, r[c]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < COUT / 16; ++c) tmem_st16_zero(taddr + c * 16);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&sh.tempty[half][slot]);
+            if (lane_on) {
+              float v[COUT];
+              const float4* b4 = reinterpret_cast<const float4*>(my_bias + sub * COUT);
+#pragma unroll
+              for (int k = 0; k < COUT / 4; ++k) {
+                const float4 bv = b4[k];
+                v[4 * k] = __uint_as_float(r[(4 * k) >> 4][(4 * k) & 15]) + bv.x;
+                v[4 * k + 1] = __uint_as_float(r[(4 * k + 1) >> 4][(4 * k + 1) & 15]) + bv.y;
+                v[4 * k + 2] = __uint_as_float(r[(4 * k + 2) >> 4][(4 * k + 2) & 15]) + bv.z;
+                v[4 * k + 3] = __uint_as_float(r[(4 * k + 3) >> 4][(4 * k + 3) & 15]) + bv.w;
+              }
+              if (!res1) {
+                if (lrelu) {
+#pragma unroll
+                  for (int k = 0; k < COUT; ++k) v[k] = fmaxf(v[k], 0.2f * v[k]);     // LeakyReLU(0.2): slope < 1
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < COUT; ++k) v[k] = fmaf(v[k], s1, r1[k]);
+                if (res2) {
+#pragma unroll
+                  for (int k = 0; k < COUT; ++k) v[k] = fmaf(v[k], s2, r2[k]);
+                }
+#pragma unroll
+                for (int q = 0; q < COUT / 8; ++q) stg256f(dst32a + toff + q * 256, &v[q * 8]);
+                if (dst32b) {
+#pragma unroll
+                  for (int q = 0; q < COUT / 8; ++q) stg256f_stream(dst32b + toff + q * 256, &v[q * 8]);
+                }
+              }
+              uint32_t w[COUT / 2];
+              if (fmt16) {
+#pragma unroll
+                for (int k = 0; k < COUT / 2; ++k) w[k] = pack2(v[2 * k], v[2 * k + 1], 1);
+              } else {
+#pragma unroll
+                for (int k = 0; k < COUT / 2; ++k) w[k] = pack2(v[2 * k], v[2 * k + 1], 0);
+              }
+              uint16_t* dst = base16 + static_cast<size_t>(P) * 64 + sub * COUT;
+              stg256(dst, reinterpret_cast<const uint32_t(&)[8]>(w[0]));
+              stg256(dst + 16, reinterpret_cast<const uint32_t(&)[8]>(w[8]));
+            }
           }
+          // this warp's 32 pixels of the row are stored (every drained pass or pair of passes ends in a published one)
+          if (dbg & 65536) fence_proxy_async_all();              // 65536: a proxy fence in every writer too (timing experiments)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sh.stored[slot]);
         }
       }
-      if (threadIdx.x == 64) TS(1, pass);
+      if (threadIdx.x == 64) TS(1, pass + nsub - 1);
+      pass += nsub - 1;
     }
   } else {
     // =========================== publisher (warp 10) ===========================
@@ -550,11 +548,16 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
       for (int pass = 0; pass < npass; ++pass) {
         if (__ldg(&passes[pass].trunk_no_publish)) continue;
         int q = 0;
+        bool half_done = false;
         while (q < nrows) {
           mbar_wait(&sh.stored[q], par);
           ++q;
           while (q < nrows && mbar_try_wait(&sh.stored[q], par)) ++q;
-          if (NESR_PROF && (__ldg(&passes[pass].debug_flags) & 131072) && q < nrows) continue;   // 131072: publish whole passes only
+          if ((dbg0 & 131072) && q < nrows) continue;            // 131072: publish whole passes only (timing experiments)
+          // A release is a membar (~1-2k cycles): at most one intermediate publication per pass, so that the one for the last
+          // row -- the one the next sweep's first slab rows wait for in the CTA below -- rarely queues behind another.
+          if (q < nrows && (q < (nrows + 1) / 2 || half_done)) continue;
+          half_done = true;
           // generic-proxy stores of the epilogue warps (observed through the mbarriers) -> async-proxy (TMA) reads of whoever
           // acquires the value released below: the one proxy fence of the chain
           fence_proxy_async_all();
@@ -572,11 +575,14 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
   tc_fence_after();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 #if NESR_PROF
-  if ((passes[0].debug_flags & 1024) && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 40)) {
-    const long long t0 = sh.ts[5][0];
-    for (int q = 0; q < kTracePasses && q < npass; ++q)
-      printf("[trunk blk %d pass %d cin=%d] first_row_acquired %lld  first_full_last_chunk %lld  mma_issued %lld  epi_rows_done %lld  published %lld\n",
-             (int)blockIdx.x, q, passes[q].cin, sh.ts[4][q] - t0, sh.ts[5][q] - t0, sh.ts[0][q] - t0, sh.ts[1][q] - t0, sh.ts[3][q] - t0);
+  if ((dbg0 & 1024) && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 40)) {
+    const long long t0 = sh.ts[4][0];
+    for (int q = 0; q < kTrace && q < nsweep; ++q)
+      printf("[trunk blk %d sweep %d S%d need=%d] producer_at_first_row %lld  mma_issued %lld\n", (int)blockIdx.x, q, q % kSweepsPerBlock + 1,
+             sweeps[q].need, sh.ts[4][q] - t0, sh.ts[0][q] - t0);
+    for (int q = 0; q < kTrace && q < npass; ++q)
+      printf("[trunk blk %d pass %d half %d] epi_rows_done %lld  published %lld\n", (int)blockIdx.x, q, passes[q].trunk_half,
+             sh.ts[1][q] - t0, sh.ts[3][q] - t0);
   }
 #endif
 }
@@ -587,9 +593,9 @@ cudaError_t conv3x3_trunk_configure() {
   return cudaFuncSetAttribute(conv3x3_trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
 }
 
-cudaError_t launch_conv3x3_trunk(const TrunkMaps& maps, const ConvParams* d_passes, int npass, unsigned* d_prog, int grid,
-                                 cudaStream_t stream) {
-  if (grid <= 0 || npass <= 0) return cudaSuccess;
+cudaError_t launch_conv3x3_trunk(const TrunkMaps& maps, const ConvParams* d_passes, int npass, const TrunkSweep* d_sweeps, int nsweep,
+                                 unsigned* d_prog, int grid, cudaStream_t stream) {
+  if (grid <= 0 || npass <= 0 || nsweep <= 0) return cudaSuccess;
   if (grid > 1024) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaMemsetAsync(d_prog, 0, static_cast<size_t>(grid) * kProgStride * sizeof(unsigned), stream);
   if (e != cudaSuccess) return e;
@@ -603,7 +609,7 @@ cudaError_t launch_conv3x3_trunk(const TrunkMaps& maps, const ConvParams* d_pass
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv3x3_trunk_kernel, maps, d_passes, npass, d_prog);
+  return cudaLaunchKernelEx(&cfg, conv3x3_trunk_kernel, maps, d_passes, npass, d_sweeps, nsweep, d_prog);
 }
 
 }  // namespace nesr

@@ -99,6 +99,8 @@ struct Batch {
   LevelPlan lv[3];
   ConvParams* d_body_passes = nullptr;   // persistent trunk kernel: one ConvParams per RDB layer pass
   int n_body_passes = 0;
+  TrunkSweep* d_sweeps = nullptr;        // trunk kernel, MMA side: eight merged chunk sweeps per residual dense block
+  int n_sweeps = 0;
   bool trunk_fits = false;               // level-0 schedule fits the TMEM-resident trunk kernel (conv3x3_trunk.cu)
   Arena arena;                           // this group's activation buffers: its own slice of the handle's allocation, or all of it
 };
@@ -137,6 +139,9 @@ struct nesr_b200_handle {
   uint16_t* d_wfold = nullptr;                         // folded weights [dx][chunk][dy: +1,0,-1][cout][64]
   int64_t wfold_rows = 0;
   CUtensorMap m_wf[3];                                 // box rows 48 / 96 / 192
+  uint16_t* d_wmerge = nullptr;                        // trunk kernel: per dense block, eight sweep blocks [3 dx][192 | 160][64] (layout.h TrunkSweep)
+  int64_t wmerge_rows = 0;
+  CUtensorMap m_wm[2];                                 // box rows 192 / 160
 
   PlanKey key;
   std::vector<Batch> batches;
@@ -301,6 +306,36 @@ void pack_layer_fold(const Layer& L, int pass, const float* w_oihw, uint16_t* ar
         }
 }
 
+// Merged trunk weights (conv3x3_trunk.cu, layout.h TrunkSweep).  One sweep block is [3 dx][nb rows][64 input channels of one
+// plane]; a row is  g*64 + n  with g = 0,1,2 <-> dy = +1,0,-1 <-> ky = 2,1,0  (the three output rows an input row feeds) and
+// n the accumulator column inside the 64-column TMEM row slot: n < 32 -> layer `la` (half A), n >= 32 -> layer `lb` (half B);
+// conv5 (la == lb, 64 outputs) fills both.  la == nullptr: half-B single sweep -- the 32 rows of half A are zero and the box
+// is cut to 160 rows (B | 0 | B | 0 | B starting at column 32 of the first slot).
+constexpr int kSweepRows192 = 3 * 192, kSweepRows160 = 3 * 160;
+constexpr int kMergeRowsPerBlock = 6 * kSweepRows192 + 2 * kSweepRows160;
+const int kSweepRowOff[kSweepsPerBlock] = {0, 576, 1056, 1632, 2208, 2688, 3264, 3840};
+
+void pack_sweep(const Layer* la, const Layer* lb, const float* wa, const float* wb, int plane, int fmt, uint16_t* dst) {
+  const bool single = la == nullptr;
+  const int nb = single ? 160 : 192;
+  for (int dx = 0; dx < 3; ++dx)
+    for (int row = 0; row < nb; ++row) {
+      const int col = single ? row + 32 : row;                  // accumulator column relative to the first slot's column 0
+      const int g = col / 64, n = col % 64;
+      const bool conv5 = la == lb;
+      const Layer* L = n < 32 ? la : lb;
+      const float* w = n < 32 ? wa : wb;
+      const int co = conv5 ? n : (n & 31);
+      uint16_t* out = dst + ((int64_t)dx * nb + row) * 64;
+      for (int k = 0; k < 64; ++k) {
+        const int ci = plane * 64 + k;
+        float v = 0.f;
+        if (L && ci < L->cin && co < L->cout) v = w[((int64_t)co * L->cin + ci) * 9 + (2 - g) * 3 + dx];
+        out[k] = to16(v, fmt);
+      }
+    }
+}
+
 int make_map(nesr_b200_handle* h, CUtensorMap* m, void* base, int64_t channels, int64_t rows, int box_rows) {
   const cuuint64_t gdim[2] = {(cuuint64_t)channels, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)channels * 2};
@@ -337,6 +372,7 @@ void free_batches(nesr_b200_handle* h) {
   for (Batch& b : h->batches) {
     if (b.d_tiles) cudaFree(b.d_tiles);
     if (b.d_body_passes) cudaFree(b.d_body_passes);
+    if (b.d_sweeps) cudaFree(b.d_sweeps);
     for (LevelPlan& l : b.lv) {
       if (l.d_blocks) cudaFree(l.d_blocks);
       if (l.d_bands) cudaFree(l.d_bands);
@@ -374,7 +410,9 @@ void layout_level(Batch& b, int level) {
 // CTA gets the same number of rows +-1 and at most a few bands, so no SM waits for a straggler
 // (a longest-first deal of fixed-size bands left 12 of 148 CTAs with 35 % more work), and the two
 // halo rows a band costs are paid as rarely as possible.
-void build_fold_schedule(Batch& b, int level, int num_sms) {
+// max_rows > 0 (level 0 of a trunk-kernel group): no CTA gets more output rows than its TMEM row slots; returns false (and
+// leaves an incomplete schedule) when the group does not fit under that limit.
+bool build_fold_schedule(Batch& b, int level, int num_sms, int max_rows = 0) {
   LevelPlan& lp = b.lv[level];
   struct Strip { int32_t seg0, nseg, h; };
   std::vector<Strip> strips;
@@ -399,7 +437,7 @@ void build_fold_schedule(Batch& b, int level, int num_sms) {
   if (!cols.empty()) {
     // every piece costs the TMA producer at least one more operation per slab row; with 8 pieces a packed strip's
     // CTAs were producer-bound and paced the whole group (9.3 instead of 6.7 ms), with 11 one-box operations likewise
-    static const int kMaxPieces = getenv("NESR_B200_MAX_PIECES") ? atoi(getenv("NESR_B200_MAX_PIECES")) : 3;
+    static const int kMaxPieces = getenv("NESR_B200_MAX_PIECES") ? atoi(getenv("NESR_B200_MAX_PIECES")) : 6;
     struct Packed { std::vector<Piece> pcs; int lanes = 0, h = 0; };
     auto plan = [&](int T, std::vector<Packed>* out) -> int64_t {
       std::vector<Piece> pcs;
@@ -457,10 +495,12 @@ void build_fold_schedule(Batch& b, int level, int num_sms) {
     for (int c = 0; c < nrun; ++c) {
       if (emit) runs[c].clear();
       int64_t left = budget;
-      while (si < strips.size() && left >= 3) {
-        const int n = (int)std::min<int64_t>(left - 2, strips[si].h - r);
+      int rows_left = max_rows > 0 ? max_rows : 1 << 30;
+      while (si < strips.size() && left >= 3 && rows_left > 0) {
+        const int n = (int)std::min<int64_t>(std::min<int64_t>(left - 2, rows_left), strips[si].h - r);
         if (emit) runs[c].push_back(FoldBand{strips[si].seg0, strips[si].nseg, r, n});
         left -= n + 2;
+        rows_left -= n;
         r += n;
         if (r == strips[si].h) { ++si; r = 0; }
       }
@@ -472,7 +512,7 @@ void build_fold_schedule(Batch& b, int level, int num_sms) {
     const int64_t mid = (lo + hi) / 2;
     if (deal(mid, false)) hi = mid; else lo = mid + 1;
   }
-  deal(lo, true);
+  const bool complete = deal(lo, true);
   lp.bands.clear();
   lp.cta_off.assign(1, 0);
   for (int c = 0; c < grid; ++c) {
@@ -480,6 +520,7 @@ void build_fold_schedule(Batch& b, int level, int num_sms) {
     lp.cta_off.push_back((int32_t)lp.bands.size());
   }
   lp.fold_grid = grid;
+  return complete;
 }
 
 int build_body_passes(nesr_b200_handle* h, Batch& b);
@@ -556,22 +597,11 @@ bool trunk_schedule_fits(const LevelPlan& lp) {
 // row-folded schedule, and the trunk kernel's halo dependency lists.  Fills h->batches.
 int plan_groups_with_cap(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w, int64_t default_cap);
 
-// Default cap of the product path: 200k feature pixels per tile group.  Tiles are atomic, so a slightly larger cap sometimes packs
-// a frame into fewer groups (the 71k-pixel tiles of a 4K frame: three instead of two per group, 1.5-2 % faster;
-// profiles/r1_config_sweep.txt): the plan under a 15 % larger cap is taken when it has strictly fewer groups and every group still
-// fits the trunk kernel.  An explicit max_batch_pixels is taken as is.
+// Default cap of the product path: a tile group is at most 8 output rows (the trunk kernel's TMEM row slots) of 128 pixels on
+// each of the SMs, which also keeps its dense-block working set (~1 KB per feature pixel, about half of it live) inside the
+// 126 MB L2.  The schedule decides whether a tile still fits; the pixel cap only prunes the candidates.
 int plan_groups(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
-  constexpr int64_t kCap = 200000;
-  int rc = plan_groups_with_cap(h, key, out_h, out_w, kCap);
-  if (rc != NESR_OK || h->cfg.conv_impl != 0 || h->cfg.max_batch_pixels > 0 || h->batches.size() < 3) return rc;
-  const size_t ngroups = h->batches.size();
-  std::vector<Batch> first = std::move(h->batches);
-  h->batches.clear();
-  rc = plan_groups_with_cap(h, key, out_h, out_w, kCap * 23 / 20);
-  bool better = rc == NESR_OK && h->batches.size() < ngroups;
-  for (const Batch& b : h->batches) better = better && b.trunk_fits;
-  if (!better) h->batches = std::move(first);
-  return NESR_OK;
+  return plan_groups_with_cap(h, key, out_h, out_w, (int64_t)kTrunkMaxRows * kBlockPixels * h->num_sms);
 }
 
 int plan_groups_with_cap(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w, int64_t default_cap) {
@@ -615,34 +645,49 @@ int plan_groups_with_cap(nesr_b200_handle* h, const PlanKey& key, int out_h, int
   const bool l2_groups = h->cfg.conv_impl == 0;
   const int64_t cap = h->cfg.max_batch_pixels > 0 ? h->cfg.max_batch_pixels : (l2_groups ? default_cap : (int64_t)3 << 20);
   // level-0 schedule of a group and whether the TMEM-resident trunk kernel can run it
-  auto sched0 = [&](Batch& bb) { layout_level(bb, 0); build_fold_schedule(bb, 0, h->num_sms); };
+  auto sched0 = [&](Batch& bb) {                                // row-capped for the trunk kernel; a group that cannot fit keeps the free schedule
+    layout_level(bb, 0);
+    if (!l2_groups || !build_fold_schedule(bb, 0, h->num_sms, kTrunkMaxRows)) build_fold_schedule(bb, 0, h->num_sms);
+  };
   auto fits0 = [&](const Batch& bb) { return trunk_schedule_fits(bb.lv[0]); };
-  size_t i = 0;
-  while (i < all.size()) {
-    Batch b;
+  auto tile_px = [&](const TileGeom& t) { return (int64_t)t.lv[0].h * t.lv[0].pitch; };
+  std::vector<std::vector<int>> groups;                         // tile indices (into `all`) of every group
+  if (l2_groups) {
+    // First-fit decreasing: tiles are independent, so a group need not be a contiguous range.  The largest tiles open the
+    // groups and the small edge tiles of a frame fill them up (1080p, tile 512: four groups of two 68k-pixel tiles + one
+    // 8k-pixel bottom-row tile each, instead of a tail group with almost no work per CTA and 414 dependent passes of latency).
+    std::vector<int> order(all.size());
+    for (size_t i = 0; i < all.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tile_px(all[x]) > tile_px(all[y]); });
+    std::vector<int64_t> gpx;
+    for (int ti : order) {
+      const int64_t n = tile_px(all[ti]);
+      bool placed = false;
+      for (size_t g = 0; g < groups.size() && !placed; ++g) {
+        if (gpx[g] + n > cap) continue;
+        Batch probe;
+        for (int k : groups[g]) probe.tiles.push_back(all[k]);
+        probe.tiles.push_back(all[ti]);
+        sched0(probe);
+        if (!fits0(probe)) continue;
+        groups[g].push_back(ti); gpx[g] += n; placed = true;
+      }
+      if (!placed) { groups.push_back({ti}); gpx.push_back(n); }
+    }
+    for (auto& g : groups) std::sort(g.begin(), g.end());
+    std::sort(groups.begin(), groups.end(), [](const std::vector<int>& x, const std::vector<int>& y) { return x.front() < y.front(); });
+  } else {
     int64_t px = 0;
-    while (i < all.size()) {
-      const int64_t n = (int64_t)all[i].lv[0].h * all[i].lv[0].pitch;
-      if (!b.tiles.empty() && px + n > cap) break;
-      b.tiles.push_back(all[i]);
-      if (l2_groups && b.tiles.size() > 1) {                    // would the group still fit the trunk kernel?
-        sched0(b);
-        if (!fits0(b)) { b.tiles.pop_back(); break; }
-      }
+    for (size_t i = 0; i < all.size(); ++i) {
+      const int64_t n = tile_px(all[i]);
+      if (groups.empty() || px + n > cap) { groups.emplace_back(); px = 0; }
+      groups.back().push_back((int)i);
       px += n;
-      ++i;
     }
-    if (l2_groups && i == all.size() && !h->batches.empty() && px * 5 < cap * 3) {
-      // A small tail group pays the trunk's per-pass latency (414 dependent passes) for almost no work: fold it into the
-      // previous group when the combined schedule still fits the trunk kernel.
-      Batch m = h->batches.back();
-      m.tiles.insert(m.tiles.end(), b.tiles.begin(), b.tiles.end());
-      sched0(m);
-      if (fits0(m)) {
-        h->batches.pop_back();
-        b = std::move(m);
-      }
-    }
+  }
+  for (const auto& g : groups) {
+    Batch b;
+    for (int k : g) b.tiles.push_back(all[k]);
     for (int l = 1; l < 3; ++l) { layout_level(b, l); build_fold_schedule(b, l, h->num_sms); }
     sched0(b);
     b.trunk_fits = l2_groups && fits0(b);
@@ -860,6 +905,7 @@ int build_body_passes(nesr_b200_handle* h, Batch& b) {
   const Arena& a = b.arena;
   const int nrdb = h->cfg.num_block * 3;
   std::vector<ConvParams> passes;
+  std::vector<TrunkSweep> sweeps;
   size_t li = 1;                     // layers[0] is conv_first
   int cur = 0;
   for (int r = 0; r < nrdb; ++r) {
@@ -886,9 +932,25 @@ int build_body_passes(nesr_b200_handle* h, Batch& b) {
         q.trunk_need = b.lv[0].d_need;
         // the first half of conv5 is needed by nobody before the second half has been published too: skip its publish
         q.trunk_no_publish = (k == 5 && ps + 1 < L.fold_passes) ? 1 : 0;
+        q.trunk_half = k == 5 ? ps : ((k - 1) & 1);      // TMEM half: conv1, conv3, conv5[0:32] -> A; conv2, conv4, conv5[32:64] -> B
         q.l2_pin_chunks = h->l2_pin_chunks;
         passes.push_back(q);
       }
+    }
+    {  // MMA side of the trunk kernel: the block's eight merged sweeps.  `need` counts epilogue passes (six per block).
+      const int pb = r * 6, wb = r * kMergeRowsPerBlock;
+      auto plane = [&](int c) { return c + ((a.shared_g && cur == 1 && c > 0) ? 1 : 0); };   // buffer B: xB | (xA) | x1x2 | x3x4
+      const TrunkSweep blk[kSweepsPerBlock] = {
+          {cur, plane(0), wb + kSweepRowOff[0], 192, 4, pb, kSweepWaitA | kSweepWaitB | kSweepCommitA, 0},
+          {cur, plane(1), wb + kSweepRowOff[1], 160, 2, pb + 1, kSweepWaitA | kSweepCommitB | kSweepSingleB, 0},
+          {cur, plane(0), wb + kSweepRowOff[2], 192, 4, pb, kSweepWaitB, 0},
+          {cur, plane(1), wb + kSweepRowOff[3], 192, 4, pb + 2, kSweepCommitA, 0},
+          {cur, plane(2), wb + kSweepRowOff[4], 160, 2, pb + 3, kSweepWaitA | kSweepCommitB | kSweepSingleB, 0},
+          {cur, plane(0), wb + kSweepRowOff[5], 192, 4, pb, kSweepWaitB, 0},
+          {cur, plane(1), wb + kSweepRowOff[6], 192, 4, pb + 2, 0, 0},
+          {cur, plane(2), wb + kSweepRowOff[7], 192, 4, pb + 4, kSweepCommitA | kSweepCommitB, 0},
+      };
+      sweeps.insert(sweeps.end(), blk, blk + kSweepsPerBlock);
     }
     cur ^= 1;
   }
@@ -897,6 +959,11 @@ int build_body_passes(nesr_b200_handle* h, Batch& b) {
   b.n_body_passes = (int)passes.size();
   CUDA_TRY(h, cudaMalloc(&b.d_body_passes, passes.size() * sizeof(ConvParams)));
   CUDA_TRY(h, cudaMemcpyAsync(b.d_body_passes, passes.data(), passes.size() * sizeof(ConvParams), cudaMemcpyHostToDevice, h->stream));
+  if (b.d_sweeps) cudaFree(b.d_sweeps);
+  b.d_sweeps = nullptr;
+  b.n_sweeps = (int)sweeps.size();
+  CUDA_TRY(h, cudaMalloc(&b.d_sweeps, sweeps.size() * sizeof(TrunkSweep)));
+  CUDA_TRY(h, cudaMemcpyAsync(b.d_sweeps, sweeps.data(), sweeps.size() * sizeof(TrunkSweep), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return NESR_OK;
 }
@@ -940,7 +1007,7 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
         tm.full[i2] = a.f_d[i2];
         for (int k = 0; k < 4; ++k) tm.box[i2][k] = a.b_d[i2][k];
       }
-      tm.w = fold_weight_map(h, 32);
+      tm.w192 = h->m_wm[0]; tm.w160 = h->m_wm[1];
     }
     if (time_trunk) {                  // events on the launching stream around the dominant kernel
       while ((int)h->ev_trunk.size() < 2 * (h->n_trunk_timed + 1)) {
@@ -951,7 +1018,7 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
       cudaEventRecord(h->ev_trunk[2 * h->n_trunk_timed], s);
     }
     cudaError_t eb = b.trunk_fits
-        ? launch_conv3x3_trunk(tm, b.d_body_passes, b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s)
+        ? launch_conv3x3_trunk(tm, b.d_body_passes, b.n_body_passes, b.d_sweeps, b.n_sweeps, h->d_gbar, b.lv[0].fold_grid, s)
         : launch_conv3x3_body(a.f_d[0], a.f_d[1], a.e_d[0], a.e_d[1], fold_weight_map(h, 32), b.d_body_passes,
                               b.n_body_passes, h->d_gbar, b.lv[0].fold_grid, s);
     if (eb != cudaSuccess) return fail(h, NESR_E_CUDA, "trunk kernel launch failed: %s", cudaGetErrorString(eb));
@@ -1197,6 +1264,7 @@ int nesr_b200_destroy(nesr_b200_handle* h) {
   if (h->d_wpack) cudaFree(h->d_wpack);
   if (h->d_bias) cudaFree(h->d_bias);
   if (h->d_wfold) cudaFree(h->d_wfold);
+  if (h->d_wmerge) cudaFree(h->d_wmerge);
   if (h->d_gbar) cudaFree(h->d_gbar);
   if (h->d_in) cudaFree(h->d_in);
   if (h->d_out) cudaFree(h->d_out);
@@ -1254,6 +1322,33 @@ int nesr_b200_finalize_weights(nesr_b200_handle* h) {
   for (int i = 0; i < 3; ++i) {
     int rc = make_map(h, &h->m_wf[i], h->d_wfold, 64, h->wfold_rows, fbox[i]);
     if (rc) return rc;
+  }
+  {  // merged trunk weights: per dense block the eight sweep blocks of layout.h TrunkSweep
+    const int nrdb = h->cfg.num_block * 3;
+    h->wmerge_rows = (int64_t)nrdb * kMergeRowsPerBlock;
+    std::vector<uint16_t> marena((size_t)h->wmerge_rows * 64, 0);
+    for (int r = 0; r < nrdb; ++r) {
+      const Layer* L[6];
+      const float* W[6];
+      for (int k = 1; k <= 5; ++k) { L[k] = &h->layers[1 + 5 * r + (k - 1)]; W[k] = h->staged[L[k]->name + ".weight"].data(); }
+      uint16_t* base = marena.data() + (int64_t)r * kMergeRowsPerBlock * 64;
+      const int fmt = h->cfg.body_format;
+      pack_sweep(L[1], L[2], W[1], W[2], 0, fmt, base + (int64_t)kSweepRowOff[0] * 64);       // S1 x      -> conv1 | conv2
+      pack_sweep(nullptr, L[2], nullptr, W[2], 1, fmt, base + (int64_t)kSweepRowOff[1] * 64); // S2 x1     -> conv2
+      pack_sweep(L[3], L[4], W[3], W[4], 0, fmt, base + (int64_t)kSweepRowOff[2] * 64);       // S3 x      -> conv3 | conv4
+      pack_sweep(L[3], L[4], W[3], W[4], 1, fmt, base + (int64_t)kSweepRowOff[3] * 64);       // S4 x1, x2 -> conv3 | conv4
+      pack_sweep(nullptr, L[4], nullptr, W[4], 2, fmt, base + (int64_t)kSweepRowOff[4] * 64); // S5 x3     -> conv4
+      for (int c = 0; c < 3; ++c)                                                               // S6-S8 x | x1,x2 | x3,x4 -> conv5
+        pack_sweep(L[5], L[5], W[5], W[5], c, fmt, base + (int64_t)kSweepRowOff[5 + c] * 64);
+    }
+    if (h->d_wmerge) { cudaFree(h->d_wmerge); h->d_wmerge = nullptr; }
+    CUDA_TRY(h, cudaMalloc(&h->d_wmerge, marena.size() * 2));
+    CUDA_TRY(h, cudaMemcpy(h->d_wmerge, marena.data(), marena.size() * 2, cudaMemcpyHostToDevice));
+    const int mbox[2] = {192, 160};
+    for (int i = 0; i < 2; ++i) {
+      int rc = make_map(h, &h->m_wm[i], h->d_wmerge, 64, h->wmerge_rows, mbox[i]);
+      if (rc) return rc;
+    }
   }
   if (!h->d_wpack) CUDA_TRY(h, cudaMalloc(&h->d_wpack, arena.size() * 2));
   if (!h->d_bias) CUDA_TRY(h, cudaMalloc(&h->d_bias, bias.size() * 4));

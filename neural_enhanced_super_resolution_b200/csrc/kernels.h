@@ -30,11 +30,11 @@ cudaError_t launch_conv3x3_body(const CUtensorMap& d0_136, const CUtensorMap& d1
 struct TrunkMaps {
   CUtensorMap full[2];
   CUtensorMap box[2][4];
-  CUtensorMap w;               // folded weights, box 96 rows
+  CUtensorMap w192, w160;      // merged trunk weights, boxes of 192 / 160 rows
 };
 cudaError_t conv3x3_trunk_configure();
-cudaError_t launch_conv3x3_trunk(const TrunkMaps& maps, const ConvParams* d_passes, int npass, unsigned* d_prog, int grid,
-                                 cudaStream_t stream);
+cudaError_t launch_conv3x3_trunk(const TrunkMaps& maps, const ConvParams* d_passes, int npass, const TrunkSweep* d_sweeps, int nsweep,
+                                 unsigned* d_prog, int grid, cudaStream_t stream);
 
 // --- conv3x3_simt.cu : plain CUDA-core conv over the same buffers (test-only cross-check) -------
 cudaError_t launch_conv3x3_simt(const ConvParams& p, cudaStream_t stream);

@@ -120,7 +120,29 @@ struct ConvParams {
   // the newest chunk may be loaded; 0: the slab row holds no pixel of that CTA
   const uint8_t* trunk_need;
   int32_t trunk_no_publish;    // trunk kernel: this pass's rows are not published (conv5 first half: implied by the second half's)
+  int32_t trunk_half;          // trunk kernel: which 32-column half of a TMEM row slot this pass's accumulator lives in (0 = A, 1 = B)
 };
+
+// conv3x3_trunk.cu, MMA side: one chunk sweep over the CTA's bands.  A residual dense block is EIGHT sweeps (SURVEY 8a4:
+// conv_k reads cat(x, x1 .. x_{k-1})), merged so that every activation plane is streamed as rarely as possible and the
+// MMAs are N = 192 wide (99 % of the tensor rate instead of 85 % at N = 96):
+//   S1 x    -> conv1 | conv2      S2 x1    -> conv2          S3 x -> conv3 | conv4      S4 x1,x2 -> conv3 | conv4
+//   S5 x3   -> conv4              S6 x     -> conv5          S7 x1,x2 -> conv5          S8 x3,x4 -> conv5
+// A TMEM row slot is 64 fp32 columns: half A (conv1, conv3, conv5[0:32]) | half B (conv2, conv4, conv5[32:64]).
+struct TrunkSweep {
+  int32_t src_sel;             // which dense-block buffer (tensor map pair) holds the plane
+  int32_t plane;               // plane index inside that buffer's tensor map
+  int32_t w_row0;              // first row of the sweep's [3 dx][nb][64] weight block in the merged-weight arena
+  int32_t nb;                  // rows of one dx box: 192 (merged pair / conv5) or 160 (half-B single, zero rows for half A)
+  int32_t ks;                  // k-steps of 16 channels (4: whole plane, 2: its first 32 channels)
+  int32_t need;                // epilogue passes [0, need) must have stored the rows a slab covers (0: none)
+  int32_t flags;               // kSweep* bits
+  int32_t pad_;
+};
+constexpr int kSweepWaitA = 1, kSweepWaitB = 2;       // first toucher of half A / B after a drain: wait for the drained slot
+constexpr int kSweepCommitA = 4, kSweepCommitB = 8;   // completes half A / B: commit every output row to the epilogue
+constexpr int kSweepSingleB = 16;                     // N = 160 sweep into half B (zero weight rows over half A)
+constexpr int kSweepsPerBlock = 8;
 
 // Timing-experiment switches (NESR_B200_DEBUG_FLAGS: results are WRONG when one is set) exist only in a -DNESR_PROF=1 build:
 // in the shipped library this folds to 0 and every `dbg & bit` branch in the kernels compiles away.
@@ -132,8 +154,8 @@ __host__ __device__
 #endif
 inline int dbg_flags(const ConvParams& p) { return NESR_PROF ? p.debug_flags : 0; }
 
-// conv3x3_trunk.cu keeps every output row of a CTA in TMEM for a whole pass: 16 row slots of 32 fp32 columns.
-constexpr int kTrunkMaxRows = 16;
+// conv3x3_trunk.cu keeps every output row of a CTA in TMEM for a whole pass: 8 row slots of 64 fp32 columns.
+constexpr int kTrunkMaxRows = 8;             // 512 TMEM columns / 64 (two 32-channel accumulators, or conv5's 64 channels, per row)
 constexpr int kTrunkMaxBands = 4;
 constexpr int kTrunkMaxDeps = 32;            // one polling lane per dependency
 constexpr int kTrunkMaxSlabRows = kTrunkMaxRows + 2 * kTrunkMaxBands;   // input rows a CTA streams per chunk sweep
