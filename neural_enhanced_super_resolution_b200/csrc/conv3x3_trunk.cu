@@ -414,21 +414,41 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
     __syncwarp();
   } else if (warp < 10) {
     // =========================== epilogue (warps 2..9) ===========================
+    // The epilogue warps are latency bound (one or two warps per scheduler; tcgen05.ld / st waits, L2 round trips), so the
+    // two kinds of pass are separate straight-line code paths and everything that does not change between passes -- which
+    // rows this warp drains, where their pixels live -- is computed once:
+    //   conv1..4 : v = lrelu(acc + bias)                               -> 16-bit, channels [coff, coff+32) of this buffer
+    //   conv5    : v = (acc + bias)*0.2 + trunk [; v = v*0.2 + rrdb_in] -> fp32 trunk [+ rrdb], 16-bit x of the next block
+    // conv5's two 32-channel passes complete together (sweep S8 commits both halves of a row at once) and are drained
+    // TOGETHER, row by row: drained one after the other, the second pass's rows all waited behind the first's and the
+    // block's last sweep was followed by a 20k-cycle epilogue tail before the next block could start.  Its fp32 trunk rows
+    // are prefetched one row ahead (both halves, two register sets): issued just before they were needed, their L2 round
+    // trip was exposed on every half row (the epilogue ran at ~2k cycles per half row against 1.2k of MMA work per row).
     const int quarter = warp & 3;
     const int group = (warp - 2) >> 2;                          // rows alternate between the two epilogue groups
     const int m = quarter * 32 + lane;                          // TMEM lane == MMA row == pixel
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    constexpr int kMyRows = kSlots / 2;                         // a group drains every other slot
+    int my_slot[kMyRows], my_px[kMyRows];                       // slot (uniform; -1: none) and flat pixel (-1: masked lane) of this warp's rows
+#pragma unroll
+    for (int k = 0; k < kMyRows; ++k) { my_slot[k] = -1; my_px[k] = -1; }
+    {
+      int n = 0;
+      for (int b = 0; b < nband; ++b) {
+        const int rows = sh.band[b].rows, slot0 = sh.band[b].slot0;
+        const int px0 = sh.lane_px[b][m], pitch = sh.lane_pitch[b][m], nmine = sh.lane_rows[b][m];
+        for (int j = 0; j < rows; ++j) {
+          if (((slot0 + j) & 1) != group) continue;
+#pragma unroll
+          for (int k = 0; k < kMyRows; ++k)
+            if (k == n) { my_slot[k] = slot0 + j; my_px[k] = (px0 >= 0 && j < nmine) ? px0 + j * pitch : -1; }
+          ++n;
+        }
+      }
+    }
     uint32_t ndrain[2] = {0, 0};                                // passes drained so far from each TMEM half
     float* const my_bias = sh.bias[warp - 2];
     for (int pass = 0; pass < npass; ++pass) {
-      // The epilogue warps are instruction-latency bound (one or two warps per scheduler, ~4 cycles per dependent
-      // instruction).  A trunk pass is one of two kinds, fixed for the whole pass, so the row loop below is straight-line
-      // code specialised at pass level:
-      //   conv1..4 : v = lrelu(acc + bias)                               -> 16-bit, channels [coff, coff+32) of this buffer
-      //   conv5    : v = (acc + bias)*0.2 + trunk [; v = v*0.2 + rrdb_in] -> fp32 trunk [+ rrdb], 16-bit x of the next block
-      // conv5's two 32-channel passes complete together (sweep S8 commits both halves of a row at once) and are drained
-      // TOGETHER, row by row (nsub = 2): drained one after the other, the second pass's rows all waited behind the first's and
-      // the block's last sweep was followed by a 20k-cycle epilogue tail before the next block could start.
       const ConvParams* pp = passes + pass;
       const int dbg = NESR_PROF ? __ldg(&pp->debug_flags) : 0;
       const float* res1 = pp->res1;
@@ -447,90 +467,134 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
       const uint32_t tpar0 = ndrain[half0] & 1u, tpar1 = ndrain[half0 ^ 1] & 1u;
       ++ndrain[half0];
       if (nsub == 2) ++ndrain[half0 ^ 1];
-      for (int b = 0; b < nband; ++b) {
-        const int rows = sh.band[b].rows, slot0 = sh.band[b].slot0;
-        const int px0 = sh.lane_px[b][m], pitch = sh.lane_pitch[b][m], my_rows = sh.lane_rows[b][m];
-        const bool band_on = px0 >= 0 && !(dbg & 1);
-        for (int j = 0; j < rows; ++j) {
-          const int slot = slot0 + j;
-          if ((slot & 1) != group) continue;
-          const bool lane_on = band_on && j < my_rows;
-          const int P = px0 + j * pitch;
-          for (int sub = 0; sub < nsub; ++sub) {
-            const int half = half0 ^ sub;
-            const int c_off = c_off0 + sub * COUT;
-            // blocked fp32 trunk layout: [pixel/32][ch/8][pixel%32][ch%8]; this lane's 32 channels are 4 runs of 8 floats
-            const size_t toff = (static_cast<size_t>(P >> 5) * 8 + (c_off >> 3)) * 256 + (static_cast<size_t>(P & 31) << 3);
-            // residual rows are fetched BEFORE waiting for the accumulator: their latency hides behind the MMAs
-            float r1[COUT], r2[COUT];
-            if (lane_on && res1) {
+      const bool off = (dbg & 1) != 0;                          // 1: no epilogue loads / stores (timing experiments)
+
+      // TMEM -> registers, slot handed back zeroed
+      auto drain = [&](int slot, int half, uint32_t par, uint32_t (&r)[COUT / 16][16]) {
+        mbar_wait(&sh.tfull[half][slot], par);
+        tc_fence_after();
+        __syncwarp();
+        const uint32_t taddr = lane_base + static_cast<uint32_t>(slot * kSlotCols + half * COUT);
 #pragma unroll
-              for (int q = 0; q < COUT / 8; ++q) ldg256(res1 + toff + q * 256, &r1[q * 8]);
+        for (int c = 0; c < COUT / 16; ++c) tmem_ld16(taddr + c * 16, r[c]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < COUT / 16; ++c) tmem_st16_zero(taddr + c * 16);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&sh.tempty[half][slot]);
+      };
+      auto add_bias = [&](const uint32_t (&r)[COUT / 16][16], int sub, float (&v)[COUT]) {
+        const float4* b4 = reinterpret_cast<const float4*>(my_bias + sub * COUT);
+#pragma unroll
+        for (int k = 0; k < COUT / 4; ++k) {
+          const float4 bv = b4[k];
+          v[4 * k] = __uint_as_float(r[(4 * k) >> 4][(4 * k) & 15]) + bv.x;
+          v[4 * k + 1] = __uint_as_float(r[(4 * k + 1) >> 4][(4 * k + 1) & 15]) + bv.y;
+          v[4 * k + 2] = __uint_as_float(r[(4 * k + 2) >> 4][(4 * k + 2) & 15]) + bv.z;
+          v[4 * k + 3] = __uint_as_float(r[(4 * k + 3) >> 4][(4 * k + 3) & 15]) + bv.w;
+        }
+      };
+      auto store16 = [&](int P, int sub, const float (&v)[COUT]) {
+        uint32_t w[COUT / 2];
+        if (fmt16) {
+#pragma unroll
+          for (int k = 0; k < COUT / 2; ++k) w[k] = pack2(v[2 * k], v[2 * k + 1], 1);
+        } else {
+#pragma unroll
+          for (int k = 0; k < COUT / 2; ++k) w[k] = pack2(v[2 * k], v[2 * k + 1], 0);
+        }
+        uint16_t* dst = base16 + static_cast<size_t>(P) * 64 + sub * COUT;
+        if (dbg & 16) return;                                    // 16: no 16-bit stores (timing experiments)
+        stg256(dst, reinterpret_cast<const uint32_t(&)[8]>(w[0]));
+        stg256(dst + 16, reinterpret_cast<const uint32_t(&)[8]>(w[8]));
+      };
+      auto row_stored = [&](int slot) {                         // this warp's 32 pixels of the row are stored
+        if (dbg & 65536) fence_proxy_async_all();                // 65536: a proxy fence in every writer too (timing experiments)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.stored[slot]);
+      };
+      // blocked fp32 trunk layout: [pixel/32][ch/8][pixel%32][ch%8]; a lane's 32 channels are 4 runs of 8 floats
+      auto trunk_off = [&](int P, int sub) {
+        return (static_cast<size_t>(P >> 5) * 8 + ((c_off0 + sub * COUT) >> 3)) * 256 + (static_cast<size_t>(P & 31) << 3);
+      };
+
+      if (!res1) {
+        // ---- conv1..4 ----
+#pragma unroll
+        for (int k = 0; k < kMyRows; ++k) {
+          const int slot = my_slot[k];
+          if (slot < 0) continue;
+          uint32_t r[COUT / 16][16];
+          drain(slot, half0, tpar0, r);
+          if (my_px[k] >= 0 && !off) {
+            float v[COUT];
+            add_bias(r, 0, v);
+            if (lrelu) {
+#pragma unroll
+              for (int q = 0; q < COUT; ++q) v[q] = fmaxf(v[q], 0.2f * v[q]);     // LeakyReLU(0.2): slope < 1
             }
-            if (lane_on && res2) {
+            store16(my_px[k], 0, v);
+          }
+          row_stored(slot);
+        }
+      } else {
+        // ---- conv5 (one or both halves per row), each half row's trunk values prefetched one half row ahead ----
+        float rt[COUT];                                         // trunk[pixel][the 32 channels of the half row about to be drained]
+        auto load_trunk = [&](int P, int sub) {
+          const size_t t = trunk_off(P, sub);
+          if (dbg & 2097152) return;                             // 2097152: no trunk loads (timing experiments)
+#pragma unroll
+          for (int q = 0; q < COUT / 8; ++q) ldg256(res1 + t + q * 256, &rt[q * 8]);
+        };
+        if (my_slot[0] >= 0 && my_px[0] >= 0 && !off) load_trunk(my_px[0], 0);
+#pragma unroll
+        for (int k = 0; k < kMyRows; ++k) {
+          const int slot = my_slot[k];
+          if (slot < 0) continue;
+          const int P = my_px[k];
+          const bool on = P >= 0 && !off;
+          constexpr int kLast = kMyRows - 1;
+          const int Pn = my_px[k < kLast ? k + 1 : k];          // next row of this warp (if any)
+          const bool next_row_on = k < kLast && my_slot[k < kLast ? k + 1 : k] >= 0 && Pn >= 0 && !off;
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            if (sub == 1 && nsub == 1) break;
+            float r2[COUT];
+            const size_t toff = trunk_off(P >= 0 ? P : 0, sub);
+            if (on && res2) {
 #pragma unroll
               for (int q = 0; q < COUT / 8; ++q) ldg256_stream(res2 + toff + q * 256, &r2[q * 8]);
             }
-            mbar_wait(&sh.tfull[half][slot], sub ? tpar1 : tpar0);
-            tc_fence_after();
-            __syncwarp();
-            const uint32_t taddr = lane_base + static_cast<uint32_t>(slot * kSlotCols + half * COUT);
             uint32_t r[COUT / 16][16];
+            drain(slot, half0 ^ sub, sub ? tpar1 : tpar0, r);
+            float v[COUT];
+            if (on) {
+              add_bias(r, sub, v);
 #pragma unroll
-            for (int c = 0; c < COUT / 16; ++c) tmem_ld16(taddr + c * 16, r[c]);
-            tmem_ld_wait();
+              for (int q = 0; q < COUT; ++q) v[q] = fmaf(v[q], s1, rt[q]);
+            }
+            // the registers just consumed take the NEXT half row's trunk values: the other half of this row, or the first
+            // half of this warp's next row
+            if (sub == 0 && nsub == 2) { if (on) load_trunk(P, 1); }
+            else if (next_row_on) load_trunk(Pn, 0);
+            if (on) {
+              if (res2) {
 #pragma unroll
-            for (int c = 0; c < COUT / 16; ++c) tmem_st16_zero(taddr + c * 16);
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&sh.tempty[half][slot]);
-            if (lane_on) {
-              float v[COUT];
-              const float4* b4 = reinterpret_cast<const float4*>(my_bias + sub * COUT);
-#pragma unroll
-              for (int k = 0; k < COUT / 4; ++k) {
-                const float4 bv = b4[k];
-                v[4 * k] = __uint_as_float(r[(4 * k) >> 4][(4 * k) & 15]) + bv.x;
-                v[4 * k + 1] = __uint_as_float(r[(4 * k + 1) >> 4][(4 * k + 1) & 15]) + bv.y;
-                v[4 * k + 2] = __uint_as_float(r[(4 * k + 2) >> 4][(4 * k + 2) & 15]) + bv.z;
-                v[4 * k + 3] = __uint_as_float(r[(4 * k + 3) >> 4][(4 * k + 3) & 15]) + bv.w;
+                for (int q = 0; q < COUT; ++q) v[q] = fmaf(v[q], s2, r2[q]);
               }
-              if (!res1) {
-                if (lrelu) {
+              if (!(dbg & 4096)) {                               // 4096: no fp32 trunk stores (timing experiments)
 #pragma unroll
-                  for (int k = 0; k < COUT; ++k) v[k] = fmaxf(v[k], 0.2f * v[k]);     // LeakyReLU(0.2): slope < 1
-                }
-              } else {
-#pragma unroll
-                for (int k = 0; k < COUT; ++k) v[k] = fmaf(v[k], s1, r1[k]);
-                if (res2) {
-#pragma unroll
-                  for (int k = 0; k < COUT; ++k) v[k] = fmaf(v[k], s2, r2[k]);
-                }
-#pragma unroll
-                for (int q = 0; q < COUT / 8; ++q) stg256f(dst32a + toff + q * 256, &v[q * 8]);
-                if (dst32b) {
-#pragma unroll
-                  for (int q = 0; q < COUT / 8; ++q) stg256f_stream(dst32b + toff + q * 256, &v[q * 8]);
-                }
+              for (int q = 0; q < COUT / 8; ++q) stg256f(dst32a + toff + q * 256, &v[q * 8]);
               }
-              uint32_t w[COUT / 2];
-              if (fmt16) {
+              if (dst32b && !(dbg & 4096)) {
 #pragma unroll
-                for (int k = 0; k < COUT / 2; ++k) w[k] = pack2(v[2 * k], v[2 * k + 1], 1);
-              } else {
-#pragma unroll
-                for (int k = 0; k < COUT / 2; ++k) w[k] = pack2(v[2 * k], v[2 * k + 1], 0);
+                for (int q = 0; q < COUT / 8; ++q) stg256f_stream(dst32b + toff + q * 256, &v[q * 8]);
               }
-              uint16_t* dst = base16 + static_cast<size_t>(P) * 64 + sub * COUT;
-              stg256(dst, reinterpret_cast<const uint32_t(&)[8]>(w[0]));
-              stg256(dst + 16, reinterpret_cast<const uint32_t(&)[8]>(w[8]));
+              store16(P, sub, v);
             }
           }
-          // this warp's 32 pixels of the row are stored (every drained pass or pair of passes ends in a published one)
-          if (dbg & 65536) fence_proxy_async_all();              // 65536: a proxy fence in every writer too (timing experiments)
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sh.stored[slot]);
+          row_stored(slot);
         }
       }
       if (threadIdx.x == 64) TS(1, pass + nsub - 1);

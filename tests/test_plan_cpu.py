@@ -57,32 +57,45 @@ def test_every_pixel_is_owned_once_and_invariants_hold(H, W, tile, pad):
     assert 1 <= st["groups"] <= nt
     assert st["strip_rows"] * 128 >= px                        # 128 lanes per strip row cover all pixels
     if st["trunk_groups"] == st["groups"]:
-        assert st["max_rows"] <= 16                            # 16 TMEM row slots of 32 fp32 columns
+        assert st["max_rows"] <= 8                             # 8 TMEM row slots of 64 fp32 columns (two accumulator halves)
     assert st["trunk_groups"] <= st["groups"]
 
 
 def test_1080p_plan_is_the_one_the_benchmark_runs():
     rc, msg, st = plan(1080, 1920, 512, 10)
     assert rc == 0, msg
-    assert st["tiles"] == 12 and st["groups"] == 3 and st["trunk_groups"] == 3
-    # ragged tile widths (266 = 2*128 + 10) and the halo rows of 8-12-row bands are the overheads DESIGN.md quotes
+    # 12 tiles = 4.7k strip rows against 148 SMs x 8 TMEM row slots per group: five groups, every one
+    # on the trunk kernel
+    assert st["tiles"] == 12 and st["groups"] == 5 and st["trunk_groups"] == 5 and st["max_rows"] <= 8
+    # ragged tile widths (266 = 2*128 + 10) and the halo rows of <= 8-row bands are the overheads DESIGN.md quotes
     lanes = st["strip_rows"] * 128
     assert 1.0 <= lanes / st["pixels"] < 1.12
-    assert 0.15 < st["halo_rows"] / st["strip_rows"] < 0.35
+    assert 0.2 < st["halo_rows"] / st["strip_rows"] < 0.4
     # the whole-frame kernels keep one group
     rc, msg, whole = plan(1080, 1920, 512, 10, impl=4)
     assert rc == 0 and whole["groups"] == 1 and whole["trunk_groups"] == 0
-    assert whole["strip_rows"] <= st["strip_rows"] * 1.01      # remainder pieces pack across the whole frame instead of per group
 
 
 def test_group_cap_and_frames():
     rc, msg, a = plan(512, 512, 0, 10, n=6)                    # six frames = six independent tiles
     assert rc == 0 and a["tiles"] == 6 and a["pixels"] == 6 * 256 * 256
-    assert a["groups"] == 2                                    # 200k-pixel groups: three 66k-pixel frames each
+    assert a["groups"] == 3                                    # 148 SMs x 8 rows x 128 px = 151k pixels: two 66k-pixel frames each
     rc, msg, b = plan(512, 512, 0, 10, n=6, cap=70000)
     assert rc == 0 and b["groups"] == 6
     rc, msg, c = plan(300, 420, 160, 10, cap=20000)
     assert rc == 0 and c["groups"] >= 2
+
+
+def test_groups_are_packed_first_fit_decreasing():
+    """Tiles are independent, so a group need not be a contiguous tile range: the small bottom-row tiles of a 1080p frame fill up
+    the groups opened by the large ones instead of forming a tail group with almost no work per CTA, and
+    a tile that cannot fit the trunk kernel's TMEM row budget on its own still gets a (whole-frame kernel) group."""
+    rc, msg, st = plan(1080, 1920, 512, 10)
+    assert rc == 0 and st["groups"] < 6                        # contiguous ranges under the same row cap need six or more
+    rc, msg, big = plan(1080, 1920, 0, 10)                     # one 518k-pixel tile: 30 rows per CTA
+    assert rc == 0 and big["groups"] == 1 and big["trunk_groups"] == 0 and big["max_rows"] > 8
+    rc, msg, c3 = plan(2160, 3840, 512, 10)
+    assert rc == 0 and c3["tiles"] == 40 and c3["trunk_groups"] == c3["groups"] <= 20
 
 
 def test_small_devices_and_errors():
@@ -93,16 +106,3 @@ def test_small_devices_and_errors():
     assert rc != 0 and "odd" in msg
     rc, msg, _ = plan(1, 1, 0, 10)
     assert rc != 0
-
-
-def test_larger_cap_is_taken_only_when_it_saves_groups():
-    """Default plan: 200k-pixel groups, or the plan under a 15 % larger cap when that has strictly fewer groups."""
-    rc, msg, dflt = plan(2160, 3840, 512, 10)                  # 4K: 71k-pixel tiles go in threes under 230k, in twos under 200k
-    assert rc == 0, msg
-    rc, msg, fixed = plan(2160, 3840, 512, 10, cap=200000)
-    assert rc == 0, msg
-    assert dflt["groups"] < fixed["groups"] and dflt["trunk_groups"] == dflt["groups"] and dflt["max_rows"] <= 16
-    assert dflt["pixels"] == fixed["pixels"]
-    rc, msg, a = plan(1080, 1920, 512, 10)
-    rc2, msg2, b = plan(1080, 1920, 512, 10, cap=200000)
-    assert rc == 0 and rc2 == 0 and a == b                     # same group count either way: the default cap's plan is kept
