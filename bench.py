@@ -183,6 +183,75 @@ def preprocess_stage(eng, img, d_in, level=0.5, reps=5):
                              "sample": "the reference's own cv2 calls (nesr/nesr.py:668-689) on the whole frame"}}
 
 
+def other_configs(eng, dev, pk):
+    """BASELINE configs[0] and [4] on one GPU, device-resident, CUDA events inside the engine (median of 5 after 2 warm-ups):
+    C1 512x512 untiled; C5 256 -> 2048 in three iterations of ESRGAN + 2-member blend + adaptive sharpen, with the achieved
+    HBM bandwidth of the two stencil kernels at the last iteration's size (algorithmic bytes: blend 3*(K+1) B/px, sharpen 6 B/px)."""
+    import torch
+    rng = np.random.default_rng(5)
+
+    def u8(*shape):
+        return torch.from_numpy(rng.integers(0, 256, shape, dtype=np.uint8)).to(dev)
+
+    def med(fn, reps=5):
+        for _ in range(2):
+            fn()
+        ms = []
+        for _ in range(reps):
+            fn()
+            ms.append(eng.stats()["last_device_ms"])
+        return float(np.median(ms))
+
+    out = {}
+    img = u8(512, 512, 3)
+    o = torch.empty((1024, 1024, 3), dtype=torch.uint8, device=dev)
+    ms = med(lambda: eng.enhance_u8(img, tile=0, out=o))
+    out["C1"] = {"workload": "512x512 -> 1024x1024, tile=0", "ms": ms, "value": 1024 * 1024 / ms / 1e3, "unit": UNIT,
+                 "conv_tflops_algorithmic": 1024 * 1024 * FLOP_PER_OUT_PIXEL / ms / 1e9}
+    cur = u8(256, 256, 3)
+    stage = {"esrgan_ms": 0.0, "blend_ms": 0.0, "sharpen_ms": 0.0}
+    last = {}
+    for _ in range(3):
+        up = eng.enhance_u8(cur, tile=0)
+        stage["esrgan_ms"] += med(lambda: eng.enhance_u8(cur, tile=0, out=up))
+        other = up.flip(0).contiguous()                           # a second ensemble member of the same size
+        ens = torch.empty_like(up)
+        b_ms = med(lambda: eng.blend_u8([up, other], out=ens))
+        shp = torch.empty_like(up)
+        s_ms = med(lambda: eng.sharpen_u8(ens, out=shp))
+        stage["blend_ms"] += b_ms
+        stage["sharpen_ms"] += s_ms
+        px = up.shape[0] * up.shape[1]
+        last = {"size": f"{up.shape[1]}x{up.shape[0]}", "blend_gbs": 9 * px / b_ms / 1e6, "sharpen_gbs": 6 * px / s_ms / 1e6}
+        cur = shp
+    total = sum(stage.values())
+    out_px = 512 * 512 + 1024 * 1024 + 2048 * 2048
+    out["C5"] = {"workload": "256 -> 512 -> 1024 -> 2048: ESRGAN x2 + blend (K=2) + adaptive sharpen per iteration, stages device-resident",
+                 "ms": total, **stage, "value": out_px / total / 1e3, "unit": UNIT,
+                 "stencils_at": last.get("size"), "blend_hbm_frac": last.get("blend_gbs", 0) / pk["hbm"],
+                 "sharpen_hbm_frac": last.get("sharpen_gbs", 0) / pk["hbm"], "note": "2048x2048 x 3 B = 12.6 MB per image: these sizes live in L2"}
+    # the stencils at 4K, inputs larger than nothing: L2 flushed before every call
+    big = [u8(2160, 3840, 3) for _ in range(2)]
+    o = torch.empty_like(big[0])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flushed(fn):
+        ms = []
+        for it in range(6):
+            flush.fill_(it)
+            fn()
+            ms.append(eng.stats()["last_device_ms"])
+        return float(np.median(ms[2:]))
+
+    px = 2160 * 3840
+    b_ms, s_ms = flushed(lambda: eng.blend_u8(big, out=o)), flushed(lambda: eng.sharpen_u8(big[0], out=o))
+    out["stencils_4k"] = {"workload": "3840x2160 RGB u8, L2 flushed before every call", "blend_k2_ms": b_ms, "sharpen_ms": s_ms,
+                          "blend_gbs": 9 * px / b_ms / 1e6, "sharpen_gbs": 6 * px / s_ms / 1e6,
+                          "blend_hbm_frac": 9 * px / b_ms / 1e6 / pk["hbm"], "sharpen_hbm_frac": 6 * px / s_ms / 1e6 / pk["hbm"],
+                          "bound": "hbm", "peak_gbs": pk["hbm"]}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -254,23 +323,78 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, conv_ms, wall_ms, e2e_ms, trunk_ms = (float(v) for v in t.cpu())
 
-    c3 = None
-    if world > 1:                                 # BASELINE configs[2]: 4K->8K, tiles sharded, NCCL stitch
-        big = torch.from_numpy(frame(2160, 3840, 7)).to(dev)
-        big_out = torch.zeros((4320, 7680, 3), dtype=torch.uint8, device=dev)
-        for _ in range(2):
-            parallel.enhance_sharded(eng, big, TILE, HALO, out=big_out)
+    # ---- BASELINE configs[2]: 3840x2160 -> 7680x4320, tile 512 / halo 10, tiles sharded by cost over the ranks, ONE NCCL all_gather
+    # of the tile-major buffers (strong scaling; at one GPU it is the plain call, the base of the curve in the same run)
+    def all_ranks(value):
+        if world == 1:
+            return [value]
+        box = [None] * world
+        dist.all_gather_object(box, value)
+        return box
+
+    big_np = frame(2160, 3840, 7)                 # the same frame on every rank
+    big = torch.from_numpy(big_np).to(dev)
+    big_out = torch.empty((4320, 7680, 3), dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        parallel.enhance_sharded(eng, big, TILE, HALO, out=big_out)
+    barrier()
+    c3_steps = max(2, min(args.steps, 5))
+    c3_ms, phases = [], []
+    for _ in range(c3_steps):
+        flush.fill_(1)
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c3_steps = max(2, min(args.steps, 5))
+        tm = {}
         t0 = time.perf_counter()
-        for _ in range(c3_steps):
-            parallel.enhance_sharded(eng, big, TILE, HALO, out=big_out)
-        barrier()
-        c3_ms = torch.tensor([1e3 * (time.perf_counter() - t0) / c3_steps], dtype=torch.float64, device=dev)
-        dist.all_reduce(c3_ms, op=dist.ReduceOp.MAX)
-        c3 = {"workload": "3840x2160->7680x4320, 40 tiles sharded over ranks, NCCL all_reduce stitch", "scaling": "strong",
-              "ms_per_step": float(c3_ms), "value": 4320 * 7680 / (float(c3_ms) / 1e3) / 1e6, "unit": UNIT}
+        parallel.enhance_sharded(eng, big, TILE, HALO, out=big_out, timing=tm)
+        torch.cuda.synchronize()
+        mine = 1e3 * (time.perf_counter() - t0)
+        tm["device_ms"] = eng.stats()["last_device_ms"]
+        t = torch.tensor([mine], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c3_ms.append(float(t))
+        phases.append(tm)
+    c3_step = float(np.median(c3_ms))
+    ph = {k: float(np.median([p[k] for p in phases])) for k in ("compute_ms", "gather_ms", "unpack_ms", "device_ms")}
+    ph["cost"] = phases[-1].get("cost")
+    per_rank = all_ranks(ph)
+    bit_identical = None
+    if rank == 0 and world > 1:                   # the sharded frame against the un-sharded call on one GPU
+        whole = eng.enhance_u8(big, tile=TILE, tile_pad=HALO)
+        bit_identical = bool(torch.equal(whole, big_out))
+        del whole
+    c3 = {"workload": "3840x2160->7680x4320, 40 tiles (tile 512 halo 10) cut into contiguous ranges of equal padded-pixel cost, one per "
+                      "rank; tile-major buffers exchanged with ONE NCCL all_gather_into_tensor, pasted by one kernel per rank",
+          "scaling": "strong", "ms_per_step": c3_step, "value": 4320 * 7680 / (c3_step / 1e3) / 1e6, "unit": UNIT, "steps": c3_steps,
+          "timing": "wall clock around the call (host-blocking phases), max over ranks, median of the steps",
+          "bit_identical_to_one_gpu": bit_identical,
+          "per_rank": {"compute_ms": [round(p["compute_ms"], 3) for p in per_rank], "device_ms": [round(p["device_ms"], 3) for p in per_rank],
+                       "gather_ms": [round(p["gather_ms"], 3) for p in per_rank], "unpack_ms": [round(p["unpack_ms"], 3) for p in per_rank],
+                       "padded_feature_pixels": [p["cost"] for p in per_rank]}}
+    del big, big_out
+
+    # ---- BASELINE configs[3]: 256 frames of 512x512 (x2), frames dealt to the ranks, no collective (throughput mode)
+    n_frames = 256
+    f0, fc = parallel.partition(n_frames, world, rank)
+    base = frame(512, 512, 3)
+    rng = np.random.default_rng(100 + rank)
+    frames = torch.from_numpy(np.clip(base[None].astype(np.int16) + rng.integers(-8, 9, (fc, 512, 512, 3)), 0, 255).astype(np.uint8)).to(dev)
+    frames_out = torch.empty((fc, 1024, 1024, 3), dtype=torch.uint8, device=dev)
+    eng.enhance_batch_u8(frames[:4], tile=0, out=frames_out[:4])
+    barrier()
+    t0 = time.perf_counter()
+    eng.enhance_batch_u8(frames, tile=0, out=frames_out)
+    c4_dev = eng.stats()["last_device_ms"]
+    barrier()
+    c4_wall = 1e3 * (time.perf_counter() - t0)
+    t = torch.tensor([c4_dev, c4_wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    c4_dev, c4_wall = (float(v) for v in t.cpu())
+    c4 = {"workload": f"{n_frames} frames of 512x512 -> 1024x1024, untiled, {fc} frames per rank in one enhance_batch_u8 call, no collective",
+          "scaling": "strong", "ms": c4_dev, "wall_ms": c4_wall, "value": n_frames * 1024 * 1024 / (c4_dev / 1e3) / 1e6, "unit": UNIT,
+          "conv_tflops_algorithmic_per_gpu": fc * 1024 * 1024 * FLOP_PER_OUT_PIXEL / (c4_dev / 1e3) / 1e12}
+    del frames, frames_out
 
     if rank == 0:
         pk = peaks()
@@ -286,7 +410,7 @@ def run_ours(args):
         n_trunk = max(1, trunk_launches // args.steps)
         achieved = TRUNK_FLOP_PER_OUT_PIXEL * out_px / (trunk_step_ms / 1e3) / 1e12 if trunk_step_ms > 0 else 0.0
         traffic = None
-        prof = os.path.join(ROOT, "profiles", "r1_trunk_ncu_full.json")
+        prof = next((q for q in (os.path.join(ROOT, "profiles", n) for n in ("r2_trunk_ncu_full.json", "r1_trunk_ncu_full.json")) if os.path.exists(q)), "")
         if os.path.exists(prof):
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         launches = (s1["kernel_launches"] - s0["kernel_launches"])
@@ -323,15 +447,15 @@ def run_ours(args):
             "e2e": {"value": world * out_px / (e2e_ms / args.steps / 1e3) / 1e6, "unit": UNIT,
                     "h2d_bytes_per_step": H * W * 3, "d2h_bytes_per_step": out_px * 3, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["bf16_sustained"], "traffic": traffic,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["bf16_burst"], "traffic": traffic,
                          "kernel": f"conv3x3_trunk_kernel ({n_trunk} launches/step: one per L2-resident tile group, "
-                                   "414 layer passes of the 69 residual dense blocks each)",
+                                   "the 69 residual dense blocks as 8 merged sweeps each)",
                          "kernel_ms_per_launch": trunk_step_ms / n_trunk, "kernel_ms_per_step": trunk_step_ms,
                          "kernel_share_of_step": trunk_step_ms / ms_step,
                          "flop_per_launch_avg": TRUNK_FLOP_PER_OUT_PIXEL * out_px / n_trunk,
-                         "peak_source": pk["source"] + " (sustained: the kernel runs inside a long step)",
-                         "frac_of_burst": achieved / pk["bf16_burst"],
+                         "peak_source": pk["source"] + " bf16_tflops (burst; SURVEY 8d fixes it as the denominator)",
+                         "frac_of_sustained": achieved / pk["bf16_sustained"],
                          "whole_network": {"tflops": net_tflops, "conv_ms_per_step": conv_step_ms,
                                            "frac_of_sustained": net_tflops / pk["bf16_sustained"],
                                            "frac_of_burst": net_tflops / pk["bf16_burst"]}},
@@ -339,6 +463,8 @@ def run_ours(args):
             "parity": parity,
             "clocks": clocks,
             "c3": c3,
+            "c4": c4,
+            "configs": other_configs(eng, dev, pk) if world == 1 else None,
             "preprocess": pre,
         })
     if world > 1:

@@ -149,6 +149,21 @@ int nesr_b200_enhance_tiles_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32
                                int32_t tile_first, int32_t tile_count, uint8_t* out_bgr,
                                int64_t out_stride, int32_t flags);
 
+/* Tile-major form of enhance_tiles_u8 -- the multi-GPU exchange format ("each GPU stitches its tiles into its
+ * slice of the output ... one gather of stitched u8 output rows").  Tile k of the range [tile_first, tile_first + tile_count)
+ * is written into slot k of `slots` (DEVICE memory, slot_h rows of slot_w BGR pixels each, slots contiguous), its cropped
+ * output rectangle at the slot's origin: a rank's whole contribution is ONE contiguous buffer, the operand of a single
+ * ncclAllGather.  slot_w / slot_h >= tile * scale (the largest rectangle a tile pastes; reference tile_process:
+ * output_tile = out[.., (in_start - in_start_pad) * s : .. + (in_end - in_start) * s]). */
+int nesr_b200_enhance_tiles_packed_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32_t H, int32_t W, int64_t in_stride,
+                                      int32_t tile, int32_t tile_pad, int32_t pre_pad, int32_t tile_first, int32_t tile_count,
+                                      uint8_t* slots, int32_t slot_w, int32_t slot_h, int32_t flags);
+/* Inverse placement: slots (device) of tiles [tile_first, tile_first + tile_count) -> their rectangles in the full 2H x 2W
+ * frame `out_bgr` (device).  Called once per rank's slice of the gathered buffer; other pixels of the frame are untouched. */
+int nesr_b200_unpack_tiles_u8(nesr_b200_handle* h, const uint8_t* slots, int32_t slot_w, int32_t slot_h, int32_t H, int32_t W,
+                              int32_t tile, int32_t pre_pad, int32_t tile_first, int32_t tile_count, uint8_t* out_bgr,
+                              int64_t out_stride);
+
 /* Replaces: RRDBNet.forward / `upsampler.model(x)` (nesr/nesr.py:887-891,930-935): device fp32
  * NCHW [n, num_in_ch, H, W] in [0,1] -> device fp32 NCHW [n, num_out_ch, 2H, 2W], unclamped.
  * Both pointers are device memory; the work is enqueued on `stream` (a cudaStream_t, taken literally:

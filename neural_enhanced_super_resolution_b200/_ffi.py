@@ -24,7 +24,8 @@ EXPORTS = (
     "nesr_b200_enhance_batch_u8", "nesr_b200_tile_count", "nesr_b200_debug_plan", "nesr_b200_enhance_tiles_u8",
     "nesr_b200_forward_nchw_f32", "nesr_b200_blend_u8", "nesr_b200_sharpen_u8", "nesr_b200_get_stats",
     "nesr_b200_synchronize", "nesr_b200_debug_conv", "nesr_b200_preprocess_u8", "nesr_b200_debug_lab_table",
-    "nesr_b200_debug_nlm_weights", "nesr_b200_forward_nchw12_f32",
+    "nesr_b200_debug_nlm_weights", "nesr_b200_forward_nchw12_f32", "nesr_b200_enhance_tiles_packed_u8",
+    "nesr_b200_unpack_tiles_u8",
 )
 
 
@@ -80,6 +81,10 @@ def load_library() -> C.CDLL:
         lib.nesr_b200_debug_plan.argtypes = [C.c_int32] * 8 + [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
         lib.nesr_b200_enhance_tiles_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                                    C.c_int32, C.c_int32, C.c_int32, u8p, C.c_int64, C.c_int32]
+        lib.nesr_b200_enhance_tiles_packed_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                                          C.c_int32, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32]
+        lib.nesr_b200_unpack_tiles_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                  C.c_int32, u8p, C.c_int64]
         lib.nesr_b200_forward_nchw_f32.argtypes = [H, f32p, C.c_int32, C.c_int32, C.c_int32, f32p, C.c_void_p]
         lib.nesr_b200_forward_nchw12_f32.argtypes = [H, f32p, C.c_int32, C.c_int32, C.c_int32, f32p, C.c_void_p]
         lib.nesr_b200_blend_u8.argtypes = [H, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32,
@@ -241,6 +246,48 @@ class Engine:
         flags = (PTR_IN_DEVICE if idev else 0) | (PTR_OUT_DEVICE if odev else 0)
         self._check(self._lib.nesr_b200_enhance_tiles_u8(self._h, ip, h, w, w * 3, tile, tile_pad, pre_pad, first,
                                                          count, op, w * self.scale * 3, flags), "enhance_tiles_u8")
+        return out
+
+    def tile_costs(self, h: int, w: int, tile: int, tile_pad: int, pre_pad: int = 0):
+        """Padded feature pixels of every tile of upstream's row-major tile_process grid (the unit of conv work)."""
+        s = self.scale
+        mod = 2 if s == 2 else 1
+        hp, wp = -(-(h + pre_pad) // mod) * mod, -(-(w + pre_pad) // mod) * mod
+        if tile <= 0:
+            return [(hp // 2) * (wp // 2)]
+        costs = []
+        for y0 in range(0, hp, tile):
+            for x0 in range(0, wp, tile):
+                th = min(min(y0 + tile, hp) + tile_pad, hp) - max(y0 - tile_pad, 0)
+                tw = min(min(x0 + tile, wp) + tile_pad, wp) - max(x0 - tile_pad, 0)
+                costs.append((th // 2) * (tw // 2))
+        return costs
+
+    def slot_shape(self, h: int, w: int, tile: int):
+        """(slot_h, slot_w) of the tile-major exchange buffer: the largest output rectangle a tile pastes."""
+        s = self.scale
+        return ((min(tile, h) if tile > 0 else h) * s, (min(tile, w) if tile > 0 else w) * s)
+
+    def enhance_tiles_packed_u8(self, img, slots, tile: int, tile_pad: int, pre_pad: int, first: int, count: int):
+        """Tiles [first, first+count) into ``slots`` (CUDA uint8 [count, slot_h, slot_w, 3]), tile k at slot k's origin."""
+        h, w = img.shape[:2]
+        ip, idev = _image_ptr(img, self.device)
+        sp, sdev = _image_ptr(slots, self.device)
+        if not sdev or slots.shape[0] < count:
+            raise ValueError("slots must be a CUDA uint8 tensor with one slot per tile of the range")
+        flags = (PTR_IN_DEVICE if idev else 0) | PTR_OUT_DEVICE
+        self._check(self._lib.nesr_b200_enhance_tiles_packed_u8(self._h, ip, h, w, w * 3, tile, tile_pad, pre_pad, first, count, sp,
+                                                                slots.shape[2], slots.shape[1], flags), "enhance_tiles_packed_u8")
+        return slots
+
+    def unpack_tiles_u8(self, slots, out, h: int, w: int, tile: int, pre_pad: int, first: int, count: int):
+        """Paste the slots of tiles [first, first+count) into the full 2h x 2w frame ``out`` (both CUDA uint8)."""
+        sp, sdev = _image_ptr(slots, self.device)
+        op, odev = _image_ptr(out, self.device)
+        if not (sdev and odev):
+            raise ValueError("unpack_tiles_u8 works on CUDA tensors")
+        self._check(self._lib.nesr_b200_unpack_tiles_u8(self._h, sp, slots.shape[2], slots.shape[1], h, w, tile, pre_pad, first, count,
+                                                        op, out.shape[1] * 3), "unpack_tiles_u8")
         return out
 
     # -- RRDBNet.forward ---------------------------------------------------------------------

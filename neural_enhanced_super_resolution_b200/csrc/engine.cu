@@ -66,10 +66,10 @@ struct LevelPlan {
 };
 
 struct PlanKey {
-  int n_frames = -1, H = 0, W = 0, tile = 0, tile_pad = 0, pre_pad = 0, first = 0, count = 0, whole = 0;
+  int n_frames = -1, H = 0, W = 0, tile = 0, tile_pad = 0, pre_pad = 0, first = 0, count = 0, whole = 0, packed = 0;
   bool operator==(const PlanKey& o) const {
     return n_frames == o.n_frames && H == o.H && W == o.W && tile == o.tile && tile_pad == o.tile_pad &&
-           pre_pad == o.pre_pad && first == o.first && count == o.count && whole == o.whole;
+           pre_pad == o.pre_pad && first == o.first && count == o.count && whole == o.whole && packed == o.packed;
   }
 };
 
@@ -165,6 +165,7 @@ struct nesr_b200_handle {
   int debug_flags = 0;        // NESR_B200_DEBUG_FLAGS: timing experiments (results are wrong when set)
   int shared_g = 1;           // NESR_B200_SHARED_G: growth planes of the dense-block buffers single-buffered (trunk kernel path; 0: classic ping-pong of all three planes)
   int l2_pin_chunks = 1;      // NESR_B200_L2_PIN: dense-block planes whose loads are tagged evict_last in the trunk passes
+  int max_pieces = 0;         // NESR_B200_MAX_PIECES: remainder pieces packed into one strip of a trunk group (0: the planner picks)
 };
 
 namespace {
@@ -412,7 +413,7 @@ void layout_level(Batch& b, int level) {
 // halo rows a band costs are paid as rarely as possible.
 // max_rows > 0 (level 0 of a trunk-kernel group): no CTA gets more output rows than its TMEM row slots; returns false (and
 // leaves an incomplete schedule) when the group does not fit under that limit.
-bool build_fold_schedule(Batch& b, int level, int num_sms, int max_rows = 0) {
+bool build_fold_schedule(Batch& b, int level, int num_sms, int max_rows = 0, int max_pieces = 3) {
   LevelPlan& lp = b.lv[level];
   struct Strip { int32_t seg0, nseg, h; };
   std::vector<Strip> strips;
@@ -437,7 +438,7 @@ bool build_fold_schedule(Batch& b, int level, int num_sms, int max_rows = 0) {
   if (!cols.empty()) {
     // every piece costs the TMA producer at least one more operation per slab row; with 8 pieces a packed strip's
     // CTAs were producer-bound and paced the whole group (9.3 instead of 6.7 ms), with 11 one-box operations likewise
-    static const int kMaxPieces = getenv("NESR_B200_MAX_PIECES") ? atoi(getenv("NESR_B200_MAX_PIECES")) : 6;
+    const int kMaxPieces = std::max(1, std::min(max_pieces, kMaxFoldSegs));
     struct Packed { std::vector<Piece> pcs; int lanes = 0, h = 0; };
     auto plan = [&](int T, std::vector<Packed>* out) -> int64_t {
       std::vector<Piece> pcs;
@@ -483,7 +484,11 @@ bool build_fold_schedule(Batch& b, int level, int num_sms, int max_rows = 0) {
   }
   int64_t total_rows = 0;
   for (const Strip& st : strips) total_rows += st.h;
-  const int min_rows = 4;                                      // do not spread tiny work over every SM
+  // Tiny groups: the edge-layer kernels (one launch per layer) prefer a few CTAs with >= 4 rows each over 148 CTAs with a
+  // row each (per-CTA weight loads); the trunk kernel (max_rows > 0) is latency bound per sweep -- a band of n rows costs
+  // n + 2 slab rows in every one of its 552 sweeps -- so its rows are spread over all SMs.
+  static const int kTrunkMinRows = getenv("NESR_B200_MIN_ROWS") ? atoi(getenv("NESR_B200_MIN_ROWS")) : 1;
+  const int min_rows = max_rows > 0 ? std::max(1, kTrunkMinRows) : 4;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms, total_rows / min_rows));
   // Contiguous runs of equal COST: a band of n rows costs n + 2 slab rows (its halo), so a CTA whose run crosses a
   // strip boundary gets fewer output rows.  The smallest per-run budget that covers everything is found by bisection.
@@ -595,16 +600,41 @@ bool trunk_schedule_fits(const LevelPlan& lp) {
 
 // Host half of the plan (no CUDA calls): tiles of the frame(s), split into tile groups, every level's flat layout and
 // row-folded schedule, and the trunk kernel's halo dependency lists.  Fills h->batches.
-int plan_groups_with_cap(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w, int64_t default_cap);
+int plan_groups_with_cap(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w, int64_t default_cap, int pieces);
 
 // Default cap of the product path: a tile group is at most 8 output rows (the trunk kernel's TMEM row slots) of 128 pixels on
 // each of the SMs, which also keeps its dense-block working set (~1 KB per feature pixel, about half of it live) inside the
 // 126 MB L2.  The schedule decides whether a tile still fits; the pixel cap only prunes the candidates.
+// The narrow right-hand remainder columns of the tiles are cut into pieces that are packed side by side into strips; more pieces
+// per strip mean fewer strip rows (a 1080p frame: 6 groups with 3 pieces, 5 with 4) but more TMA operations per slab row in the
+// CTAs that own them.  Measured (profiles/r2_plan_sweep.txt): a launch costs ~0.27 ms + 0.214 ms per slab row of its busiest CTA,
+// plus ~0.12 ms for every piece beyond five.  The planner evaluates 3..6 pieces with that model and keeps the cheapest plan.
 int plan_groups(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
-  return plan_groups_with_cap(h, key, out_h, out_w, (int64_t)kTrunkMaxRows * kBlockPixels * h->num_sms);
+  const int64_t cap = (int64_t)kTrunkMaxRows * kBlockPixels * h->num_sms;
+  if (h->cfg.conv_impl != 0 || h->max_pieces > 0) return plan_groups_with_cap(h, key, out_h, out_w, cap, h->max_pieces > 0 ? h->max_pieces : 3);
+  double best = 1e30;
+  std::vector<Batch> keep;
+  for (int pieces = 3; pieces <= 6; ++pieces) {
+    h->batches.clear();
+    const int rc = plan_groups_with_cap(h, key, out_h, out_w, cap, pieces);
+    if (rc != NESR_OK) return rc;
+    double score = 0;
+    for (const Batch& b : h->batches) {
+      int busiest = 0;
+      for (int c = 0; c < b.lv[0].fold_grid; ++c) {
+        int cost = 0;
+        for (int q = b.lv[0].cta_off[c]; q < b.lv[0].cta_off[c + 1]; ++q) cost += b.lv[0].bands[q].rows + 2;
+        busiest = std::max(busiest, cost);
+      }
+      score += 0.27 + 0.214 * busiest + (b.trunk_fits ? 0.12 * std::max(0, pieces - 5) : 1.0 * busiest);   // a whole-frame-kernel group is ~5x slower
+    }
+    if (score < best - 1e-9) { best = score; keep = std::move(h->batches); }
+  }
+  h->batches = std::move(keep);
+  return NESR_OK;
 }
 
-int plan_groups_with_cap(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w, int64_t default_cap) {
+int plan_groups_with_cap(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w, int64_t default_cap, int pieces) {
   const int scale = h->cfg.scale;
   const Grid g = tile_grid_dims(key.H, key.W, key.tile, key.pre_pad, scale);
   std::vector<TileGeom> all;
@@ -637,6 +667,9 @@ int plan_groups_with_cap(nesr_b200_handle* h, const PlanKey& key, int out_h, int
       t.out_y0 = y0 * scale; t.out_x0 = x0 * scale;
       t.crop_h = std::max(0, std::min((y1 - y0) * scale, out_h - t.out_y0));
       t.crop_w = std::max(0, std::min((x1 - x0) * scale, out_w - t.out_x0));
+      if (key.packed) {                 // tile-major output: tile k of the range is "frame" k of the slot buffer, pasted at its origin
+        t.frame = ti - first; t.out_y0 = 0; t.out_x0 = 0;
+      }
       all.push_back(t);
     }
   // Split into batches (tile groups) bounded by feature pixels.  Product path (conv_impl 0): a group's dense-block
@@ -647,7 +680,7 @@ int plan_groups_with_cap(nesr_b200_handle* h, const PlanKey& key, int out_h, int
   // level-0 schedule of a group and whether the TMEM-resident trunk kernel can run it
   auto sched0 = [&](Batch& bb) {                                // row-capped for the trunk kernel; a group that cannot fit keeps the free schedule
     layout_level(bb, 0);
-    if (!l2_groups || !build_fold_schedule(bb, 0, h->num_sms, kTrunkMaxRows)) build_fold_schedule(bb, 0, h->num_sms);
+    if (!l2_groups || !build_fold_schedule(bb, 0, h->num_sms, kTrunkMaxRows, pieces)) build_fold_schedule(bb, 0, h->num_sms);
   };
   auto fits0 = [&](const Batch& bb) { return trunk_schedule_fits(bb.lv[0]); };
   auto tile_px = [&](const TileGeom& t) { return (int64_t)t.lv[0].h * t.lv[0].pitch; };
@@ -696,6 +729,19 @@ int plan_groups_with_cap(nesr_b200_handle* h, const PlanKey& key, int out_h, int
       b.trunk_fits = !b.lv[0].deps.empty();
     }
     if (b.lv[2].pixels >= ((int64_t)1 << 31) - 4096) return fail(h, NESR_E_INVALID, "batch too large for 32-bit pixel indices");
+    if (getenv("NESR_B200_PLAN_DEBUG")) {
+      int64_t px = 0, rows = 0;
+      for (const TileGeom& t : b.tiles) px += tile_px(t);
+      for (const FoldBand& fb : b.lv[0].bands) rows += fb.rows;
+      int max_cost = 0;
+      for (int c = 0; c < b.lv[0].fold_grid; ++c) {
+        int cost = 0;
+        for (int q = b.lv[0].cta_off[c]; q < b.lv[0].cta_off[c + 1]; ++q) cost += b.lv[0].bands[q].rows + 2;
+        max_cost = std::max(max_cost, cost);
+      }
+      fprintf(stderr, "nesr_b200 plan: group %zu: %zu tiles, %lld px, %lld strip rows on %d CTAs, %zu bands, max slab rows per CTA %d, trunk %d (deps %s)\n", h->batches.size(),
+              b.tiles.size(), (long long)px, (long long)rows, b.lv[0].fold_grid, b.lv[0].bands.size(), max_cost, (int)b.trunk_fits, b.lv[0].deps.empty() ? "none" : "ok");
+    }
     h->batches.push_back(std::move(b));
   }
   return NESR_OK;
@@ -1091,18 +1137,19 @@ int ensure(nesr_b200_handle* h, uint8_t** buf, size_t* cap, size_t need) {
 
 int enhance_impl(nesr_b200_handle* h, const uint8_t* in, int n_frames, int H, int W, int64_t in_stride,
                  int64_t in_frame_stride, int tile, int tile_pad, int pre_pad, int first, int count, int whole,
-                 uint8_t* out, int64_t out_stride, int64_t out_frame_stride, int flags) {
+                 uint8_t* out, int64_t out_stride, int64_t out_frame_stride, int flags, int packed = 0) {
   if (!h) return NESR_E_INVALID;
   if (!h->finalized) return fail(h, NESR_E_STATE, "weights not finalized");
   if (!in || !out || n_frames < 1 || H < 2 || W < 2) return fail(h, NESR_E_INVALID, "bad image arguments (H=%d W=%d n=%d)", H, W, n_frames);
   if (tile < 0 || tile_pad < 0 || pre_pad < 0 || pre_pad >= H || pre_pad >= W)
     return fail(h, NESR_E_INVALID, "bad tile/pad arguments (tile=%d tile_pad=%d pre_pad=%d)", tile, tile_pad, pre_pad);
-  if (in_stride < (int64_t)W * 3 || out_stride < (int64_t)W * h->cfg.scale * 3) return fail(h, NESR_E_INVALID, "row stride smaller than a row");
+  if (in_stride < (int64_t)W * 3 || (!packed && out_stride < (int64_t)W * h->cfg.scale * 3)) return fail(h, NESR_E_INVALID, "row stride smaller than a row");
+  if (packed && (n_frames != 1 || !(flags & NESR_PTR_OUT_DEVICE))) return fail(h, NESR_E_INVALID, "tile-major output needs one frame and a device buffer");
   DEVICE_SCOPE(h);
   if (int wrc = wait_external(h)) return wrc;
   const int s = h->cfg.scale, OH = H * s, OW = W * s;
   PlanKey key; key.n_frames = n_frames; key.H = H; key.W = W; key.tile = tile; key.tile_pad = tile_pad;
-  key.pre_pad = pre_pad; key.first = first; key.count = count; key.whole = whole;
+  key.pre_pad = pre_pad; key.first = first; key.count = count; key.whole = whole; key.packed = packed;
   int rc = build_plan(h, key, OH, OW);
   if (rc) return rc;
 
@@ -1130,7 +1177,7 @@ int enhance_impl(nesr_b200_handle* h, const uint8_t* in, int n_frames, int H, in
   cudaEventRecord(h->ev0, h->stream);
   h->n_trunk_timed = 0;
   PackParams pk{};
-  pk.in_u8 = d_in; pk.in_stride = d_in_stride; pk.in_frame_stride = d_in_fs; pk.H = H; pk.W = W; pk.pre_pad = pre_pad;
+  pk.in_u8 = d_in; pk.in_stride = d_in_stride; pk.in_frame_stride = packed ? 0 : d_in_fs; pk.H = H; pk.W = W; pk.pre_pad = pre_pad;
   Sink sink; sink.out_u8 = d_out; sink.out_stride = d_out_stride; sink.out_frame_stride = d_out_fs;
   // Host output of a whole frame: every tile group's stitched rectangles go back on a second stream while the next group
   // computes (the tiles' crop rectangles partition the frame).  A tile range keeps the single full-frame copy.
@@ -1250,6 +1297,7 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
 #endif
   if (const char* pin = getenv("NESR_B200_L2_PIN")) h->l2_pin_chunks = atoi(pin);
   if (const char* sg = getenv("NESR_B200_SHARED_G")) h->shared_g = atoi(sg);
+  if (const char* mp = getenv("NESR_B200_MAX_PIECES")) h->max_pieces = atoi(mp);
   if (const char* al = getenv("NESR_B200_ARENA_LIMIT_MB")) h->arena_limit = (size_t)atoll(al) << 20;
   *out = h;
   return NESR_OK;
@@ -1506,6 +1554,36 @@ int nesr_b200_enhance_tiles_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32
                                int64_t out_stride, int32_t flags) {
   if (tile_count == 0) return NESR_OK;
   return enhance_impl(h, in_bgr, 1, H, W, in_stride, 0, tile, tile_pad, pre_pad, tile_first, tile_count, 0, out_bgr, out_stride, 0, flags);
+}
+
+int nesr_b200_enhance_tiles_packed_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32_t H, int32_t W, int64_t in_stride, int32_t tile,
+                                      int32_t tile_pad, int32_t pre_pad, int32_t tile_first, int32_t tile_count, uint8_t* slots,
+                                      int32_t slot_w, int32_t slot_h, int32_t flags) {
+  if (tile_count == 0) return NESR_OK;
+  if (!h) return NESR_E_INVALID;
+  const int s = h->cfg.scale;
+  const int need_w = (tile > 0 ? std::min(tile, W) : W) * s, need_h = (tile > 0 ? std::min(tile, H) : H) * s;
+  if (slot_w < need_w || slot_h < need_h) return fail(h, NESR_E_INVALID, "tile slot %dx%d smaller than a tile's output %dx%d", slot_w, slot_h, need_w, need_h);
+  return enhance_impl(h, in_bgr, 1, H, W, in_stride, 0, tile, tile_pad, pre_pad, tile_first, tile_count, 0, slots, (int64_t)slot_w * 3,
+                      (int64_t)slot_w * 3 * slot_h, flags | NESR_PTR_OUT_DEVICE, 1);
+}
+
+int nesr_b200_unpack_tiles_u8(nesr_b200_handle* h, const uint8_t* slots, int32_t slot_w, int32_t slot_h, int32_t H, int32_t W, int32_t tile,
+                              int32_t pre_pad, int32_t tile_first, int32_t tile_count, uint8_t* out_bgr, int64_t out_stride) {
+  if (tile_count == 0) return NESR_OK;
+  if (!h) return NESR_E_INVALID;
+  if (!slots || !out_bgr || H < 1 || W < 1 || tile < 0 || tile_first < 0 || tile_count < 0) return fail(h, NESR_E_INVALID, "unpack_tiles: bad arguments");
+  DEVICE_SCOPE(h);
+  if (int wrc = wait_external(h)) return wrc;
+  const int s = h->cfg.scale;
+  const Grid g = tile_grid_dims(H, W, tile, pre_pad, s);
+  if (tile_first + tile_count > g.tiles_x * g.tiles_y) return fail(h, NESR_E_INVALID, "unpack_tiles: tile range outside the grid");
+  cudaError_t e = launch_unpack_tiles(slots, slot_w, slot_h, g.tiles_x, (tile > 0 ? tile : std::max(H, W)) * s, H * s, W * s, tile_first, tile_count, out_bgr,
+                                      out_stride, h->stream);
+  h->stats.kernel_launches++;
+  if (e != cudaSuccess) return fail(h, NESR_E_CUDA, "unpack_tiles launch failed: %s", cudaGetErrorString(e));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return NESR_OK;
 }
 
 namespace {

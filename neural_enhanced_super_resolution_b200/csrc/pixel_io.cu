@@ -62,4 +62,37 @@ cudaError_t launch_pack(const PackParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+namespace {
+// One block per (tile, 8 output rows): copies the tile's rectangle from its slot to its place in the frame, 16 bytes per
+// thread where both sides allow it (tile origins are multiples of tile_out * 3 bytes; edge tiles and odd strides fall back to bytes).
+__global__ void __launch_bounds__(256) unpack_tiles_kernel(const uint8_t* __restrict__ slots, int slot_w, int slot_h, int tiles_x, int tile_out,
+                                                           int out_h, int out_w, int first, uint8_t* __restrict__ out, int64_t out_stride) {
+  const int k = blockIdx.y, t = first + k;
+  const int ty = t / tiles_x, tx = t - ty * tiles_x;
+  const int y0 = ty * tile_out, x0 = tx * tile_out;
+  const int h = min(tile_out, out_h - y0), w = min(tile_out, out_w - x0);
+  if (h <= 0 || w <= 0) return;
+  const uint8_t* src = slots + static_cast<size_t>(k) * slot_w * 3 * slot_h;
+  const int64_t row_bytes = static_cast<int64_t>(w) * 3;
+  for (int r = blockIdx.x * 8; r < min(h, blockIdx.x * 8 + 8); ++r) {
+    const uint8_t* s = src + static_cast<size_t>(r) * slot_w * 3;
+    uint8_t* d = out + static_cast<int64_t>(y0 + r) * out_stride + static_cast<int64_t>(x0) * 3;
+    if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d) | static_cast<uintptr_t>(row_bytes)) & 15) == 0) {
+      for (int64_t i = threadIdx.x; i < row_bytes / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(d)[i] = __ldg(reinterpret_cast<const uint4*>(s) + i);
+    } else {
+      for (int64_t i = threadIdx.x; i < row_bytes; i += blockDim.x) d[i] = s[i];
+    }
+  }
+}
+}  // namespace
+
+cudaError_t launch_unpack_tiles(const uint8_t* slots, int slot_w, int slot_h, int tiles_x, int tile_out, int out_h, int out_w, int first,
+                                int count, uint8_t* out, int64_t out_stride, cudaStream_t stream) {
+  if (count <= 0) return cudaSuccess;
+  const int rows = tile_out < out_h ? tile_out : out_h;
+  unpack_tiles_kernel<<<dim3((rows + 7) / 8, count), 256, 0, stream>>>(slots, slot_w, slot_h, tiles_x, tile_out, out_h, out_w, first, out, out_stride);
+  return cudaGetLastError();
+}
+
 }  // namespace nesr

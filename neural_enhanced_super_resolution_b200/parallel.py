@@ -1,18 +1,22 @@
 """Multi-GPU sharding of the upscaling stage: one process per GPU (``torch.distributed``, NCCL).
 
 The path shards without any data-path exchange: tiles (with their halos) and frames are independent
-forwards, weights are replicated (33 MB).  The only collective is the final stitch of the u8 output:
+forwards, weights are replicated (33 MB).  The only collective is the final gather of the u8 output:
 
   * ``enhance_sharded``        -- BASELINE config 3: the row-major tile grid of ONE frame is cut into
-    ``world_size`` contiguous, equally sized ranges; every rank pastes its tiles into a zero-filled
-    full-size u8 frame and ONE ``all_reduce(SUM)`` over NCCL/NVLink merges the disjoint supports
-    (<= 100 MB for an 8K frame; the ranges are disjoint so the sum is a gather).
+    ``world_size`` contiguous ranges of equal COST (padded feature pixels, ``partition_by_cost``); every rank
+    writes its tiles TILE-MAJOR into one contiguous buffer (``nesr_b200_enhance_tiles_packed_u8``), ONE
+    ``all_gather_into_tensor`` over NCCL/NVLink exchanges the buffers (each rank sends only its own pixels: 1/N of
+    the frame, ~12 MB at 8 GPUs for an 8K frame) and one small kernel per rank pastes the slots into the frame
+    (``nesr_b200_unpack_tiles_u8``).  With one rank it is the plain ``enhance_u8`` call.
   * ``enhance_frames_sharded`` -- BASELINE config 4: frames are dealt round-robin-contiguously to ranks;
     no collective unless the caller asks for the frames back (``gather=True``).
 
 The reference has no distributed code at all; this module is new surface.
 """
 from __future__ import annotations
+
+import time
 
 import numpy as np
 import torch
@@ -26,33 +30,84 @@ def partition(n_items: int, world_size: int, rank: int) -> tuple[int, int]:
     return first, base + (1 if rank < extra else 0)
 
 
+def partition_by_cost(costs, world_size: int):
+    """Contiguous split of ``costs`` into ``world_size`` ranges minimising the largest range sum: ``[(first, count)]``.
+    (Bisection on the bound + greedy fill; ranges may be empty when there are fewer items than ranks.)"""
+    costs = [int(c) for c in costs]
+    n = len(costs)
+
+    def fill(bound):
+        parts, i = [], 0
+        for r in range(world_size):
+            first, acc = i, 0
+            while i < n and acc + costs[i] <= bound and (n - i) > 0:
+                acc += costs[i]
+                i += 1
+            parts.append((first, i - first))
+        return parts if i == n else None
+
+    lo, hi = (max(costs) if costs else 0), sum(costs)
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if fill(mid) is None:
+            lo = mid + 1
+        else:
+            hi = mid
+    return fill(lo)
+
+
 def _world(group):
     if dist.is_available() and dist.is_initialized():
         return dist.get_world_size(group), dist.get_rank(group)
     return 1, 0
 
 
-def enhance_sharded(engine, img_bgr, tile: int, tile_pad: int, pre_pad: int = 0, group=None, out=None):
+def enhance_sharded(engine, img_bgr, tile: int, tile_pad: int, pre_pad: int = 0, group=None, out=None, timing=None):
     """Tile-sharded ``RealESRGANer.enhance`` of one frame; every rank returns the full x2 frame.
 
-    ``engine`` needs ``tile_count`` / ``enhance_tiles_u8`` / ``scale`` (an ``_ffi.Engine``);
-    ``img_bgr`` is a CUDA uint8 tensor (NCCL) or a numpy array (gloo tests)."""
+    ``engine`` needs ``tile_costs`` / ``slot_shape`` / ``enhance_tiles_packed_u8`` / ``unpack_tiles_u8`` / ``enhance_u8`` /
+    ``scale`` (an ``_ffi.Engine``); ``img_bgr`` is a CUDA uint8 tensor (NCCL) or a numpy array (gloo tests).
+    ``timing``: a dict that receives this rank's ``compute_ms`` / ``gather_ms`` / ``unpack_ms`` (wall clock, phases are
+    synchronous) and its tile range."""
     world, rank = _world(group)
     h, w = img_bgr.shape[:2]
     s = engine.scale
-    n_tiles = engine.tile_count(h, w, tile, pre_pad)
-    first, count = partition(n_tiles, world, rank)
     on_device = isinstance(img_bgr, torch.Tensor)
+    if world == 1:
+        t0 = time.perf_counter()
+        out = engine.enhance_u8(img_bgr, tile=tile, tile_pad=tile_pad, pre_pad=pre_pad, out=out)
+        if timing is not None:
+            timing.update(compute_ms=1e3 * (time.perf_counter() - t0), gather_ms=0.0, unpack_ms=0.0, tiles=None)
+        return out
+    parts = partition_by_cost(engine.tile_costs(h, w, tile, tile_pad, pre_pad), world)
+    first, count = parts[rank]
+    slots_per_rank = max(c for _, c in parts)
+    sh, sw = engine.slot_shape(h, w, tile)
     if out is None:
-        out = (torch.zeros((h * s, w * s, 3), dtype=torch.uint8, device=img_bgr.device) if on_device
-               else np.zeros((h * s, w * s, 3), np.uint8))
+        out = (torch.empty((h * s, w * s, 3), dtype=torch.uint8, device=img_bgr.device) if on_device
+               else np.empty((h * s, w * s, 3), np.uint8))
+    if on_device:
+        gathered = torch.empty((world, slots_per_rank, sh, sw, 3), dtype=torch.uint8, device=img_bgr.device)
+        mine = torch.empty((slots_per_rank, sh, sw, 3), dtype=torch.uint8, device=img_bgr.device)
     else:
-        out.zero_() if on_device else out.fill(0)
+        gathered = torch.empty((world, slots_per_rank, sh, sw, 3), dtype=torch.uint8)
+        mine = np.zeros((slots_per_rank, sh, sw, 3), np.uint8)
+    t0 = time.perf_counter()
     if count:
-        engine.enhance_tiles_u8(img_bgr, out, tile, tile_pad, pre_pad, first, count)
-    if world > 1:
-        t = out if on_device else torch.from_numpy(out)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)      # disjoint supports: sum == stitch
+        engine.enhance_tiles_packed_u8(img_bgr, mine, tile, tile_pad, pre_pad, first, count)
+    t1 = time.perf_counter()
+    send = mine if on_device else torch.from_numpy(mine)
+    dist.all_gather_into_tensor(gathered.view(-1), send.reshape(-1), group=group)
+    if on_device:
+        torch.cuda.current_stream(img_bgr.device).synchronize()
+    t2 = time.perf_counter()
+    for r, (f, c) in enumerate(parts):                             # every rank pastes every rank's slots (its own included)
+        if c:
+            engine.unpack_tiles_u8(gathered[r] if on_device else gathered[r].numpy(), out, h, w, tile, pre_pad, f, c)
+    t3 = time.perf_counter()
+    if timing is not None:
+        timing.update(compute_ms=1e3 * (t1 - t0), gather_ms=1e3 * (t2 - t1), unpack_ms=1e3 * (t3 - t2), tiles=(first, count),
+                      cost=sum(engine.tile_costs(h, w, tile, tile_pad, pre_pad)[first:first + count]))
     return out
 
 

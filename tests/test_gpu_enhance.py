@@ -197,6 +197,27 @@ def test_batch_tiles_and_multibatch_are_bit_identical(up_random):
     assert np.array_equal(small.enhance_u8(img, tile=32, tile_pad=4), singles[0])
 
 
+def test_tile_major_exchange_format_reassembles_the_frame(up_random):
+    """The multi-GPU exchange format on one GPU: every "rank's" cost-balanced tile range written tile-major
+    (nesr_b200_enhance_tiles_packed_u8), pasted back (nesr_b200_unpack_tiles_u8) == the whole-frame call, bit for bit --
+    ragged edge tiles, odd image sizes and a pre-pad included."""
+    eng = up_random.model.engine()
+    for (h, w), tile, pad, pre, world in (((150, 200), 64, 6, 0, 3), ((96, 130), 32, 4, 0, 8), ((75, 101), 48, 8, 4, 2), ((64, 80), 0, 10, 0, 2)):
+        img = torch.from_numpy(natural_image(h, w, seed=h + w)).cuda()
+        want = eng.enhance_u8(img, tile=tile, tile_pad=pad, pre_pad=pre)
+        parts = parallel.partition_by_cost(eng.tile_costs(h, w, tile, pad, pre), world)
+        assert sum(c for _, c in parts) == eng.tile_count(h, w, tile, pre)
+        sh, sw = eng.slot_shape(h, w, tile)
+        out = torch.full((2 * h, 2 * w, 3), 7, dtype=torch.uint8, device="cuda")
+        for first, count in parts:
+            if not count:
+                continue
+            slots = torch.zeros((count, sh, sw, 3), dtype=torch.uint8, device="cuda")
+            eng.enhance_tiles_packed_u8(img, slots, tile, pad, pre, first, count)
+            eng.unpack_tiles_u8(slots, out, h, w, tile, pre, first, count)
+        assert torch.equal(out, want), (h, w, tile)
+
+
 def test_device_tensor_in_out(up_random):
     img = natural_image(64, 80, seed=1)
     host, _ = up_random.enhance(img)

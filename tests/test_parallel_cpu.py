@@ -11,7 +11,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from neural_enhanced_super_resolution_b200.parallel import enhance_frames_sharded, enhance_sharded, partition
+from neural_enhanced_super_resolution_b200 import _ffi
+from neural_enhanced_super_resolution_b200.parallel import enhance_frames_sharded, enhance_sharded, partition, partition_by_cost
 
 
 def test_partition_is_balanced_and_contiguous():
@@ -26,6 +27,33 @@ def test_partition_is_balanced_and_contiguous():
                 pos += count
     assert [partition(40, 8, r)[1] for r in range(8)] == [5] * 8          # BASELINE config 3
     assert [partition(12, 8, r)[1] for r in range(8)] == [2, 2, 2, 2, 1, 1, 1, 1]
+
+
+def test_partition_by_cost_minimises_the_largest_share():
+    rng = np.random.default_rng(4)
+    for n in (0, 1, 3, 12, 40):
+        costs = [int(c) for c in rng.integers(1, 100, n)]
+        for world in (1, 2, 3, 8):
+            parts = partition_by_cost(costs, world)
+            assert len(parts) == world and sum(c for _, c in parts) == n
+            pos = 0
+            for first, count in parts:
+                assert first == pos
+                pos += count
+            best = max((sum(costs[f:f + c]) for f, c in parts), default=0)
+            # brute force over contiguous splits for small cases
+            if n <= 12 and world <= 3 and n:
+                import itertools
+                opt = min(max(sum(costs[a:b]) for a, b in zip((0,) + cut, cut + (n,)))
+                          for cut in itertools.combinations_with_replacement(range(n + 1), world - 1))
+                assert best == opt
+    # BASELINE config 3: the 8 x 5 tile grid of a 4K frame (last column half as wide, last row a fifth as tall) over 8 ranks:
+    # the largest share is within 13 % of the mean (tiles are atomic), where equal COUNTS (5 each) would be 25 % over
+    costs = _ffi.Engine.tile_costs(type("E", (), {"scale": 2})(), 2160, 3840, 512, 10)
+    assert len(costs) == 40
+    shares = [sum(costs[f:f + c]) for f, c in partition_by_cost(costs, 8)]
+    by_count = [sum(costs[f:f + c]) for f, c in (partition(40, 8, r) for r in range(8))]
+    assert max(shares) <= 1.13 * sum(costs) / 8 and max(shares) < max(by_count)
 
 
 class OracleTileEngine:
@@ -53,6 +81,33 @@ class OracleTileEngine:
         for t in tile_grid(hp, wp, tile, tile_pad)[first:first + count]:
             ys, ye, xs, xe = t.y0 * 2, min(t.y1 * 2, 2 * h), t.x0 * 2, min(t.x1 * 2, 2 * w)
             out[ys:ye, xs:xe] = full[ys:ye, xs:xe]
+        return out
+
+    tile_costs = _ffi.Engine.tile_costs
+    slot_shape = _ffi.Engine.slot_shape
+
+    def enhance_u8(self, img, tile=0, tile_pad=10, pre_pad=0, out=None):
+        return self._mk(tile, tile_pad, pre_pad).enhance(img)[0]
+
+    def _rects(self, h, w, tile, pre_pad):
+        hp, wp = h + pre_pad, w + pre_pad
+        hp, wp = hp + hp % 2, wp + wp % 2
+        rects = []
+        for y0 in range(0, hp, tile):
+            for x0 in range(0, wp, tile):
+                rects.append((2 * y0, min(2 * min(y0 + tile, hp), 2 * h), 2 * x0, min(2 * min(x0 + tile, wp), 2 * w)))
+        return rects
+
+    def enhance_tiles_packed_u8(self, img, slots, tile, tile_pad, pre_pad, first, count):
+        h, w = img.shape[:2]
+        full, _ = self._mk(tile, tile_pad, pre_pad).enhance(img)
+        for k, (ys, ye, xs, xe) in enumerate(self._rects(h, w, tile, pre_pad)[first:first + count]):
+            slots[k, :ye - ys, :xe - xs] = full[ys:ye, xs:xe]
+        return slots
+
+    def unpack_tiles_u8(self, slots, out, h, w, tile, pre_pad, first, count):
+        for k, (ys, ye, xs, xe) in enumerate(self._rects(h, w, tile, pre_pad)[first:first + count]):
+            out[ys:ye, xs:xe] = slots[k, :ye - ys, :xe - xs]
         return out
 
     def enhance_batch_u8(self, frames, tile=0, tile_pad=10, pre_pad=0):
