@@ -76,6 +76,32 @@ __global__ void __launch_bounds__(256) blend_kernel_k(const BlendParams p, const
   }
 }
 
+// Two members with weights exactly 0.5 (the reference's 1/K for K = 2): f32(a * 0.5) and f32(acc + b * 0.5) are exact (multiples of
+// 0.5 below 256), so the truncated result is floor((a + b) / 2) -- one SIMD halving add per four bytes ("K=2 => exactly
+// (a+b)>>1").  No conversions, no f64: the kernel is a pure stream of 16-byte loads and stores, four vectors in flight per thread.
+__global__ void __launch_bounds__(256) blend_half_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint8_t* __restrict__ out,
+                                                         const int64_t nbytes, const int vec_ok) {
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t nvec = vec_ok ? nbytes / 16 : 0;
+  const uint4* va = reinterpret_cast<const uint4*>(a);
+  const uint4* vb = reinterpret_cast<const uint4*>(b);
+  uint4* vo = reinterpret_cast<uint4*>(out);
+  auto avg = [](const uint4& x, const uint4& y) {
+    return make_uint4(__vhaddu4(x.x, y.x), __vhaddu4(x.y, y.y), __vhaddu4(x.z, y.z), __vhaddu4(x.w, y.w));
+  };
+  int64_t i = tid;
+  for (; i + 3 * nthreads < nvec; i += 4 * nthreads) {
+    uint4 x[4], y[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { x[k] = __ldcs(va + i + k * nthreads); y[k] = __ldcs(vb + i + k * nthreads); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) __stcs(vo + i + k * nthreads, avg(x[k], y[k]));
+  }
+  for (; i < nvec; i += nthreads) __stcs(vo + i, avg(__ldcs(va + i), __ldcs(vb + i)));
+  for (int64_t j = nvec * 16 + tid; j < nbytes; j += nthreads) out[j] = static_cast<uint8_t>((a[j] + b[j]) >> 1);
+}
+
 // any K up to kMaxBlendMembers (members indexed at run time)
 __global__ void __launch_bounds__(256) blend_kernel(const BlendParams p, const int vec_ok) {
   const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -303,6 +329,10 @@ cudaError_t launch_blend(const BlendParams& p, cudaStream_t stream) {
   int64_t blocks = (work + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   const unsigned g = static_cast<unsigned>(blocks);
+  if (p.k == 2 && p.weights[0] == 0.5 && p.weights[1] == 0.5) {
+    blend_half_kernel<<<g, 256, 0, stream>>>(p.members[0], p.members[1], p.out, p.nbytes, vec_ok);
+    return cudaGetLastError();
+  }
   switch (p.k) {
     case 1: blend_kernel_k<1><<<g, 256, 0, stream>>>(p, vec_ok); break;
     case 2: blend_kernel_k<2><<<g, 256, 0, stream>>>(p, vec_ok); break;

@@ -21,6 +21,7 @@ from __future__ import annotations
 import logging
 import os
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import cv2
 import numpy as np
@@ -55,6 +56,10 @@ _DEFAULTS = {
     "tile_pad": 10,                  # halo of RealESRGANer.tile_process (standalone/direct_esrgan.py:123)
     "pre_pad": 0,
     "ensemble_members": None,        # callable(rgb_u8_in, rgb_u8_esrgan) -> list of extra RGB u8 members
+    "cuda_megapixel_threshold": 8,   # reference nesr/nesr.py:762-775: the ESRGAN stage tiles only above this many MP (2^20 px) ...
+    "always_tile": False,            # ... True: tile every image with max_tile_size (the benchmarked 1080p configuration)
+    "async_io": True,                # image files are encoded + written on a worker thread (cv2.imwrite of iteration n overlaps
+                                     # iteration n+1; reference nesr/nesr.py:618-625,644-647 write inline).  Same bytes either way.
     "head_compat": False,            # True: the ESRGAN stage exactly as the reference's HEAD runs it (nesr/nesr.py:845-986):
                                      # RRDBNet(num_in_ch=12) fed a 12-channel full-resolution tensor, x4 out, truncating u8
 }
@@ -109,6 +114,8 @@ class SuperResolutionPipeline:
             self.config.update(config)
         os.makedirs(self.config["output_dir"], exist_ok=True)
         self.models = {}
+        self._io_pool = None
+        self._io_pending = []
 
     # -- models --------------------------------------------------------------------------------
     def _load_models(self):
@@ -121,11 +128,10 @@ class SuperResolutionPipeline:
                 model = RRDBNet(num_in_ch=12, num_out_ch=3, num_feat=64, num_block=23, num_grow_ch=32)
                 self.models["esrgan"] = RealESRGANer(scale=int(self.config["upscale_factor"]), model_path=path, model=model,
                                                      tile=0, tile_pad=0, pre_pad=0, half=False, device=self.device)
-            else:
+            else:                                                    # the tile size is decided per image (_use_tiling)
                 model = RRDBNet(num_in_ch=3, num_out_ch=3, scale=2, num_feat=64, num_block=23, num_grow_ch=32)
-                tile = int(self.config["max_tile_size"]) if self.config["enable_tiling"] else 0
                 self.models["esrgan"] = RealESRGANer(scale=int(self.config["upscale_factor"]), model_path=path, model=model,
-                                                     tile=tile, tile_pad=int(self.config["tile_pad"]),
+                                                     tile=0, tile_pad=int(self.config["tile_pad"]),
                                                      pre_pad=int(self.config["pre_pad"]), half=False, device=self.device)
             logger.info("Real-ESRGAN model loaded on %s (libnesr_b200)", self.device)
         for key, what in (("use_diffusion", "diffusion"), ("segment_enhancement", "segmentation")):
@@ -154,12 +160,25 @@ class SuperResolutionPipeline:
         src = image if isinstance(image, torch.Tensor) else np.ascontiguousarray(image)
         return self._engine().preprocess_u8(src, denoise_level=float(self.config["denoise_level"]))
 
+    def _use_tiling(self, h, w):
+        """The reference's tiling policy on CUDA (``nesr/nesr.py:761-790``): tile when tiling is enabled and the image is larger
+        than ``cuda_megapixel_threshold`` MP (default 8), and always above 16 MP.  ``always_tile`` is this implementation's opt-in
+        to tile every image (tiles are independent forwards: with halo < receptive field, tiling changes border pixels)."""
+        mp = (h * w) / (1024 * 1024)
+        use = bool(self.config["enable_tiling"]) and (bool(self.config.get("always_tile")) or
+                                                      mp > self.config.get("cuda_megapixel_threshold", 8))
+        return use or mp > 16
+
     def _apply_esrgan(self, image):
         """RGB HWC u8 (ndarray or CUDA tensor) -> RGB HWC u8 at x2, same container kind."""
         if not self.config["use_esrgan"] or "esrgan" not in self.models:
             return None
+        h, w = image.shape[:2]
         if self.config["head_compat"]:
+            if self._use_tiling(h, w):
+                return self._process_with_tiling(self._apply_esrgan_head, image, tile_size=int(self.config["max_tile_size"]), padding=16)
             return self._apply_esrgan_head(image)
+        self.models["esrgan"].tile_size = int(self.config["max_tile_size"]) if self._use_tiling(h, w) else 0
         if isinstance(image, torch.Tensor):
             out, _ = self.models["esrgan"].enhance(image.flip(-1).contiguous())
             return out.flip(-1).contiguous()
@@ -170,8 +189,8 @@ class SuperResolutionPipeline:
         """The reference HEAD's ESRGAN stage (``_apply_esrgan_12channel`` / ``_apply_esrgan_3channel``, ``nesr/nesr.py:845-986``),
         untiled: BGR / 255 -> 12 channels (image, x1.1, x0.9 clamped, 3x3 Gaussian blur -- or four copies with
         ``force_3channel``) -> ``model(x12)`` -> ``clip(out * 255, 0, 255)`` TRUNCATED to u8 -> RGB.  x4 per call (the 12-channel
-        network is the x2plus network without its un-shuffle).  The reference tiles images above ``cuda_megapixel_threshold`` with
-        ``_process_with_tiling`` (``:311-475``); that host loop is not restated -- larger images run untiled here."""
+        network is the x2plus network without its un-shuffle).  Images above ``cuda_megapixel_threshold`` go through
+        ``_process_with_tiling`` below, tile by tile."""
         host = not isinstance(image, torch.Tensor)
         rgb = torch.from_numpy(np.ascontiguousarray(image)).to(self.device) if host else image
         bgr = rgb.flip(-1).permute(2, 0, 1).contiguous()                                     # 3 x H x W u8
@@ -184,6 +203,68 @@ class SuperResolutionPipeline:
         out = torch.clamp(out.permute(1, 2, 0) * 255.0, 0, 255).to(torch.uint8)              # truncation, as astype(np.uint8)
         out = out.flip(-1).contiguous()
         return out.cpu().numpy() if host else out
+
+    def _process_with_tiling(self, processor_func, image, tile_size=512, padding=10):
+        """The reference HEAD's own tiler (``nesr/nesr.py:311-475``), used by ``head_compat`` above the megapixel threshold.
+        Tiles of ``tile_size`` extended by ``padding`` (clamped at the image edge) are processed one by one; the un-padded
+        interior of each result is pasted at ``upscale_factor`` times its input position.  The processor's real scale (x4 in HEAD)
+        need not equal ``upscale_factor``: the interior is cut with the tile's measured scale, ``int()``-truncated, and brought to
+        the destination size with LANCZOS4 -- exactly the reference's arithmetic, including its probe forward on the top-left
+        ``min(256, tile_size)`` corner (whose result it discards) and its per-tile bicubic fallback."""
+        host = not isinstance(image, torch.Tensor)
+        img = image if host else image.cpu().numpy()
+        h, w, c = img.shape
+        if h <= tile_size and w <= tile_size:
+            return processor_func(image)
+        f = self.config["upscale_factor"]
+        out_h, out_w = int(h * f), int(w * f)
+        output = np.zeros((out_h, out_w, c), np.uint8)
+        probe = min(256, tile_size)
+        try:
+            processor_func(np.ascontiguousarray(img[:probe, :probe]))
+            works = True
+        except Exception as exc:                                     # noqa: BLE001 -- the reference degrades to bicubic tiles
+            logger.warning("Tile processor test failed: %s", exc)
+            works = False
+
+        def bicubic(tile):
+            return cv2.resize(tile, (int(tile.shape[1] * f), int(tile.shape[0] * f)), interpolation=cv2.INTER_CUBIC)
+
+        for i in range(-(-h // tile_size)):
+            for j in range(-(-w // tile_size)):
+                y0, y1 = max(0, i * tile_size - padding), min(h, (i + 1) * tile_size + padding)
+                x0, x1 = max(0, j * tile_size - padding), min(w, (j + 1) * tile_size + padding)
+                tile = np.ascontiguousarray(img[y0:y1, x0:x1])
+                try:
+                    done = processor_func(tile) if works else bicubic(tile)
+                    oy0, oy1, ox0, ox1 = int(y0 * f), int(y1 * f), int(x0 * f), int(x1 * f)
+                    if padding > 0:
+                        pad_up = int(padding * f)
+                        oy0 += pad_up if y0 > 0 else 0
+                        oy1 -= pad_up if y1 < h else 0
+                        ox0 += pad_up if x0 > 0 else 0
+                        ox1 -= pad_up if x1 < w else 0
+                    th, tw = done.shape[:2]
+                    sy, sx = th / tile.shape[0], tw / tile.shape[1]
+                    ty0 = 0 if y0 == 0 else int(padding * sy)
+                    ty1 = th if y1 == h else int(th - padding * sy)
+                    tx0 = 0 if x0 == 0 else int(padding * sx)
+                    tx1 = tw if x1 == w else int(tw - padding * sx)
+                    ty0 = max(0, min(ty0, th - 1)); ty1 = max(ty0 + 1, min(ty1, th))
+                    tx0 = max(0, min(tx0, tw - 1)); tx1 = max(tx0 + 1, min(tx1, tw))
+                    if oy1 - oy0 <= 0 or ox1 - ox0 <= 0:
+                        continue
+                    region = done[ty0:ty1, tx0:tx1]
+                    if region.shape[0] != oy1 - oy0 or region.shape[1] != ox1 - ox0:
+                        region = cv2.resize(region, (ox1 - ox0, oy1 - oy0), interpolation=cv2.INTER_LANCZOS4)
+                    output[oy0:oy1, ox0:ox1] = region
+                except Exception as exc:                             # noqa: BLE001 -- reference: bicubic for this tile only
+                    logger.warning("Error processing tile (%d,%d): %s", i, j, exc)
+                    oy0, oy1 = int(i * tile_size * f), min(int(h * f), int((i + 1) * tile_size * f))
+                    ox0, ox1 = int(j * tile_size * f), min(int(w * f), int((j + 1) * tile_size * f))
+                    if oy1 > oy0 and ox1 > ox0:
+                        output[oy0:oy1, ox0:ox1] = cv2.resize(bicubic(tile), (ox1 - ox0, oy1 - oy0), interpolation=cv2.INTER_CUBIC)
+        return output if host else torch.from_numpy(output).to(image.device)
 
     def _ensemble_results(self, upscaled_images):
         if len(upscaled_images) == 1:
@@ -209,6 +290,26 @@ class SuperResolutionPipeline:
             return image
         img = image.contiguous() if isinstance(image, torch.Tensor) else np.ascontiguousarray(image)
         return self._engine().sharpen_u8(img, bgr=False)
+
+    # -- file output (reference nesr/nesr.py:618-625, 644-647: cv2.imwrite inline) ------------------
+    def _save_image(self, path, rgb):
+        """Encode + write ``rgb`` (H x W x 3 u8 ndarray, not modified afterwards) to ``path``.  With ``async_io`` the PNG / JPEG
+        encode -- by now the slowest step of an iteration -- runs on a worker thread while the GPU works on the next
+        iteration; ``_flush_io`` joins the writes before ``enhance_image`` returns.  The file bytes do not depend on the mode."""
+        def write():
+            if not cv2.imwrite(path, cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR)):
+                raise IOError(f"could not write {path}")
+        if not self.config.get("async_io", True):
+            write()
+            return
+        if self._io_pool is None:
+            self._io_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="nesr-io")   # one writer: files appear in order
+        self._io_pending.append(self._io_pool.submit(write))
+
+    def _flush_io(self):
+        pending, self._io_pending = self._io_pending, []
+        for fut in pending:
+            fut.result()                                           # re-raises a failed write
 
     # -- the loop (reference nesr/nesr.py:477-659) ------------------------------------------------
     def _progress(self, stage, it, msg):
@@ -251,8 +352,7 @@ class SuperResolutionPipeline:
             dev = self._postprocess_image(dev)
             current = dev.cpu().numpy()
             if self.config["intermediate_saves"]:
-                p = os.path.join(self.config["output_dir"], f"intermediate_iter{iteration + 1}.png")
-                cv2.imwrite(p, cv2.cvtColor(current, cv2.COLOR_RGB2BGR))
+                self._save_image(os.path.join(self.config["output_dir"], f"intermediate_iter{iteration + 1}.png"), current)
             if self.config.get("image_callback"):
                 self.config["image_callback"](current)
             logger.info(f"Completed iteration {iteration + 1} in {time.time() - t0:.1f}s")
@@ -260,7 +360,8 @@ class SuperResolutionPipeline:
         scale_achieved = round(final_h / original_h, 1)
         base_name, ext = os.path.splitext(os.path.basename(image_path))
         final_path = os.path.join(self.config["output_dir"], f"{base_name}_enhanced_x{scale_achieved}{ext}")
-        cv2.imwrite(final_path, cv2.cvtColor(current, cv2.COLOR_RGB2BGR))
+        self._save_image(final_path, current)
+        self._flush_io()                                           # the returned path exists, complete, when we return (a failed write raises here)
         self._progress("Complete", n_iter, f"Enhancement complete: {original_w}x{original_h} → {final_w}x{final_h} (x{scale_achieved})")
         return final_path
 

@@ -27,7 +27,7 @@ def test_enhance_image_chain_and_contract(tmp_path):
     pipe = pkg.SuperResolutionPipeline(device="cuda", config={
         "iterations": 2, "use_diffusion": False, "segment_enhancement": False, "denoise_level": 0.5,
         "output_dir": str(tmp_path / "out"), "esrgan_model_path": checkpoint("calibrated"),
-        "max_tile_size": 32, "tile_pad": 4, "ensemble_members": _bicubic_member, "intermediate_saves": True,
+        "max_tile_size": 32, "tile_pad": 4, "always_tile": True, "ensemble_members": _bicubic_member, "intermediate_saves": True,
         "progress_callback": lambda stage, it, total, msg: stages.append(stage),
         "image_callback": lambda im: images.append(im.copy())})
     path = pipe.enhance_image(src)
@@ -125,3 +125,49 @@ def test_head_compat_pipeline_matches_reference_golden(golden, tmp_path):
     d = np.abs(out - want)
     print("head_compat vs reference golden: max", d.max(), "frac>1", float((d > 1).mean()), "frac>4", float((d > 4).mean()), "psnr", psnr(out, want))
     assert float((d > 4).mean()) < 5e-4 and float((d > 1).mean()) < 2e-3 and psnr(out, want) >= 55.0
+
+
+def test_head_compat_tiled_pipeline_matches_reference_golden(golden, tmp_path):
+    """``enhance_image`` with ``head_compat`` ABOVE the tiling threshold against the UNMODIFIED reference's own end-to-end output
+    (``pipeline_tiled.npz``, generated by ``oracle/make_golden_tiled.py``): ``_apply_esrgan`` -> ``_process_with_tiling`` with
+    24-pixel tiles and 16 pixels of padding around a x4 processor, every interior LANCZOS4-resized to x2 (``nesr/nesr.py:311-475``)."""
+    from oracle import shims
+    from oracle.make_golden import state_dict_digest as _digest
+    g = golden("pipeline_tiled.npz")
+    head = _head_state_dict(seed=1)
+    if _digest(head.state_dict()) != str(g["weights_sha256"]):
+        pytest.skip("this torch build seeds the random weights differently from the fixture's")
+    ckpt = shims.write_checkpoint(head.state_dict(), str(tmp_path))
+    src = str(tmp_path / "in.png")
+    cv2.imwrite(src, cv2.cvtColor(g["small_rgb"], cv2.COLOR_RGB2BGR))
+    pipe = pkg.SuperResolutionPipeline(device="cuda", config={
+        "iterations": 1, "use_diffusion": False, "segment_enhancement": False, "denoise_level": 0, "head_compat": True,
+        "max_tile_size": int(g["max_tile_size"]), "cuda_megapixel_threshold": float(g["megapixel_threshold"]),
+        "esrgan_model_path": ckpt, "output_dir": str(tmp_path / "out")})
+    path = pipe.enhance_image(src)
+    assert os.path.basename(path) == str(g["result_name"]) == "in_enhanced_x2.0.png"
+    out = cv2.cvtColor(cv2.imread(path), cv2.COLOR_BGR2RGB).astype(np.int32)
+    want = g["head_out"].astype(np.int32)
+    assert out.shape == want.shape == (80, 112, 3)
+    d = np.abs(out - want)
+    print("tiled head_compat vs reference golden: max", d.max(), "frac>1", float((d > 1).mean()), "frac>4", float((d > 4).mean()), "psnr", psnr(out, want))
+    assert float((d > 4).mean()) < 2e-3 and float((d > 1).mean()) < 1e-2 and psnr(out, want) >= 50.0
+
+
+def test_async_file_output_writes_the_same_bytes(tmp_path):
+    """``async_io`` (encode + write on a worker thread while the next iteration runs) changes when files are written, not what:
+    intermediate and final files are byte-identical to the inline mode (reference ``nesr/nesr.py:618-625,644-647``)."""
+    rgb = natural_image(40, 48, seed=3)[:, :, ::-1].copy()
+    src = str(tmp_path / "frame.png")
+    cv2.imwrite(src, cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR))
+    files = {}
+    for mode in (True, False):
+        out_dir = tmp_path / f"out_{int(mode)}"
+        pipe = pkg.SuperResolutionPipeline(device="cuda", config={
+            "iterations": 3, "use_diffusion": False, "segment_enhancement": False, "denoise_level": 0.5, "intermediate_saves": True,
+            "output_dir": str(out_dir), "esrgan_model_path": checkpoint("calibrated"), "async_io": mode})
+        path = pipe.enhance_image(src)
+        assert os.path.exists(path) and not pipe._io_pending
+        files[mode] = {n: open(out_dir / n, "rb").read() for n in sorted(os.listdir(out_dir))}
+    assert list(files[True]) == list(files[False]) and len(files[True]) == 4          # three intermediates + the result
+    assert files[True] == files[False]

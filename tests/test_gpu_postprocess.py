@@ -48,6 +48,17 @@ def test_blend_matches_reference_golden(engine, golden, k):
     assert np.array_equal(engine.blend_u8(members), g[f"k{k}_out"])
 
 
+def test_blend_two_members_all_byte_pairs(engine):
+    """K = 2 with the reference's weights (1/2 each) takes the integer fast path (one halving add per four bytes): every (a, b)
+    byte pair, vector body and ragged tail, against the oracle's f32 op order; explicit unequal weights keep the general path."""
+    a, b = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    for n in (256 * 256 - 16, 256 * 256 - 1 - 3 * 7):            # 48-byte multiple (vector body only) / ragged tail; n % 3 == 0
+        ms = [np.ascontiguousarray(a.reshape(-1)[:n].reshape(-1, 1, 3)), np.ascontiguousarray(b.reshape(-1)[:n].reshape(-1, 1, 3))]
+        assert np.array_equal(engine.blend_u8(ms), O.ensemble_results(ms))
+        assert np.array_equal(engine.blend_u8(ms), ((ms[0].astype(np.uint16) + ms[1]) >> 1).astype(np.uint8))
+        assert np.array_equal(engine.blend_u8(ms, weights=[0.75, 0.25]), O.ensemble_results(ms, weights=[0.75, 0.25]))
+
+
 def test_blend_lattice_and_sizes(engine, golden):
     g = golden("ensemble.npz")
     assert np.array_equal(engine.blend_u8([np.ascontiguousarray(m) for m in g["lattice3_in"]]), g["lattice3_out"])

@@ -26,3 +26,57 @@ def test_head_layout_holds_the_x2plus_weights():
         head(torch.zeros(1, 12, 8, 8))                                   # CPU tensor: no CPU path
     with pytest.raises(RuntimeError):
         pkg.RRDBNet(num_in_ch=3, num_out_ch=3, scale=4).engine("cuda:0")  # a true x4 network is not this build
+
+
+class _Stub:
+    """``self`` for the pipeline's host-only methods (they read ``self.config`` only)."""
+
+    def __init__(self, **config):
+        self.config = {"upscale_factor": 2, "enable_tiling": True, "always_tile": False, "cuda_megapixel_threshold": 8, **config}
+
+
+def test_tiling_policy_follows_the_reference():
+    """``nesr/nesr.py:761-790`` on CUDA: tile above ``cuda_megapixel_threshold`` MP (default 8) when tiling is enabled, always above
+    16 MP; ``always_tile`` is this implementation's opt-in."""
+    use = pkg.SuperResolutionPipeline._use_tiling
+    assert not use(_Stub(), 1080, 1920)                                   # 1.98 MP: the reference runs 1080p untiled
+    assert not use(_Stub(), 2160, 3840)                                   # 7.9 MP
+    assert use(_Stub(), 2200, 3900) and use(_Stub(), 4320, 7680)
+    assert not use(_Stub(enable_tiling=False), 2200, 3900)
+    assert use(_Stub(enable_tiling=False), 4320, 7680)                    # > 16 MP: forced
+    assert use(_Stub(always_tile=True), 64, 64) and not use(_Stub(always_tile=True, enable_tiling=False), 64, 64)
+    assert use(_Stub(cuda_megapixel_threshold=0.0005), 40, 56)
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("shape,tile,pad,scale", [((40, 56), 24, 16, 4), ((61, 37), 32, 10, 2), ((30, 90), 32, 16, 4), ((20, 20), 32, 16, 4),
+                                                  ((70, 70), 24, 16, 3)])
+def test_head_tiler_is_the_reference_tiler(shape, tile, pad, scale):
+    """``_process_with_tiling`` against the reference's own method (``nesr/nesr.py:311-475``) imported live, with the same
+    deterministic stand-in processor (bicubic x``scale`` -- x4 like HEAD's network, x2, and a non-integer fit): padded tile
+    windows, int-truncated interior cuts and the LANCZOS4 resize of every interior must agree bit for bit."""
+    from oracle import shims
+    Ref = shims.import_reference("/root/reference")
+    img = np.random.default_rng(shape[0] + tile).integers(0, 256, (*shape, 3), dtype=np.uint8)
+    calls = []
+
+    def processor(t):
+        calls.append(t.shape)
+        return cv2.resize(t, (t.shape[1] * scale, t.shape[0] * scale), interpolation=cv2.INTER_CUBIC)
+
+    mine = pkg.SuperResolutionPipeline._process_with_tiling(_Stub(), processor, img, tile_size=tile, padding=pad)
+    n_mine, calls[:] = len(calls), []
+    want = Ref._process_with_tiling(_Stub(), processor, img, tile_size=tile, padding=pad)
+    assert np.array_equal(mine, want) and n_mine == len(calls)             # same forwards, the probe included
+
+    if shape[0] <= tile and shape[1] <= tile:
+        return                                                             # one tile: the processor is called directly
+
+    def flaky(t):                                                          # a processor that fails on the top-left tile: bicubic for that tile only
+        if t.shape[0] * t.shape[1] == corner_pixels:
+            raise RuntimeError("boom")
+        return processor(t)
+    corner_pixels = img[:tile + pad, :tile + pad].size // 3
+    mine = pkg.SuperResolutionPipeline._process_with_tiling(_Stub(), flaky, img, tile_size=tile, padding=pad)
+    want = Ref._process_with_tiling(_Stub(), flaky, img, tile_size=tile, padding=pad)
+    assert np.array_equal(mine, want)
