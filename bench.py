@@ -384,8 +384,8 @@ def run_ours(args):
         whole = eng.enhance_u8(big, tile=TILE, tile_pad=HALO)
         bit_identical = bool(torch.equal(whole, big_out))
         del whole
-    c3 = {"workload": "3840x2160->7680x4320, 40 tiles (tile 512 halo 10) cut into contiguous ranges of equal padded-pixel cost, one per "
-                      "rank; tile-major buffers exchanged with ONE NCCL all_gather_into_tensor, pasted by one kernel per rank",
+    c3 = {"workload": "3840x2160->7680x4320, 40 tiles (tile 512 halo 10) dealt longest-first to the ranks by padded-pixel cost; "
+                      "tile-major buffers exchanged with ONE NCCL all_gather_into_tensor, pasted by one kernel per run of tiles",
           "scaling": "strong", "ms_per_step": c3_step, "value": 4320 * 7680 / (c3_step / 1e3) / 1e6, "unit": UNIT, "steps": c3_steps,
           "timing": "wall clock around the call (host-blocking phases), max over ranks, median of the steps",
           "bit_identical_to_one_gpu": bit_identical,

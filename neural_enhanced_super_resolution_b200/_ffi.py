@@ -25,7 +25,7 @@ EXPORTS = (
     "nesr_b200_forward_nchw_f32", "nesr_b200_blend_u8", "nesr_b200_sharpen_u8", "nesr_b200_get_stats",
     "nesr_b200_synchronize", "nesr_b200_debug_conv", "nesr_b200_preprocess_u8", "nesr_b200_debug_lab_table",
     "nesr_b200_debug_nlm_weights", "nesr_b200_forward_nchw12_f32", "nesr_b200_enhance_tiles_packed_u8",
-    "nesr_b200_unpack_tiles_u8",
+    "nesr_b200_unpack_tiles_u8", "nesr_b200_enhance_tile_list_packed_u8",
 )
 
 
@@ -83,6 +83,8 @@ def load_library() -> C.CDLL:
                                                    C.c_int32, C.c_int32, C.c_int32, u8p, C.c_int64, C.c_int32]
         lib.nesr_b200_enhance_tiles_packed_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                                           C.c_int32, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32]
+        lib.nesr_b200_enhance_tile_list_packed_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                                              C.POINTER(C.c_int32), C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32]
         lib.nesr_b200_unpack_tiles_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                   C.c_int32, u8p, C.c_int64]
         lib.nesr_b200_forward_nchw_f32.argtypes = [H, f32p, C.c_int32, C.c_int32, C.c_int32, f32p, C.c_void_p]
@@ -278,6 +280,20 @@ class Engine:
         flags = (PTR_IN_DEVICE if idev else 0) | PTR_OUT_DEVICE
         self._check(self._lib.nesr_b200_enhance_tiles_packed_u8(self._h, ip, h, w, w * 3, tile, tile_pad, pre_pad, first, count, sp,
                                                                 slots.shape[2], slots.shape[1], flags), "enhance_tiles_packed_u8")
+        return slots
+
+    def enhance_tile_list_packed_u8(self, img, slots, tile: int, tile_pad: int, pre_pad: int, tile_ids):
+        """Tiles ``tile_ids`` (any subset of the grid) into ``slots`` (CUDA uint8 [>= len, slot_h, slot_w, 3]), tile ``tile_ids[k]`` at slot k."""
+        h, w = img.shape[:2]
+        ip, idev = _image_ptr(img, self.device)
+        sp, sdev = _image_ptr(slots, self.device)
+        n = len(tile_ids)
+        if not sdev or slots.shape[0] < n:
+            raise ValueError("slots must be a CUDA uint8 tensor with one slot per listed tile")
+        ids = (C.c_int32 * n)(*[int(t) for t in tile_ids])
+        flags = (PTR_IN_DEVICE if idev else 0) | PTR_OUT_DEVICE
+        self._check(self._lib.nesr_b200_enhance_tile_list_packed_u8(self._h, ip, h, w, w * 3, tile, tile_pad, pre_pad, ids, n, sp,
+                                                                    slots.shape[2], slots.shape[1], flags), "enhance_tile_list_packed_u8")
         return slots
 
     def unpack_tiles_u8(self, slots, out, h: int, w: int, tile: int, pre_pad: int, first: int, count: int):

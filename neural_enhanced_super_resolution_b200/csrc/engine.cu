@@ -67,8 +67,9 @@ struct LevelPlan {
 
 struct PlanKey {
   int n_frames = -1, H = 0, W = 0, tile = 0, tile_pad = 0, pre_pad = 0, first = 0, count = 0, whole = 0, packed = 0;
+  std::vector<int32_t> list;             // packed tile-major output of an arbitrary tile subset (slot k = list[k]); empty: the range [first, first+count)
   bool operator==(const PlanKey& o) const {
-    return n_frames == o.n_frames && H == o.H && W == o.W && tile == o.tile && tile_pad == o.tile_pad &&
+    return list == o.list && n_frames == o.n_frames && H == o.H && W == o.W && tile == o.tile && tile_pad == o.tile_pad &&
            pre_pad == o.pre_pad && first == o.first && count == o.count && whole == o.whole && packed == o.packed;
   }
 };
@@ -643,8 +644,12 @@ int plan_groups_with_cap(nesr_b200_handle* h, const PlanKey& key, int out_h, int
   const int count = key.whole ? ntile : key.count;
   if (first < 0 || count < 0 || first + count > ntile)
     return fail(h, NESR_E_INVALID, "tile range [%d,%d) outside the %d-tile grid", first, first + count, ntile);
+  std::vector<int32_t> ids(key.list);
+  if (ids.empty()) for (int ti = first; ti < first + count; ++ti) ids.push_back(ti);
+  for (int32_t ti : ids) if (ti < 0 || ti >= ntile) return fail(h, NESR_E_INVALID, "tile %d outside the %d-tile grid", ti, ntile);
   for (int f = 0; f < key.n_frames; ++f)
-    for (int ti = first; ti < first + count; ++ti) {
+    for (size_t slot = 0; slot < ids.size(); ++slot) {
+      const int ti = ids[slot];
       const int ty = ti / g.tiles_x, tx = ti % g.tiles_x;
       int y0 = 0, y1 = g.H2, x0 = 0, x1 = g.W2, y0p = 0, y1p = g.H2, x0p = 0, x1p = g.W2;
       if (key.tile > 0) {
@@ -668,7 +673,7 @@ int plan_groups_with_cap(nesr_b200_handle* h, const PlanKey& key, int out_h, int
       t.crop_h = std::max(0, std::min((y1 - y0) * scale, out_h - t.out_y0));
       t.crop_w = std::max(0, std::min((x1 - x0) * scale, out_w - t.out_x0));
       if (key.packed) {                 // tile-major output: tile k of the range is "frame" k of the slot buffer, pasted at its origin
-        t.frame = ti - first; t.out_y0 = 0; t.out_x0 = 0;
+        t.frame = (int32_t)slot; t.out_y0 = 0; t.out_x0 = 0;
       }
       all.push_back(t);
     }
@@ -1137,7 +1142,8 @@ int ensure(nesr_b200_handle* h, uint8_t** buf, size_t* cap, size_t need) {
 
 int enhance_impl(nesr_b200_handle* h, const uint8_t* in, int n_frames, int H, int W, int64_t in_stride,
                  int64_t in_frame_stride, int tile, int tile_pad, int pre_pad, int first, int count, int whole,
-                 uint8_t* out, int64_t out_stride, int64_t out_frame_stride, int flags, int packed = 0) {
+                 uint8_t* out, int64_t out_stride, int64_t out_frame_stride, int flags, int packed = 0,
+                 const int32_t* tile_ids = nullptr) {
   if (!h) return NESR_E_INVALID;
   if (!h->finalized) return fail(h, NESR_E_STATE, "weights not finalized");
   if (!in || !out || n_frames < 1 || H < 2 || W < 2) return fail(h, NESR_E_INVALID, "bad image arguments (H=%d W=%d n=%d)", H, W, n_frames);
@@ -1150,6 +1156,7 @@ int enhance_impl(nesr_b200_handle* h, const uint8_t* in, int n_frames, int H, in
   const int s = h->cfg.scale, OH = H * s, OW = W * s;
   PlanKey key; key.n_frames = n_frames; key.H = H; key.W = W; key.tile = tile; key.tile_pad = tile_pad;
   key.pre_pad = pre_pad; key.first = first; key.count = count; key.whole = whole; key.packed = packed;
+  if (tile_ids) { key.list.assign(tile_ids, tile_ids + count); key.first = 0; key.count = 0; }
   int rc = build_plan(h, key, OH, OW);
   if (rc) return rc;
 
@@ -1566,6 +1573,19 @@ int nesr_b200_enhance_tiles_packed_u8(nesr_b200_handle* h, const uint8_t* in_bgr
   if (slot_w < need_w || slot_h < need_h) return fail(h, NESR_E_INVALID, "tile slot %dx%d smaller than a tile's output %dx%d", slot_w, slot_h, need_w, need_h);
   return enhance_impl(h, in_bgr, 1, H, W, in_stride, 0, tile, tile_pad, pre_pad, tile_first, tile_count, 0, slots, (int64_t)slot_w * 3,
                       (int64_t)slot_w * 3 * slot_h, flags | NESR_PTR_OUT_DEVICE, 1);
+}
+
+int nesr_b200_enhance_tile_list_packed_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32_t H, int32_t W, int64_t in_stride, int32_t tile,
+                                          int32_t tile_pad, int32_t pre_pad, const int32_t* tile_ids, int32_t tile_count, uint8_t* slots,
+                                          int32_t slot_w, int32_t slot_h, int32_t flags) {
+  if (tile_count == 0) return NESR_OK;
+  if (!h) return NESR_E_INVALID;
+  if (!tile_ids || tile_count < 0) return fail(h, NESR_E_INVALID, "tile list: bad arguments");
+  const int s = h->cfg.scale;
+  const int need_w = (tile > 0 ? std::min(tile, W) : W) * s, need_h = (tile > 0 ? std::min(tile, H) : H) * s;
+  if (slot_w < need_w || slot_h < need_h) return fail(h, NESR_E_INVALID, "tile slot %dx%d smaller than a tile's output %dx%d", slot_w, slot_h, need_w, need_h);
+  return enhance_impl(h, in_bgr, 1, H, W, in_stride, 0, tile, tile_pad, pre_pad, 0, tile_count, 0, slots, (int64_t)slot_w * 3,
+                      (int64_t)slot_w * 3 * slot_h, flags | NESR_PTR_OUT_DEVICE, 1, tile_ids);
 }
 
 int nesr_b200_unpack_tiles_u8(nesr_b200_handle* h, const uint8_t* slots, int32_t slot_w, int32_t slot_h, int32_t H, int32_t W, int32_t tile,

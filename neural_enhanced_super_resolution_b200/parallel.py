@@ -4,8 +4,10 @@ The path shards without any data-path exchange: tiles (with their halos) and fra
 forwards, weights are replicated (33 MB).  The only collective is the final gather of the u8 output:
 
   * ``enhance_sharded``        -- BASELINE config 3: the row-major tile grid of ONE frame is cut into
-    ``world_size`` contiguous ranges of equal COST (padded feature pixels, ``partition_by_cost``); every rank
-    writes its tiles TILE-MAJOR into one contiguous buffer (``nesr_b200_enhance_tiles_packed_u8``), ONE
+    ``world_size`` shares of equal COST (padded feature pixels; a longest-first deal, ``partition_lpt``: tiles are independent,
+    so a share need not be contiguous -- 2.5 % imbalance for the 40 tiles of a 4K frame over 8 ranks, where the best contiguous cut,
+    ``partition_by_cost``, is 12 % off); every rank
+    writes its tiles TILE-MAJOR into one contiguous buffer (``nesr_b200_enhance_tile_list_packed_u8``), ONE
     ``all_gather_into_tensor`` over NCCL/NVLink exchanges the buffers (each rank sends only its own pixels: 1/N of
     the frame, ~12 MB at 8 GPUs for an 8K frame) and one small kernel per rank pastes the slots into the frame
     (``nesr_b200_unpack_tiles_u8``).  With one rank it is the plain ``enhance_u8`` call.
@@ -56,6 +58,30 @@ def partition_by_cost(costs, world_size: int):
     return fill(lo)
 
 
+def partition_lpt(costs, world_size: int):
+    """Longest-processing-time deal of items to ``world_size`` ranks: ``[sorted item ids]`` per rank.  Tiles are independent
+    forwards, so a rank's share need not be contiguous; every rank computes the same deal (ties broken by index)."""
+    loads = [0] * world_size
+    parts = [[] for _ in range(world_size)]
+    for i in sorted(range(len(costs)), key=lambda i: (-int(costs[i]), i)):
+        r = min(range(world_size), key=lambda r: (loads[r], r))
+        parts[r].append(i)
+        loads[r] += int(costs[i])
+    return [sorted(p) for p in parts]
+
+
+def _runs(ids):
+    """Maximal runs of consecutive ids: ``[(position in ids, first id, length)]``."""
+    out, k = [], 0
+    while k < len(ids):
+        j = k
+        while j + 1 < len(ids) and ids[j + 1] == ids[j] + 1:
+            j += 1
+        out.append((k, ids[k], j - k + 1))
+        k = j + 1
+    return out
+
+
 def _world(group):
     if dist.is_available() and dist.is_initialized():
         return dist.get_world_size(group), dist.get_rank(group)
@@ -65,7 +91,7 @@ def _world(group):
 def enhance_sharded(engine, img_bgr, tile: int, tile_pad: int, pre_pad: int = 0, group=None, out=None, timing=None):
     """Tile-sharded ``RealESRGANer.enhance`` of one frame; every rank returns the full x2 frame.
 
-    ``engine`` needs ``tile_costs`` / ``slot_shape`` / ``enhance_tiles_packed_u8`` / ``unpack_tiles_u8`` / ``enhance_u8`` /
+    ``engine`` needs ``tile_costs`` / ``slot_shape`` / ``enhance_tile_list_packed_u8`` / ``unpack_tiles_u8`` / ``enhance_u8`` /
     ``scale`` (an ``_ffi.Engine``); ``img_bgr`` is a CUDA uint8 tensor (NCCL) or a numpy array (gloo tests).
     ``timing``: a dict that receives this rank's ``compute_ms`` / ``gather_ms`` / ``unpack_ms`` (wall clock, phases are
     synchronous) and its tile range."""
@@ -79,9 +105,10 @@ def enhance_sharded(engine, img_bgr, tile: int, tile_pad: int, pre_pad: int = 0,
         if timing is not None:
             timing.update(compute_ms=1e3 * (time.perf_counter() - t0), gather_ms=0.0, unpack_ms=0.0, tiles=None)
         return out
-    parts = partition_by_cost(engine.tile_costs(h, w, tile, tile_pad, pre_pad), world)
-    first, count = parts[rank]
-    slots_per_rank = max(c for _, c in parts)
+    costs = engine.tile_costs(h, w, tile, tile_pad, pre_pad)
+    parts = partition_lpt(costs, world)
+    mine_ids = parts[rank]
+    slots_per_rank = max(len(p) for p in parts)
     sh, sw = engine.slot_shape(h, w, tile)
     if out is None:
         out = (torch.empty((h * s, w * s, 3), dtype=torch.uint8, device=img_bgr.device) if on_device
@@ -93,21 +120,22 @@ def enhance_sharded(engine, img_bgr, tile: int, tile_pad: int, pre_pad: int = 0,
         gathered = torch.empty((world, slots_per_rank, sh, sw, 3), dtype=torch.uint8)
         mine = np.zeros((slots_per_rank, sh, sw, 3), np.uint8)
     t0 = time.perf_counter()
-    if count:
-        engine.enhance_tiles_packed_u8(img_bgr, mine, tile, tile_pad, pre_pad, first, count)
+    if mine_ids:
+        engine.enhance_tile_list_packed_u8(img_bgr, mine, tile, tile_pad, pre_pad, mine_ids)
     t1 = time.perf_counter()
     send = mine if on_device else torch.from_numpy(mine)
     dist.all_gather_into_tensor(gathered.view(-1), send.reshape(-1), group=group)
     if on_device:
         torch.cuda.current_stream(img_bgr.device).synchronize()
     t2 = time.perf_counter()
-    for r, (f, c) in enumerate(parts):                             # every rank pastes every rank's slots (its own included)
-        if c:
-            engine.unpack_tiles_u8(gathered[r] if on_device else gathered[r].numpy(), out, h, w, tile, pre_pad, f, c)
+    for r, ids in enumerate(parts):                                # every rank pastes every rank's slots (its own included)
+        slots_r = gathered[r] if on_device else gathered[r].numpy()
+        for k, f, c in _runs(ids):                                 # one paste per run of consecutive tiles
+            engine.unpack_tiles_u8(slots_r[k:k + c], out, h, w, tile, pre_pad, f, c)
     t3 = time.perf_counter()
     if timing is not None:
-        timing.update(compute_ms=1e3 * (t1 - t0), gather_ms=1e3 * (t2 - t1), unpack_ms=1e3 * (t3 - t2), tiles=(first, count),
-                      cost=sum(engine.tile_costs(h, w, tile, tile_pad, pre_pad)[first:first + count]))
+        timing.update(compute_ms=1e3 * (t1 - t0), gather_ms=1e3 * (t2 - t1), unpack_ms=1e3 * (t3 - t2), tiles=list(mine_ids),
+                      cost=sum(costs[i] for i in mine_ids))
     return out
 
 

@@ -216,6 +216,16 @@ def test_tile_major_exchange_format_reassembles_the_frame(up_random):
             eng.enhance_tiles_packed_u8(img, slots, tile, pad, pre, first, count)
             eng.unpack_tiles_u8(slots, out, h, w, tile, pre, first, count)
         assert torch.equal(out, want), (h, w, tile)
+        # arbitrary tile subsets (the longest-first deal of parallel.enhance_sharded), pasted run by run
+        out.fill_(9)
+        for ids in parallel.partition_lpt(eng.tile_costs(h, w, tile, pad, pre), world):
+            if not ids:
+                continue
+            slots = torch.zeros((len(ids), sh, sw, 3), dtype=torch.uint8, device="cuda")
+            eng.enhance_tile_list_packed_u8(img, slots, tile, pad, pre, ids)
+            for k, first, count in parallel._runs(ids):
+                eng.unpack_tiles_u8(slots[k:k + count], out, h, w, tile, pre, first, count)
+        assert torch.equal(out, want), (h, w, tile, "lpt")
 
 
 def test_device_tensor_in_out(up_random):
