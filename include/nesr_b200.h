@@ -164,6 +164,12 @@ int nesr_b200_enhance_tiles_packed_u8(nesr_b200_handle* h, const uint8_t* in_bgr
 int nesr_b200_enhance_tile_list_packed_u8(nesr_b200_handle* h, const uint8_t* in_bgr, int32_t H, int32_t W, int64_t in_stride,
                                           int32_t tile, int32_t tile_pad, int32_t pre_pad, const int32_t* tile_ids, int32_t tile_count,
                                           uint8_t* slots, int32_t slot_w, int32_t slot_h, int32_t flags);
+/* The reference HEAD's ESRGAN stage in one call (`_apply_esrgan_12channel` / `_apply_esrgan_3channel`, nesr/nesr.py:845-986), for a handle
+ * created with the x2plus weights: RGB H x W x 3 u8 -> the 12-channel tensor the reference builds (BGR / 255; x1.1 and x0.9 clamped;
+ * cv2.GaussianBlur 3x3 -- or four copies with force_3channel), computed inside the input pack kernel -> model(x12) (the 12-channel scale-4
+ * architecture is the x2plus network behind its un-shuffle) -> clip(out * 255, 0, 255) TRUNCATED to u8 -> RGB, 4H x 4W x 3. */
+int nesr_b200_enhance_head_u8(nesr_b200_handle* h, const uint8_t* in_rgb, int32_t H, int32_t W, int64_t in_stride, int32_t force_3channel,
+                              uint8_t* out_rgb, int64_t out_stride, int32_t flags);
 /* Inverse placement: slots (device) of tiles [tile_first, tile_first + tile_count) -> their rectangles in the full 2H x 2W
  * frame `out_bgr` (device).  Called once per rank's slice of the gathered buffer; other pixels of the frame are untouched. */
 int nesr_b200_unpack_tiles_u8(nesr_b200_handle* h, const uint8_t* slots, int32_t slot_w, int32_t slot_h, int32_t H, int32_t W,

@@ -25,7 +25,7 @@ EXPORTS = (
     "nesr_b200_forward_nchw_f32", "nesr_b200_blend_u8", "nesr_b200_sharpen_u8", "nesr_b200_get_stats",
     "nesr_b200_synchronize", "nesr_b200_debug_conv", "nesr_b200_preprocess_u8", "nesr_b200_debug_lab_table",
     "nesr_b200_debug_nlm_weights", "nesr_b200_forward_nchw12_f32", "nesr_b200_enhance_tiles_packed_u8",
-    "nesr_b200_unpack_tiles_u8", "nesr_b200_enhance_tile_list_packed_u8",
+    "nesr_b200_unpack_tiles_u8", "nesr_b200_enhance_tile_list_packed_u8", "nesr_b200_enhance_head_u8",
 )
 
 
@@ -85,6 +85,7 @@ def load_library() -> C.CDLL:
                                                           C.c_int32, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32]
         lib.nesr_b200_enhance_tile_list_packed_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                                               C.POINTER(C.c_int32), C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32]
+        lib.nesr_b200_enhance_head_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, u8p, C.c_int64, C.c_int32]
         lib.nesr_b200_unpack_tiles_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                   C.c_int32, u8p, C.c_int64]
         lib.nesr_b200_forward_nchw_f32.argtypes = [H, f32p, C.c_int32, C.c_int32, C.c_int32, f32p, C.c_void_p]
@@ -232,6 +233,21 @@ class Engine:
         self._check(self._lib.nesr_b200_enhance_batch_u8(self._h, ip, n, h, w, w * 3, h * w * 3, tile, tile_pad,
                                                          pre_pad, op, w * s * 3, h * s * w * s * 3, flags),
                     "enhance_batch_u8")
+        return out
+
+    def enhance_head_u8(self, rgb, force_3channel: bool = False, out=None):
+        """The reference HEAD's ESRGAN stage (``nesr/nesr.py:845-986``): RGB H x W x 3 u8 -> RGB 4H x 4W x 3 u8 (12-channel input built in
+        the pack kernel, truncating u8 quantisation).  Same container kind out as in."""
+        h, w = rgb.shape[:2]
+        if rgb.ndim != 3 or rgb.shape[2] != 3:
+            raise ValueError("enhance_head_u8 expects H x W x 3")
+        if out is None:
+            out = self._alloc_like(rgb, (4 * h, 4 * w, 3))
+        ip, idev = _image_ptr(rgb, self.device)
+        op, odev = _image_ptr(out, self.device)
+        flags = (PTR_IN_DEVICE if idev else 0) | (PTR_OUT_DEVICE if odev else 0)
+        self._check(self._lib.nesr_b200_enhance_head_u8(self._h, ip, h, w, w * 3, int(bool(force_3channel)), op, 4 * w * 3, flags),
+                    "enhance_head_u8")
         return out
 
     def tile_count(self, h: int, w: int, tile: int, pre_pad: int = 0) -> int:

@@ -1021,6 +1021,7 @@ int build_body_passes(nesr_b200_handle* h, Batch& b) {
 
 struct Sink {
   uint8_t* out_u8 = nullptr; int64_t out_stride = 0, out_frame_stride = 0;
+  int out_trunc = 0;
   float* out_f32 = nullptr; int out_h = 0, out_w = 0;
 };
 
@@ -1112,7 +1113,7 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
   }
   {  // conv_last -> clamp, BGR, u8, halo crop + stitch  (or unclamped fp32 NCHW)
     ConvParams p{};
-    p.out_u8 = sink.out_u8; p.out_stride = sink.out_stride; p.out_frame_stride = sink.out_frame_stride;
+    p.out_u8 = sink.out_u8; p.out_stride = sink.out_stride; p.out_frame_stride = sink.out_frame_stride; p.out_trunc = sink.out_trunc;
     p.out_f32 = sink.out_f32; p.out_h = sink.out_h; p.out_w = sink.out_w;
     if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], &a.f_g4[0], &a.e_g4[0], a.g4[0], 1, 2}, p, s))) return rc;
   }
@@ -1143,13 +1144,13 @@ int ensure(nesr_b200_handle* h, uint8_t** buf, size_t* cap, size_t need) {
 int enhance_impl(nesr_b200_handle* h, const uint8_t* in, int n_frames, int H, int W, int64_t in_stride,
                  int64_t in_frame_stride, int tile, int tile_pad, int pre_pad, int first, int count, int whole,
                  uint8_t* out, int64_t out_stride, int64_t out_frame_stride, int flags, int packed = 0,
-                 const int32_t* tile_ids = nullptr) {
+                 const int32_t* tile_ids = nullptr, int head = 0) {
   if (!h) return NESR_E_INVALID;
   if (!h->finalized) return fail(h, NESR_E_STATE, "weights not finalized");
   if (!in || !out || n_frames < 1 || H < 2 || W < 2) return fail(h, NESR_E_INVALID, "bad image arguments (H=%d W=%d n=%d)", H, W, n_frames);
   if (tile < 0 || tile_pad < 0 || pre_pad < 0 || pre_pad >= H || pre_pad >= W)
     return fail(h, NESR_E_INVALID, "bad tile/pad arguments (tile=%d tile_pad=%d pre_pad=%d)", tile, tile_pad, pre_pad);
-  if (in_stride < (int64_t)W * 3 || (!packed && out_stride < (int64_t)W * h->cfg.scale * 3)) return fail(h, NESR_E_INVALID, "row stride smaller than a row");
+  if (in_stride < (int64_t)(head ? W / 2 : W) * 3 || (!packed && out_stride < (int64_t)W * h->cfg.scale * 3)) return fail(h, NESR_E_INVALID, "row stride smaller than a row");
   if (packed && (n_frames != 1 || !(flags & NESR_PTR_OUT_DEVICE))) return fail(h, NESR_E_INVALID, "tile-major output needs one frame and a device buffer");
   DEVICE_SCOPE(h);
   if (int wrc = wait_external(h)) return wrc;
@@ -1162,11 +1163,12 @@ int enhance_impl(nesr_b200_handle* h, const uint8_t* in, int n_frames, int H, in
 
   const uint8_t* d_in = in;
   int64_t d_in_stride = in_stride, d_in_fs = in_frame_stride;
+  const int in_h = head ? H / 2 : H, in_w = head ? W / 2 : W;      // HEAD mode: (H, W) is the virtual frame whose un-shuffle the 12 channels are
   if (!(flags & NESR_PTR_IN_DEVICE)) {
-    d_in_stride = (int64_t)W * 3; d_in_fs = d_in_stride * H;
+    d_in_stride = (int64_t)in_w * 3; d_in_fs = d_in_stride * in_h;
     if ((rc = ensure(h, &h->d_in, &h->d_in_bytes, (size_t)d_in_fs * n_frames))) return rc;
     for (int f = 0; f < n_frames; ++f)
-      CUDA_TRY(h, cudaMemcpy2DAsync(h->d_in + f * d_in_fs, d_in_stride, in + f * in_frame_stride, in_stride, (size_t)W * 3, H,
+      CUDA_TRY(h, cudaMemcpy2DAsync(h->d_in + f * d_in_fs, d_in_stride, in + f * in_frame_stride, in_stride, (size_t)in_w * 3, in_h,
                                     cudaMemcpyHostToDevice, h->stream));
     d_in = h->d_in;
   }
@@ -1185,7 +1187,9 @@ int enhance_impl(nesr_b200_handle* h, const uint8_t* in, int n_frames, int H, in
   h->n_trunk_timed = 0;
   PackParams pk{};
   pk.in_u8 = d_in; pk.in_stride = d_in_stride; pk.in_frame_stride = packed ? 0 : d_in_fs; pk.H = H; pk.W = W; pk.pre_pad = pre_pad;
-  Sink sink; sink.out_u8 = d_out; sink.out_stride = d_out_stride; sink.out_frame_stride = d_out_fs;
+  if (head) { pk.in_u8 = nullptr; pk.in_u8_head = d_in; pk.head_replicate = head == 2; }
+  Sink sink;
+  sink.out_trunc = head ? 1 : 0; sink.out_u8 = d_out; sink.out_stride = d_out_stride; sink.out_frame_stride = d_out_fs;
   // Host output of a whole frame: every tile group's stitched rectangles go back on a second stream while the next group
   // computes (the tiles' crop rectangles partition the frame).  A tile range keeps the single full-frame copy.
   const bool overlap_d2h = !(flags & NESR_PTR_OUT_DEVICE) && whole && h->batches.size() > 1 && h->copy_stream;
@@ -1586,6 +1590,15 @@ int nesr_b200_enhance_tile_list_packed_u8(nesr_b200_handle* h, const uint8_t* in
   if (slot_w < need_w || slot_h < need_h) return fail(h, NESR_E_INVALID, "tile slot %dx%d smaller than a tile's output %dx%d", slot_w, slot_h, need_w, need_h);
   return enhance_impl(h, in_bgr, 1, H, W, in_stride, 0, tile, tile_pad, pre_pad, 0, tile_count, 0, slots, (int64_t)slot_w * 3,
                       (int64_t)slot_w * 3 * slot_h, flags | NESR_PTR_OUT_DEVICE, 1, tile_ids);
+}
+
+int nesr_b200_enhance_head_u8(nesr_b200_handle* h, const uint8_t* in_rgb, int32_t H, int32_t W, int64_t in_stride, int32_t force_3channel,
+                              uint8_t* out_rgb, int64_t out_stride, int32_t flags) {
+  if (!h) return NESR_E_INVALID;
+  if (H < 1 || W < 1) return fail(h, NESR_E_INVALID, "bad image arguments (H=%d W=%d)", H, W);
+  // the 12-channel scale-4 architecture is the x2plus network behind its un-shuffle: the H x W image's 12 channels are the un-shuffle of a
+  // virtual 2H x 2W frame, the output is 4H x 4W; one untiled forward (the reference tiles with its own host loop above this call)
+  return enhance_impl(h, in_rgb, 1, 2 * H, 2 * W, in_stride, 0, 0, 0, 0, 0, 0, 1, out_rgb, out_stride, 0, flags, 0, nullptr, force_3channel ? 2 : 1);
 }
 
 int nesr_b200_unpack_tiles_u8(nesr_b200_handle* h, const uint8_t* slots, int32_t slot_w, int32_t slot_h, int32_t H, int32_t W, int32_t tile,

@@ -120,6 +120,7 @@ struct EpiRegs {
   int64_t out_stride, out_frame_stride;
   float* out_f32;
   int32_t out_h, out_w;
+  int32_t out_trunc;
   int32_t debug_flags;
 };
 template <bool kTrunk>
@@ -131,7 +132,7 @@ __device__ __forceinline__ EpiRegs make_epi_regs(const ConvParams& p) {
   e.dst16 = p.dst16; e.dst16_plane_px = p.dst16_plane_px; e.dst16_coff = p.dst16_coff; e.dst16_fmt = p.dst16_fmt;
   e.dst16_up = kTrunk ? 0 : p.dst16_up;
   e.out_u8 = kTrunk ? nullptr : p.out_u8; e.out_stride = p.out_stride; e.out_frame_stride = p.out_frame_stride;
-  e.out_f32 = kTrunk ? nullptr : p.out_f32; e.out_h = p.out_h; e.out_w = p.out_w;
+  e.out_f32 = kTrunk ? nullptr : p.out_f32; e.out_h = p.out_h; e.out_w = p.out_w; e.out_trunc = p.out_trunc;
   e.debug_flags = dbg_flags(p);
   return e;
 }
@@ -203,8 +204,12 @@ __device__ __forceinline__ void epilogue16(const Params& p, const TileGeom& tg, 
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           if (c < p.cout) {
-            const float cl = fminf(fmaxf(v[c], 0.f), 1.f);
-            o[2 - c] = static_cast<uint8_t>(rintf(__fmul_rn(cl, 255.f)));     // RGB -> BGR, half-to-even
+            if (p.out_trunc) {                                              // reference HEAD: clip(out * 255, 0, 255).astype(uint8)
+              o[2 - c] = static_cast<uint8_t>(fminf(fmaxf(__fmul_rn(v[c], 255.f), 0.f), 255.f));
+            } else {
+              const float cl = fminf(fmaxf(v[c], 0.f), 1.f);
+              o[2 - c] = static_cast<uint8_t>(rintf(__fmul_rn(cl, 255.f)));   // RGB -> BGR, half-to-even
+            }
           }
         }
       } else {

@@ -98,6 +98,8 @@ struct ConvParams {
   uint8_t* out_u8;             // BGR HWC frames or null
   int64_t out_stride;          // bytes per row
   int64_t out_frame_stride;    // bytes per frame
+  int32_t out_trunc;           // out_u8: clip(v * 255, 0, 255) TRUNCATED (the reference HEAD's astype(np.uint8), nesr/nesr.py:897-899) instead of
+                               // clamp(v, 0, 1) * 255 rounded half-to-even (upstream RealESRGANer.enhance)
   float* out_f32;              // NCHW frames (unclamped) or null
   int32_t out_h, out_w;        // frame dims for out_f32
   // row-folded kernel (conv3x3_fold.cu)

@@ -18,6 +18,31 @@ __device__ __forceinline__ int unreflect(int s, int len, int pre_pad) {
   return s;
 }
 
+// The reference HEAD's 12-channel network input (nesr/nesr.py:859-880 `_apply_esrgan_12channel`, :916-925 `_3channel`), computed from the
+// u8 image on the fly: t = BGR / 255 (the reference feeds BGR unswapped); channels 0-2 t, 3-5 clamp(t * 1.1, 0, 1), 6-8 clamp(t * 0.9, 0, 1),
+// 9-11 cv2.GaussianBlur(img, (3, 3), 0) / 255 -- the fixed 1-2-1 kernel, BORDER_REFLECT_101, (sum + 8) >> 4 -- or four copies of t.  Same
+// fp32 operations as the torch expressions (true division, multiplication by float32(1.1) / float32(0.9)).
+__device__ __forceinline__ float head_channel(const PackParams& p, int k, int y, int x) {
+  const int h = p.H >> 1, w = p.W >> 1;
+  const int variant = p.head_replicate ? 0 : k / 3, color = 2 - k % 3;          // t[0] = B = rgb[2]
+  auto at = [&](int yy, int xx) {
+    yy = yy < 0 ? -yy : (yy >= h ? 2 * (h - 1) - yy : yy);
+    xx = xx < 0 ? -xx : (xx >= w ? 2 * (w - 1) - xx : xx);
+    yy = yy < 0 ? 0 : (yy >= h ? h - 1 : yy);                                     // 1-pixel-wide images
+    xx = xx < 0 ? 0 : (xx >= w ? w - 1 : xx);
+    return static_cast<int>(p.in_u8_head[static_cast<int64_t>(yy) * p.in_stride + static_cast<int64_t>(xx) * 3 + color]);
+  };
+  if (variant == 3) {
+    const int s = at(y - 1, x - 1) + 2 * at(y - 1, x) + at(y - 1, x + 1) + 2 * (at(y, x - 1) + 2 * at(y, x) + at(y, x + 1)) +
+                  at(y + 1, x - 1) + 2 * at(y + 1, x) + at(y + 1, x + 1);
+    return __fdiv_rn(static_cast<float>((s + 8) >> 4), 255.f);
+  }
+  const float t = __fdiv_rn(static_cast<float>(at(y, x)), 255.f);
+  if (variant == 1) return fminf(fmaxf(__fmul_rn(t, 1.1f), 0.f), 1.f);
+  if (variant == 2) return fminf(fmaxf(__fmul_rn(t, 0.9f), 0.f), 1.f);
+  return t;
+}
+
 __global__ void __launch_bounds__(kBlockPixels) pack_kernel(const PackParams p) {
   const BlockRef b = p.blocks[blockIdx.x];
   const TileGeom& tg = p.tiles[b.tile];
@@ -34,7 +59,9 @@ __global__ void __launch_bounds__(kBlockPixels) pack_kernel(const PackParams p) 
         const int sy = unreflect(tg.src_y0 + 2 * px.y + i, p.H, p.pre_pad);
         const int sx = unreflect(tg.src_x0 + 2 * px.x + j, p.W, p.pre_pad);
         float f;
-        if (p.in_f32_12) {                                   // channel c*4 + i*2 + j of the feature grid (H/2 x W/2), no padding
+        if (p.in_u8_head) {                                  // channel c*4 + i*2 + j of the HEAD's 12-channel tensor, built here
+          f = head_channel(p, c * 4 + i * 2 + j, (tg.src_y0 >> 1) + px.y, (tg.src_x0 >> 1) + px.x);
+        } else if (p.in_f32_12) {                            // channel c*4 + i*2 + j of the feature grid (H/2 x W/2), no padding
           f = p.in_f32_12[((static_cast<size_t>(tg.frame) * 12 + c * 4 + i * 2 + j) * (p.H >> 1) + (tg.src_y0 >> 1) + px.y) * (p.W >> 1) +
                           (tg.src_x0 >> 1) + px.x];
         } else if (p.in_u8) {

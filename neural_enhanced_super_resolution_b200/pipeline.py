@@ -187,10 +187,17 @@ class SuperResolutionPipeline:
 
     def _apply_esrgan_head(self, image):
         """The reference HEAD's ESRGAN stage (``_apply_esrgan_12channel`` / ``_apply_esrgan_3channel``, ``nesr/nesr.py:845-986``),
-        untiled: BGR / 255 -> 12 channels (image, x1.1, x0.9 clamped, 3x3 Gaussian blur -- or four copies with
-        ``force_3channel``) -> ``model(x12)`` -> ``clip(out * 255, 0, 255)`` TRUNCATED to u8 -> RGB.  x4 per call (the 12-channel
-        network is the x2plus network without its un-shuffle).  Images above ``cuda_megapixel_threshold`` go through
-        ``_process_with_tiling`` below, tile by tile."""
+        untiled, in ONE library call (``nesr_b200_enhance_head_u8``): BGR / 255 -> 12 channels (image, x1.1, x0.9 clamped, 3x3 Gaussian
+        blur -- or four copies with ``force_3channel``), built inside the input pack kernel -> ``model(x12)`` -> ``clip(out * 255, 0, 255)``
+        TRUNCATED to u8 in conv_last's epilogue -> RGB.  x4 per call (the 12-channel network is the x2plus network without its
+        un-shuffle).  Images above ``cuda_megapixel_threshold`` go through ``_process_with_tiling`` below, tile by tile.
+        (``head_reference_glue`` below is the same stage written with torch expressions, kept as the test's second opinion.)"""
+        src = image.contiguous() if isinstance(image, torch.Tensor) else np.ascontiguousarray(image)
+        return self.models["esrgan"].model.engine(self.device).enhance_head_u8(src, force_3channel=bool(self.config["force_3channel"]))
+
+    def head_reference_glue(self, image):
+        """``_apply_esrgan_head`` as round 1 ran it: the 12-channel tensor and the u8 quantisation as torch expressions around
+        ``model(x12)`` -- the statement-by-statement mirror of ``nesr/nesr.py:859-899``.  Test cross-check only."""
         host = not isinstance(image, torch.Tensor)
         rgb = torch.from_numpy(np.ascontiguousarray(image)).to(self.device) if host else image
         bgr = rgb.flip(-1).permute(2, 0, 1).contiguous()                                     # 3 x H x W u8

@@ -5,6 +5,7 @@ import os
 import cv2
 import numpy as np
 import pytest
+import torch
 
 import neural_enhanced_super_resolution_b200 as pkg
 from oracle import postprocess as O
@@ -171,3 +172,24 @@ def test_async_file_output_writes_the_same_bytes(tmp_path):
         files[mode] = {n: open(out_dir / n, "rb").read() for n in sorted(os.listdir(out_dir))}
     assert list(files[True]) == list(files[False]) and len(files[True]) == 4          # three intermediates + the result
     assert files[True] == files[False]
+
+
+@pytest.mark.parametrize("force3", [False, True])
+def test_head_stage_in_one_call_equals_the_torch_glue(tmp_path, force3):
+    """``nesr_b200_enhance_head_u8`` (12-channel input built in the pack kernel, truncating u8 in conv_last's epilogue) against the
+    statement-by-statement torch mirror of ``nesr/nesr.py:859-899`` around ``model(x12)``: the same fp32 operations, bit-identical --
+    odd sizes, one-pixel-wide images (REFLECT_101 of the 3x3 blur), host and device containers."""
+    from oracle import shims
+    head = _head_state_dict(seed=5)
+    ckpt = shims.write_checkpoint(head.state_dict(), str(tmp_path))
+    pipe = pkg.SuperResolutionPipeline(device="cuda", config={"head_compat": True, "use_diffusion": False, "segment_enhancement": False,
+                                                              "force_3channel": force3, "esrgan_model_path": ckpt,
+                                                              "output_dir": str(tmp_path / "out")})
+    pipe._load_models()
+    for shape in ((36, 44), (17, 23), (1, 9), (8, 1), (2, 2)):
+        rgb = natural_image(*shape, seed=sum(shape))
+        a = pipe._apply_esrgan_head(rgb)
+        b = pipe.head_reference_glue(rgb)
+        assert a.shape == (4 * shape[0], 4 * shape[1], 3) and np.array_equal(a, b), shape
+    dev = torch.from_numpy(natural_image(20, 28, seed=1)).cuda()
+    assert torch.equal(pipe._apply_esrgan_head(dev), pipe.head_reference_glue(dev))
