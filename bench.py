@@ -385,7 +385,7 @@ def run_ours(args):
         bit_identical = bool(torch.equal(whole, big_out))
         del whole
     c3 = {"workload": "3840x2160->7680x4320, 40 tiles (tile 512 halo 10) dealt longest-first to the ranks by padded-pixel cost; "
-                      "tile-major buffers exchanged with ONE NCCL all_gather_into_tensor, pasted by one kernel per run of tiles",
+                      "tile-major buffers exchanged with ONE NCCL all_gather_into_tensor, pasted by one kernel",
           "scaling": "strong", "ms_per_step": c3_step, "value": 4320 * 7680 / (c3_step / 1e3) / 1e6, "unit": UNIT, "steps": c3_steps,
           "timing": "wall clock around the call (host-blocking phases), max over ranks, median of the steps",
           "bit_identical_to_one_gpu": bit_identical,

@@ -175,6 +175,11 @@ int nesr_b200_enhance_head_u8(nesr_b200_handle* h, const uint8_t* in_rgb, int32_
 int nesr_b200_unpack_tiles_u8(nesr_b200_handle* h, const uint8_t* slots, int32_t slot_w, int32_t slot_h, int32_t H, int32_t W,
                               int32_t tile, int32_t pre_pad, int32_t tile_first, int32_t tile_count, uint8_t* out_bgr,
                               int64_t out_stride);
+/* The same for slots holding an arbitrary tile list: slot k holds tile tile_ids[k]; an id < 0 marks an empty (padding) slot.  One call
+ * pastes the whole gathered buffer of every rank. */
+int nesr_b200_unpack_tile_list_u8(nesr_b200_handle* h, const uint8_t* slots, int32_t slot_w, int32_t slot_h, int32_t H, int32_t W,
+                                  int32_t tile, int32_t pre_pad, const int32_t* tile_ids, int32_t slot_count, uint8_t* out_bgr,
+                                  int64_t out_stride);
 
 /* Replaces: RRDBNet.forward / `upsampler.model(x)` (nesr/nesr.py:887-891,930-935): device fp32
  * NCHW [n, num_in_ch, H, W] in [0,1] -> device fp32 NCHW [n, num_out_ch, 2H, 2W], unclamped.

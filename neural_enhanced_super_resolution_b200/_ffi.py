@@ -25,7 +25,7 @@ EXPORTS = (
     "nesr_b200_forward_nchw_f32", "nesr_b200_blend_u8", "nesr_b200_sharpen_u8", "nesr_b200_get_stats",
     "nesr_b200_synchronize", "nesr_b200_debug_conv", "nesr_b200_preprocess_u8", "nesr_b200_debug_lab_table",
     "nesr_b200_debug_nlm_weights", "nesr_b200_forward_nchw12_f32", "nesr_b200_enhance_tiles_packed_u8",
-    "nesr_b200_unpack_tiles_u8", "nesr_b200_enhance_tile_list_packed_u8", "nesr_b200_enhance_head_u8",
+    "nesr_b200_unpack_tiles_u8", "nesr_b200_enhance_tile_list_packed_u8", "nesr_b200_enhance_head_u8", "nesr_b200_unpack_tile_list_u8",
 )
 
 
@@ -85,6 +85,8 @@ def load_library() -> C.CDLL:
                                                           C.c_int32, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32]
         lib.nesr_b200_enhance_tile_list_packed_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                                               C.POINTER(C.c_int32), C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32]
+        lib.nesr_b200_unpack_tile_list_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                      C.POINTER(C.c_int32), C.c_int32, u8p, C.c_int64]
         lib.nesr_b200_enhance_head_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, u8p, C.c_int64, C.c_int32]
         lib.nesr_b200_unpack_tiles_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                   C.c_int32, u8p, C.c_int64]
@@ -320,6 +322,18 @@ class Engine:
             raise ValueError("unpack_tiles_u8 works on CUDA tensors")
         self._check(self._lib.nesr_b200_unpack_tiles_u8(self._h, sp, slots.shape[2], slots.shape[1], h, w, tile, pre_pad, first, count,
                                                         op, out.shape[1] * 3), "unpack_tiles_u8")
+        return out
+
+    def unpack_tile_list_u8(self, slots, out, h: int, w: int, tile: int, pre_pad: int, tile_ids):
+        """Paste ``slots`` (CUDA uint8 [len(tile_ids), slot_h, slot_w, 3]; slot k holds tile ``tile_ids[k]``, < 0: empty) into ``out``."""
+        sp, sdev = _image_ptr(slots, self.device)
+        op, odev = _image_ptr(out, self.device)
+        n = len(tile_ids)
+        if not (sdev and odev) or slots.shape[0] < n:
+            raise ValueError("unpack_tile_list_u8 works on CUDA tensors with one slot per list entry")
+        ids = (C.c_int32 * n)(*[int(t) for t in tile_ids])
+        self._check(self._lib.nesr_b200_unpack_tile_list_u8(self._h, sp, slots.shape[2], slots.shape[1], h, w, tile, pre_pad, ids, n, op,
+                                                            out.shape[1] * 3), "unpack_tile_list_u8")
         return out
 
     # -- RRDBNet.forward ---------------------------------------------------------------------

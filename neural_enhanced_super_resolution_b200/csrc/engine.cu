@@ -1601,8 +1601,25 @@ int nesr_b200_enhance_head_u8(nesr_b200_handle* h, const uint8_t* in_rgb, int32_
   return enhance_impl(h, in_rgb, 1, 2 * H, 2 * W, in_stride, 0, 0, 0, 0, 0, 0, 1, out_rgb, out_stride, 0, flags, 0, nullptr, force_3channel ? 2 : 1);
 }
 
+namespace {
+int unpack_impl(nesr_b200_handle* h, const uint8_t* slots, int32_t slot_w, int32_t slot_h, int32_t H, int32_t W, int32_t tile, int32_t pre_pad,
+                int32_t tile_first, int32_t tile_count, const int32_t* tile_ids, uint8_t* out_bgr, int64_t out_stride);
+}
+
 int nesr_b200_unpack_tiles_u8(nesr_b200_handle* h, const uint8_t* slots, int32_t slot_w, int32_t slot_h, int32_t H, int32_t W, int32_t tile,
                               int32_t pre_pad, int32_t tile_first, int32_t tile_count, uint8_t* out_bgr, int64_t out_stride) {
+  return unpack_impl(h, slots, slot_w, slot_h, H, W, tile, pre_pad, tile_first, tile_count, nullptr, out_bgr, out_stride);
+}
+
+int nesr_b200_unpack_tile_list_u8(nesr_b200_handle* h, const uint8_t* slots, int32_t slot_w, int32_t slot_h, int32_t H, int32_t W, int32_t tile,
+                                  int32_t pre_pad, const int32_t* tile_ids, int32_t slot_count, uint8_t* out_bgr, int64_t out_stride) {
+  if (!tile_ids && slot_count > 0) return fail(h, NESR_E_INVALID, "unpack_tile_list: null list");
+  return unpack_impl(h, slots, slot_w, slot_h, H, W, tile, pre_pad, 0, slot_count, tile_ids, out_bgr, out_stride);
+}
+
+namespace {
+int unpack_impl(nesr_b200_handle* h, const uint8_t* slots, int32_t slot_w, int32_t slot_h, int32_t H, int32_t W, int32_t tile, int32_t pre_pad,
+                int32_t tile_first, int32_t tile_count, const int32_t* tile_ids, uint8_t* out_bgr, int64_t out_stride) {
   if (tile_count == 0) return NESR_OK;
   if (!h) return NESR_E_INVALID;
   if (!slots || !out_bgr || H < 1 || W < 1 || tile < 0 || tile_first < 0 || tile_count < 0) return fail(h, NESR_E_INVALID, "unpack_tiles: bad arguments");
@@ -1610,14 +1627,18 @@ int nesr_b200_unpack_tiles_u8(nesr_b200_handle* h, const uint8_t* slots, int32_t
   if (int wrc = wait_external(h)) return wrc;
   const int s = h->cfg.scale;
   const Grid g = tile_grid_dims(H, W, tile, pre_pad, s);
-  if (tile_first + tile_count > g.tiles_x * g.tiles_y) return fail(h, NESR_E_INVALID, "unpack_tiles: tile range outside the grid");
-  cudaError_t e = launch_unpack_tiles(slots, slot_w, slot_h, g.tiles_x, (tile > 0 ? tile : std::max(H, W)) * s, H * s, W * s, tile_first, tile_count, out_bgr,
-                                      out_stride, h->stream);
+  if (!tile_ids && tile_first + tile_count > g.tiles_x * g.tiles_y) return fail(h, NESR_E_INVALID, "unpack_tiles: tile range outside the grid");
+  if (tile_ids)
+    for (int k = 0; k < tile_count; ++k)
+      if (tile_ids[k] >= g.tiles_x * g.tiles_y) return fail(h, NESR_E_INVALID, "unpack_tile_list: tile %d outside the grid", tile_ids[k]);
+  cudaError_t e = launch_unpack_tiles(slots, slot_w, slot_h, g.tiles_x, (tile > 0 ? tile : std::max(H, W)) * s, H * s, W * s, tile_first, tile_count, tile_ids,
+                                      out_bgr, out_stride, h->stream);
   h->stats.kernel_launches++;
   if (e != cudaSuccess) return fail(h, NESR_E_CUDA, "unpack_tiles launch failed: %s", cudaGetErrorString(e));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return NESR_OK;
 }
+}  // namespace
 
 namespace {
 int forward_nchw(nesr_b200_handle* h, const float* x, bool unshuffled, int32_t n, int32_t H, int32_t W, float* y, void* stream) {

@@ -57,8 +57,9 @@ struct PackParams {
 };
 cudaError_t launch_pack(const PackParams& p, cudaStream_t stream);
 // tile-major slots (tile k of [first, first+count) in slot k, its output rectangle at the slot's origin) -> their places in the frame
+constexpr int kUnpackMaxTiles = 64;     // tile ids per launch (kernel parameter space); longer lists are pasted in several launches
 cudaError_t launch_unpack_tiles(const uint8_t* slots, int slot_w, int slot_h, int tiles_x, int tile_out, int out_h, int out_w, int first,
-                                int count, uint8_t* out, int64_t out_stride, cudaStream_t stream);
+                                int count, const int32_t* tile_ids, uint8_t* out, int64_t out_stride, cudaStream_t stream);
 
 // --- stencil.cu : bit-exact integer post-process kernels ----------------------------------------
 constexpr int kMaxBlendMembers = 16;

@@ -92,9 +92,12 @@ cudaError_t launch_pack(const PackParams& p, cudaStream_t stream) {
 namespace {
 // One block per (tile, 8 output rows): copies the tile's rectangle from its slot to its place in the frame, 16 bytes per
 // thread where both sides allow it (tile origins are multiples of tile_out * 3 bytes; edge tiles and odd strides fall back to bytes).
+struct TileIds { int32_t id[kUnpackMaxTiles]; };     // slot k holds tile id[k] (< 0: empty slot); id[0] < -1: slots are the range first, first+1, ...
 __global__ void __launch_bounds__(256) unpack_tiles_kernel(const uint8_t* __restrict__ slots, int slot_w, int slot_h, int tiles_x, int tile_out,
-                                                           int out_h, int out_w, int first, uint8_t* __restrict__ out, int64_t out_stride) {
-  const int k = blockIdx.y, t = first + k;
+                                                           int out_h, int out_w, int first, const __grid_constant__ TileIds ids,
+                                                           uint8_t* __restrict__ out, int64_t out_stride) {
+  const int k = blockIdx.y, t = ids.id[0] < -1 ? first + k : ids.id[k];
+  if (t < 0) return;
   const int ty = t / tiles_x, tx = t - ty * tiles_x;
   const int y0 = ty * tile_out, x0 = tx * tile_out;
   const int h = min(tile_out, out_h - y0), w = min(tile_out, out_w - x0);
@@ -115,10 +118,18 @@ __global__ void __launch_bounds__(256) unpack_tiles_kernel(const uint8_t* __rest
 }  // namespace
 
 cudaError_t launch_unpack_tiles(const uint8_t* slots, int slot_w, int slot_h, int tiles_x, int tile_out, int out_h, int out_w, int first,
-                                int count, uint8_t* out, int64_t out_stride, cudaStream_t stream) {
+                                int count, const int32_t* tile_ids, uint8_t* out, int64_t out_stride, cudaStream_t stream) {
   if (count <= 0) return cudaSuccess;
   const int rows = tile_out < out_h ? tile_out : out_h;
-  unpack_tiles_kernel<<<dim3((rows + 7) / 8, count), 256, 0, stream>>>(slots, slot_w, slot_h, tiles_x, tile_out, out_h, out_w, first, out, out_stride);
+  const size_t slot_bytes = static_cast<size_t>(slot_w) * 3 * slot_h;
+  for (int k0 = 0; k0 < count; k0 += kUnpackMaxTiles) {
+    const int n = count - k0 < kUnpackMaxTiles ? count - k0 : kUnpackMaxTiles;
+    TileIds ids;
+    ids.id[0] = -2;
+    if (tile_ids) for (int k = 0; k < n; ++k) ids.id[k] = tile_ids[k0 + k] < 0 ? -1 : tile_ids[k0 + k];
+    unpack_tiles_kernel<<<dim3((rows + 7) / 8, n), 256, 0, stream>>>(slots + k0 * slot_bytes, slot_w, slot_h, tiles_x, tile_out, out_h, out_w,
+                                                                      first + k0, ids, out, out_stride);
+  }
   return cudaGetLastError();
 }
 

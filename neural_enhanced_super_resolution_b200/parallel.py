@@ -9,8 +9,8 @@ forwards, weights are replicated (33 MB).  The only collective is the final gath
     ``partition_by_cost``, is 12 % off); every rank
     writes its tiles TILE-MAJOR into one contiguous buffer (``nesr_b200_enhance_tile_list_packed_u8``), ONE
     ``all_gather_into_tensor`` over NCCL/NVLink exchanges the buffers (each rank sends only its own pixels: 1/N of
-    the frame, ~12 MB at 8 GPUs for an 8K frame) and one small kernel per rank pastes the slots into the frame
-    (``nesr_b200_unpack_tiles_u8``).  With one rank it is the plain ``enhance_u8`` call.
+    the frame, ~12 MB at 8 GPUs for an 8K frame) and one small kernel pastes every rank's slots into the frame
+    (``nesr_b200_unpack_tile_list_u8``).  With one rank it is the plain ``enhance_u8`` call.
   * ``enhance_frames_sharded`` -- BASELINE config 4: frames are dealt round-robin-contiguously to ranks;
     no collective unless the caller asks for the frames back (``gather=True``).
 
@@ -91,7 +91,7 @@ def _world(group):
 def enhance_sharded(engine, img_bgr, tile: int, tile_pad: int, pre_pad: int = 0, group=None, out=None, timing=None):
     """Tile-sharded ``RealESRGANer.enhance`` of one frame; every rank returns the full x2 frame.
 
-    ``engine`` needs ``tile_costs`` / ``slot_shape`` / ``enhance_tile_list_packed_u8`` / ``unpack_tiles_u8`` / ``enhance_u8`` /
+    ``engine`` needs ``tile_costs`` / ``slot_shape`` / ``enhance_tile_list_packed_u8`` / ``unpack_tile_list_u8`` / ``enhance_u8`` /
     ``scale`` (an ``_ffi.Engine``); ``img_bgr`` is a CUDA uint8 tensor (NCCL) or a numpy array (gloo tests).
     ``timing``: a dict that receives this rank's ``compute_ms`` / ``gather_ms`` / ``unpack_ms`` (wall clock, phases are
     synchronous) and its tile range."""
@@ -128,10 +128,10 @@ def enhance_sharded(engine, img_bgr, tile: int, tile_pad: int, pre_pad: int = 0,
     if on_device:
         torch.cuda.current_stream(img_bgr.device).synchronize()
     t2 = time.perf_counter()
-    for r, ids in enumerate(parts):                                # every rank pastes every rank's slots (its own included)
-        slots_r = gathered[r] if on_device else gathered[r].numpy()
-        for k, f, c in _runs(ids):                                 # one paste per run of consecutive tiles
-            engine.unpack_tiles_u8(slots_r[k:k + c], out, h, w, tile, pre_pad, f, c)
+    # every rank pastes every rank's slots (its own included): ONE call over the whole gathered buffer, empty slots marked -1
+    all_ids = [ids[k] if k < len(ids) else -1 for ids in parts for k in range(slots_per_rank)]
+    flat = gathered.view(world * slots_per_rank, sh, sw, 3)
+    engine.unpack_tile_list_u8(flat if on_device else flat.numpy(), out, h, w, tile, pre_pad, all_ids)
     t3 = time.perf_counter()
     if timing is not None:
         timing.update(compute_ms=1e3 * (t1 - t0), gather_ms=1e3 * (t2 - t1), unpack_ms=1e3 * (t3 - t2), tiles=list(mine_ids),

@@ -226,6 +226,16 @@ def test_tile_major_exchange_format_reassembles_the_frame(up_random):
             for k, first, count in parallel._runs(ids):
                 eng.unpack_tiles_u8(slots[k:k + count], out, h, w, tile, pre, first, count)
         assert torch.equal(out, want), (h, w, tile, "lpt")
+        # ... and the whole "gathered" buffer of every rank in one call, empty slots marked -1
+        parts_l = parallel.partition_lpt(eng.tile_costs(h, w, tile, pad, pre), world)
+        per = max(len(p) for p in parts_l)
+        gathered = torch.zeros((world * per, sh, sw, 3), dtype=torch.uint8, device="cuda")
+        for r, ids in enumerate(parts_l):
+            if ids:
+                eng.enhance_tile_list_packed_u8(img, gathered[r * per:(r + 1) * per], tile, pad, pre, ids)
+        out.fill_(3)
+        eng.unpack_tile_list_u8(gathered, out, h, w, tile, pre, [ids[k] if k < len(ids) else -1 for ids in parts_l for k in range(per)])
+        assert torch.equal(out, want), (h, w, tile, "one paste")
 
 
 def test_device_tensor_in_out(up_random):

@@ -137,6 +137,14 @@ class OracleTileEngine:
             out[ys:ye, xs:xe] = slots[k, :ye - ys, :xe - xs]
         return out
 
+    def unpack_tile_list_u8(self, slots, out, h, w, tile, pre_pad, tile_ids):
+        rects = self._rects(h, w, tile, pre_pad)
+        for k, t in enumerate(tile_ids):
+            if t >= 0:
+                ys, ye, xs, xe = rects[t]
+                out[ys:ye, xs:xe] = slots[k, :ye - ys, :xe - xs]
+        return out
+
     def enhance_batch_u8(self, frames, tile=0, tile_pad=10, pre_pad=0):
         up = self._mk(tile, tile_pad, pre_pad)
         return np.stack([up.enhance(f)[0] for f in frames]) if len(frames) else np.zeros((0,), np.uint8)
