@@ -134,7 +134,10 @@ __device__ __forceinline__ TrunkSweep load_sweep(const TrunkSweep* sweeps, int i
 // clamped to the rows that exist (N and the first weight row shrink).  wait[X]: this sweep is the first toucher of half X
 // after its drain: every slot is waited for (drained + re-zeroed) before the first MMA that touches it; commit[X]: this sweep
 // completes half X: every output row is committed to the epilogue as soon as its last contribution is issued.
-template <int KS, bool SINGLE>
+// HALF_A (the two single-layer sweeps S2 / S5, KS = 2): the plane's first 32 channels only, loaded as a half-width slab -- 64-byte rows,
+// SWIZZLE_64B (8.7 KB instead of 17 KB per slab row: these sweeps were bound by the slab stream, 8.7k cycles against 4.8k of MMA work);
+// the dx shift is then a 64-byte offset of the A descriptor.
+template <int KS, bool SINGLE, bool HALF_A = false>
 __device__ __forceinline__ void sweep_band(Shared& sh, const int rows, const int slot0, const uint32_t tmem_base, const uint32_t hw,
                                            const uint32_t hi, const uint32_t a_lo0, const uint32_t w_lo, const uint32_t box_lo,
                                            const bool wait_a, const uint32_t par_a, const bool wait_b, const uint32_t par_b,
@@ -158,7 +161,11 @@ __device__ __forceinline__ void sweep_band(Shared& sh, const int rows, const int
       b_lo = w_lo + static_cast<uint32_t>(lo - (i - 1)) * kBlkLo;
     }
     const uint32_t a_lo = a_lo0 + stage * kSlabLo;
-    if (mma_on) umma_f16_ksteps<KS>(d, a_lo, b_lo, hi, id);
+    constexpr uint32_t kDx = HALF_A ? 4u : 8u;                  // one pixel row of the slab in descriptor units (16 bytes)
+    if (mma_on) {
+      if (HALF_A) umma_f16_2ksteps_half_a(d, a_lo, b_lo, hi, id, umma_desc_hi_sw64());
+      else umma_f16_ksteps<KS>(d, a_lo, b_lo, hi, id);
+    }
     // while those run: is the next input row ready?  (slot i+2 is first touched by input row i+1)
     const int nstage = stage + 1 == kStages ? 0 : stage + 1;
     if (i < rows) {
@@ -170,8 +177,13 @@ __device__ __forceinline__ void sweep_band(Shared& sh, const int rows, const int
       tc_fence_after();
     }
     if (mma_on) {
-      umma_f16_ksteps<KS>(d, a_lo + 8, b_lo + box_lo, hi, id);
-      umma_f16_ksteps<KS>(d, a_lo + 16, b_lo + 2 * box_lo, hi, id);
+      if (HALF_A) {
+        umma_f16_2ksteps_half_a(d, a_lo + kDx, b_lo + box_lo, hi, id, umma_desc_hi_sw64());
+        umma_f16_2ksteps_half_a(d, a_lo + 2 * kDx, b_lo + 2 * box_lo, hi, id, umma_desc_hi_sw64());
+      } else {
+        umma_f16_ksteps<KS>(d, a_lo + kDx, b_lo + box_lo, hi, id);
+        umma_f16_ksteps<KS>(d, a_lo + 2 * kDx, b_lo + 2 * box_lo, hi, id);
+      }
     }
     umma_commit(&sh.empty[stage]);                              // slab may be overwritten once these MMAs have read it
     if (i >= 1) {                                               // output row i-1 has all its contributions
@@ -199,6 +211,7 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.full[0]); tma_prefetch_desc(&maps.full[1]);
     tma_prefetch_desc(&maps.w192); tma_prefetch_desc(&maps.w160);
+    tma_prefetch_desc(&maps.half[0]); tma_prefetch_desc(&maps.half[1]);
     for (int i = 0; i < kWStages; ++i) { mbar_init(&sh.wfull[i], 1); mbar_init(&sh.wempty[i], 1); }
     for (int i = 0; i < kStages; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 1); }
     for (int i = 0; i < kSlots; ++i) {
@@ -317,15 +330,16 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
       const unsigned need = static_cast<unsigned>(sw.need);
       const bool rowwise = need > known && !(dbg0 & 16384);     // 16384: no dependency waits (timing experiments)
       const unsigned row_base = (need - 1) * kProgUnit;
-      const CUtensorMap* amap = &maps.full[sw.src_sel & 1];
-      const CUtensorMap* bmap = &maps.box[sw.src_sel & 1][0];
+      const bool half = sw.ks == 2 && (sw.flags & kSweepSingleB);   // S2 / S5: the plane's first 32 channels, half-width slab rows
+      const CUtensorMap* amap = half ? &maps.half[sw.src_sel & 1] : &maps.full[sw.src_sel & 1];
+      const CUtensorMap* bmap = half ? &maps.hbox[sw.src_sel & 1][0] : &maps.box[sw.src_sel & 1][0];
       const int plane = sw.plane * plane_px;
       int t = 0;                                                // slab row of the CTA (bands in order, input rows -1 .. rows)
       for (int b = 0; b < nband; ++b) {
         const BandInfo& bi = sh.band[b];
         const int nrow = bi.rows + 2;
         const bool full_strip = bi.full_strip != 0;
-        const uint32_t row_bytes = bi.row_bytes;
+        const uint32_t row_bytes = half ? bi.row_bytes >> 1 : bi.row_bytes;
         for (int i = 0; i < nrow; ++i, ++t) {
           if (rowwise) {
             const unsigned req = sh.need_rows[t][lane];
@@ -358,7 +372,7 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
                 tma_load_2d_hint(slab, amap, &sh.full[stage], 0, plane + bi.op_px[0] + i * bi.op_pitch[0], keep);
               } else {
                 for (int k = 0; k < bi.nop; ++k)
-                  tma_load_2d_hint(slab + bi.op_off[k], bmap + bi.op_box[k], &sh.full[stage], 0,
+                  tma_load_2d_hint(slab + (half ? bi.op_off[k] >> 1 : bi.op_off[k]), bmap + bi.op_box[k], &sh.full[stage], 0,
                                    plane + bi.op_px[k] + i * bi.op_pitch[k], keep);
               }
             }
@@ -401,7 +415,7 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
             case 0: sweep_band<4, false>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, box_lo, wait_a, par_a, wait_b, par_b, commit_a, commit_b, stage, phase, mma_on); break;
             case 1: sweep_band<2, false>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, box_lo, wait_a, par_a, wait_b, par_b, commit_a, commit_b, stage, phase, mma_on); break;
             case 2: sweep_band<4, true>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, box_lo, wait_a, par_a, wait_b, par_b, commit_a, commit_b, stage, phase, mma_on); break;
-            default: sweep_band<2, true>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, box_lo, wait_a, par_a, wait_b, par_b, commit_a, commit_b, stage, phase, mma_on); break;
+            default: sweep_band<2, true, true>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, box_lo, wait_a, par_a, wait_b, par_b, commit_a, commit_b, stage, phase, mma_on); break;
           }
         }
         umma_commit(&sh.wempty[ws]);

@@ -91,6 +91,7 @@ struct Arena {
   CUtensorMap f_x0, f_d[2], f_g2, f_g4[2];             // box 136 px (row-folded kernel, full strips)
   CUtensorMap e_x0, e_d[2], e_g2, e_g4[2];             // box 8 px (row-folded kernel, packed remainder strips)
   CUtensorMap b_d[2][4];                               // boxes 8 / 16 / 32 / 64 px of the dense-block buffers (trunk kernel)
+  CUtensorMap hf_d[2], hb_d[2][4];                     // the same as 32-channel (64-byte, SWIZZLE_64B) boxes: 136 px and 8 / 16 / 32 / 64 px
   bool shared_g = false;                               // growth planes shared by both dense buffers (see build_plan)
 };
 
@@ -338,13 +339,15 @@ void pack_sweep(const Layer* la, const Layer* lb, const float* wa, const float* 
     }
 }
 
-int make_map(nesr_b200_handle* h, CUtensorMap* m, void* base, int64_t channels, int64_t rows, int box_rows) {
+// half = true: a box of the FIRST or SECOND 32 channels of the 64-channel pixel rows (inner coordinate 0 or 32), written to shared
+// memory as 64-byte rows with the 64-byte swizzle -- the half-width slabs of the trunk kernel's single-layer sweeps.
+int make_map(nesr_b200_handle* h, CUtensorMap* m, void* base, int64_t channels, int64_t rows, int box_rows, bool half = false) {
   const cuuint64_t gdim[2] = {(cuuint64_t)channels, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)channels * 2};
-  const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {half ? 32u : 64u, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1u, 1u};
   CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, half ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(h, NESR_E_CUDA, "cuTensorMapEncodeTiled failed (%d) ch=%lld rows=%lld", (int)r,
                                      (long long)channels, (long long)rows);
@@ -855,6 +858,10 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
     for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.e_d[i2], a.d[i2], 64, dpx[i2], 8))) return rc;
     for (int i2 = 0; i2 < 2; ++i2)
       for (int k = 0; k < 4; ++k) if ((rc = make_map(h, &a.b_d[i2][k], a.d[i2], 64, dpx[i2], 8 << k))) return rc;
+    for (int i2 = 0; i2 < 2; ++i2) {
+      if ((rc = make_map(h, &a.hf_d[i2], a.d[i2], 64, dpx[i2], kSlab, true))) return rc;
+      for (int k = 0; k < 4; ++k) if ((rc = make_map(h, &a.hb_d[i2][k], a.d[i2], 64, dpx[i2], 8 << k, true))) return rc;
+    }
     if ((rc = make_map(h, &a.e_g2, a.g2, 64, Pb[1], 8))) return rc;
     for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.e_g4[i2], a.g4[i2], 64, Pb[2], 8))) return rc;
   }
@@ -1057,7 +1064,8 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
     if (b.trunk_fits) {
       for (int i2 = 0; i2 < 2; ++i2) {
         tm.full[i2] = a.f_d[i2];
-        for (int k = 0; k < 4; ++k) tm.box[i2][k] = a.b_d[i2][k];
+        for (int k = 0; k < 4; ++k) { tm.box[i2][k] = a.b_d[i2][k]; tm.hbox[i2][k] = a.hb_d[i2][k]; }
+        tm.half[i2] = a.hf_d[i2];
       }
       tm.w192 = h->m_wm[0]; tm.w160 = h->m_wm[1];
     }

@@ -30,6 +30,7 @@ cudaError_t launch_conv3x3_body(const CUtensorMap& d0_136, const CUtensorMap& d1
 struct TrunkMaps {
   CUtensorMap full[2];
   CUtensorMap box[2][4];
+  CUtensorMap half[2], hbox[2][4];   // 32-channel (64-byte rows, SWIZZLE_64B) boxes of the same buffers: the half-width slabs of sweeps S2 / S5
   CUtensorMap w192, w160;      // merged trunk weights, boxes of 192 / 160 rows
 };
 cudaError_t conv3x3_trunk_configure();

@@ -199,6 +199,21 @@ __device__ __forceinline__ constexpr uint32_t umma_desc_hi_sw128(uint32_t sbo_by
   return (sbo_bytes >> 4) | (1u << 14) | (2u << 29);
 }
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+// K-major operand written by TMA with CU_TENSOR_MAP_SWIZZLE_64B: rows of 64 bytes (32 16-bit elements), 8-row groups of 512 B
+__device__ __forceinline__ constexpr uint32_t umma_desc_hi_sw64(uint32_t sbo_bytes = 512) {
+  return (sbo_bytes >> 4) | (1u << 14) | (4u << 29);
+}
+// Two k-steps of a half-width (64-byte-row) A operand against a 128-byte-row B operand: separate descriptor high words.
+#define NESR_UMMA_STEP_AB(K)                                           \
+  "add.u32 ta, %1, " #K ";\n\t"                                        \
+  "add.u32 tb, %2, " #K ";\n\t"                                        \
+  "mov.b64 da, {ta, %5};\n\t"                                          \
+  "mov.b64 db, {tb, %3};\n\t"                                          \
+  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+__device__ __forceinline__ void umma_f16_2ksteps_half_a(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi_b, uint32_t idesc, uint32_t hi_a) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 ta, tb;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               NESR_UMMA_STEP_AB(0) NESR_UMMA_STEP_AB(2) "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi_b), "r"(idesc), "r"(hi_a) : "memory");
+}
 
 #define NESR_UMMA_STEP(K)                                              \
   "add.u32 ta, %1, " #K ";\n\t"                                        \
