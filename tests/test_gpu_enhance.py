@@ -340,6 +340,27 @@ def test_outscale_gray_rgba_and_16bit(up_random):
     assert out.dtype == np.uint16 and np.abs(out.astype(int) - want.astype(int)).max() <= TOL_ABS * 257
 
 
+def test_dni_interpolates_two_checkpoints_like_upstream(tmp_path):
+    """``RealESRGANer(model_path=[a, b], dni_weight=[w, 1-w])`` (upstream ``dni``: linear interpolation of the two checkpoints' 'params'
+    tensors before ``load_state_dict``): the mirror class against the oracle's restatement on the same two checkpoints."""
+    from oracle import shims
+    paths = []
+    for seed in (0, 7):
+        sd = torch.load(checkpoint("calibrated", seed=seed))["params_ema"]
+        d = tmp_path / f"net{seed}"
+        d.mkdir()
+        p = d / "net.pth"
+        torch.save({"params": sd}, p)                              # upstream's dni reads the 'params' key
+        paths.append(str(p))
+    img = natural_image(48, 64, seed=13)
+    out, _ = pkg.RealESRGANer(2, paths, dni_weight=[0.3, 0.7], model=pkg.RRDBNet(3, 3, scale=2), tile=0, pre_pad=0, device="cuda:0").enhance(img)
+    want, _ = OracleUp(2, paths, dni_weight=[0.3, 0.7], model=x2plus(None), tile=0, pre_pad=0).enhance(img)
+    single, _ = gpu_up("calibrated").enhance(img)
+    d = np.abs(out.astype(np.int32) - want.astype(np.int32))
+    assert d.max() <= TOL_ABS and psnr(out, want) >= TOL_PSNR
+    assert (out != single).any()                                   # the interpolated network is a different network
+
+
 def test_errors_are_exceptions_not_fallbacks(up_random, tmp_path):
     with pytest.raises(RuntimeError, match="even"):
         gpu_up("random", 15, 4).enhance(natural_image(40, 40))
