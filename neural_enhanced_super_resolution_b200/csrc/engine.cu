@@ -946,11 +946,17 @@ ConvParams rdb_conv_params(const nesr_b200_handle* h, const Arena& a, int r, int
     p.lrelu = 1;
     p.dst16 = a.d[a.shared_g ? 0 : cur]; p.dst16_coff = kFeat + (k - 1) * kGrow; p.dst16_fmt = c.body_format;   // shared growth planes sit behind xA
   } else {                           // x5*0.2 + x  (+ RRDB skip on every third block)
-    p.res1 = a.trunk; p.s1 = 0.2f;
+    // fp32 residuals: Y = a.trunk carries the running sum inside an RRDB, X = a.rrdb holds the RRDB's input (the first RRDB's is
+    // conv_first's output, a.feat, which the long skip needs again).  The block that closes an RRDB reads Y and the RRDB input and
+    // writes its result ONCE, into X (a lane reads its own channels before it overwrites them): that value is both the next RRDB's
+    // input and its first block's residual, which therefore reads X and writes Y.  (Round 1 wrote it twice, into trunk and rrdb.)
+    const int i = r / 3, j = r % 3;
+    p.s1 = 0.2f;
+    p.res1 = (j == 0 && i > 0) ? a.rrdb : a.trunk;
     p.dst32a = a.trunk;
-    if (r % 3 == 2) {
-      p.res2 = (r == 2) ? a.feat : a.rrdb; p.s2 = 0.2f;
-      p.dst32b = a.rrdb;
+    if (j == 2) {
+      p.res2 = (i == 0) ? a.feat : a.rrdb; p.s2 = 0.2f;
+      p.dst32a = a.rrdb;
     }
     p.dst16 = a.d[cur ^ 1]; p.dst16_coff = 0;
     p.dst16_fmt = (r == nrdb - 1) ? c.edge_format : c.body_format;    // conv_body reads the last one
