@@ -70,7 +70,8 @@ constexpr int kMaxBands = kTrunkMaxBands;
 constexpr int kProgUnit = 32;                          // progress value = pass * kProgUnit + rows stored (rows <= 8)
 #if NESR_PROF
 constexpr int kTrace = 48;
-#define TS(k, idx) do { if ((idx) < kTrace) sh.ts[k][idx] = clock64(); } while (0)
+// sweeps [kTrace0 * 8, +kTrace) and passes [kTrace0 * 6, +kTrace) are recorded: dense block kTrace0 onwards (0 when the net is shorter)
+#define TS(k, idx) do { const int i_ = (idx) - ts_base[(k) == 0 || (k) == 4 ? 0 : 1]; if (i_ >= 0 && i_ < kTrace) sh.ts[k][i_] = clock64(); } while (0)
 #else
 #define TS(k, idx) do {} while (0)
 #endif
@@ -93,6 +94,10 @@ struct Shared {
   uint32_t tmem_slot;
   int32_t nband, nrows;                                // bands / output rows of this CTA
   BandInfo band[kMaxBands];
+  TrunkOrder order;                                    // phase order of the CTA's input rows, completion order of its output rows (layout.h)
+  // what the MMA issuer does with the t-th slab row of that order (the same in every sweep): first slot it feeds | slots - 1 << 4 |
+  // weight blocks skipped at the band's upper end << 6 | slots it touches first << 8 | slots it completes << 16
+  uint32_t step[kTrunkMaxSlabRows];
   int32_t lane_px[kMaxBands][128];                     // flat pixel of (r0, x) of each MMA lane, or -1 (masked lane)
   int32_t lane_pitch[kMaxBands][128];
   int32_t lane_rows[kMaxBands][128];                   // band rows [0, lane_rows) belong to the lane's piece
@@ -128,51 +133,57 @@ __device__ __forceinline__ TrunkSweep load_sweep(const TrunkSweep* sweeps, int i
   return s;
 }
 
-// One sweep over one band, executed by the single MMA-issuing thread.  KS k-steps per (row, dx).  SINGLE: an N = 160 sweep
-// into half B whose weight rows over half A are zero (D starts at column 32 of the first slot); otherwise both halves of
-// every slot, N = 192.  Input row i feeds output rows i-1, i, i+1 = three consecutive slots; at the band's ends the MMA is
-// clamped to the rows that exist (N and the first weight row shrink).  wait[X]: this sweep is the first toucher of half X
-// after its drain: every slot is waited for (drained + re-zeroed) before the first MMA that touches it; commit[X]: this sweep
-// completes half X: every output row is committed to the epilogue as soon as its last contribution is issued.
+// One sweep over the CTA's input rows, executed by the single MMA-issuing thread.  KS k-steps per (row, dx).  SINGLE: an N = 160
+// sweep into half B whose weight rows over half A are zero (D starts at column 32 of the first slot); otherwise both halves of
+// every slot, N = 192.  Slab row i of a band (input row i-1) feeds output rows i-2, i-1, i = three consecutive slots; at the
+// band's ends the MMA is clamped to the rows that exist (N and the first weight row shrink).  The rows are taken in the CTA's
+// PHASE ORDER (layout.h trunk_order), bands interleaved.  wait[X]: this sweep is the first toucher of half X after its drain:
+// every slot is waited for (drained + re-zeroed) before the first MMA that touches it; commit[X]: this sweep completes half X:
+// every output row is committed to the epilogue as soon as its third contribution is issued.
 // HALF_A (the two single-layer sweeps S2 / S5, KS = 2): the plane's first 32 channels only, loaded as a half-width slab -- 64-byte rows,
 // SWIZZLE_64B (8.7 KB instead of 17 KB per slab row: these sweeps were bound by the slab stream, 8.7k cycles against 4.8k of MMA work);
 // the dx shift is then a 64-byte offset of the A descriptor.
 template <int KS, bool SINGLE, bool HALF_A = false>
-__device__ __forceinline__ void sweep_band(Shared& sh, const int rows, const int slot0, const uint32_t tmem_base, const uint32_t hw,
-                                           const uint32_t hi, const uint32_t a_lo0, const uint32_t w_lo, const uint32_t box_lo,
-                                           const bool wait_a, const uint32_t par_a, const bool wait_b, const uint32_t par_b,
-                                           const bool commit_a, const bool commit_b, int& stage, uint32_t& phase, const bool mma_on) {
+__device__ __forceinline__ void sweep_cta(Shared& sh, const uint32_t tmem_base, const uint32_t hw,
+                                          const uint32_t hi, const uint32_t a_lo0, const uint32_t w_lo, const uint32_t box_lo,
+                                          const bool wait_a, const uint32_t par_a, const bool wait_b, const uint32_t par_b,
+                                          const bool commit_a, const bool commit_b, int& stage, uint32_t& phase, const bool mma_on) {
   constexpr uint32_t kSlabLo = kSlabBytes >> 4;
   constexpr uint32_t kBlkLo = (kSlotCols * 128) >> 4;           // weight rows of one output row (64 rows of 128 bytes)
-  const uint32_t id_full = umma_idesc_f16(hw, SINGLE ? 160u : 192u);
-  if (wait_a) mbar_wait(&sh.tempty[0][slot0], par_a);
-  if (wait_b) mbar_wait(&sh.tempty[1][slot0], par_b);
+  constexpr uint32_t kDx = HALF_A ? 4u : 8u;                    // one pixel row of the slab in descriptor units (16 bytes)
+  const int n_in = sh.order.n_in;
+  if (n_in == 0) return;                                        // a CTA the deal left without rows
+  const uint32_t id1 = umma_idesc_f16(hw, SINGLE ? 32u : 64u), id2 = umma_idesc_f16(hw, SINGLE ? 96u : 128u),
+                 id3 = umma_idesc_f16(hw, SINGLE ? 160u : 192u);
+  const bool waits = wait_a || wait_b, commits = commit_a || commit_b;
+  auto wait_slots = [&](uint32_t m) {                           // drained + re-zeroed?
+    while (m) {
+      const int sl = __ffs(m) - 1;
+      m &= m - 1;
+      if (wait_a) mbar_wait(&sh.tempty[0][sl], par_a);
+      if (wait_b) mbar_wait(&sh.tempty[1][sl], par_b);
+    }
+  };
+  uint32_t w = sh.step[0];
+  if (waits) wait_slots((w >> 8) & 0xffu);
   mbar_wait(&sh.full[stage], phase);
   tc_fence_after();
-  for (int i = -1; i <= rows; ++i) {
-    uint32_t d, id, b_lo;
-    if (i >= 1 && i + 1 <= rows - 1) {                          // interior: output rows i-1, i, i+1
-      d = tmem_base + static_cast<uint32_t>(slot0 + i - 1) * kSlotCols + (SINGLE ? 32u : 0u); id = id_full; b_lo = w_lo;
-    } else {
-      const int lo = i - 1 < 0 ? 0 : i - 1;
-      const int hi_row = i + 1 > rows - 1 ? rows - 1 : i + 1;
-      d = tmem_base + static_cast<uint32_t>(slot0 + lo) * kSlotCols + (SINGLE ? 32u : 0u);
-      id = umma_idesc_f16(hw, static_cast<uint32_t>(SINGLE ? (hi_row - lo) * kSlotCols + 32 : (hi_row - lo + 1) * kSlotCols));
-      b_lo = w_lo + static_cast<uint32_t>(lo - (i - 1)) * kBlkLo;
-    }
+  for (int t = 0; t < n_in; ++t) {
+    const uint32_t nsl = (w >> 4) & 3u;
+    const uint32_t d = tmem_base + (w & 15u) * kSlotCols + (SINGLE ? 32u : 0u);
+    const uint32_t id = nsl == 2u ? id3 : (nsl == 1u ? id2 : id1);
+    const uint32_t b_lo = w_lo + ((w >> 6) & 3u) * kBlkLo;
     const uint32_t a_lo = a_lo0 + stage * kSlabLo;
-    constexpr uint32_t kDx = HALF_A ? 4u : 8u;                  // one pixel row of the slab in descriptor units (16 bytes)
     if (mma_on) {
       if (HALF_A) umma_f16_2ksteps_half_a(d, a_lo, b_lo, hi, id, umma_desc_hi_sw64());
       else umma_f16_ksteps<KS>(d, a_lo, b_lo, hi, id);
     }
-    // while those run: is the next input row ready?  (slot i+2 is first touched by input row i+1)
+    // while those run: are the next input row and the slots it touches first ready?
     const int nstage = stage + 1 == kStages ? 0 : stage + 1;
-    if (i < rows) {
-      if (i + 2 <= rows - 1) {
-        if (wait_a) mbar_wait(&sh.tempty[0][slot0 + i + 2], par_a);
-        if (wait_b) mbar_wait(&sh.tempty[1][slot0 + i + 2], par_b);
-      }
+    uint32_t wn = 0;
+    if (t + 1 < n_in) {
+      wn = sh.step[t + 1];
+      if (waits) wait_slots((wn >> 8) & 0xffu);
       mbar_wait(&sh.full[nstage], nstage == 0 ? phase ^ 1 : phase);
       tc_fence_after();
     }
@@ -186,10 +197,16 @@ __device__ __forceinline__ void sweep_band(Shared& sh, const int rows, const int
       }
     }
     umma_commit(&sh.empty[stage]);                              // slab may be overwritten once these MMAs have read it
-    if (i >= 1) {                                               // output row i-1 has all its contributions
-      if (commit_a) umma_commit(&sh.tfull[0][slot0 + i - 1]);
-      if (commit_b) umma_commit(&sh.tfull[1][slot0 + i - 1]);
+    if (commits) {
+      uint32_t m = (w >> 16) & 0xffu;                           // output rows that now have their three contributions
+      while (m) {
+        const int sl = __ffs(m) - 1;
+        m &= m - 1;
+        if (commit_a) umma_commit(&sh.tfull[0][sl]);
+        if (commit_b) umma_commit(&sh.tfull[1][sl]);
+      }
     }
+    w = wn;
     stage = nstage;
     if (stage == 0) phase ^= 1;
   }
@@ -261,6 +278,31 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
         bi.row_bytes = bi.full_strip ? kSlabBytes : row_bytes;
       }
       sh.nrows = slot0;
+      int brows[kMaxBands], by0[kMaxBands];
+      for (int b = 0; b < nband; ++b) {
+        const FoldBand band = p0.bands[band_begin + b];
+        brows[b] = band.rows; by0[b] = band.r0;
+        for (int sgi = 0; sgi < band.nseg; ++sgi) {
+          const FoldSeg sg = p0.segs[band.seg0 + sgi];
+          if (band.r0 < sg.h) { by0[b] = sg.y0 + band.r0; break; }   // pieces of a packed strip start at multiples of 8 tile rows
+        }
+      }
+      trunk_order(brows, by0, nband, sh.order);
+      uint32_t swept[kMaxBands] = {0, 0, 0, 0}, touched = 0;
+      for (int t = 0; t < sh.order.n_in; ++t) {
+        const int b = sh.order.in_band[t], i = sh.order.in_row[t];
+        const int rows = sh.band[b].rows, s0 = sh.band[b].slot0;
+        const int lo = i - 2 < 0 ? 0 : i - 2, hi_row = i > rows - 1 ? rows - 1 : i;
+        uint32_t first = 0, complete = 0;
+        swept[b] |= 1u << i;
+        for (int j = lo; j <= hi_row; ++j) {
+          if (!((touched >> (s0 + j)) & 1u)) first |= 1u << (s0 + j);
+          if (((swept[b] >> j) & 7u) == 7u) complete |= 1u << (s0 + j);   // slab rows j, j + 1, j + 2
+        }
+        touched |= first;
+        sh.step[t] = static_cast<uint32_t>(s0 + lo) | static_cast<uint32_t>(hi_row - lo) << 4 | static_cast<uint32_t>(lo - (i - 2)) << 6 |
+                     first << 8 | complete << 16;
+      }
     }
     if (threadIdx.x < 128) {
       const int m = threadIdx.x;
@@ -299,6 +341,10 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
   tc_fence_after();
   const int nband = sh.nband;
   [[maybe_unused]] const int dbg0 = NESR_PROF ? __ldg(&passes[0].debug_flags) : 0;
+#if NESR_PROF
+  const int trace_blk = nsweep >= 40 * kSweepsPerBlock ? 30 : 0;
+  const int ts_base[2] = {trace_blk * kSweepsPerBlock, trace_blk * 6};
+#endif
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -334,13 +380,13 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
       const CUtensorMap* amap = half ? &maps.half[sw.src_sel & 1] : &maps.full[sw.src_sel & 1];
       const CUtensorMap* bmap = half ? &maps.hbox[sw.src_sel & 1][0] : &maps.box[sw.src_sel & 1][0];
       const int plane = sw.plane * plane_px;
-      int t = 0;                                                // slab row of the CTA (bands in order, input rows -1 .. rows)
-      for (int b = 0; b < nband; ++b) {
-        const BandInfo& bi = sh.band[b];
-        const int nrow = bi.rows + 2;
-        const bool full_strip = bi.full_strip != 0;
-        const uint32_t row_bytes = half ? bi.row_bytes >> 1 : bi.row_bytes;
-        for (int i = 0; i < nrow; ++i, ++t) {
+      const int n_in = sh.order.n_in;
+      for (int t = 0; t < n_in; ++t) {                          // slab rows of the CTA in phase order
+        {
+          const BandInfo& bi = sh.band[sh.order.in_band[t]];
+          const int i = sh.order.in_row[t];
+          const bool full_strip = bi.full_strip != 0;
+          const uint32_t row_bytes = half ? bi.row_bytes >> 1 : bi.row_bytes;
           if (rowwise) {
             const unsigned req = sh.need_rows[t][lane];
             unsigned target = req ? row_base + req : 0u;
@@ -409,14 +455,11 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
         mbar_wait(&sh.wfull[ws], wphase);
         const uint32_t w_lo = w_lo0 + ws * kWStageLo;
         const int variant = ((sw.flags & kSweepSingleB) ? 2 : 0) + (sw.ks == 4 ? 0 : 1);
-        for (int b = 0; b < nband; ++b) {
-          const int rows = sh.band[b].rows, slot0 = sh.band[b].slot0;
-          switch (variant) {
-            case 0: sweep_band<4, false>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, box_lo, wait_a, par_a, wait_b, par_b, commit_a, commit_b, stage, phase, mma_on); break;
-            case 1: sweep_band<2, false>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, box_lo, wait_a, par_a, wait_b, par_b, commit_a, commit_b, stage, phase, mma_on); break;
-            case 2: sweep_band<4, true>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, box_lo, wait_a, par_a, wait_b, par_b, commit_a, commit_b, stage, phase, mma_on); break;
-            default: sweep_band<2, true, true>(sh, rows, slot0, tmem_base, hw, hi, a_lo0, w_lo, box_lo, wait_a, par_a, wait_b, par_b, commit_a, commit_b, stage, phase, mma_on); break;
-          }
+        switch (variant) {
+          case 0: sweep_cta<4, false>(sh, tmem_base, hw, hi, a_lo0, w_lo, box_lo, wait_a, par_a, wait_b, par_b, commit_a, commit_b, stage, phase, mma_on); break;
+          case 1: sweep_cta<2, false>(sh, tmem_base, hw, hi, a_lo0, w_lo, box_lo, wait_a, par_a, wait_b, par_b, commit_a, commit_b, stage, phase, mma_on); break;
+          case 2: sweep_cta<4, true>(sh, tmem_base, hw, hi, a_lo0, w_lo, box_lo, wait_a, par_a, wait_b, par_b, commit_a, commit_b, stage, phase, mma_on); break;
+          default: sweep_cta<2, true, true>(sh, tmem_base, hw, hi, a_lo0, w_lo, box_lo, wait_a, par_a, wait_b, par_b, commit_a, commit_b, stage, phase, mma_on); break;
         }
         umma_commit(&sh.wempty[ws]);
         if (++ws == kWStages) { ws = 0; wphase ^= 1; }
@@ -446,19 +489,15 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
     int my_slot[kMyRows], my_px[kMyRows];                       // slot (uniform; -1: none) and flat pixel (-1: masked lane) of this warp's rows
 #pragma unroll
     for (int k = 0; k < kMyRows; ++k) { my_slot[k] = -1; my_px[k] = -1; }
-    {
-      int n = 0;
-      for (int b = 0; b < nband; ++b) {
-        const int rows = sh.band[b].rows, slot0 = sh.band[b].slot0;
-        const int px0 = sh.lane_px[b][m], pitch = sh.lane_pitch[b][m], nmine = sh.lane_rows[b][m];
-        for (int j = 0; j < rows; ++j) {
-          if (((slot0 + j) & 1) != group) continue;
+    for (int q = group; q < sh.order.n_out; q += 2) {           // rows in the order they complete, alternating between the groups
+      const int slot = sh.order.out_slot[q];
+      int b = 0;
+      while (b + 1 < nband && slot >= sh.band[b + 1].slot0) ++b;
+      const int j = slot - sh.band[b].slot0;
+      const int px0 = sh.lane_px[b][m], pitch = sh.lane_pitch[b][m], nmine = sh.lane_rows[b][m];
 #pragma unroll
-          for (int k = 0; k < kMyRows; ++k)
-            if (k == n) { my_slot[k] = slot0 + j; my_px[k] = (px0 >= 0 && j < nmine) ? px0 + j * pitch : -1; }
-          ++n;
-        }
-      }
+      for (int k = 0; k < kMyRows; ++k)
+        if (k == (q >> 1)) { my_slot[k] = slot; my_px[k] = (px0 >= 0 && j < nmine) ? px0 + j * pitch : -1; }
     }
     uint32_t ndrain[2] = {0, 0};                                // passes drained so far from each TMEM half
     float* const my_bias = sh.bias[warp - 2];
@@ -477,6 +516,9 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
       uint16_t* const base16 = reinterpret_cast<uint16_t*>(pp->dst16) + static_cast<size_t>(coff16 >> 6) * pp->dst16_plane_px * 64 + (coff16 & 63);
       __syncwarp();                                             // every lane is done with the previous pass's bias
       for (int k = lane; k < nsub * COUT; k += 32) my_bias[k] = __ldg(pp->bias + k);   // conv5's halves: consecutive channels of one layer
+      const int init = res1 ? 0 : __ldg(&pp->trunk_init);       // (uniform) conv3 / conv4: the drained half receives conv5's bias + residuals
+      const ConvParams* p5 = pp + 2;                            // the conv5 pass of that half
+      if (init) my_bias[COUT + lane] = __ldg(p5->bias + lane);
       __syncwarp();
       const uint32_t tpar0 = ndrain[half0] & 1u, tpar1 = ndrain[half0 ^ 1] & 1u;
       ++ndrain[half0];
@@ -533,8 +575,8 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
         return (static_cast<size_t>(P >> 5) * 8 + ((c_off0 + sub * COUT) >> 3)) * 256 + (static_cast<size_t>(P & 31) << 3);
       };
 
-      if (!res1) {
-        // ---- conv1..4 ----
+      if (!res1 && !init) {
+        // ---- conv1, conv2 ----
 #pragma unroll
         for (int k = 0; k < kMyRows; ++k) {
           const int slot = my_slot[k];
@@ -552,16 +594,23 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
           }
           row_stored(slot);
         }
-      } else {
-        // ---- conv5 (one or both halves per row), each half row's trunk values prefetched one half row ahead ----
-        float rt[COUT];                                         // trunk[pixel][the 32 channels of the half row about to be drained]
-        auto load_trunk = [&](int P, int sub) {
-          const size_t t = trunk_off(P, sub);
-          if (dbg & 2097152) return;                             // 2097152: no trunk loads (timing experiments)
+      } else if (!res1) {
+        // ---- conv3, conv4: drained half <- conv5's bias + res1 / s1 [+ res2 / (s1 s2)] for its 32 channels of that half ----
+        // conv5 is  v = (acc + bias) s1 + res1 [; v = v s2 + res2]  =  (acc + bias + res1 / s1 [+ res2 / (s1 s2)]) * s1 [s2]: with the
+        // bracket's constant part already in the accumulator, conv5's epilogue loads nothing.  The residual rows are this lane's own
+        // pixels (written by its conv5 epilogue of the previous block) and are prefetched one row ahead.
+        const float* const i1 = p5->res1;
+        const float* const i2 = p5->res2;
+        const float inv1 = 1.0f / p5->s1, inv2 = i2 ? inv1 / p5->s2 : 0.0f;
+        const int icoff = p5->c_off;
+        auto res_off = [&](int P) { return (static_cast<size_t>(P >> 5) * 8 + (icoff >> 3)) * 256 + (static_cast<size_t>(P & 31) << 3); };
+        float rt[COUT];
+        auto load_res1 = [&](int P) {
+          const size_t t = res_off(P);
 #pragma unroll
-          for (int q = 0; q < COUT / 8; ++q) ldg256(res1 + t + q * 256, &rt[q * 8]);
+          for (int q = 0; q < COUT / 8; ++q) ldg256(i1 + t + q * 256, &rt[q * 8]);
         };
-        if (my_slot[0] >= 0 && my_px[0] >= 0 && !off) load_trunk(my_px[0], 0);
+        if (my_slot[0] >= 0 && my_px[0] >= 0 && !off) load_res1(my_px[0]);
 #pragma unroll
         for (int k = 0; k < kMyRows; ++k) {
           const int slot = my_slot[k];
@@ -569,43 +618,77 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
           const int P = my_px[k];
           const bool on = P >= 0 && !off;
           constexpr int kLast = kMyRows - 1;
-          const int Pn = my_px[k < kLast ? k + 1 : k];          // next row of this warp (if any)
+          const int Pn = my_px[k < kLast ? k + 1 : k];
           const bool next_row_on = k < kLast && my_slot[k < kLast ? k + 1 : k] >= 0 && Pn >= 0 && !off;
+          float r2[COUT];
+          if (on && i2) {
+            const size_t t = res_off(P);
+#pragma unroll
+            for (int q = 0; q < COUT / 8; ++q) ldg256_stream(i2 + t + q * 256, &r2[q * 8]);
+          }
+          uint32_t r[COUT / 16][16];
+          mbar_wait(&sh.tfull[half0][slot], tpar0);
+          tc_fence_after();
+          __syncwarp();
+          const uint32_t taddr = lane_base + static_cast<uint32_t>(slot * kSlotCols + half0 * COUT);
+#pragma unroll
+          for (int c = 0; c < COUT / 16; ++c) tmem_ld16(taddr + c * 16, r[c]);
+          uint32_t iv[COUT / 16][16];
+#pragma unroll
+          for (int q = 0; q < COUT; ++q) {
+            float x = 0.0f;
+            if (on) {
+              x = fmaf(rt[q], inv1, my_bias[COUT + q]);
+              if (i2) x = fmaf(r2[q], inv2, x);
+            }
+            iv[q >> 4][q & 15] = __float_as_uint(x);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < COUT / 16; ++c) tmem_st16(taddr + c * 16, iv[c]);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&sh.tempty[half0][slot]);
+          if (next_row_on) load_res1(Pn);
+          if (on) {
+            float v[COUT];
+            add_bias(r, 0, v);
+            if (lrelu) {
+#pragma unroll
+              for (int q = 0; q < COUT; ++q) v[q] = fmaxf(v[q], 0.2f * v[q]);
+            }
+            store16(P, 0, v);
+          }
+          row_stored(slot);
+        }
+      } else {
+        // ---- conv5 (one or both halves per row): the accumulator already holds bias and residuals (see conv3 / conv4) ----
+        const float sc = res2 ? s1 * s2 : s1;
+#pragma unroll
+        for (int k = 0; k < kMyRows; ++k) {
+          const int slot = my_slot[k];
+          if (slot < 0) continue;
+          const int P = my_px[k];
+          const bool on = P >= 0 && !off;
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
             if (sub == 1 && nsub == 1) break;
-            float r2[COUT];
-            const size_t toff = trunk_off(P >= 0 ? P : 0, sub);
-            if (on && res2) {
-#pragma unroll
-              for (int q = 0; q < COUT / 8; ++q) ldg256_stream(res2 + toff + q * 256, &r2[q * 8]);
-            }
             uint32_t r[COUT / 16][16];
             drain(slot, half0 ^ sub, sub ? tpar1 : tpar0, r);
-            float v[COUT];
             if (on) {
-              add_bias(r, sub, v);
+              float v[COUT];
 #pragma unroll
-              for (int q = 0; q < COUT; ++q) v[q] = fmaf(v[q], s1, rt[q]);
-            }
-            // the registers just consumed take the NEXT half row's trunk values: the other half of this row, or the first
-            // half of this warp's next row
-            if (sub == 0 && nsub == 2) { if (on) load_trunk(P, 1); }
-            else if (next_row_on) load_trunk(Pn, 0);
-            if (on) {
-              if (res2) {
-#pragma unroll
-                for (int q = 0; q < COUT; ++q) v[q] = fmaf(v[q], s2, r2[q]);
-              }
+              for (int q = 0; q < COUT; ++q) v[q] = __uint_as_float(r[q >> 4][q & 15]) * sc;
+              store16(P, sub, v);                                // what the next block's first sweep waits for
+              const size_t toff = trunk_off(P, sub);
               if (!(dbg & 4096)) {                               // 4096: no fp32 trunk stores (timing experiments)
 #pragma unroll
-              for (int q = 0; q < COUT / 8; ++q) stg256f(dst32a + toff + q * 256, &v[q * 8]);
-              }
-              if (dst32b && !(dbg & 4096)) {
+                for (int q = 0; q < COUT / 8; ++q) stg256f(dst32a + toff + q * 256, &v[q * 8]);
+                if (dst32b) {
 #pragma unroll
-                for (int q = 0; q < COUT / 8; ++q) stg256f_stream(dst32b + toff + q * 256, &v[q * 8]);
+                  for (int q = 0; q < COUT / 8; ++q) stg256f_stream(dst32b + toff + q * 256, &v[q * 8]);
+                }
               }
-              store16(P, sub, v);
             }
           }
           row_stored(slot);
@@ -616,9 +699,9 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
     }
   } else {
     // =========================== publisher (warp 10) ===========================
-    // Advances this CTA's row counter in slot order (the two epilogue groups finish rows out of order).  Rows that are
-    // already stored when the previous one is seen are folded into one release: the gpu-scope release is a membar and
-    // must not become a per-row cost when the epilogue is ahead.
+    // Advances this CTA's row counter in the order the rows complete (layout.h trunk_order; the two epilogue groups may
+    // finish neighbouring rows out of order).  Rows that are already stored when the previous one is seen are folded into
+    // one release: the gpu-scope release is a membar and must not become a per-row cost when the epilogue is ahead.
     if (lane == 0) {
       unsigned* my_word = prog + static_cast<size_t>(blockIdx.x) * kProgStride;
       const int nrows = sh.nrows;
@@ -626,16 +709,12 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
       for (int pass = 0; pass < npass; ++pass) {
         if (__ldg(&passes[pass].trunk_no_publish)) continue;
         int q = 0;
-        bool half_done = false;
         while (q < nrows) {
-          mbar_wait(&sh.stored[q], par);
+          mbar_wait(&sh.stored[sh.order.out_slot[q]], par);
           ++q;
-          while (q < nrows && mbar_try_wait(&sh.stored[q], par)) ++q;
+          while (q < nrows && mbar_try_wait(&sh.stored[sh.order.out_slot[q]], par)) ++q;
           if ((dbg0 & 131072) && q < nrows) continue;            // 131072: publish whole passes only (timing experiments)
-          // A release is a membar (~1-2k cycles): at most one intermediate publication per pass, so that the one for the last
-          // row -- the one the next sweep's first slab rows wait for in the CTA below -- rarely queues behind another.
-          if (q < nrows && (q < (nrows + 1) / 2 || half_done)) continue;
-          half_done = true;
+          // A release is a membar (~1-2k cycles): rows that complete while one is under way are published together by the next.
           // generic-proxy stores of the epilogue warps (observed through the mbarriers) -> async-proxy (TMA) reads of whoever
           // acquires the value released below: the one proxy fence of the chain
           fence_proxy_async_all();
@@ -655,11 +734,11 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
 #if NESR_PROF
   if ((dbg0 & 1024) && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 40)) {
     const long long t0 = sh.ts[4][0];
-    for (int q = 0; q < kTrace && q < nsweep; ++q)
-      printf("[trunk blk %d sweep %d S%d need=%d] producer_at_first_row %lld  mma_issued %lld\n", (int)blockIdx.x, q, q % kSweepsPerBlock + 1,
-             sweeps[q].need, sh.ts[4][q] - t0, sh.ts[0][q] - t0);
-    for (int q = 0; q < kTrace && q < npass; ++q)
-      printf("[trunk blk %d pass %d half %d] epi_rows_done %lld  published %lld\n", (int)blockIdx.x, q, passes[q].trunk_half,
+    for (int q = 0; q < kTrace && q + ts_base[0] < nsweep; ++q)
+      printf("[trunk blk %d sweep %d S%d need=%d] producer_at_first_row %lld  mma_issued %lld\n", (int)blockIdx.x, q + ts_base[0], q % kSweepsPerBlock + 1,
+             sweeps[q + ts_base[0]].need, sh.ts[4][q] - t0, sh.ts[0][q] - t0);
+    for (int q = 0; q < kTrace && q + ts_base[1] < npass; ++q)
+      printf("[trunk blk %d pass %d half %d] epi_rows_done %lld  published %lld\n", (int)blockIdx.x, q + ts_base[1], passes[q + ts_base[1]].trunk_half,
              sh.ts[1][q] - t0, sh.ts[3][q] - t0);
   }
 #endif

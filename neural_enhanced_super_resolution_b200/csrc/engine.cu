@@ -10,6 +10,7 @@
 // over the 148 SMs.  The dense-block concat is two ping-pong [pixels][192] buffers written at
 // channel offsets; the residual trunk is carried in fp32 ([pixels][64]) next to its 16-bit copy.
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -447,7 +448,9 @@ bool build_fold_schedule(Batch& b, int level, int num_sms, int max_rows = 0, int
     auto plan = [&](int T, std::vector<Packed>* out) -> int64_t {
       std::vector<Piece> pcs;
       for (const Piece& c : cols) {
-        const int n = (c.h + T - 1) / T, hp = (c.h + n - 1) / n;
+        // trunk groups: pieces start at multiples of 8 tile rows, so that every piece of a packed strip row is in the same
+        // phase of the trunk kernel's row order (layout.h trunk_order)
+        const int n = (c.h + T - 1) / T, hp = max_rows > 0 ? ((c.h + n - 1) / n + 7) / 8 * 8 : (c.h + n - 1) / n;
         for (int y = 0; y < c.h; y += hp) pcs.push_back(Piece{c.tile, c.x0, c.rem, c.span, y, std::min(hp, c.h - y)});
       }
       std::stable_sort(pcs.begin(), pcs.end(), [](const Piece& a, const Piece& o) { return a.h > o.h; });
@@ -538,13 +541,36 @@ int build_body_passes(nesr_b200_handle* h, Batch& b);
 // Row dependencies of the trunk kernel.  CTA c streams, per chunk sweep, the input rows -1 .. rows of each of its bands
 // ("slab rows", pixels x0-1 .. x0+width of every segment).  A slab row of the chunk that another layer pass has just
 // written may be loaded once every CTA owning one of its pixels has stored that tile row.  Output: lp.deps[c][d] = the
-// CTAs (c itself first) that own such pixels, lp.need[c][t][d] = how many of its output rows (slot order: bands in order)
-// CTA deps[c][d] must have stored before c loads its slab row t.  Strip rows of a packed piece beyond the piece's height
+// CTAs (c itself first) that own such pixels, lp.need[c][t][d] = how many of its output rows (in the order it completes
+// them) CTA deps[c][d] must have stored before c loads the t-th slab row of its phase order (layout.h trunk_order).  Strip rows of a packed piece beyond the piece's height
 // + 1 feed masked lanes only and carry no dependency; rows outside the tile are zero guard rows.
+// Phase order of CTA c's rows (layout.h trunk_order): the kernel derives the same from the same bands.
+bool cta_order(const LevelPlan& lp, int c, TrunkOrder& o) {
+  int rows[kTrunkMaxBands], y0[kTrunkMaxBands];
+  const int b0 = lp.cta_off[c], nb = lp.cta_off[c + 1] - b0;
+  if (nb > kTrunkMaxBands) return false;
+  for (int b = 0; b < nb; ++b) {
+    const FoldBand& band = lp.bands[b0 + b];
+    rows[b] = band.rows; y0[b] = band.r0;
+    for (int sgi = 0; sgi < band.nseg; ++sgi) {
+      const FoldSeg& sg = lp.segs[band.seg0 + sgi];
+      if (band.r0 < sg.h) { y0[b] = sg.y0 + band.r0; break; }
+    }
+  }
+  return trunk_order(rows, y0, nb, o);
+}
+
 void build_trunk_deps(const std::vector<TileGeom>& tiles, LevelPlan& lp) {
   const int grid = lp.fold_grid;
   struct Rect { int tile, x0, x1, y0, y1, cta, q0; };          // inclusive pixel rectangle of one segment of one band; q0 = slot of tile row y0
   std::vector<Rect> rects;
+  std::vector<TrunkOrder> order(grid);
+  std::vector<std::array<uint8_t, kTrunkMaxRows>> done_at(grid);   // [cta][slot]: how many rows the CTA has completed once this one is
+  for (int c = 0; c < grid; ++c) {
+    if (!cta_order(lp, c, order[c])) { lp.deps.clear(); lp.need.clear(); return; }
+    done_at[c].fill(0);
+    for (int q = 0; q < order[c].n_out; ++q) done_at[c][order[c].out_slot[q]] = (uint8_t)(q + 1);
+  }
   for (int c = 0; c < grid; ++c) {
     int slot0 = 0;
     for (int b = lp.cta_off[c]; b < lp.cta_off[c + 1]; ++b) {
@@ -561,11 +587,10 @@ void build_trunk_deps(const std::vector<TileGeom>& tiles, LevelPlan& lp) {
   lp.need.assign((size_t)grid * kTrunkMaxSlabRows * kTrunkMaxDeps, 0);
   for (int c = 0; c < grid; ++c) {
     std::vector<int32_t> dep(1, c);
-    int t = 0;
-    for (int b = lp.cta_off[c]; b < lp.cta_off[c + 1]; ++b) {
-      const FoldBand& band = lp.bands[b];
-      for (int i = -1; i <= band.rows; ++i, ++t) {
-        if (t >= kTrunkMaxSlabRows) { lp.deps.clear(); lp.need.clear(); return; }
+    for (int t = 0; t < order[c].n_in; ++t) {
+      {
+        const FoldBand& band = lp.bands[lp.cta_off[c] + order[c].in_band[t]];
+        const int i = order[c].in_row[t] - 1;                     // input row of the band: -1 .. rows
         for (int sgi = 0; sgi < band.nseg; ++sgi) {
           const FoldSeg& sg = lp.segs[band.seg0 + sgi];
           const int s = band.r0 + i;                              // strip row of this slab row
@@ -582,7 +607,7 @@ void build_trunk_deps(const std::vector<TileGeom>& tiles, LevelPlan& lp) {
               dep.push_back(o.cta);
             }
             uint8_t& n = lp.need[((size_t)c * kTrunkMaxSlabRows + t) * kTrunkMaxDeps + d];
-            n = std::max<uint8_t>(n, (uint8_t)(o.q0 + (y - o.y0) + 1));
+            n = std::max<uint8_t>(n, done_at[o.cta][o.q0 + (y - o.y0)]);
           }
         }
       }
@@ -997,6 +1022,7 @@ int build_body_passes(nesr_b200_handle* h, Batch& b) {
         // the first half of conv5 is needed by nobody before the second half has been published too: skip its publish
         q.trunk_no_publish = (k == 5 && ps + 1 < L.fold_passes) ? 1 : 0;
         q.trunk_half = k == 5 ? ps : ((k - 1) & 1);      // TMEM half: conv1, conv3, conv5[0:32] -> A; conv2, conv4, conv5[32:64] -> B
+        q.trunk_init = (k == 3 || k == 4) ? 1 : 0;       // its drained half receives conv5's bias + residuals (pass + 2)
         q.l2_pin_chunks = h->l2_pin_chunks;
         passes.push_back(q);
       }
@@ -1517,8 +1543,9 @@ int nesr_b200_debug_plan(int32_t n_frames, int32_t H, int32_t W, int32_t tile, i
         for (const TileGeom& t : b.tiles) out[2] += (int64_t)t.lv[0].h * t.lv[0].w;
         if (b.trunk_fits) {
           if (!trunk_schedule_fits(lp)) return fail(nullptr, NESR_E_STATE, "group %zu: trunk fit flag wrong", bi);
-          // Row-dependency table, checked pixel by pixel against an owner map built independently of build_trunk_deps:
-          // every pixel of every slab row that feeds an output row must be covered by need[c][t][lane of its owner] > its slot.
+          // Row-dependency table, checked pixel by pixel against an owner map built independently of build_trunk_deps: every
+          // pixel of every slab row that feeds an output row must be covered by need[c][t][lane of its owner] >= the number of
+          // rows its owner has completed when it completes that pixel's row.
           if ((int)lp.deps.size() != lp.fold_grid * kTrunkMaxDeps || (int)lp.need.size() != lp.fold_grid * kTrunkMaxSlabRows * kTrunkMaxDeps)
             return fail(nullptr, NESR_E_STATE, "group %zu: dependency table size", bi);
           std::vector<std::vector<int32_t>> owner(b.tiles.size());                  // cta * 32 + slot per pixel
@@ -1536,13 +1563,54 @@ int nesr_b200_debug_plan(int32_t n_frames, int32_t H, int32_t W, int32_t tile, i
               slot0 += band.rows;
             }
           }
+          // the order in which every CTA sweeps its slab rows and completes its output rows: every slab row once, every output
+          // row once and only after its three slab rows; the pieces of a packed band agree on the tile row modulo 8
+          std::vector<TrunkOrder> order(lp.fold_grid);
+          std::vector<std::array<uint8_t, kTrunkMaxRows>> done_at(lp.fold_grid);
+          for (int c = 0; c < lp.fold_grid; ++c) {
+            TrunkOrder& o = order[c];
+            if (!cta_order(lp, c, o)) return fail(nullptr, NESR_E_STATE, "group %zu: CTA %d has no phase order", bi, c);
+            int nin = 0, nout = 0;
+            uint32_t swept[kTrunkMaxBands] = {0, 0, 0, 0}, outs = 0;
+            for (int q = lp.cta_off[c]; q < lp.cta_off[c + 1]; ++q) {
+              const FoldBand& band = lp.bands[q];
+              nin += band.rows + 2; nout += band.rows;
+              int res = -1;
+              for (int sgi = 0; sgi < band.nseg; ++sgi) {
+                const FoldSeg& sg = lp.segs[band.seg0 + sgi];
+                if (band.r0 >= sg.h) continue;
+                if (res >= 0 && res != ((sg.y0 + band.r0) & 7)) return fail(nullptr, NESR_E_STATE, "group %zu: packed pieces out of phase", bi);
+                res = (sg.y0 + band.r0) & 7;
+              }
+            }
+            if (o.n_in != nin || o.n_out != nout) return fail(nullptr, NESR_E_STATE, "group %zu: CTA %d phase order size", bi, c);
+            done_at[c].fill(0);
+            int t_out = 0;
+            for (int t = 0; t < o.n_in; ++t) {
+              const int bb = o.in_band[t], i = o.in_row[t];
+              if (bb >= lp.cta_off[c + 1] - lp.cta_off[c] || i > lp.bands[lp.cta_off[c] + bb].rows + 1 || ((swept[bb] >> i) & 1))
+                return fail(nullptr, NESR_E_STATE, "group %zu: CTA %d slab row swept twice", bi, c);
+              swept[bb] |= 1u << i;
+              int slot0 = 0;
+              for (int q = 0; q < bb; ++q) slot0 += lp.bands[lp.cta_off[c] + q].rows;
+              // rows listed as complete after this slab row must have all three of theirs
+              while (t_out < o.n_out) {
+                const int sl = o.out_slot[t_out], j = sl - slot0;
+                if (j < 0 || j >= lp.bands[lp.cta_off[c] + bb].rows || ((swept[bb] >> j) & 7u) != 7u || j < i - 2 || j > i) break;
+                if ((outs >> sl) & 1) return fail(nullptr, NESR_E_STATE, "group %zu: CTA %d output row completed twice", bi, c);
+                outs |= 1u << sl;
+                done_at[c][sl] = (uint8_t)++t_out;
+              }
+            }
+            if (t_out != nout) return fail(nullptr, NESR_E_STATE, "group %zu: CTA %d completes %d of %d rows", bi, c, t_out, nout);
+          }
           for (int c = 0; c < lp.fold_grid; ++c) {
             const int32_t* dep = &lp.deps[(size_t)c * kTrunkMaxDeps];
             if (dep[0] != c) return fail(nullptr, NESR_E_STATE, "group %zu: CTA %d is not its own first dependency", bi, c);
-            int t = 0;
-            for (int q = lp.cta_off[c]; q < lp.cta_off[c + 1]; ++q) {
-              const FoldBand& band = lp.bands[q];
-              for (int i = -1; i <= band.rows; ++i, ++t) {
+            for (int t = 0; t < order[c].n_in; ++t) {
+              {
+                const FoldBand& band = lp.bands[lp.cta_off[c] + order[c].in_band[t]];
+                const int i = order[c].in_row[t] - 1;
                 for (int sgi = 0; sgi < band.nseg; ++sgi) {
                   const FoldSeg& sg = lp.segs[band.seg0 + sgi];
                   const LevelGeom& g = b.tiles[sg.tile].lv[0];
@@ -1555,7 +1623,7 @@ int nesr_b200_debug_plan(int32_t n_frames, int32_t H, int32_t W, int32_t tile, i
                     if (o < 0) return fail(nullptr, NESR_E_STATE, "group %zu: unowned pixel in a slab row", bi);
                     int lane = -1;
                     for (int k = 0; k < kTrunkMaxDeps; ++k) if (dep[k] == o / 32) { lane = k; break; }
-                    if (lane < 0 || lp.need[((size_t)c * kTrunkMaxSlabRows + t) * kTrunkMaxDeps + lane] < (o % 32) + 1)
+                    if (lane < 0 || lp.need[((size_t)c * kTrunkMaxSlabRows + t) * kTrunkMaxDeps + lane] < done_at[o / 32][o % 32])
                       return fail(nullptr, NESR_E_STATE, "group %zu: CTA %d slab row %d does not wait for CTA %d row %d", bi, c, t, o / 32, o % 32);
                   }
                 }

@@ -118,11 +118,16 @@ struct ConvParams {
   // [grid][kTrunkMaxDeps] CTAs (its own first) that own a pixel of this CTA's input slab rows; padded with its own index
   const int32_t* trunk_deps;
   // [grid][kTrunkMaxSlabRows][kTrunkMaxDeps] for slab row t of the CTA (its bands in order, input rows -1 .. rows of each) and
-  // dependency lane d: how many of its output rows (in slot order) CTA trunk_deps[d] must have stored before the slab row of
+  // dependency lane d: how many of its output rows (in the order it completes them) CTA trunk_deps[d] must have stored before the slab row of
   // the newest chunk may be loaded; 0: the slab row holds no pixel of that CTA
   const uint8_t* trunk_need;
   int32_t trunk_no_publish;    // trunk kernel: this pass's rows are not published (conv5 first half: implied by the second half's)
   int32_t trunk_half;          // trunk kernel: which 32-column half of a TMEM row slot this pass's accumulator lives in (0 = A, 1 = B)
+  // trunk kernel, conv3 / conv4 passes: instead of re-zeroing the half it has drained, the epilogue leaves conv5's bias and
+  // fp32 residuals there -- bias + res1 / s1 [+ res2 / (s1 s2)] of pass + 2, the conv5 pass of that half -- so that conv5's own
+  // epilogue is a multiply and stores: its residual loads (L2 round trips, two per channel in every third block) were what
+  // the next block's first sweep waited for.  The other conv kernels ignore the field and evaluate the residuals as written.
+  int32_t trunk_init;
 };
 
 // conv3x3_trunk.cu, MMA side: one chunk sweep over the CTA's bands.  A residual dense block is EIGHT sweeps (SURVEY 8a4:
@@ -161,5 +166,60 @@ constexpr int kTrunkMaxRows = 8;             // 512 TMEM columns / 64 (two 32-ch
 constexpr int kTrunkMaxBands = 4;
 constexpr int kTrunkMaxDeps = 32;            // one polling lane per dependency
 constexpr int kTrunkMaxSlabRows = kTrunkMaxRows + 2 * kTrunkMaxBands;   // input rows a CTA streams per chunk sweep
+
+// PHASE ORDER of the trunk kernel's rows (round 2).  Swept top to bottom, the first slab row of a dependent sweep is the LAST
+// row the CTA above completes, so no sweep could start before its neighbours' previous pass had ended, however finely rows
+// were published (profiles/r2_trunk_experiments.txt, 1. and 5.: ~10k cycles per exposed hand-over, 30k behind conv5).
+// Instead every CTA streams its input rows -- halo rows included -- sorted by a key of the TILE row they hold: residue
+// y mod 8 in the middle-out sequence 3 4 2 5 1 6 0 7.  An output row is complete once rows y-1, y, y+1 have been swept, so
+// rows also COMPLETE in that sequence (it is its own completion order), in every CTA of the group at about the same time
+// whatever its row offset: what a sweep needs first is what the previous pass finished first, everywhere, and a row is
+// asked for 6-8 row times (~8k cycles) after it was completed -- the hand-over is hidden behind the rest of the sweep.
+// Two input rows with the same residue are 8 rows apart and never feed the same output row, so the order in which an output
+// row receives its three contributions depends on its tile row alone: results do not depend on how rows are dealt to CTAs.
+#if defined(__CUDACC__)
+#define NESR_HD __host__ __device__
+#else
+#define NESR_HD
+#endif
+NESR_HD inline int trunk_phase(int tile_row) {
+  return (0x75310246 >> (4 * (tile_row & 7))) & 7;     // residue 0..7 -> position 6 4 2 0 1 3 5 7
+}
+struct TrunkOrder {
+  int32_t n_in, n_out;
+  uint8_t in_band[kTrunkMaxSlabRows];        // processing order of the CTA's input rows: band ...
+  uint8_t in_row[kTrunkMaxSlabRows];         // ... and slab row of the band (0: halo above, r + 1: own row r, rows + 1: halo below)
+  uint8_t out_slot[kTrunkMaxRows];           // completion order of its output rows (TMEM slot = rows of earlier bands + r)
+};
+// rows[b], y0[b]: output rows of band b and the tile row of its first one.  Returns false if the CTA does not fit.
+NESR_HD inline bool trunk_order(const int* rows, const int* y0, int nband, TrunkOrder& o) {
+  o.n_in = 0; o.n_out = 0;
+  uint8_t key[kTrunkMaxSlabRows];
+  int total = 0;
+  if (nband > kTrunkMaxBands) return false;
+  for (int b = 0; b < nband; ++b) {
+    total += rows[b];
+    if (total > kTrunkMaxRows || rows[b] < 1) return false;
+    for (int i = 0; i <= rows[b] + 1; ++i) {
+      const int k = trunk_phase(y0[b] + i - 1 + 8);            // + 8: the halo above row 0 is row -1
+      int at = o.n_in++;
+      while (at > 0 && key[at - 1] > k) {                      // stable insertion
+        key[at] = key[at - 1]; o.in_band[at] = o.in_band[at - 1]; o.in_row[at] = o.in_row[at - 1];
+        --at;
+      }
+      key[at] = static_cast<uint8_t>(k); o.in_band[at] = static_cast<uint8_t>(b); o.in_row[at] = static_cast<uint8_t>(i);
+    }
+  }
+  uint32_t seen[kTrunkMaxBands] = {0, 0, 0, 0};
+  for (int t = 0; t < o.n_in; ++t) {
+    const int b = o.in_band[t], i = o.in_row[t];
+    seen[b] |= 1u << i;
+    int slot0 = 0;
+    for (int q = 0; q < b; ++q) slot0 += rows[q];
+    for (int j = i - 2; j <= i; ++j)                           // output row j is fed by slab rows j, j + 1, j + 2
+      if (j >= 0 && j < rows[b] && ((seen[b] >> j) & 7u) == 7u) o.out_slot[o.n_out++] = static_cast<uint8_t>(slot0 + j);
+  }
+  return true;
+}
 
 }  // namespace nesr
