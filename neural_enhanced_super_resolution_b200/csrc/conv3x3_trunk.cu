@@ -525,17 +525,23 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
       if (nsub == 2) ++ndrain[half0 ^ 1];
       const bool off = (dbg & 1) != 0;                          // 1: no epilogue loads / stores (timing experiments)
 
-      // TMEM -> registers, slot handed back zeroed
-      auto drain = [&](int slot, int half, uint32_t par, uint32_t (&r)[COUT / 16][16]) {
+      // TMEM -> registers; the slot is handed back (zeroed, or holding conv5's residuals) AFTER the row's activations are stored
+      // and signalled: the stores start the long chain (publish -> acquire -> TMA) the next sweep waits for in every neighbour,
+      // the drained slot only a wait inside this CTA.
+      auto fetch = [&](int slot, int half, uint32_t par, uint32_t (&r)[COUT / 16][16]) {
         mbar_wait(&sh.tfull[half][slot], par);
         tc_fence_after();
         __syncwarp();
         const uint32_t taddr = lane_base + static_cast<uint32_t>(slot * kSlotCols + half * COUT);
 #pragma unroll
         for (int c = 0; c < COUT / 16; ++c) tmem_ld16(taddr + c * 16, r[c]);
-        tmem_ld_wait();
+      };
+      auto hand_back_zeroed = [&](int slot, int half) {
+        const uint32_t taddr = lane_base + static_cast<uint32_t>(slot * kSlotCols + half * COUT);
 #pragma unroll
         for (int c = 0; c < COUT / 16; ++c) tmem_st16_zero(taddr + c * 16);
+      };
+      auto handed_back = [&](int slot, int half) {
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&sh.tempty[half][slot]);
@@ -582,7 +588,8 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
           const int slot = my_slot[k];
           if (slot < 0) continue;
           uint32_t r[COUT / 16][16];
-          drain(slot, half0, tpar0, r);
+          fetch(slot, half0, tpar0, r);
+          tmem_ld_wait();
           if (my_px[k] >= 0 && !off) {
             float v[COUT];
             add_bias(r, 0, v);
@@ -593,6 +600,8 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
             store16(my_px[k], 0, v);
           }
           row_stored(slot);
+          hand_back_zeroed(slot, half0);
+          handed_back(slot, half0);
         }
       } else if (!res1) {
         // ---- conv3, conv4: drained half <- conv5's bias + res1 / s1 [+ res2 / (s1 s2)] for its 32 channels of that half ----
@@ -627,29 +636,8 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
             for (int q = 0; q < COUT / 8; ++q) ldg256_stream(i2 + t + q * 256, &r2[q * 8]);
           }
           uint32_t r[COUT / 16][16];
-          mbar_wait(&sh.tfull[half0][slot], tpar0);
-          tc_fence_after();
-          __syncwarp();
-          const uint32_t taddr = lane_base + static_cast<uint32_t>(slot * kSlotCols + half0 * COUT);
-#pragma unroll
-          for (int c = 0; c < COUT / 16; ++c) tmem_ld16(taddr + c * 16, r[c]);
-          uint32_t iv[COUT / 16][16];
-#pragma unroll
-          for (int q = 0; q < COUT; ++q) {
-            float x = 0.0f;
-            if (on) {
-              x = fmaf(rt[q], inv1, my_bias[COUT + q]);
-              if (i2) x = fmaf(r2[q], inv2, x);
-            }
-            iv[q >> 4][q & 15] = __float_as_uint(x);
-          }
+          fetch(slot, half0, tpar0, r);
           tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < COUT / 16; ++c) tmem_st16(taddr + c * 16, iv[c]);
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&sh.tempty[half0][slot]);
-          if (next_row_on) load_res1(Pn);
           if (on) {
             float v[COUT];
             add_bias(r, 0, v);
@@ -660,6 +648,24 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
             store16(P, 0, v);
           }
           row_stored(slot);
+          const uint32_t taddr = lane_base + static_cast<uint32_t>(slot * kSlotCols + half0 * COUT);
+#pragma unroll
+          for (int c = 0; c < COUT / 16; ++c) {
+            uint32_t iv[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int q = c * 16 + e;
+              float x = 0.0f;
+              if (on) {
+                x = fmaf(rt[q], inv1, my_bias[COUT + q]);
+                if (i2) x = fmaf(r2[q], inv2, x);
+              }
+              iv[e] = __float_as_uint(x);
+            }
+            tmem_st16(taddr + c * 16, iv);
+          }
+          handed_back(slot, half0);
+          if (next_row_on) load_res1(Pn);
         }
       } else {
         // ---- conv5 (one or both halves per row): the accumulator already holds bias and residuals (see conv3 / conv4) ----
@@ -670,28 +676,47 @@ conv3x3_trunk_kernel(const __grid_constant__ TrunkMaps maps, const ConvParams* _
           if (slot < 0) continue;
           const int P = my_px[k];
           const bool on = P >= 0 && !off;
+          // both halves' 16-bit activations first -- what the next block's first sweep waits for, in every neighbour -- then the
+          // row's signal; the fp32 residual (read back by this lane only) is written from a second read of the accumulator
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
             if (sub == 1 && nsub == 1) break;
             uint32_t r[COUT / 16][16];
-            drain(slot, half0 ^ sub, sub ? tpar1 : tpar0, r);
+            fetch(slot, half0 ^ sub, sub ? tpar1 : tpar0, r);
+            tmem_ld_wait();
             if (on) {
               float v[COUT];
 #pragma unroll
               for (int q = 0; q < COUT; ++q) v[q] = __uint_as_float(r[q >> 4][q & 15]) * sc;
-              store16(P, sub, v);                                // what the next block's first sweep waits for
-              const size_t toff = trunk_off(P, sub);
-              if (!(dbg & 4096)) {                               // 4096: no fp32 trunk stores (timing experiments)
-#pragma unroll
-                for (int q = 0; q < COUT / 8; ++q) stg256f(dst32a + toff + q * 256, &v[q * 8]);
-                if (dst32b) {
-#pragma unroll
-                  for (int q = 0; q < COUT / 8; ++q) stg256f_stream(dst32b + toff + q * 256, &v[q * 8]);
-                }
-              }
+              store16(P, sub, v);
             }
           }
           row_stored(slot);
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            if (sub == 1 && nsub == 1) break;
+            if (!(dbg & 4096)) {                                 // 4096: no fp32 trunk stores (timing experiments)
+              uint32_t r[COUT / 16][16];                         // (the TMEM load is warp-wide: outside the per-lane mask)
+              const uint32_t taddr = lane_base + static_cast<uint32_t>(slot * kSlotCols + (half0 ^ sub) * COUT);
+#pragma unroll
+              for (int c = 0; c < COUT / 16; ++c) tmem_ld16(taddr + c * 16, r[c]);
+              tmem_ld_wait();
+              if (on) {
+                const size_t toff = trunk_off(P, sub);
+#pragma unroll
+                for (int q = 0; q < COUT / 8; ++q) {
+                  float v[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[(q * 8 + e) >> 4][(q * 8 + e) & 15]) * sc;
+                  stg256f(dst32a + toff + q * 256, v);
+                  if (dst32b) stg256f_stream(dst32b + toff + q * 256, v);
+                }
+              }
+            }
+            hand_back_zeroed(slot, half0 ^ sub);
+          }
+          handed_back(slot, half0);
+          if (nsub == 2) { tc_fence_before(); mbar_arrive(&sh.tempty[half0 ^ 1][slot]); }
         }
       }
       if (threadIdx.x == 64) TS(1, pass + nsub - 1);

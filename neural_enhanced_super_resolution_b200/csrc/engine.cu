@@ -657,6 +657,7 @@ int plan_groups(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
       }
       score += 0.27 + 0.214 * busiest + (b.trunk_fits ? 0.12 * std::max(0, pieces - 5) : 1.0 * busiest);   // a whole-frame-kernel group is ~5x slower
     }
+    if (getenv("NESR_B200_PLAN_DEBUG")) fprintf(stderr, "nesr_b200 plan: %d pieces per strip: %zu groups, model %.2f ms\n", pieces, h->batches.size(), score);
     if (score < best - 1e-9) { best = score; keep = std::move(h->batches); }
   }
   h->batches = std::move(keep);
@@ -1494,6 +1495,7 @@ int nesr_b200_debug_plan(int32_t n_frames, int32_t H, int32_t W, int32_t tile, i
   nesr_b200_default_config(&hd.cfg, 0);
   hd.cfg.conv_impl = conv_impl; hd.cfg.max_batch_pixels = max_batch_pixels;
   hd.num_sms = num_sms;
+  if (const char* mp = getenv("NESR_B200_MAX_PIECES")) hd.max_pieces = atoi(mp);
   (void)pairs; (void)sets;                                     // reserved (round-1 planner variants, removed): ignored
   PlanKey key; key.n_frames = n_frames; key.H = H; key.W = W; key.tile = tile; key.tile_pad = tile_pad; key.pre_pad = pre_pad;
   key.first = 0; key.count = 0; key.whole = 1;
