@@ -22,27 +22,38 @@
 //   against 80).  The epilogue still drains 32 columns at a time, in six passes per block, each as soon as its half is complete.
 //   The weights stream too: one [3 dx][192|160][64] box set (72 KB) per sweep through a 2-deep ring.
 //   DEPENDENCIES ARRIVE LAST.  The sweep that needs the newest channels (S2, S4, S5, S8 and the next block's S1) is the one
-//   that completes an accumulator; the sweeps between them (S3, S6, S7) need nothing new and hide the hand-over.
+//   that completes an accumulator; the sweeps between them (S3, S6, S7) need nothing new.
 //   ROW-GRANULAR HAND-OVER (round 2).  The round-1 kernel published "pass complete" once per pass and CTA, so every pass
 //   was a serial chain  acquire -> first slab -> dependent sweep -> epilogue tail -> fence + barrier + publish  (22k cycles
 //   per conv1-4 pass against 9-22k cycles of MMA work: profiles/r1_trunk_chain_trace.txt).  Now every CTA publishes a
 //   ROW counter (pass * 32 + rows stored) in its own 128-byte line, advanced by a dedicated PUBLISHER warp as the epilogue
 //   warps signal stored rows on shared-memory mbarriers, and the TMA producer waits per slab row for exactly the rows of
 //   the neighbouring CTAs (and of its own) that the slab covers -- a host-built table [slab row][dependency] of row counts.
-//   The dependent sweep of pass k+1 therefore trails pass k's epilogue by a row or two instead of waiting for its tail,
-//   the gpu-scope release (a membar) is paid by a warp that has nothing else to do, and nothing in the kernel is a
+//   The gpu-scope release (a membar) is paid by a warp that has nothing else to do, and nothing in the kernel is a
 //   CTA-wide barrier any more.
+//   PHASE-ORDERED ROWS (round 2, layout.h trunk_order).  Swept top to bottom, a dependent sweep's first slab row is the last
+//   row the CTA above completes: no sweep could start before its neighbours' previous pass had ended.  Every CTA now sweeps
+//   its input rows (halo rows included, bands interleaved) sorted by the tile row's residue mod 8 in the sequence
+//   3 4 2 5 1 6 0 7 -- which is also the order in which its output rows complete, in every CTA of the group whatever its row
+//   offset -- so what a sweep needs first is what the previous pass finished first, everywhere, and the hand-over
+//   (drain -> store -> publish -> acquire -> TMA, ~10k cycles) hides behind the remaining 8 rows of the sweep.
+//   CONV5'S RESIDUALS LIVE IN THE ACCUMULATOR (round 2).  The conv3 / conv4 epilogues leave  bias + res1/s1 [+ res2/(s1 s2)]
+//   of conv5's 32 channels in the half they have drained instead of zeros, so conv5's epilogue is a multiply and stores: its
+//   residual loads were what the next block's first sweep waited for.
 //
 // Memory-model argument for the publisher (PTX causality order is transitive): epilogue thread's st.global (+ its
 // fence.proxy.async) -> mbarrier.arrive (release.cta) -> publisher's mbarrier wait (acquire.cta) -> publisher's
 // st.release.gpu -> consumer lane's ld.acquire.gpu -> __syncwarp -> fence.proxy.async -> TMA load.  Round 1 used the same
 // shape with bar.sync in place of the mbarrier.
 //
-// Write-after-read safety of the single-buffered growth planes under row granularity: a CTA writes row j of a plane only
-// after it has LOADED slab rows j-1..j+1 of a pass that depends on the previous dense block's conv5, i.e. after every CTA
-// that can read row j of the old contents has stored the corresponding conv5 rows -- and a CTA storing any conv5 row has
-// finished every TMA load of that block's earlier chunks and of the last chunk's rows up to one below it (MMAs complete
-// in issue order, the epilogue runs after the last chunk's MMAs of the row).
+// Write-after-read safety of the single-buffered growth planes (x itself ping-pongs between two buffers).  A CTA overwrites
+// pixel p of plane x_k (block n+1) when its conv_k epilogue drains p's row, i.e. after a sweep of block n+1 has swept the
+// three input rows around p -- rows that hold, for every CTA C that reads p (C owns a pixel within one row and one column of
+// p), one of C's own pixels of a plane C stored in block n+1 or in conv5 of block n.  C stored that pixel from an epilogue
+// that ran after a commit of one of ITS block-n+1 sweeps (or of S8 of block n), the commit covers every MMA C issued before
+// it, and C issues sweeps in program order: every sweep of block n that reads x_k (for x3 / x4: S8, the last one) had
+// consumed its slabs before p is overwritten.  The argument uses the order of SWEEPS, not of rows inside a sweep, so it
+// holds for any row order.
 //
 // Roles (fold_roles.cuh explains the row fold itself): warp 0 TMA producer (weights + row slabs), warp 1 MMA issuer,
 // warps 2..9 epilogue (two groups alternating rows), warp 10 publisher.  Launched cooperatively (grid <= #SMs).
