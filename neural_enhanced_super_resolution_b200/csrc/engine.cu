@@ -494,7 +494,7 @@ bool build_fold_schedule(Batch& b, int level, int num_sms, int max_rows = 0, int
   // Tiny groups: the edge-layer kernels (one launch per layer) prefer a few CTAs with >= 4 rows each over 148 CTAs with a
   // row each (per-CTA weight loads); the trunk kernel (max_rows > 0) is latency bound per sweep -- a band of n rows costs
   // n + 2 slab rows in every one of its 552 sweeps -- so its rows are spread over all SMs.
-  static const int kTrunkMinRows = getenv("NESR_B200_MIN_ROWS") ? atoi(getenv("NESR_B200_MIN_ROWS")) : 1;
+  const int kTrunkMinRows = getenv("NESR_B200_MIN_ROWS") ? atoi(getenv("NESR_B200_MIN_ROWS")) : 1;   // (read per plan: tests vary it)
   const int min_rows = max_rows > 0 ? std::max(1, kTrunkMinRows) : 4;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms, total_rows / min_rows));
   // Contiguous runs of equal COST: a band of n rows costs n + 2 slab rows (its halo), so a CTA whose run crosses a

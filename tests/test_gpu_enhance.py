@@ -289,6 +289,14 @@ def test_trunk_kernel_variants_are_bit_identical(monkeypatch):
     classic, _ = gpu_up("calibrated", 512, 10).enhance(big)
     monkeypatch.delenv("NESR_B200_SHARED_G")
     assert np.array_equal(classic, want_big)
+    # Rows are swept in an order keyed on the TILE row (layout.h trunk_order), so a pixel's accumulation order does not depend on
+    # which CTA owns its row or where that CTA's rows start: other group plans (6 groups instead of 5; small groups on fewer CTAs
+    # with >= 4 rows each) give the same bits.
+    for var, val in (("NESR_B200_MAX_PIECES", "3"), ("NESR_B200_MIN_ROWS", "4")):
+        monkeypatch.setenv(var, val)
+        other, _ = gpu_up("calibrated", 512, 10).enhance(big)
+        monkeypatch.delenv(var)
+        assert np.array_equal(other, want_big), var
     monkeypatch.setenv("NESR_B200_ARENA_LIMIT_MB", "1")          # tile groups share one arena slice (re-zeroed per group)
     shared, _ = gpu_up("calibrated", 160, 10, max_batch_pixels=20000).enhance(img)
     monkeypatch.delenv("NESR_B200_ARENA_LIMIT_MB")
