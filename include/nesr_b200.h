@@ -208,6 +208,16 @@ int nesr_b200_blend_u8(nesr_b200_handle* h, const uint8_t* const* members, int32
 int nesr_b200_sharpen_u8(nesr_b200_handle* h, const uint8_t* in, int32_t H, int32_t W,
                          int32_t bgr, uint8_t* out, int32_t flags);
 
+/* Replaces: the unsharp stage of SuperResolutionPipeline._segment_and_enhance (nesr/nesr.py:728-747; SURVEY.md 8f row f4,
+ * "segmentation-masked unsharp reusing K6"): object_mask = cv2.dilate(object_mask, ones((3, 3))); blurred =
+ * cv2.GaussianBlur(img, (0, 0), 3); sharpened = cv2.addWeighted(img, 1.5, blurred, -0.5, 0); out = where(object_mask == 1,
+ * sharpened, img).  `object_mask` is the H x W u8 mask at image resolution BEFORE the dilation (the reference's
+ * cv2.resize(object_mask, (W, H)), nesr/nesr.py:730), on the same side (host / device) as `in`; the dilation is done here.
+ * Same kernel and fixed-point arithmetic as nesr_b200_sharpen_u8, bit-exact with cv2 4.13.  The segmentation model itself
+ * (SegFormer via transformers) is out of scope. */
+int nesr_b200_masked_unsharp_u8(nesr_b200_handle* h, const uint8_t* in, const uint8_t* object_mask, int32_t H, int32_t W,
+                                int32_t bgr, uint8_t* out, int32_t flags);
+
 /* Replaces: SuperResolutionPipeline._preprocess_image (nesr/nesr.py:668-689): RGB H x W x 3 u8 ->
  * same layout.  denoise_h > 0: cv2.fastNlMeansDenoisingColored(img, None, denoise_h, denoise_h_color, 7, 21) (the reference
  * passes 10 * config['denoise_level'] for both; denoise_h_color <= 0 means "same as denoise_h"); denoise_h <= 0 skips the

@@ -22,7 +22,7 @@ EXPORTS = (
     "nesr_b200_default_config", "nesr_b200_create", "nesr_b200_destroy", "nesr_b200_last_error",
     "nesr_b200_load_weight", "nesr_b200_finalize_weights", "nesr_b200_enhance_u8",
     "nesr_b200_enhance_batch_u8", "nesr_b200_tile_count", "nesr_b200_debug_plan", "nesr_b200_enhance_tiles_u8",
-    "nesr_b200_forward_nchw_f32", "nesr_b200_blend_u8", "nesr_b200_sharpen_u8", "nesr_b200_get_stats",
+    "nesr_b200_forward_nchw_f32", "nesr_b200_blend_u8", "nesr_b200_sharpen_u8", "nesr_b200_masked_unsharp_u8", "nesr_b200_get_stats",
     "nesr_b200_synchronize", "nesr_b200_debug_conv", "nesr_b200_preprocess_u8", "nesr_b200_debug_lab_table",
     "nesr_b200_debug_nlm_weights", "nesr_b200_forward_nchw12_f32", "nesr_b200_enhance_tiles_packed_u8",
     "nesr_b200_unpack_tiles_u8", "nesr_b200_enhance_tile_list_packed_u8", "nesr_b200_enhance_head_u8", "nesr_b200_unpack_tile_list_u8",
@@ -95,6 +95,7 @@ def load_library() -> C.CDLL:
         lib.nesr_b200_blend_u8.argtypes = [H, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32,
                                            C.POINTER(C.c_double), u8p, C.c_int32]
         lib.nesr_b200_sharpen_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int32, u8p, C.c_int32]
+        lib.nesr_b200_masked_unsharp_u8.argtypes = [H, u8p, u8p, C.c_int32, C.c_int32, C.c_int32, u8p, C.c_int32]
         lib.nesr_b200_preprocess_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32,
                                                 C.c_int32, u8p, C.c_int32]
         lib.nesr_b200_debug_lab_table.argtypes = [C.c_int32, C.c_void_p, C.c_int32]
@@ -394,6 +395,23 @@ class Engine:
         op, odev = _image_ptr(out, self.device)
         flags = (PTR_IN_DEVICE if idev else 0) | (PTR_OUT_DEVICE if odev else 0)
         self._check(self._lib.nesr_b200_sharpen_u8(self._h, ip, h, w, int(bool(bgr)), op, flags), "sharpen_u8")
+        return out
+
+    def masked_unsharp_u8(self, img, object_mask, bgr: bool = False, out=None):
+        """The unsharp stage of ``SuperResolutionPipeline._segment_and_enhance`` (``nesr/nesr.py:728-747``): ``object_mask`` (H x W u8, on
+        the same side as ``img``) is dilated 3 x 3 and the sigma-3 unsharp replaces the pixels where the dilated mask is 1."""
+        h, w = img.shape[:2]
+        if img.ndim != 3 or img.shape[2] != 3 or tuple(object_mask.shape) != (h, w):
+            raise ValueError("masked_unsharp_u8 expects an H x W x 3 image and an H x W mask")
+        if out is None:
+            out = self._alloc_like(img, (h, w, 3))
+        ip, idev = _image_ptr(img, self.device)
+        mp, mdev = _image_ptr(object_mask, self.device)
+        if mdev != idev:
+            raise ValueError("image and mask must both be host arrays or both be device tensors")
+        op, odev = _image_ptr(out, self.device)
+        flags = (PTR_IN_DEVICE if idev else 0) | (PTR_OUT_DEVICE if odev else 0)
+        self._check(self._lib.nesr_b200_masked_unsharp_u8(self._h, ip, mp, h, w, int(bool(bgr)), op, flags), "masked_unsharp_u8")
         return out
 
     def preprocess_u8(self, img, denoise_level: float = 0.5, clip: float = 2.0, tiles=(8, 8), out=None):

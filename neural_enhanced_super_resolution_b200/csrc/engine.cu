@@ -1869,9 +1869,10 @@ int nesr_b200_debug_nlm_weights(float h, int32_t channels, int32_t* out, int32_t
   return (int32_t)tab.size();
 }
 
-int nesr_b200_sharpen_u8(nesr_b200_handle* h, const uint8_t* in, int32_t H, int32_t W, int32_t bgr, uint8_t* out, int32_t flags) {
-  if (!h) return NESR_E_INVALID;
-  if (!in || !out || H < 1 || W < 1) return fail(h, NESR_E_INVALID, "sharpen: bad arguments");
+}  // extern "C"
+namespace {
+// _postprocess_image (mask == null) and the segmentation-masked unsharp of _segment_and_enhance (mask: H x W u8 on the side `in` is on)
+int sharpen_impl(nesr_b200_handle* h, const uint8_t* in, const uint8_t* mask, int32_t H, int32_t W, int32_t bgr, uint8_t* out, int32_t flags) {
   DEVICE_SCOPE(h);
   if (int wrc = wait_external(h)) return wrc;
   const int64_t n = (int64_t)H * W * 3;
@@ -1888,8 +1889,14 @@ int nesr_b200_sharpen_u8(nesr_b200_handle* h, const uint8_t* in, int32_t H, int3
     d_out = h->d_out;
   }
   if (d_in == d_out) return fail(h, NESR_E_INVALID, "sharpen: in-place operation is not supported");
+  const uint8_t* d_mask = mask;
+  if (mask && !(flags & NESR_PTR_IN_DEVICE)) {
+    if ((rc = ensure(h, &h->d_tmp, &h->d_tmp_bytes, (size_t)H * W))) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_tmp, mask, (size_t)H * W, cudaMemcpyHostToDevice, h->stream));
+    d_mask = h->d_tmp;
+  }
   cudaEventRecord(h->ev0, h->stream);
-  cudaError_t e = launch_sharpen(d_in, d_out, H, W, bgr, h->stream);
+  cudaError_t e = launch_sharpen(d_in, d_out, H, W, bgr, d_mask, h->stream);
   cudaEventRecord(h->ev1, h->stream);
   h->stats.kernel_launches++;
   if (e != cudaSuccess) return fail(h, NESR_E_CUDA, "sharpen launch failed: %s", cudaGetErrorString(e));
@@ -1898,6 +1905,21 @@ int nesr_b200_sharpen_u8(nesr_b200_handle* h, const uint8_t* in, int32_t H, int3
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->stats.last_device_ms = ms;
   return NESR_OK;
+}
+}  // namespace
+extern "C" {
+
+int nesr_b200_sharpen_u8(nesr_b200_handle* h, const uint8_t* in, int32_t H, int32_t W, int32_t bgr, uint8_t* out, int32_t flags) {
+  if (!h) return NESR_E_INVALID;
+  if (!in || !out || H < 1 || W < 1) return fail(h, NESR_E_INVALID, "sharpen: bad arguments");
+  return sharpen_impl(h, in, nullptr, H, W, bgr, out, flags);
+}
+
+int nesr_b200_masked_unsharp_u8(nesr_b200_handle* h, const uint8_t* in, const uint8_t* object_mask, int32_t H, int32_t W, int32_t bgr,
+                                uint8_t* out, int32_t flags) {
+  if (!h) return NESR_E_INVALID;
+  if (!in || !object_mask || !out || H < 1 || W < 1) return fail(h, NESR_E_INVALID, "masked_unsharp: bad arguments");
+  return sharpen_impl(h, in, object_mask, H, W, bgr, out, flags);
 }
 
 int nesr_b200_get_stats(const nesr_b200_handle* h, nesr_b200_stats* out) {

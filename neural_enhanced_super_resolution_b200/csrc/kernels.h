@@ -72,7 +72,8 @@ struct BlendParams {
   uint8_t* out;
 };
 cudaError_t launch_blend(const BlendParams& p, cudaStream_t stream);
-cudaError_t launch_sharpen(const uint8_t* in, uint8_t* out, int32_t H, int32_t W, int32_t bgr, cudaStream_t stream);
+// ext_mask == null: the adaptive detail mask of _postprocess_image; else the segmentation-masked unsharp (H x W u8 object mask, dilated 3 x 3 here)
+cudaError_t launch_sharpen(const uint8_t* in, uint8_t* out, int32_t H, int32_t W, int32_t bgr, const uint8_t* ext_mask, cudaStream_t stream);
 
 // --- preprocess.cu : NLM denoise in Lab + CLAHE, bit-exact with cv2 (reference nesr/nesr.py:668-689) --------------
 std::vector<int32_t> nlm_weight_table(float h, int channels);                    // non-zero prefix of cv2's almost_dist2weight_

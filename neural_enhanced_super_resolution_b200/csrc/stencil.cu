@@ -190,8 +190,14 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 //   load   : tile + 9-pixel halo -> planar R, G, B and gray bytes (BORDER_REFLECT_101)
 //   rows   : 19-tap (three channels) and 13-tap (gray) horizontal sums, Q8.8 in 16 bits
 //   columns: vertical sums, one rounding, threshold mask, unsharp with round-half-even, saturate
+//
+// kExtMask (the segmentation-masked unsharp of the reference, nesr/nesr.py:728-747): the same unsharp -- GaussianBlur(img, sigma 3),
+// addWeighted(img, 1.5, blurred, -0.5) -- applied where cv2.dilate(object_mask, ones(3, 3)) == 1 instead of where the image has
+// detail: `ext_mask` is the H x W u8 object mask at image resolution, its 3 x 3 dilation (a maximum over the pixels INSIDE the
+// image: cv2's default border value for dilate never wins) is taken here, and the gray plane / 13-tap blur are not computed.
+template <bool kExtMask>
 __global__ void __launch_bounds__(256) sharpen_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
-                                                      const int H, const int W, const int bgr) {
+                                                      const int H, const int W, const int bgr, const uint8_t* __restrict__ ext_mask) {
   __shared__ __align__(16) uint8_t s_in[4][kInH][kInWp];     // planar R, G, B, gray
   __shared__ __align__(16) uint8_t s_t3[3][2][kTW][kTp];     // row sums of the 19-tap blur: [channel][high | low byte][column][row]
   __shared__ __align__(16) uint8_t s_t2[2][kTW][kTp];        // row sums of the 13-tap blur on gray: [high | low][column][row - 3]
@@ -214,18 +220,18 @@ __global__ void __launch_bounds__(256) sharpen_kernel(const uint8_t* __restrict_
       const int c0 = px[0], c1 = px[1], c2 = px[2];
       const int r = bgr ? c2 : c0, b = bgr ? c0 : c2;
       pr |= static_cast<uint32_t>(r) << (8 * e); pg |= static_cast<uint32_t>(c1) << (8 * e); pb |= static_cast<uint32_t>(b) << (8 * e);
-      py |= static_cast<uint32_t>((9798 * r + 19235 * c1 + 3735 * b + 16384) >> 15) << (8 * e);
+      if (!kExtMask) py |= static_cast<uint32_t>((9798 * r + 19235 * c1 + 3735 * b + 16384) >> 15) << (8 * e);
     }
     *reinterpret_cast<uint32_t*>(&s_in[0][ly][lx]) = pr;
     *reinterpret_cast<uint32_t*>(&s_in[1][ly][lx]) = pg;
     *reinterpret_cast<uint32_t*>(&s_in[2][ly][lx]) = pb;
-    *reinterpret_cast<uint32_t*>(&s_in[3][ly][lx]) = py;
+    if (!kExtMask) *reinterpret_cast<uint32_t*>(&s_in[3][ly][lx]) = py;
   }
   __syncthreads();
 
   // rows: item = (plane, run of four outputs, tile row); consecutive threads take consecutive rows, so the transposed byte
   // stores of a warp fall into consecutive bytes
-  for (int idx = tid; idx < 4 * kRuns * kInH; idx += 256) {
+  for (int idx = tid; idx < (kExtMask ? 3 : 4) * kRuns * kInH; idx += 256) {
     const int plane = idx / (kRuns * kInH);
     const int rem = idx - plane * (kRuns * kInH);
     const int run = rem / kInH, ly = rem - run * kInH;
@@ -258,7 +264,18 @@ __global__ void __launch_bounds__(256) sharpen_kernel(const uint8_t* __restrict_
     if (gx >= W || y0 + oy0 >= H) continue;
     bool mask[4];
     bool any = false;
-    {
+    if (kExtMask) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gy = y0 + oy0 + j;
+        int m = 0;
+        if (gy < H)
+          for (int yy = max(gy - 1, 0); yy <= min(gy + 1, H - 1); ++yy)
+            for (int xx = max(gx - 1, 0); xx <= min(gx + 1, W - 1); ++xx) m = max(m, static_cast<int>(__ldg(ext_mask + static_cast<size_t>(yy) * W + xx)));
+        mask[j] = m == 1;                                      // np.where(mask == 1, ...): a label other than 1 selects nothing
+        any |= mask[j];
+      }
+    } else {
       const uint32_t* hi = reinterpret_cast<const uint32_t*>(&s_t2[0][ox][oy0]);
       const uint32_t* lo = reinterpret_cast<const uint32_t*>(&s_t2[1][ox][oy0]);
       uint32_t hv[4], lv[4];
@@ -343,10 +360,11 @@ cudaError_t launch_blend(const BlendParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_sharpen(const uint8_t* in, uint8_t* out, int32_t H, int32_t W, int32_t bgr, cudaStream_t stream) {
+cudaError_t launch_sharpen(const uint8_t* in, uint8_t* out, int32_t H, int32_t W, int32_t bgr, const uint8_t* ext_mask, cudaStream_t stream) {
   if (H <= 0 || W <= 0) return cudaSuccess;
   dim3 grid((W + kTW - 1) / kTW, (H + kTH - 1) / kTH);
-  sharpen_kernel<<<grid, 256, 0, stream>>>(in, out, H, W, bgr);
+  if (ext_mask) sharpen_kernel<true><<<grid, 256, 0, stream>>>(in, out, H, W, bgr, ext_mask);
+  else sharpen_kernel<false><<<grid, 256, 0, stream>>>(in, out, H, W, bgr, nullptr);
   return cudaGetLastError();
 }
 

@@ -6,10 +6,14 @@ ESRGAN path, with its four stages on the GPU:
                                                          standalone/superres_project.py:277-286 makes)
     _ensemble_results   -> nesr_b200_blend_u8           (reference nesr/nesr.py:1033-1054)
     _postprocess_image  -> nesr_b200_sharpen_u8         (reference nesr/nesr.py:1056-1084)
+    _segment_and_enhance-> nesr_b200_masked_unsharp_u8  (reference nesr/nesr.py:690-751: the unsharp where the dilated object
+                                                         mask is 1; the segmentation MODEL is the caller's, see below)
 
 ``enhance_image(image_path, prompt=None) -> str`` keeps the reference's loop, config keys, progress /
-image callbacks, intermediate saves and output naming (``nesr/nesr.py:477-659``).  Diffusion and
-segmentation are out of scope (BASELINE north_star) and are reported as disabled.
+image callbacks, intermediate saves and output naming (``nesr/nesr.py:477-659``).  Diffusion and the
+segmentation network are out of scope (BASELINE north_star): diffusion is reported as disabled; the segmentation stage runs
+when the caller supplies the model pair the reference would load from ``transformers`` (``config["segmentation_model"]`` and
+``config["segmentation_extractor"]``, same call interface), and is reported as disabled otherwise.
 
 Within one iteration the image stays in GPU memory between the four stages.
 
@@ -60,6 +64,8 @@ _DEFAULTS = {
     "always_tile": False,            # ... True: tile every image with max_tile_size (the benchmarked 1080p configuration)
     "async_io": True,                # image files are encoded + written on a worker thread (cv2.imwrite of iteration n overlaps
                                      # iteration n+1; reference nesr/nesr.py:618-625,644-647 write inline).  Same bytes either way.
+    "segmentation_model": None,      # callable(pixel_values) -> object with .logits [1, classes, h, w]  } the pair the reference loads
+    "segmentation_extractor": None,  # callable(images=PIL, return_tensors="pt") -> .to(device).pixel_values } at nesr/nesr.py:243-262
     "head_compat": False,            # True: the ESRGAN stage exactly as the reference's HEAD runs it (nesr/nesr.py:845-986):
                                      # RRDBNet(num_in_ch=12) fed a 12-channel full-resolution tensor, x4 out, truncating u8
 }
@@ -83,6 +89,26 @@ def _find_checkpoint(explicit=None):
         if os.path.exists(path):
             return path
     return None
+
+
+def _object_mask(models, device, image) -> np.ndarray:
+    """The host glue of ``_segment_and_enhance`` around the segmentation model (``nesr/nesr.py:698-730``), statement by statement:
+    RGB H x W x 3 u8 ndarray -> H x W u8 object mask (before the dilation).  Raises what the reference's statements raise, so that
+    the caller degrades exactly as it does."""
+    from PIL import Image
+    pil_image = Image.fromarray(image)
+    orig_size = pil_image.size
+    max_size = 1024
+    if max(orig_size) > max_size:
+        scale = max_size / max(orig_size)
+        pil_image = pil_image.resize((int(orig_size[0] * scale), int(orig_size[1] * scale)), Image.LANCZOS)
+    inputs = models["segmentation_extractor"](images=pil_image, return_tensors="pt").to(device)
+    outputs = models["segmentation"](inputs.pixel_values)
+    seg_map = outputs.logits.argmax(dim=1)[0].cpu().numpy()
+    if max(orig_size) > max_size:
+        seg_map = cv2.resize(seg_map, (orig_size[0], orig_size[1]), interpolation=cv2.INTER_NEAREST)
+    object_mask = (seg_map > 0).astype(np.uint8)
+    return np.ascontiguousarray(cv2.resize(object_mask, (image.shape[1], image.shape[0])))
 
 
 def gaussian_blur3_u8(chw_u8: torch.Tensor) -> torch.Tensor:
@@ -134,8 +160,12 @@ class SuperResolutionPipeline:
                                                      tile=0, tile_pad=int(self.config["tile_pad"]),
                                                      pre_pad=int(self.config["pre_pad"]), half=False, device=self.device)
             logger.info("Real-ESRGAN model loaded on %s (libnesr_b200)", self.device)
+        if self.config.get("segment_enhancement") and self.config.get("segmentation_model") is not None \
+                and self.config.get("segmentation_extractor") is not None:
+            self.models["segmentation"] = self.config["segmentation_model"]
+            self.models["segmentation_extractor"] = self.config["segmentation_extractor"]
         for key, what in (("use_diffusion", "diffusion"), ("segment_enhancement", "segmentation")):
-            if self.config.get(key):
+            if self.config.get(key) and not (key == "segment_enhancement" and "segmentation" in self.models):
                 logger.info("%s stage is outside this implementation's scope; disabled", what)
                 self.config[key] = False
 
@@ -159,6 +189,23 @@ class SuperResolutionPipeline:
         bit-exact with cv2 (``nesr_b200_preprocess_u8``).  ndarray in -> ndarray out, CUDA tensor in -> CUDA tensor out."""
         src = image if isinstance(image, torch.Tensor) else np.ascontiguousarray(image)
         return self._engine().preprocess_u8(src, denoise_level=float(self.config["denoise_level"]))
+
+    def _segment_and_enhance(self, image):
+        """Reference ``nesr/nesr.py:690-751``: class map of the caller's segmentation model -> object mask (class > 0) at image
+        resolution -> 3 x 3 dilation -> sigma-3 unsharp where the dilated mask is 1.  The glue around the model is the reference's
+        (PIL LANCZOS shrink above 1024 pixels, ``argmax``, ``cv2.resize``); dilation, blur, unsharp and select are ONE kernel
+        (``nesr_b200_masked_unsharp_u8``), bit-exact with the reference's cv2 calls.  ndarray in -> ndarray out, CUDA tensor in ->
+        CUDA tensor out; any failure returns the image unchanged, as the reference does."""
+        if "segmentation" not in self.models or "segmentation_extractor" not in self.models:
+            return image
+        try:
+            mask = _object_mask(self.models, self.device, image.cpu().numpy() if isinstance(image, torch.Tensor) else image)
+            if isinstance(image, torch.Tensor):
+                return self._engine().masked_unsharp_u8(image.contiguous(), torch.from_numpy(mask).to(image.device))
+            return self._engine().masked_unsharp_u8(np.ascontiguousarray(image), mask)
+        except Exception as exc:                                     # noqa: BLE001 -- reference nesr/nesr.py:749-751
+            logger.warning("Segmentation enhancement failed: %s", exc)
+            return image
 
     def _use_tiling(self, h, w):
         """The reference's tiling policy on CUDA (``nesr/nesr.py:761-790``): tile when tiling is enabled and the image is larger
@@ -336,6 +383,9 @@ class SuperResolutionPipeline:
             self._progress("Enhancement", iteration, f"Starting iteration {iteration + 1}/{n_iter}")
             self._progress("Preprocessing", iteration, "Applying denoising and contrast enhancement")
             dev_in = self._preprocess_image(torch.from_numpy(np.ascontiguousarray(current)).to(self.device))
+            if self.config["segment_enhancement"] and "segmentation" in self.models:
+                self._progress("Segmentation", iteration, "Performing region-based analysis and enhancement")
+                dev_in = self._segment_and_enhance(dev_in)
             upscaled = []
             if self.config["use_esrgan"] and "esrgan" in self.models:
                 self._progress("ESRGAN", iteration, "Applying Real-ESRGAN upscaling")
@@ -441,7 +491,17 @@ def install(reference_cls, engine_getter=None) -> None:
     def _preprocess_image(self, image):
         return _engine(self).preprocess_u8(np.ascontiguousarray(image), denoise_level=float(self.config["denoise_level"]))
 
+    def _segment_and_enhance(self, image):
+        if "segmentation" not in self.models or "segmentation_extractor" not in self.models:
+            return image
+        try:
+            return _engine(self).masked_unsharp_u8(np.ascontiguousarray(image), _object_mask(self.models, self.device, image))
+        except Exception as exc:                                     # noqa: BLE001 -- reference nesr/nesr.py:749-751
+            logger.warning("Segmentation enhancement failed: %s", exc)
+            return image
+
     reference_cls._preprocess_image = _preprocess_image
+    reference_cls._segment_and_enhance = _segment_and_enhance
     reference_cls._apply_esrgan = _apply_esrgan
     reference_cls._ensemble_results = _ensemble_results
     reference_cls._postprocess_image = _postprocess_image

@@ -7,6 +7,7 @@ committed fixtures in ``tests/golden``.
 
 * ``ensemble_results``  follows ``SuperResolutionPipeline._ensemble_results`` (``nesr/nesr.py:1033-1054``)
 * ``postprocess_image`` follows ``SuperResolutionPipeline._postprocess_image`` (``nesr/nesr.py:1056-1084``)
+* ``masked_unsharp``    follows the unsharp stage of ``_segment_and_enhance`` (``nesr/nesr.py:732-747``)
 
 cv2 semantics restated (verified against cv2 4.13.0 in this container):
   cvtColor RGB2GRAY (u8)   : (9798 R + 19235 G + 3735 B + 2^14) >> 15   (``rgb_to_gray``)
@@ -16,6 +17,7 @@ cv2 semantics restated (verified against cv2 4.13.0 in this container):
   subtract (u8)            : saturating;  convertScaleAbs of a u8 is the identity
   threshold(10, BINARY)    : > 10
   addWeighted(1.5,-0.5)    : saturate_u8(rint(1.5*a - 0.5*b)), rint = half-to-even
+  dilate(u8, ones(3,3))    : maximum over the 3x3 neighbours INSIDE the image (default border value never wins)
 """
 from __future__ import annotations
 
@@ -139,5 +141,30 @@ def postprocess_image(img: np.ndarray, adaptive_sharpening: bool = True) -> np.n
     g2 = gaussian_blur_u8(gray, SHARPEN_MASK_SIGMA)
     detail = np.maximum(gray.astype(np.int64) - g2.astype(np.int64), 0)       # saturating subtract
     mask = detail > SHARPEN_THRESHOLD
+    sharp = add_weighted_unsharp(img, gaussian_blur_u8(img, SHARPEN_BLUR_SIGMA))
+    return np.where(mask[..., None], sharp, img).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------
+# segmentation-masked unsharp  (nesr/nesr.py:732-747)
+# ---------------------------------------------------------------------------------------------
+
+def dilate3(mask: np.ndarray) -> np.ndarray:
+    """Bit-exact ``cv2.dilate(mask, np.ones((3, 3), np.uint8), iterations=1)`` for a 2-D u8 array: the default border is a
+    constant that never exceeds a pixel, i.e. the maximum runs over the neighbours inside the image."""
+    h, w = mask.shape
+    padded = np.zeros((h + 2, w + 2), dtype=mask.dtype)
+    padded[1:-1, 1:-1] = mask
+    out = np.zeros_like(mask)
+    for dy in range(3):
+        for dx in range(3):
+            out = np.maximum(out, padded[dy:dy + h, dx:dx + w])
+    return out
+
+
+def masked_unsharp(img: np.ndarray, object_mask: np.ndarray) -> np.ndarray:
+    """RGB HWC u8 + H x W u8 object mask at image resolution (the reference's ``cv2.resize(object_mask, (W, H))``, ``:730``)
+    -> RGB HWC u8: ``where(dilate(object_mask) == 1, addWeighted(img, 1.5, GaussianBlur(img, sigma 3), -0.5), img)``."""
+    mask = dilate3(object_mask) == 1
     sharp = add_weighted_unsharp(img, gaussian_blur_u8(img, SHARPEN_BLUR_SIGMA))
     return np.where(mask[..., None], sharp, img).astype(np.uint8)

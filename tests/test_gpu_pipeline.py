@@ -101,6 +101,74 @@ def test_head_layout_forward_matches_oracle():
     assert float((b > 0).mean()) > 0.5 and float((b < 255).mean()) > 0.5              # not a saturated comparison
 
 
+def test_segment_stage_matches_reference_golden(golden, tmp_path):
+    """``_segment_and_enhance`` of the mirror (and of ``install()`` on a reference-like class) with the stand-in segmentation model
+    of ``oracle/make_golden_segment.py`` against the unmodified reference method's output; in ``enhance_image`` the stage runs
+    between pre-process and ESRGAN (``nesr/nesr.py:539-550``) when the caller supplies the model pair."""
+    from oracle.make_golden_segment import StandInExtractor, StandInSegmenter
+    g = golden("segment.npz")
+    cfg = {"use_esrgan": False, "use_diffusion": False, "output_dir": str(tmp_path / "o"), "segmentation_model": StandInSegmenter(),
+           "segmentation_extractor": StandInExtractor(), "iterations": 1, "denoise_level": 0, "adaptive_sharpening": False}
+    pipe = pkg.SuperResolutionPipeline(device="cuda", config=cfg)
+    pipe._load_models()
+    assert pipe.config["segment_enhancement"] and "segmentation" in pipe.models
+    for name in ("photo", "noise_ragged", "noise_row"):
+        img = np.ascontiguousarray(g[name + "_in"])
+        assert np.array_equal(pipe._segment_and_enhance(img), g[name + "_out"])
+        dev = pipe._segment_and_enhance(torch.from_numpy(img).cuda())
+        assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), g[name + "_out"])
+    # without the model pair the stage is reported as disabled and the image passes through
+    plain = pkg.SuperResolutionPipeline(device="cuda", config={**cfg, "segmentation_model": None})
+    plain._load_models()
+    assert not plain.config["segment_enhancement"] and plain._segment_and_enhance(img) is img
+
+    class Ref:                                                    # what install() patches: numpy in, numpy out
+        models = {"segmentation": StandInSegmenter(), "segmentation_extractor": StandInExtractor()}
+        device = "cuda"
+    pkg.pipeline.install(Ref)
+    assert np.array_equal(Ref()._segment_and_enhance(np.ascontiguousarray(g["photo_in"])), g["photo_out"])
+    # stage order inside enhance_image: CLAHE-only pre-process -> segmentation unsharp -> bicubic fallback (no ESRGAN)
+    calls = []
+    src = str(tmp_path / "in.png")
+    cv2.imwrite(src, cv2.cvtColor(np.ascontiguousarray(g["photo_small_in"]), cv2.COLOR_RGB2BGR))
+    pipe.config["progress_callback"] = lambda stage, *a: calls.append(stage)
+    out = cv2.cvtColor(cv2.imread(pipe.enhance_image(src)), cv2.COLOR_BGR2RGB)
+    assert calls.index("Preprocessing") < calls.index("Segmentation") < calls.index("Ensemble")
+    pre = P.preprocess_image(np.ascontiguousarray(g["photo_small_in"]), 0)
+    from neural_enhanced_super_resolution_b200.pipeline import _object_mask
+    seg = O.masked_unsharp(pre, _object_mask(pipe.models, "cpu", pre))
+    assert np.array_equal(out, cv2.resize(seg, (seg.shape[1] * 2, seg.shape[0] * 2), interpolation=cv2.INTER_CUBIC))
+
+
+def test_x4_network_matches_oracle(tmp_path):
+    """``RRDBNet(3, 3, scale=4)`` (x4plus architecture, SURVEY 8f row f4: "scale 4 nets"): forward against the fp32 oracle of the same
+    architecture, +-2 / 45 dB; and ``RealESRGANer(scale=4, ...).enhance`` with tiles against the oracle's RealESRGANer."""
+    from oracle import shims
+    from oracle.realesrganer import RealESRGANer as OracleUpsampler
+    from oracle.rrdbnet import RRDBNet as OracleNet, calibrate_conv_last_
+    torch.manual_seed(11)
+    oracle_net = OracleNet(3, 3, scale=4).eval()
+    img = natural_image(40, 52, seed=4)
+    x = torch.from_numpy(img[:, :, ::-1].copy()).permute(2, 0, 1).float()[None] / 255
+    calibrate_conv_last_(oracle_net, x)
+    with torch.no_grad():
+        want = oracle_net(x)[0]
+    net = pkg.RRDBNet(3, 3, scale=4)
+    net.load_state_dict(oracle_net.state_dict(), strict=True)
+    got = net.cuda()(x.cuda())[0].cpu()
+    assert got.shape == want.shape == (3, 160, 208)
+    a = (want.clamp(0, 1) * 255).round().numpy().astype(np.int32)
+    b = (got.clamp(0, 1) * 255).round().numpy().astype(np.int32)
+    assert np.abs(a - b).max() <= 2 and psnr(a, b) >= 45.0
+    assert float((a > 0).mean()) > 0.5 and float((a < 255).mean()) > 0.5              # not a saturated comparison
+    ckpt = shims.write_checkpoint(oracle_net.state_dict(), str(tmp_path))
+    ref, _ = OracleUpsampler(4, ckpt, model=OracleNet(3, 3, scale=4), tile=32, tile_pad=6, pre_pad=3).enhance(img)
+    out, mode = pkg.RealESRGANer(4, ckpt, model=pkg.RRDBNet(3, 3, scale=4), tile=32, tile_pad=6, pre_pad=3, device="cuda:0").enhance(img)
+    assert mode == "RGB" and out.shape == ref.shape == (160, 208, 3)
+    d = np.abs(out.astype(np.int32) - ref.astype(np.int32))
+    assert d.max() <= 2 and psnr(out, ref) >= 45.0
+
+
 def test_head_compat_pipeline_matches_reference_golden(golden, tmp_path):
     """``enhance_image`` with ``head_compat`` against the UNMODIFIED reference's own end-to-end output (``pipeline.npz``: HEAD,
     12-channel mode, x4, CLAHE pre-process, sharpen) made with the fp32 oracle behind it -- same seeded weights."""

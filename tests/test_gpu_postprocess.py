@@ -41,6 +41,34 @@ def test_sharpen_bgr_flag_and_device_tensors(engine):
     assert out.is_cuda and np.array_equal(out.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("name", ["photo", "photo_small", "noise_ragged", "noise_tiny", "noise_row"])
+def test_masked_unsharp_matches_reference_golden(engine, golden, name):
+    """The unsharp stage of ``_segment_and_enhance`` (``nesr/nesr.py:732-747``) against the unmodified reference method's output
+    (``oracle/make_golden_segment.py``): 3 x 3 dilation, sigma-3 blur, unsharp and select in one kernel, bit-exact."""
+    g = golden("segment.npz")
+    got = engine.masked_unsharp_u8(np.ascontiguousarray(g[name + "_in"]), np.ascontiguousarray(g[name + "_mask"]))
+    assert np.array_equal(got, g[name + "_out"])
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (2, 3), (31, 33), (64, 64), (65, 129), (200, 77), (1080, 1920)])
+def test_masked_unsharp_matches_oracle(engine, shape):
+    rng = np.random.default_rng(shape[0] * 5 + shape[1])
+    img = rng.integers(0, 256, (*shape, 3), dtype=np.uint8) if shape[0] < 1000 else natural_image(*shape, seed=2)
+    mask = (rng.random(shape) < 0.05).astype(np.uint8)            # sparse objects: the dilation matters everywhere
+    mask[rng.random(shape) < 0.01] = 2                            # a label other than 1 wins the dilation and selects nothing
+    want = O.masked_unsharp(img, mask)
+    assert np.array_equal(engine.masked_unsharp_u8(img, mask), want)
+    if shape == (65, 129):                                        # BGR order and device tensors
+        got = engine.masked_unsharp_u8(np.ascontiguousarray(img[:, :, ::-1]), mask, bgr=True)
+        assert np.array_equal(got[:, :, ::-1], want)
+        out = engine.masked_unsharp_u8(torch.from_numpy(img).cuda(), torch.from_numpy(mask).cuda())
+        assert out.is_cuda and np.array_equal(out.cpu().numpy(), want)
+        with pytest.raises(ValueError):
+            engine.masked_unsharp_u8(img, torch.from_numpy(mask).cuda())
+        with pytest.raises(ValueError):
+            engine.masked_unsharp_u8(img, mask[:-1])
+
+
 @pytest.mark.parametrize("k", [2, 3, 4])
 def test_blend_matches_reference_golden(engine, golden, k):
     g = golden("ensemble.npz")

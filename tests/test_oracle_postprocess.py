@@ -59,6 +59,62 @@ def test_unsharp_rounds_half_to_even():
     assert O.add_weighted_unsharp(np.uint8([[[0]]]), np.uint8([[[255]]])).item() == 0
 
 
+SEG_CASES = ["photo", "photo_small", "noise_ragged", "noise_tiny", "noise_row"]
+
+
+@pytest.mark.parametrize("name", SEG_CASES)
+def test_masked_unsharp_matches_reference_golden(golden, name):
+    """``_segment_and_enhance`` (``nesr/nesr.py:690-751``) run unmodified with a stand-in segmentation model
+    (``oracle/make_golden_segment.py``): the restated dilation + sigma-3 unsharp + select must give the reference's pixels."""
+    import cv2
+    g = golden("segment.npz")
+    img, seg = g[name + "_in"], g[name + "_seg"]
+    mask = cv2.resize((seg > 0).astype(np.uint8), (img.shape[1], img.shape[0]))     # nesr/nesr.py:729-730, the same cv2 call
+    assert np.array_equal(mask, g[name + "_mask"])
+    out = O.masked_unsharp(img, mask)
+    assert out.dtype == np.uint8 and np.array_equal(out, g[name + "_out"])
+
+
+def test_dilate3_is_cv2():
+    import cv2
+    rng = np.random.default_rng(8)
+    for shape in [(1, 1), (1, 9), (7, 1), (2, 2), (33, 47)]:
+        for hi in (2, 3, 256):
+            m = rng.integers(0, hi, shape, dtype=np.uint8)
+            assert np.array_equal(O.dilate3(m), cv2.dilate(m, np.ones((3, 3), np.uint8), iterations=1))
+
+
+def test_masked_unsharp_selects_label_one_only():
+    """``np.where(mask == 1, ...)``: a dilated value other than 1 selects nothing (``nesr/nesr.py:741-745``)."""
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, 256, (12, 12, 3), dtype=np.uint8)
+    m = np.zeros((12, 12), np.uint8)
+    m[3, 3] = 1
+    m[8, 8] = 2
+    out = O.masked_unsharp(img, m)
+    changed = (out != img).any(axis=2)
+    assert not changed[7:10, 7:10].any() and not changed[:2].any()
+    sharp = O.add_weighted_unsharp(img, O.gaussian_blur_u8(img, 3.0))
+    assert np.array_equal(out[2:5, 2:5], sharp[2:5, 2:5])
+
+
+@pytest.mark.reference
+def test_live_reference_segment_and_enhance():
+    from oracle import shims
+    from oracle.make_golden_segment import StandInExtractor, StandInSegmenter, class_map
+    import cv2
+    Pipeline = shims.import_reference()
+
+    class Self:
+        models = {"segmentation": StandInSegmenter(), "segmentation_extractor": StandInExtractor()}
+        device = "cpu"
+    rng = np.random.default_rng(6)
+    for shape in [(50, 71, 3), (130, 97, 3)]:
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        mask = cv2.resize((class_map(img) > 0).astype(np.uint8), (shape[1], shape[0]))
+        assert np.array_equal(O.masked_unsharp(img, mask), Pipeline._segment_and_enhance(Self(), img))
+
+
 @pytest.mark.reference
 def test_live_reference_postprocess_and_ensemble():
     import cv2

@@ -25,7 +25,50 @@ def test_head_layout_holds_the_x2plus_weights():
     with pytest.raises(RuntimeError):
         head(torch.zeros(1, 12, 8, 8))                                   # CPU tensor: no CPU path
     with pytest.raises(RuntimeError):
-        pkg.RRDBNet(num_in_ch=3, num_out_ch=3, scale=4).engine("cuda:0")  # a true x4 network is not this build
+        pkg.RRDBNet(num_in_ch=3, num_out_ch=3, scale=1).engine("cuda:0")  # the scale-1 (un-shuffle by 4) network is not this build
+
+
+def test_x4_layout_holds_the_x4plus_tensors():
+    """``RRDBNet(3, 3, scale=4)`` (RealESRGAN_x4plus / ESRGAN: upstream ``rrdbnet_arch.py``, no un-shuffle) has upstream's tensors --
+    ``conv_first`` [64, 3, 3, 3] -- and loads the oracle's scale-4 state dict strictly."""
+    from oracle.rrdbnet import RRDBNet as OracleNet
+    net = pkg.RRDBNet(num_in_ch=3, num_out_ch=3, scale=4)
+    assert net.conv_first.weight.shape == (64, 3, 3, 3) and net._x4_layout and not net._head_layout
+    net.load_state_dict(OracleNet(3, 3, scale=4).state_dict(), strict=True)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 8, 8))                                     # CPU tensor: no CPU path
+
+
+@pytest.mark.parametrize("name", ["photo", "photo_small", "noise_ragged", "noise_tiny", "noise_row"])
+def test_object_mask_glue_matches_reference_golden(golden, name):
+    """The host glue of ``_segment_and_enhance`` around the segmentation model (``nesr/nesr.py:698-730``) with the stand-in model
+    pair of ``oracle/make_golden_segment.py``: the object mask handed to the GPU stage is the one the reference computes."""
+    from neural_enhanced_super_resolution_b200.pipeline import _object_mask
+    from oracle.make_golden_segment import StandInExtractor, StandInSegmenter
+    g = golden("segment.npz")
+    models = {"segmentation": StandInSegmenter(), "segmentation_extractor": StandInExtractor()}
+    mask = _object_mask(models, "cpu", g[name + "_in"])
+    assert mask.dtype == np.uint8 and mask.flags["C_CONTIGUOUS"] and np.array_equal(mask, g[name + "_mask"])
+
+
+@pytest.mark.reference
+def test_segment_stage_above_1024_pixels_is_the_reference():
+    """Above 1024 pixels the reference shrinks the image for the model and brings the class map back with INTER_NEAREST
+    (``nesr/nesr.py:701-724``): mirror glue + oracle unsharp against the reference's live method."""
+    from neural_enhanced_super_resolution_b200.pipeline import _object_mask
+    from oracle import postprocess as O
+    from oracle import shims
+    from oracle.make_golden_segment import StandInExtractor, StandInSegmenter
+    Ref = shims.import_reference("/root/reference")
+
+    class Self:
+        models = {"segmentation": StandInSegmenter(), "segmentation_extractor": StandInExtractor()}
+        device = "cpu"
+    img = np.random.default_rng(12).integers(0, 256, (60, 1100, 3), dtype=np.uint8)
+    img[:, :500] = (img[:, :500] // 4)                                   # a dark half: background for the stand-in
+    want = Ref._segment_and_enhance(Self(), img)
+    assert want is not img and (want != img).any()
+    assert np.array_equal(O.masked_unsharp(img, _object_mask(Self.models, "cpu", img)), want)
 
 
 class _Stub:
