@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libnesr_b200.so")
-SOURCES = ["conv3x3_fold.cu", "conv3x3_body.cu", "conv3x3_trunk.cu", "conv3x3_simt.cu", "pixel_io.cu", "stencil.cu", "preprocess.cu", "engine.cu"]
+SOURCES = ["conv3x3_fold.cu", "conv3x3_body.cu", "conv3x3_trunk.cu", "conv3x3_simt.cu", "pixel_io.cu", "stencil.cu", "sharpen_mma.cu", "preprocess.cu", "engine.cu"]
 HEADERS = ["ptx.cuh", "layout.h", "epilogue.cuh", "fold_roles.cuh", "kernels.h", "lab_tables.inc", os.path.join("..", "..", "include", "nesr_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -74,6 +74,9 @@ struct BlendParams {
 cudaError_t launch_blend(const BlendParams& p, cudaStream_t stream);
 // ext_mask == null: the adaptive detail mask of _postprocess_image; else the segmentation-masked unsharp (H x W u8 object mask, dilated 3 x 3 here)
 cudaError_t launch_sharpen(const uint8_t* in, uint8_t* out, int32_t H, int32_t W, int32_t bgr, const uint8_t* ext_mask, cudaStream_t stream);
+// sharpen_mma.cu: the same stage with both Gaussian passes as banded-Toeplitz products on the tensor pipe (IMMA.16832.U8.U8) -- the
+// product path; launch_sharpen dispatches to it unless NESR_B200_SHARPEN_IMPL=1 selects the dp4a kernel (cross-check, bit-identical)
+cudaError_t launch_sharpen_mma(const uint8_t* in, uint8_t* out, int32_t H, int32_t W, int32_t bgr, const uint8_t* ext_mask, cudaStream_t stream);
 
 // --- preprocess.cu : NLM denoise in Lab + CLAHE, bit-exact with cv2 (reference nesr/nesr.py:668-689) --------------
 std::vector<int32_t> nlm_weight_table(float h, int channels);                    // non-zero prefix of cv2's almost_dist2weight_

@@ -10,6 +10,8 @@
 //             out = mask ? sat_u8(round_half_even(1.5*img - 0.5*G3(img))) : img
 // The sharpen kernel is a single shared-memory-tiled pass: each image byte is read from HBM once
 // (plus halo) and written once.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace nesr {
@@ -362,6 +364,8 @@ cudaError_t launch_blend(const BlendParams& p, cudaStream_t stream) {
 
 cudaError_t launch_sharpen(const uint8_t* in, uint8_t* out, int32_t H, int32_t W, int32_t bgr, const uint8_t* ext_mask, cudaStream_t stream) {
   if (H <= 0 || W <= 0) return cudaSuccess;
+  const char* impl = getenv("NESR_B200_SHARPEN_IMPL");          // 1: the dp4a kernel below (cross-check); default: sharpen_mma.cu
+  if (!impl || atoi(impl) != 1) return launch_sharpen_mma(in, out, H, W, bgr, ext_mask, stream);
   dim3 grid((W + kTW - 1) / kTW, (H + kTH - 1) / kTH);
   if (ext_mask) sharpen_kernel<true><<<grid, 256, 0, stream>>>(in, out, H, W, bgr, ext_mask);
   else sharpen_kernel<false><<<grid, 256, 0, stream>>>(in, out, H, W, bgr, nullptr);
