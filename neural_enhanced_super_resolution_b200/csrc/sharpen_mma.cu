@@ -83,37 +83,48 @@ __global__ void __launch_bounds__(256) sharpen_mma_kernel(const uint8_t* __restr
 
   // ---- load: item = four horizontally adjacent pixels of a tile row -> one word per plane
   const bool fast_x = aligned4 && x0 - kHalo >= 0 && x0 + kTW + kHalo <= W;
-  for (int idx = tid; idx < kInH * (kInW / 4); idx += 256) {
-    const int ly = idx / (kInW / 4), lx = 4 * (idx - ly * (kInW / 4));
-    const int gy = reflect101(y0 + ly - kHalo, H);
-    const uint8_t* row = in + static_cast<size_t>(gy) * W * 3;
-    const int gx0 = x0 + lx - kHalo;
-    uint32_t p0, p1, p2;
-    if (fast_x) {
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(row + static_cast<size_t>(gx0) * 3);
-      const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);    // c0 c1 c2 c0 | c1 c2 c0 c1 | c2 c0 c1 c2
-      p0 = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);                   // bytes 0, 3, 6, 9 of the 12
-      p1 = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);                   // bytes 1, 4, 7, 10
-      p2 = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);                   // bytes 2, 5, 8, 11
-    } else {
-      p0 = p1 = p2 = 0;
+  if (fast_x) {
+    // interior tile, 4-byte aligned rows: three aligned words hold the four pixels (c0 c1 c2 c0 | c1 c2 c0 c1 | c2 c0 c1 c2); the planes
+    // come out of byte permutes and gray out of dp4a on the interleaved words: 9798 = 38 * 256 + 70, 19235 = 75 * 256 + 35,
+    // 3735 = 14 * 256 + 151, so gray = (256 * dp4a(px, high weights) + dp4a(px, low weights) + 2^14) >> 15, exactly.
+    const uint32_t h0 = static_cast<uint32_t>(wr) >> 8, h1 = 75u, h2 = static_cast<uint32_t>(wb) >> 8;
+    const uint32_t l0 = static_cast<uint32_t>(wr) & 255u, l1 = 35u, l2 = static_cast<uint32_t>(wb) & 255u;
+    const uint32_t hA = h0 | h1 << 8 | h2 << 16, hB0 = h0 << 24, hB1 = h1 | h2 << 8, hC1 = h0 << 16 | h1 << 24, hC2 = h2, hD = h0 << 8 | h1 << 16 | h2 << 24;
+    const uint32_t lA = l0 | l1 << 8 | l2 << 16, lB0 = l0 << 24, lB1 = l1 | l2 << 8, lC1 = l0 << 16 | l1 << 24, lC2 = l2, lD = l0 << 8 | l1 << 16 | l2 << 24;
+    for (int idx = tid; idx < kInH * (kInW / 4); idx += 256) {
+      const int ly = idx / (kInW / 4), lx = 4 * (idx - ly * (kInW / 4));
+      const int gy = reflect101(y0 + ly - kHalo, H);
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(in + (static_cast<size_t>(gy) * W + (x0 + lx - kHalo)) * 3);
+      const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+      *reinterpret_cast<uint32_t*>(&s_in[0][ly][lx]) = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);   // bytes 0, 3, 6, 9 of the 12
+      *reinterpret_cast<uint32_t*>(&s_in[1][ly][lx]) = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);   // bytes 1, 4, 7, 10
+      *reinterpret_cast<uint32_t*>(&s_in[2][ly][lx]) = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);   // bytes 2, 5, 8, 11
+      if (!kExtMask) {
+        const uint32_t g0 = (__dp4a(w0, hA, 0u) * 256u + __dp4a(w0, lA, 16384u)) >> 15;
+        const uint32_t g1 = (__dp4a(w1, hB1, __dp4a(w0, hB0, 0u)) * 256u + __dp4a(w1, lB1, __dp4a(w0, lB0, 16384u))) >> 15;
+        const uint32_t g2 = (__dp4a(w2, hC2, __dp4a(w1, hC1, 0u)) * 256u + __dp4a(w2, lC2, __dp4a(w1, lC1, 16384u))) >> 15;
+        const uint32_t g3 = (__dp4a(w2, hD, 0u) * 256u + __dp4a(w2, lD, 16384u)) >> 15;
+        *reinterpret_cast<uint32_t*>(&s_in[3][ly][lx]) = g0 | g1 << 8 | g2 << 16 | g3 << 24;
+      }
+    }
+  } else {
+    for (int idx = tid; idx < kInH * (kInW / 4); idx += 256) {
+      const int ly = idx / (kInW / 4), lx = 4 * (idx - ly * (kInW / 4));
+      const int gy = reflect101(y0 + ly - kHalo, H);
+      const uint8_t* row = in + static_cast<size_t>(gy) * W * 3;
+      const int gx0 = x0 + lx - kHalo;
+      uint32_t p0 = 0, p1 = 0, p2 = 0, py = 0;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const uint8_t* px = row + static_cast<size_t>(reflect101(gx0 + e, W)) * 3;
-        p0 |= static_cast<uint32_t>(px[0]) << (8 * e); p1 |= static_cast<uint32_t>(px[1]) << (8 * e); p2 |= static_cast<uint32_t>(px[2]) << (8 * e);
-      }
-    }
-    *reinterpret_cast<uint32_t*>(&s_in[0][ly][lx]) = p0;
-    *reinterpret_cast<uint32_t*>(&s_in[1][ly][lx]) = p1;
-    *reinterpret_cast<uint32_t*>(&s_in[2][ly][lx]) = p2;
-    if (!kExtMask) {
-      uint32_t py = 0;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int c0 = (p0 >> (8 * e)) & 255, c1 = (p1 >> (8 * e)) & 255, c2 = (p2 >> (8 * e)) & 255;
+        const int c0 = px[0], c1 = px[1], c2 = px[2];
+        p0 |= static_cast<uint32_t>(c0) << (8 * e); p1 |= static_cast<uint32_t>(c1) << (8 * e); p2 |= static_cast<uint32_t>(c2) << (8 * e);
         py |= static_cast<uint32_t>((wr * c0 + 19235 * c1 + wb * c2 + 16384) >> 15) << (8 * e);
       }
-      *reinterpret_cast<uint32_t*>(&s_in[3][ly][lx]) = py;
+      *reinterpret_cast<uint32_t*>(&s_in[0][ly][lx]) = p0;
+      *reinterpret_cast<uint32_t*>(&s_in[1][ly][lx]) = p1;
+      *reinterpret_cast<uint32_t*>(&s_in[2][ly][lx]) = p2;
+      if (!kExtMask) *reinterpret_cast<uint32_t*>(&s_in[3][ly][lx]) = py;
     }
   }
   uint32_t a3[4], a2[4];
@@ -124,27 +135,34 @@ __global__ void __launch_bounds__(256) sharpen_mma_kernel(const uint8_t* __restr
   }
   __syncthreads();
 
-  // ---- rows: unit = (plane, 16 output columns, 8 tile rows)
-  constexpr int kRowUnits = (kExtMask ? 3 : 4) * (kTW / 16) * (kInH / 8);
-  for (int u = warp; u < kRowUnits; u += 8) {
-    const int plane = u / ((kTW / 16) * (kInH / 8));
-    const int rem = u - plane * ((kTW / 16) * (kInH / 8));
-    const int mb = rem / (kInH / 8), nb = rem - mb * (kInH / 8);
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&s_in[plane][8 * nb + g][16 * mb + 4 * t]);
-    int d[4] = {0, 0, 0, 0};
-    if (plane == 3) imma(d, a2, src[0], src[4]); else imma(d, a3, src[0], src[4]);
-    // d0, d1: column 16 mb + g, rows 8 nb + 2t, + 1;  d2, d3: column + 8
-    const int col = 16 * mb + g, r = 8 * nb + 2 * t;
-    *reinterpret_cast<uint16_t*>(&s_t[plane][0][col][r]) = static_cast<uint16_t>(__byte_perm(d[0], d[1], 0x0051));
-    *reinterpret_cast<uint16_t*>(&s_t[plane][1][col][r]) = static_cast<uint16_t>(__byte_perm(d[0], d[1], 0x0040));
-    *reinterpret_cast<uint16_t*>(&s_t[plane][0][col + 8][r]) = static_cast<uint16_t>(__byte_perm(d[2], d[3], 0x0051));
-    *reinterpret_cast<uint16_t*>(&s_t[plane][1][col + 8][r]) = static_cast<uint16_t>(__byte_perm(d[2], d[3], 0x0040));
+  // ---- rows: unit = (plane, 16 output columns, 8 tile rows); a warp keeps its 16 columns and three of the six row groups, so that every
+  // address below is one base plus a compile-time offset
+  {
+    const int mb = warp & 3, nb0 = (warp >> 2) * 3;
+    const uint8_t* src0 = &s_in[0][8 * nb0 + g][16 * mb + 4 * t];
+    uint8_t* dst0 = &s_t[0][0][16 * mb + g][8 * nb0 + 2 * t];
+#pragma unroll
+    for (int plane = 0; plane < (kExtMask ? 3 : 4); ++plane)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(src0 + plane * (kInH * kInW) + j * 8 * kInW);
+        int d[4] = {0, 0, 0, 0};
+        if (plane == 3) imma(d, a2, src[0], src[4]); else imma(d, a3, src[0], src[4]);
+        // d0, d1: column 16 mb + g, rows 8 nb + 2t, + 1;  d2, d3: column + 8
+        uint8_t* dst = dst0 + plane * (2 * kTW * kInH) + j * 8;
+        *reinterpret_cast<uint16_t*>(dst) = static_cast<uint16_t>(__byte_perm(d[0], d[1], 0x0051));
+        *reinterpret_cast<uint16_t*>(dst + kTW * kInH) = static_cast<uint16_t>(__byte_perm(d[0], d[1], 0x0040));
+        *reinterpret_cast<uint16_t*>(dst + 8 * kInH) = static_cast<uint16_t>(__byte_perm(d[2], d[3], 0x0051));
+        *reinterpret_cast<uint16_t*>(dst + kTW * kInH + 8 * kInH) = static_cast<uint16_t>(__byte_perm(d[2], d[3], 0x0040));
+      }
   }
   __syncthreads();
 
   // ---- columns + mask + unsharp: block = (16 output rows, 8 columns); the thread's four pixels are rows oy, oy + 8, columns ox, ox + 1
-  for (int blk = warp; blk < (kTH / 16) * (kTW / 8); blk += 8) {
-    const int vb = blk / (kTW / 8), cb = blk - vb * (kTW / 8);
+  static_assert(kTW / 8 == 8, "one 8-column block per warp");
+#pragma unroll
+  for (int vb = 0; vb < kTH / 16; ++vb) {
+    const int cb = warp;
     int blur[4][4];                                              // [plane][accumulator]
 #pragma unroll
     for (int plane = 0; plane < 4; ++plane) {
