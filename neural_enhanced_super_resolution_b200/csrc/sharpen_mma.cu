@@ -91,11 +91,26 @@ __global__ void __launch_bounds__(256) sharpen_mma_kernel(const uint8_t* __restr
     const uint32_t l0 = static_cast<uint32_t>(wr) & 255u, l1 = 35u, l2 = static_cast<uint32_t>(wb) & 255u;
     const uint32_t hA = h0 | h1 << 8 | h2 << 16, hB0 = h0 << 24, hB1 = h1 | h2 << 8, hC1 = h0 << 16 | h1 << 24, hC2 = h2, hD = h0 << 8 | h1 << 16 | h2 << 24;
     const uint32_t lA = l0 | l1 << 8 | l2 << 16, lB0 = l0 << 24, lB1 = l1 | l2 << 8, lC1 = l0 << 16 | l1 << 24, lC2 = l2, lD = l0 << 8 | l1 << 16 | l2 << 24;
-    for (int idx = tid; idx < kInH * (kInW / 4); idx += 256) {
+    // all twelve loads of a thread are issued before the first is used
+    constexpr int kItems = kInH * (kInW / 4), kIters = (kItems + 255) / 256;
+    const bool fast_y = y0 - kHalo >= 0 && y0 + kTH + kHalo <= H;
+    uint32_t w[kIters][3];
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int idx = tid + 256 * it;
+      if (idx < kItems) {
+        const int ly = idx / (kInW / 4), lx = 4 * (idx - ly * (kInW / 4));
+        const int gy = fast_y ? y0 + ly - kHalo : reflect101(y0 + ly - kHalo, H);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(in + (static_cast<size_t>(gy) * W + (x0 + lx - kHalo)) * 3);
+        w[it][0] = __ldg(src); w[it][1] = __ldg(src + 1); w[it][2] = __ldg(src + 2);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int idx = tid + 256 * it;
+      if (idx >= kItems) break;
       const int ly = idx / (kInW / 4), lx = 4 * (idx - ly * (kInW / 4));
-      const int gy = reflect101(y0 + ly - kHalo, H);
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(in + (static_cast<size_t>(gy) * W + (x0 + lx - kHalo)) * 3);
-      const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+      const uint32_t w0 = w[it][0], w1 = w[it][1], w2 = w[it][2];
       *reinterpret_cast<uint32_t*>(&s_in[0][ly][lx]) = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);   // bytes 0, 3, 6, 9 of the 12
       *reinterpret_cast<uint32_t*>(&s_in[1][ly][lx]) = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);   // bytes 1, 4, 7, 10
       *reinterpret_cast<uint32_t*>(&s_in[2][ly][lx]) = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);   // bytes 2, 5, 8, 11

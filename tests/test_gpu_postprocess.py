@@ -31,6 +31,23 @@ def test_sharpen_matches_oracle(engine, shape):
     assert np.array_equal(engine.sharpen_u8(img), O.postprocess_image(img))
 
 
+def test_sharpen_tensor_pipe_kernel_equals_dp4a_kernel(engine, monkeypatch):
+    """The product kernel runs both Gaussian passes as banded-Toeplitz IMMA products (csrc/sharpen_mma.cu); the first-generation dp4a
+    kernel (csrc/stencil.cu, NESR_B200_SHARPEN_IMPL=1, read per launch) must give the same bytes -- 4-byte-aligned rows (fast loads /
+    stores), odd widths (byte path), border-only sizes, BGR order and the segmentation-masked variant."""
+    rng = np.random.default_rng(21)
+    for shape in [(96, 256), (97, 255), (40, 70), (9, 300), (200, 64)]:
+        img = rng.integers(0, 256, (*shape, 3), dtype=np.uint8)
+        mask = (rng.random(shape) < 0.1).astype(np.uint8)
+        monkeypatch.delenv("NESR_B200_SHARPEN_IMPL", raising=False)
+        a, am, ab = engine.sharpen_u8(img), engine.masked_unsharp_u8(img, mask), engine.sharpen_u8(img, bgr=True)
+        monkeypatch.setenv("NESR_B200_SHARPEN_IMPL", "1")
+        b, bm, bb = engine.sharpen_u8(img), engine.masked_unsharp_u8(img, mask), engine.sharpen_u8(img, bgr=True)
+        assert np.array_equal(a, b) and np.array_equal(am, bm) and np.array_equal(ab, bb)
+        assert np.array_equal(a, O.postprocess_image(img))
+    monkeypatch.delenv("NESR_B200_SHARPEN_IMPL", raising=False)
+
+
 def test_sharpen_bgr_flag_and_device_tensors(engine):
     img = natural_image(90, 70, seed=3)                      # treat as RGB
     want = O.postprocess_image(img)
