@@ -76,7 +76,9 @@ typedef struct nesr_b200_config {
                                  trunk kernel with a grid-wide arrival counter (conv3x3_body.cu; also what a
                                  tile too large for the trunk kernel's TMEM row budget runs on).  2 is
                                  rejected (the first-generation per-tap kernel was removed in round 2) */
-  int32_t reserved0;
+  int32_t feat_in_ch;         /* input channels of conv_first ON THE FEATURE GRID, 1..64; 0 = num_in_ch * 4, the x2plus un-shuffle
+                                 (12).  Other values serve nesr_b200_forward_feat_f32 only: 3 = the scale-4 architecture
+                                 (x4plus: no un-shuffle), 48 = the scale-1 architecture (un-shuffle by 4) */
   int64_t max_batch_pixels;   /* cap on feature-grid pixels per tile group (batch); 0 = default (200k for
                                  conv_impl 0: the group's dense-block activations stay in the 126 MB L2) */
 } nesr_b200_config;
@@ -195,6 +197,12 @@ int nesr_b200_forward_nchw_f32(nesr_b200_handle* h, const float* x, int32_t n, i
  * unclamped; stream semantics as nesr_b200_forward_nchw_f32. */
 int nesr_b200_forward_nchw12_f32(nesr_b200_handle* h, const float* x12, int32_t n, int32_t H,
                                  int32_t W, float* y, void* stream);
+
+/* Replaces: RRDBNet.forward for the architectures whose first op is NOT the x2 un-shuffle (upstream rrdbnet_arch.py: scale 4 feeds x
+ * itself to conv_first, scale 1 feeds pixel_unshuffle(x, 4); SURVEY.md 8f row f4 "scale 1/4 nets"): `feat` is that tensor --
+ * DEVICE float32 [n, C, h, w] with C == the handle's feat_in_ch (12 when 0) -- and y is [n, num_out_ch, 4h, 4w]: conv_first .. conv_last
+ * as for the x2plus network, whose nchw12 entry is the C == 12 case. */
+int nesr_b200_forward_feat_f32(nesr_b200_handle* h, const float* feat, int32_t n, int32_t C, int32_t H, int32_t W, float* y, void* stream);
 
 /* Replaces: SuperResolutionPipeline._ensemble_results (nesr/nesr.py:1033-1054) for K >= 2
  * equally sized H x W x 3 u8 members: acc(f32) += f64(img) * w[i] rounded to f32 per member,

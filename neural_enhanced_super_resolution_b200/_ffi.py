@@ -22,7 +22,7 @@ EXPORTS = (
     "nesr_b200_default_config", "nesr_b200_create", "nesr_b200_destroy", "nesr_b200_last_error",
     "nesr_b200_load_weight", "nesr_b200_finalize_weights", "nesr_b200_enhance_u8",
     "nesr_b200_enhance_batch_u8", "nesr_b200_tile_count", "nesr_b200_debug_plan", "nesr_b200_enhance_tiles_u8",
-    "nesr_b200_forward_nchw_f32", "nesr_b200_blend_u8", "nesr_b200_sharpen_u8", "nesr_b200_masked_unsharp_u8", "nesr_b200_get_stats",
+    "nesr_b200_forward_nchw_f32", "nesr_b200_forward_feat_f32", "nesr_b200_blend_u8", "nesr_b200_sharpen_u8", "nesr_b200_masked_unsharp_u8", "nesr_b200_get_stats",
     "nesr_b200_synchronize", "nesr_b200_debug_conv", "nesr_b200_preprocess_u8", "nesr_b200_debug_lab_table",
     "nesr_b200_debug_nlm_weights", "nesr_b200_forward_nchw12_f32", "nesr_b200_enhance_tiles_packed_u8",
     "nesr_b200_unpack_tiles_u8", "nesr_b200_enhance_tile_list_packed_u8", "nesr_b200_enhance_head_u8", "nesr_b200_unpack_tile_list_u8",
@@ -33,7 +33,7 @@ class Config(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("num_in_ch", C.c_int32),
                 ("num_out_ch", C.c_int32), ("scale", C.c_int32), ("num_feat", C.c_int32),
                 ("num_block", C.c_int32), ("num_grow_ch", C.c_int32), ("body_format", C.c_int32),
-                ("edge_format", C.c_int32), ("conv_impl", C.c_int32), ("reserved0", C.c_int32),
+                ("edge_format", C.c_int32), ("conv_impl", C.c_int32), ("feat_in_ch", C.c_int32),
                 ("max_batch_pixels", C.c_int64)]
 
 
@@ -92,6 +92,7 @@ def load_library() -> C.CDLL:
                                                   C.c_int32, u8p, C.c_int64]
         lib.nesr_b200_forward_nchw_f32.argtypes = [H, f32p, C.c_int32, C.c_int32, C.c_int32, f32p, C.c_void_p]
         lib.nesr_b200_forward_nchw12_f32.argtypes = [H, f32p, C.c_int32, C.c_int32, C.c_int32, f32p, C.c_void_p]
+        lib.nesr_b200_forward_feat_f32.argtypes = [H, f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, f32p, C.c_void_p]
         lib.nesr_b200_blend_u8.argtypes = [H, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32,
                                            C.POINTER(C.c_double), u8p, C.c_int32]
         lib.nesr_b200_sharpen_u8.argtypes = [H, u8p, C.c_int32, C.c_int32, C.c_int32, u8p, C.c_int32]
@@ -161,7 +162,7 @@ class Engine:
     def __init__(self, device: int = 0, num_block: int = 23, body_format: int = FMT_BF16,
                  edge_format: int = FMT_FP16, conv_impl: int = 0, max_batch_pixels: int = 0,
                  num_in_ch: int = 3, num_out_ch: int = 3, scale: int = 2, num_feat: int = 64,
-                 num_grow_ch: int = 32):
+                 num_grow_ch: int = 32, feat_in_ch: int = 0):
         self._lib = load_library()
         cfg = Config()
         self._lib.nesr_b200_default_config(C.byref(cfg), int(device))
@@ -169,6 +170,7 @@ class Engine:
         cfg.conv_impl, cfg.max_batch_pixels = int(conv_impl), int(max_batch_pixels)
         cfg.num_in_ch, cfg.num_out_ch, cfg.scale = int(num_in_ch), int(num_out_ch), int(scale)
         cfg.num_feat, cfg.num_grow_ch = int(num_feat), int(num_grow_ch)
+        cfg.feat_in_ch = int(feat_in_ch)
         self.config = cfg
         self.device = int(device)
         self.scale = int(scale)
@@ -363,6 +365,20 @@ class Engine:
         stream = torch.cuda.current_stream(x12.device).cuda_stream
         self._check(self._lib.nesr_b200_forward_nchw12_f32(self._h, x12.data_ptr(), n, h, w, y.data_ptr(),
                                                            C.c_void_p(stream)), "forward_nchw12_f32")
+        return y
+
+    def forward_feat(self, feat):
+        """conv_first .. conv_last on a tensor that is already on the feature grid (scale-4 nets: x itself; scale-1 nets:
+        ``pixel_unshuffle(x, 4)``): CUDA float32 [n, feat_in_ch, h, w] -> [n, num_out_ch, 4h, 4w]."""
+        import torch
+        if not (feat.is_cuda and feat.dtype == torch.float32 and feat.dim() == 4):
+            raise ValueError("forward_feat expects a CUDA float32 N x C x H x W tensor")
+        feat = feat.contiguous()
+        n, c, h, w = feat.shape
+        y = torch.empty((n, self.config.num_out_ch, 4 * h, 4 * w), dtype=torch.float32, device=feat.device)
+        stream = torch.cuda.current_stream(feat.device).cuda_stream
+        self._check(self._lib.nesr_b200_forward_feat_f32(self._h, feat.data_ptr(), n, c, h, w, y.data_ptr(), C.c_void_p(stream)),
+                    "forward_feat_f32")
         return y
 
     # -- post-process ------------------------------------------------------------------------

@@ -236,7 +236,7 @@ void add_layer(nesr_b200_handle* h, const std::string& name, int cin, int cout, 
 
 void build_layers(nesr_b200_handle* h) {
   const nesr_b200_config& c = h->cfg;
-  const int in_ch = c.num_in_ch * (c.scale == 2 ? 4 : 1);
+  const int in_ch = c.feat_in_ch > 0 ? c.feat_in_ch : c.num_in_ch * (c.scale == 2 ? 4 : 1);
   add_layer(h, "conv_first", in_ch, c.num_feat, c.edge_format);
   for (int i = 0; i < c.num_block; ++i)
     for (int j = 1; j <= 3; ++j) {
@@ -1188,6 +1188,8 @@ int enhance_impl(nesr_b200_handle* h, const uint8_t* in, int n_frames, int H, in
                  const int32_t* tile_ids = nullptr, int head = 0) {
   if (!h) return NESR_E_INVALID;
   if (!h->finalized) return fail(h, NESR_E_STATE, "weights not finalized");
+  if (h->cfg.feat_in_ch > 0 && h->cfg.feat_in_ch != 12)
+    return fail(h, NESR_E_STATE, "this handle's conv_first takes %d feature channels (a scale-4 / scale-1 network): images go through nesr_b200_forward_feat_f32", h->cfg.feat_in_ch);
   if (!in || !out || n_frames < 1 || H < 2 || W < 2) return fail(h, NESR_E_INVALID, "bad image arguments (H=%d W=%d n=%d)", H, W, n_frames);
   if (tile < 0 || tile_pad < 0 || pre_pad < 0 || pre_pad >= H || pre_pad >= W)
     return fail(h, NESR_E_INVALID, "bad tile/pad arguments (tile=%d tile_pad=%d pre_pad=%d)", tile, tile_pad, pre_pad);
@@ -1297,6 +1299,7 @@ int nesr_b200_create(const nesr_b200_config* cfg, nesr_b200_handle** out) {
   if (cfg->abi_version != NESR_B200_ABI_VERSION) return fail(nullptr, NESR_E_INVALID, "ABI version %d != %d", cfg->abi_version, NESR_B200_ABI_VERSION);
   if (cfg->scale != 2 || cfg->num_feat != 64 || cfg->num_grow_ch != 32 || cfg->num_in_ch != 3 || cfg->num_out_ch != 3 || cfg->num_block < 1)
     return fail(nullptr, NESR_E_INVALID, "unsupported architecture: this build implements RRDBNet(3,3,scale=2,num_feat=64,num_grow_ch=32)");
+  if (cfg->feat_in_ch < 0 || cfg->feat_in_ch > 64) return fail(nullptr, NESR_E_INVALID, "feat_in_ch %d outside 0..64", cfg->feat_in_ch);
   if ((cfg->body_format | cfg->edge_format) & ~1) return fail(nullptr, NESR_E_INVALID, "bad operand format");
   if (cfg->conv_impl != 0 && cfg->conv_impl != 1 && cfg->conv_impl != 3 && cfg->conv_impl != 4)
     return fail(nullptr, NESR_E_INVALID, "conv_impl %d: 0 product (L2-resident trunk kernel), 1 SIMT validation kernel, 3 one launch per layer pass, "
@@ -1727,6 +1730,8 @@ int unpack_impl(nesr_b200_handle* h, const uint8_t* slots, int32_t slot_w, int32
 namespace {
 int forward_nchw(nesr_b200_handle* h, const float* x, bool unshuffled, int32_t n, int32_t H, int32_t W, float* y, void* stream) {
   if (!h) return NESR_E_INVALID;
+  if (!unshuffled && h->cfg.feat_in_ch > 0 && h->cfg.feat_in_ch != 12)
+    return fail(h, NESR_E_STATE, "this handle's conv_first takes %d feature channels: use nesr_b200_forward_feat_f32", h->cfg.feat_in_ch);
   if (!h->finalized) return fail(h, NESR_E_STATE, "weights not finalized");
   if (!x || !y || n < 1 || H < 2 || W < 2) return fail(h, NESR_E_INVALID, "bad tensor arguments");
   if ((H | W) & 1) return fail(h, NESR_E_INVALID, "pixel_unshuffle(2): H and W must be even (got %dx%d)", H, W);
@@ -1739,7 +1744,7 @@ int forward_nchw(nesr_b200_handle* h, const float* x, bool unshuffled, int32_t n
   CUDA_TRY(h, cudaEventRecord(h->ev_own, h->stream));          // plan uploads / memset (and any earlier u8 call) ran on our own stream
   CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_own, 0));
   PackParams pk{};
-  if (unshuffled) pk.in_f32_12 = x; else pk.in_f32 = x;
+  if (unshuffled) { pk.in_f32_12 = x; pk.feat_ch = h->cfg.feat_in_ch > 0 ? h->cfg.feat_in_ch : 12; } else pk.in_f32 = x;
   pk.H = H; pk.W = W; pk.pre_pad = 0;
   Sink sink; sink.out_f32 = y; sink.out_h = H * sc; sink.out_w = W * sc;
   for (const Batch& b : h->batches)
@@ -1755,8 +1760,18 @@ int nesr_b200_forward_nchw_f32(nesr_b200_handle* h, const float* x, int32_t n, i
 }
 
 int nesr_b200_forward_nchw12_f32(nesr_b200_handle* h, const float* x12, int32_t n, int32_t H, int32_t W, float* y, void* stream) {
+  if (!h) return NESR_E_INVALID;
   if (H < 1 || W < 1) return fail(h, NESR_E_INVALID, "bad tensor arguments");
+  if (h->cfg.feat_in_ch > 0 && h->cfg.feat_in_ch != 12) return fail(h, NESR_E_STATE, "this handle's conv_first takes %d feature channels, not 12", h->cfg.feat_in_ch);
   return forward_nchw(h, x12, true, n, 2 * H, 2 * W, y, stream);        // the 12 channels are the un-shuffle of a 2H x 2W image
+}
+
+int nesr_b200_forward_feat_f32(nesr_b200_handle* h, const float* feat, int32_t n, int32_t C, int32_t H, int32_t W, float* y, void* stream) {
+  if (!h) return NESR_E_INVALID;
+  if (H < 1 || W < 1) return fail(h, NESR_E_INVALID, "bad tensor arguments");
+  const int want = h->cfg.feat_in_ch > 0 ? h->cfg.feat_in_ch : 12;
+  if (C != want) return fail(h, NESR_E_INVALID, "feature tensor has %d channels, this handle's conv_first takes %d", C, want);
+  return forward_nchw(h, feat, true, n, 2 * H, 2 * W, y, stream);       // the engine's geometry is that of a 2H x 2W x2plus input
 }
 
 int nesr_b200_blend_u8(nesr_b200_handle* h, const uint8_t* const* members, int32_t K, int32_t H, int32_t W, const double* weights,

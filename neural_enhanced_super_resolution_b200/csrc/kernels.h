@@ -48,7 +48,8 @@ struct PackParams {
   const uint8_t* in_u8;        // BGR HWC frames, or null
   int64_t in_stride, in_frame_stride;
   const float* in_f32;         // RGB NCHW frames, or null
-  const float* in_f32_12;      // already un-shuffled frames [frame][12][H/2][W/2] (the reference HEAD's 12-channel tensor), or null
+  const float* in_f32_12;      // frames already on the feature grid, [frame][feat_ch][H/2][W/2] (feat_ch 12: the reference HEAD's 12-channel tensor), or null
+  int32_t feat_ch;             // in_f32_12: channels per frame (12: un-shuffled x2plus input; 3: scale-4 nets; 48: scale-1 nets)
   const uint8_t* in_u8_head;   // RGB HWC u8 image of H/2 x W/2 from which the reference HEAD builds its 12 channels (nesr/nesr.py:859-880), or null
   int32_t head_replicate;      // in_u8_head: force_3channel -- four copies of the image instead of image, x1.1, x0.9, 3x3 blur
   int32_t H, W;                // un-padded frame size

@@ -48,6 +48,15 @@ __global__ void __launch_bounds__(kBlockPixels) pack_kernel(const PackParams p) 
   const TileGeom& tg = p.tiles[b.tile];
   const PixelRef px = locate(tg.lv[0], b.px + threadIdx.x);
   if (!px.valid) return;
+  if (p.in_f32_12 && p.feat_ch != 12) {                      // any channel count on the feature grid (scale-4 / scale-1 architectures)
+    const size_t plane = static_cast<size_t>(p.H >> 1) * (p.W >> 1);
+    const float* src = p.in_f32_12 + static_cast<size_t>(tg.frame) * p.feat_ch * plane +
+                       static_cast<size_t>((tg.src_y0 >> 1) + px.y) * (p.W >> 1) + (tg.src_x0 >> 1) + px.x;
+    uint32_t* d32 = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.x0) + static_cast<size_t>(px.P) * kChunkChannels);
+    for (int k = 0; k < p.feat_ch; k += 2)
+      d32[k >> 1] = pack2(src[k * plane], k + 1 < p.feat_ch ? src[(k + 1) * plane] : 0.f, p.fmt);
+    return;
+  }
   uint32_t packed[6];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {

@@ -184,11 +184,11 @@ __global__ void __launch_bounds__(256) sharpen_mma_kernel(const uint8_t* __restr
       if (kExtMask && plane == 3) continue;
       const uint32_t* hi = reinterpret_cast<const uint32_t*>(&s_t[plane][0][8 * cb + g][16 * vb + 4 * t]);
       const uint32_t* lo = reinterpret_cast<const uint32_t*>(&s_t[plane][1][8 * cb + g][16 * vb + 4 * t]);
-      int dh[4] = {0, 0, 0, 0}, dl[4] = {0, 0, 0, 0};
+      int dh[4] = {0, 0, 0, 0}, dl[4] = {32768, 32768, 32768, 32768};   // the rounding constant rides in the accumulator
       if (plane == 3) { imma(dh, a2, hi[0], hi[4]); imma(dl, a2, lo[0], lo[4]); }
       else { imma(dh, a3, hi[0], hi[4]); imma(dl, a3, lo[0], lo[4]); }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) blur[plane][i] = static_cast<int>((static_cast<uint32_t>(dh[i]) * 256u + static_cast<uint32_t>(dl[i]) + 32768u) >> 16);
+      for (int i = 0; i < 4; ++i) blur[plane][i] = static_cast<int>((static_cast<uint32_t>(dh[i]) * 256u + static_cast<uint32_t>(dl[i])) >> 16);
     }
     const int ox = 8 * cb + 2 * t;
 #pragma unroll

@@ -54,11 +54,10 @@ class RRDBNet(nn.Module):
     ``forward`` hands the 12 channels to ``nesr_b200_forward_nchw12_f32``, whose pack kernel reads them as the un-shuffle of a
     3 x 2H x 2W image (an index permutation, exact) and runs the same engine.
 
-    The 3-channel scale-4 architecture (``RRDBNet(3, 3, scale=4)``: RealESRGAN_x4plus and the ESRGAN checkpoints, upstream
-    ``rrdbnet_arch.py`` with ``scale == 4``: no un-shuffle, x4 out) runs on the same engine: its ``conv_first`` ([64, 3, 3, 3]) is
-    loaded as the first three of the twelve input channels of the un-shuffled layout with nine zero channels beside them, and
-    ``forward`` feeds ``cat(x, zeros)`` -- the zero products add exactly 0 to the fp32 accumulators, so the result is the one a
-    3-channel ``conv_first`` would give.  ``scale=1`` (un-shuffle by 4, 48 input channels) is not built.
+    The other two architectures of upstream ``rrdbnet_arch.py`` run on the same engine through ``nesr_b200_forward_feat_f32``
+    (SURVEY 8f row f4), which takes the tensor ``conv_first`` sees: ``scale=4`` (RealESRGAN_x4plus and the ESRGAN checkpoints: no
+    un-shuffle, ``conv_first`` [64, 3, 3, 3], x4 out) feeds ``x`` itself, ``scale=1`` (un-shuffle by 4, ``conv_first`` [64, 48, 3, 3],
+    x1 out) feeds ``pixel_unshuffle(x, 4)`` -- an index permutation done by torch; every convolution runs in the library.
 
     Extra keyword-only knobs (not in upstream): ``body_format`` / ``edge_format`` select the 16-bit
     operand format of the dense-block / edge convolutions ("bf16" | "fp16").
@@ -72,7 +71,8 @@ class RRDBNet(nn.Module):
         self.num_feat, self.num_block, self.num_grow_ch = num_feat, num_block, num_grow_ch
         in_ch = num_in_ch * (4 if scale == 2 else 16 if scale == 1 else 1)
         self._head_layout = (scale == 4 and num_in_ch == 12)       # the reference HEAD's constructor call
-        self._x4_layout = (scale == 4 and num_in_ch == 3)          # x4plus: three of the twelve un-shuffled channels, the rest zero
+        self._feat_layout = scale in (1, 4) and not self._head_layout  # conv_first sees x (scale 4) or pixel_unshuffle(x, 4) (scale 1)
+        self._feat_ch = in_ch
         self.conv_first = _conv(in_ch, num_feat)
         self.body = nn.Sequential(*[RRDB(num_feat, num_grow_ch) for _ in range(num_block)])
         self.conv_body = _conv(num_feat, num_feat)
@@ -101,24 +101,18 @@ class RRDBNet(nn.Module):
         index = device.index if device.index is not None else torch.cuda.current_device()
         version = (index,) + self._params_version()
         if self._engine is None or self._engine_version != version:
-            if self.scale != 2 and not (self._head_layout or self._x4_layout):
-                raise RuntimeError("this build implements the x2plus network RRDBNet(num_in_ch=3, num_out_ch=3, scale=2, ...), its "
-                                   "un-shuffled form RRDBNet(num_in_ch=12, num_out_ch=3) as the reference's HEAD builds it, and the "
-                                   "x4 network RRDBNet(num_in_ch=3, num_out_ch=3, scale=4); scale=1 is not built")
-            grid_layout = self._head_layout or self._x4_layout       # feature grid = input grid, x4 out
+            if self.scale not in (1, 2, 4) or self._feat_ch > 64:
+                raise RuntimeError(f"RRDBNet(num_in_ch={self.num_in_ch}, scale={self.scale}): upstream's scales are 1, 2 and 4 and conv_first "
+                                   "takes at most 64 channels on the feature grid in this build")
+            grid_layout = self._head_layout or self._feat_layout     # the engine's geometry: feature grid in, x4 of it out
             if self._engine is not None:
                 self._engine.close()
             eng = _ffi.Engine(device=index, num_block=self.num_block, body_format=self._formats[0],
                               edge_format=self._formats[1], conv_impl=self._conv_impl,
                               max_batch_pixels=self._max_batch_pixels, num_in_ch=3 if grid_layout else self.num_in_ch,
                               num_out_ch=self.num_out_ch, scale=2 if grid_layout else self.scale, num_feat=self.num_feat,
-                              num_grow_ch=self.num_grow_ch)
-            state = self.state_dict()
-            if self._x4_layout:
-                w3 = state["conv_first.weight"]
-                state = dict(state)
-                state["conv_first.weight"] = torch.cat([w3, w3.new_zeros((w3.shape[0], 9, 3, 3))], dim=1)
-            eng.load_state_dict(state)
+                              num_grow_ch=self.num_grow_ch, feat_in_ch=self._feat_ch if self._feat_layout else 0)
+            eng.load_state_dict(self.state_dict())
             self._engine, self._engine_version = eng, version
         return self._engine
 
@@ -129,12 +123,11 @@ class RRDBNet(nn.Module):
             if x.dim() != 4 or x.shape[1] != 12:
                 raise RuntimeError(f"expected a N x 12 x H x W tensor, got {tuple(x.shape)}")
             return self.engine(x.device).forward_nchw12(x.float()).to(x.dtype)   # the pack kernel reads the 12 channels in place
-        if self._x4_layout:
-            if x.dim() != 4 or x.shape[1] != 3:
-                raise RuntimeError(f"expected a N x 3 x H x W tensor, got {tuple(x.shape)}")
-            x12 = x.new_zeros((x.shape[0], 12, x.shape[2], x.shape[3]), dtype=torch.float32)
-            x12[:, 0:3] = x
-            return self.engine(x.device).forward_nchw12(x12).to(x.dtype)
+        if self._feat_layout:
+            if x.dim() != 4 or x.shape[1] != self.num_in_ch:
+                raise RuntimeError(f"expected a N x {self.num_in_ch} x H x W tensor, got {tuple(x.shape)}")
+            feat = x.float() if self.scale == 4 else torch.nn.functional.pixel_unshuffle(x.float(), 4)   # upstream's channel order
+            return self.engine(x.device).forward_feat(feat).to(x.dtype)
         return self.engine(x.device).forward_nchw(x.float()).to(x.dtype)
 
 

@@ -169,6 +169,41 @@ def test_x4_network_matches_oracle(tmp_path):
     assert d.max() <= 2 and psnr(out, ref) >= 45.0
 
 
+def test_x1_network_matches_oracle(tmp_path):
+    """``RRDBNet(3, 3, scale=1)`` (upstream ``rrdbnet_arch.py``: ``pixel_unshuffle(x, 4)``, 48 input channels, x1 out) through
+    ``nesr_b200_forward_feat_f32``: forward and ``RealESRGANer(scale=1).enhance`` (mod-4 reflect pad) against the fp32 oracle."""
+    from oracle import shims
+    from oracle.realesrganer import RealESRGANer as OracleUpsampler
+    from oracle.rrdbnet import RRDBNet as OracleNet, calibrate_conv_last_
+    torch.manual_seed(13)
+    oracle_net = OracleNet(3, 3, scale=1).eval()
+    img = natural_image(120, 152, seed=6)
+    x = torch.from_numpy(img[:, :, ::-1].copy()).permute(2, 0, 1).float()[None] / 255
+    calibrate_conv_last_(oracle_net, x)
+    with torch.no_grad():
+        want = oracle_net(x)[0]
+    net = pkg.RRDBNet(3, 3, scale=1)
+    net.load_state_dict(oracle_net.state_dict(), strict=True)
+    got = net.cuda()(x.cuda())[0].cpu()
+    assert got.shape == want.shape == (3, 120, 152)
+    a = (want.clamp(0, 1) * 255).round().numpy().astype(np.int32)
+    b = (got.clamp(0, 1) * 255).round().numpy().astype(np.int32)
+    assert np.abs(a - b).max() <= 2 and psnr(a, b) >= 45.0
+    assert float((a > 0).mean()) > 0.5 and float((a < 255).mean()) > 0.5
+    eng = net.engine()
+    with pytest.raises(RuntimeError):
+        eng.enhance_u8(img)                                       # the u8 entry is the x2plus un-shuffle: refused on this handle
+    with pytest.raises(RuntimeError):
+        eng.forward_feat(torch.zeros(1, 12, 8, 8, device="cuda"))
+    ckpt = shims.write_checkpoint(oracle_net.state_dict(), str(tmp_path))
+    odd = np.ascontiguousarray(img[:117, :150])                   # 117 x 150: mod-4 pad of 3 and 2
+    ref, _ = OracleUpsampler(1, ckpt, model=OracleNet(3, 3, scale=1), tile=0, tile_pad=8, pre_pad=0).enhance(odd)
+    out, mode = pkg.RealESRGANer(1, ckpt, model=pkg.RRDBNet(3, 3, scale=1), tile=0, tile_pad=8, pre_pad=0, device="cuda:0").enhance(odd)
+    assert mode == "RGB" and out.shape == ref.shape == odd.shape
+    d = np.abs(out.astype(np.int32) - ref.astype(np.int32))
+    assert d.max() <= 2 and psnr(out, ref) >= 45.0
+
+
 def test_head_compat_pipeline_matches_reference_golden(golden, tmp_path):
     """``enhance_image`` with ``head_compat`` against the UNMODIFIED reference's own end-to-end output (``pipeline.npz``: HEAD,
     12-channel mode, x4, CLAHE pre-process, sharpen) made with the fp32 oracle behind it -- same seeded weights."""

@@ -25,7 +25,7 @@ def test_head_layout_holds_the_x2plus_weights():
     with pytest.raises(RuntimeError):
         head(torch.zeros(1, 12, 8, 8))                                   # CPU tensor: no CPU path
     with pytest.raises(RuntimeError):
-        pkg.RRDBNet(num_in_ch=3, num_out_ch=3, scale=1).engine("cuda:0")  # the scale-1 (un-shuffle by 4) network is not this build
+        pkg.RRDBNet(num_in_ch=3, num_out_ch=3, scale=3).engine("cuda:0")  # upstream's scales are 1, 2 and 4
 
 
 def test_x4_layout_holds_the_x4plus_tensors():
@@ -33,10 +33,17 @@ def test_x4_layout_holds_the_x4plus_tensors():
     ``conv_first`` [64, 3, 3, 3] -- and loads the oracle's scale-4 state dict strictly."""
     from oracle.rrdbnet import RRDBNet as OracleNet
     net = pkg.RRDBNet(num_in_ch=3, num_out_ch=3, scale=4)
-    assert net.conv_first.weight.shape == (64, 3, 3, 3) and net._x4_layout and not net._head_layout
+    assert net.conv_first.weight.shape == (64, 3, 3, 3) and net._feat_layout and not net._head_layout
     net.load_state_dict(OracleNet(3, 3, scale=4).state_dict(), strict=True)
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 3, 8, 8))                                     # CPU tensor: no CPU path
+    x1 = pkg.RRDBNet(num_in_ch=3, num_out_ch=3, scale=1)                 # un-shuffle by 4: 48 channels on the feature grid
+    assert x1.conv_first.weight.shape == (64, 48, 3, 3) and x1._feat_layout and x1._feat_ch == 48
+    x1.load_state_dict(OracleNet(3, 3, scale=1).state_dict(), strict=True)
+    # upstream's pixel_unshuffle (view / permute / reshape) orders channels as torch's: c * s^2 + i * s + j
+    from oracle.rrdbnet import pixel_unshuffle
+    t = torch.arange(2 * 3 * 8 * 12, dtype=torch.float32).reshape(2, 3, 8, 12)
+    assert torch.equal(pixel_unshuffle(t, 4), torch.nn.functional.pixel_unshuffle(t, 4))
 
 
 @pytest.mark.parametrize("name", ["photo", "photo_small", "noise_ragged", "noise_tiny", "noise_row"])
