@@ -27,7 +27,7 @@ constexpr int kTW = 64, kTH = 32;          // output tile
 constexpr int kHalo = 8;                   // radius of the 17 non-zero taps of the sigma-3 kernel (sigma 2: 6)
 constexpr int kInW = kTW + 2 * kHalo;      // 80 bytes: row pitch of the planar input, 20 words
 constexpr int kInH = kTH + 2 * kHalo;      // 48 bytes: column pitch of the transposed row sums, 12 words
-constexpr int kOutPitch = kTW * 3 + 4;     // 196 bytes = 49 words: the eight rows a warp writes at once fall into different banks
+constexpr int kOutPitch = kTW * 3 + 16;    // 208 bytes = 52 words (4 mod 8): the eight rows a warp writes at once fall into different banks; 16-byte rows
 
 // The A fragments of the two Toeplitz matrices, per lane (g = lane / 4, t = lane % 4; register r: row g + 8 (r & 1), k = 4t + 16 (r >> 1) + i in
 // byte i):  A[m][k] = tap[k - m], zero outside the kernel.  sigma 3: 19 taps of which the 17 inner ones are non-zero (tap index k - m);
@@ -71,7 +71,7 @@ __device__ __forceinline__ void imma(int (&d)[4], const uint32_t (&a)[4], uint32
 
 template <bool kExtMask>
 __global__ void __launch_bounds__(256) sharpen_mma_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int H, const int W,
-                                                          const int bgr, const uint8_t* __restrict__ ext_mask, const int aligned4) {
+                                                          const int bgr, const uint8_t* __restrict__ ext_mask, const int aligned4, const int aligned16) {
   __shared__ __align__(16) uint8_t s_in[4][kInH][kInW];          // planar channel 0, 1, 2 (memory order) and gray
   __shared__ __align__(16) uint8_t s_t[4][2][kTW][kInH];         // row sums: [plane][high | low byte][column][row]
   __shared__ __align__(16) uint8_t s_out[kTH][kOutPitch];        // interleaved output tile
@@ -91,35 +91,36 @@ __global__ void __launch_bounds__(256) sharpen_mma_kernel(const uint8_t* __restr
     const uint32_t l0 = static_cast<uint32_t>(wr) & 255u, l1 = 35u, l2 = static_cast<uint32_t>(wb) & 255u;
     const uint32_t hA = h0 | h1 << 8 | h2 << 16, hB0 = h0 << 24, hB1 = h1 | h2 << 8, hC1 = h0 << 16 | h1 << 24, hC2 = h2, hD = h0 << 8 | h1 << 16 | h2 << 24;
     const uint32_t lA = l0 | l1 << 8 | l2 << 16, lB0 = l0 << 24, lB1 = l1 | l2 << 8, lC1 = l0 << 16 | l1 << 24, lC2 = l2, lD = l0 << 8 | l1 << 16 | l2 << 24;
-    // all twelve loads of a thread are issued before the first is used
-    constexpr int kItems = kInH * (kInW / 4), kIters = (kItems + 255) / 256;
-    const bool fast_y = y0 - kHalo >= 0 && y0 + kTH + kHalo <= H;
-    uint32_t w[kIters][3];
+    // 240 threads take 12 tile rows x 20 items per step, four steps: a thread keeps its column and walks down 12 rows at a time, so every
+    // address is a base plus a step-constant offset; all twelve loads of a thread are issued before the first is used
+    constexpr int kRowsPerStep = 12, kSteps = kInH / kRowsPerStep;
+    static_assert(kRowsPerStep * (kInW / 4) <= 256 && kSteps * kRowsPerStep == kInH, "load mapping");
+    if (tid < kRowsPerStep * (kInW / 4)) {
+      const int r = tid / (kInW / 4), lx = 4 * (tid - r * (kInW / 4));
+      const bool fast_y = y0 - kHalo >= 0 && y0 + kTH + kHalo <= H;
+      const uint8_t* col = in + static_cast<size_t>(x0 + lx - kHalo) * 3;
+      uint32_t w[kSteps][3];
 #pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int idx = tid + 256 * it;
-      if (idx < kItems) {
-        const int ly = idx / (kInW / 4), lx = 4 * (idx - ly * (kInW / 4));
-        const int gy = fast_y ? y0 + ly - kHalo : reflect101(y0 + ly - kHalo, H);
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(in + (static_cast<size_t>(gy) * W + (x0 + lx - kHalo)) * 3);
+      for (int it = 0; it < kSteps; ++it) {
+        const int ty = y0 + r + kRowsPerStep * it - kHalo;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(col + static_cast<size_t>(fast_y ? ty : reflect101(ty, H)) * W * 3);
         w[it][0] = __ldg(src); w[it][1] = __ldg(src + 1); w[it][2] = __ldg(src + 2);
       }
-    }
+      uint8_t* dst = &s_in[0][r][lx];
 #pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int idx = tid + 256 * it;
-      if (idx >= kItems) break;
-      const int ly = idx / (kInW / 4), lx = 4 * (idx - ly * (kInW / 4));
-      const uint32_t w0 = w[it][0], w1 = w[it][1], w2 = w[it][2];
-      *reinterpret_cast<uint32_t*>(&s_in[0][ly][lx]) = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);   // bytes 0, 3, 6, 9 of the 12
-      *reinterpret_cast<uint32_t*>(&s_in[1][ly][lx]) = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);   // bytes 1, 4, 7, 10
-      *reinterpret_cast<uint32_t*>(&s_in[2][ly][lx]) = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);   // bytes 2, 5, 8, 11
-      if (!kExtMask) {
-        const uint32_t g0 = (__dp4a(w0, hA, 0u) * 256u + __dp4a(w0, lA, 16384u)) >> 15;
-        const uint32_t g1 = (__dp4a(w1, hB1, __dp4a(w0, hB0, 0u)) * 256u + __dp4a(w1, lB1, __dp4a(w0, lB0, 16384u))) >> 15;
-        const uint32_t g2 = (__dp4a(w2, hC2, __dp4a(w1, hC1, 0u)) * 256u + __dp4a(w2, lC2, __dp4a(w1, lC1, 16384u))) >> 15;
-        const uint32_t g3 = (__dp4a(w2, hD, 0u) * 256u + __dp4a(w2, lD, 16384u)) >> 15;
-        *reinterpret_cast<uint32_t*>(&s_in[3][ly][lx]) = g0 | g1 << 8 | g2 << 16 | g3 << 24;
+      for (int it = 0; it < kSteps; ++it) {
+        const uint32_t w0 = w[it][0], w1 = w[it][1], w2 = w[it][2];
+        uint8_t* d = dst + it * kRowsPerStep * kInW;
+        *reinterpret_cast<uint32_t*>(d) = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);                       // bytes 0, 3, 6, 9 of the 12
+        *reinterpret_cast<uint32_t*>(d + kInH * kInW) = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);         // bytes 1, 4, 7, 10
+        *reinterpret_cast<uint32_t*>(d + 2 * kInH * kInW) = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);     // bytes 2, 5, 8, 11
+        if (!kExtMask) {
+          const uint32_t g0 = (__dp4a(w0, hA, 0u) * 256u + __dp4a(w0, lA, 16384u)) >> 15;
+          const uint32_t g1 = (__dp4a(w1, hB1, __dp4a(w0, hB0, 0u)) * 256u + __dp4a(w1, lB1, __dp4a(w0, lB0, 16384u))) >> 15;
+          const uint32_t g2 = (__dp4a(w2, hC2, __dp4a(w1, hC1, 0u)) * 256u + __dp4a(w2, lC2, __dp4a(w1, lC1, 16384u))) >> 15;
+          const uint32_t g3 = (__dp4a(w2, hD, 0u) * 256u + __dp4a(w2, lD, 16384u)) >> 15;
+          *reinterpret_cast<uint32_t*>(d + 3 * kInH * kInW) = g0 | g1 << 8 | g2 << 16 | g3 << 24;
+        }
       }
     }
   } else {
@@ -238,7 +239,12 @@ __global__ void __launch_bounds__(256) sharpen_mma_kernel(const uint8_t* __restr
 
   // ---- store
   const int rows = min(kTH, H - y0), cols = min(kTW, W - x0);
-  if (aligned4 && cols == kTW) {
+  if (aligned16 && cols == kTW) {                                // 12 x 16 bytes per row
+    for (int idx = tid; idx < rows * (kTW * 3 / 16); idx += 256) {
+      const int oy = idx / (kTW * 3 / 16), q = idx - oy * (kTW * 3 / 16);
+      reinterpret_cast<uint4*>(out + (static_cast<size_t>(y0 + oy) * W + x0) * 3)[q] = reinterpret_cast<const uint4*>(&s_out[oy][0])[q];
+    }
+  } else if (aligned4 && cols == kTW) {
     for (int idx = tid; idx < rows * (kTW * 3 / 4); idx += 256) {
       const int oy = idx / (kTW * 3 / 4), wd = idx - oy * (kTW * 3 / 4);
       reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(y0 + oy) * W + x0) * 3)[wd] = reinterpret_cast<const uint32_t*>(&s_out[oy][0])[wd];
@@ -257,8 +263,9 @@ cudaError_t launch_sharpen_mma(const uint8_t* in, uint8_t* out, int32_t H, int32
   if (H <= 0 || W <= 0) return cudaSuccess;
   dim3 grid((W + kTW - 1) / kTW, (H + kTH - 1) / kTH);
   const int aligned4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 3) == 0;
-  if (ext_mask) sharpen_mma_kernel<true><<<grid, 256, 0, stream>>>(in, out, H, W, bgr, ext_mask, aligned4);
-  else sharpen_mma_kernel<false><<<grid, 256, 0, stream>>>(in, out, H, W, bgr, nullptr, aligned4);
+  const int aligned16 = (W % 16 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;      // rows of the output are 16-byte aligned
+  if (ext_mask) sharpen_mma_kernel<true><<<grid, 256, 0, stream>>>(in, out, H, W, bgr, ext_mask, aligned4, aligned16);
+  else sharpen_mma_kernel<false><<<grid, 256, 0, stream>>>(in, out, H, W, bgr, nullptr, aligned4, aligned16);
   return cudaGetLastError();
 }
 
