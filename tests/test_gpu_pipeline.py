@@ -94,6 +94,7 @@ def test_head_layout_forward_matches_oracle():
     xb = torch.cat([x12, x12.flip(-1)], 0).cuda()
     eng = net.engine()
     assert torch.equal(eng.forward_nchw12(xb), eng.forward_nchw(torch.nn.functional.pixel_shuffle(xb, 2)))
+    assert torch.equal(eng.forward_feat(xb), eng.forward_nchw12(xb))                  # the generic feature-grid entry, C == 12
     assert got.shape == want.shape == (3, 144, 176)
     a = np.clip(got.numpy() * 255.0, 0, 255).astype(np.uint8).astype(np.int32)        # the reference's truncating u8
     b = np.clip(want.numpy() * 255.0, 0, 255).astype(np.uint8).astype(np.int32)
