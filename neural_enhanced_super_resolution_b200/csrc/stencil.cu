@@ -26,19 +26,35 @@ __device__ __forceinline__ float blend_step(float acc, uint32_t byte, double w) 
   return static_cast<float>(__dadd_rn(static_cast<double>(acc), __dmul_rn(static_cast<double>(byte), w)));
 }
 
-// K members known at compile time: pointers, weights and the 16-byte vectors live in registers.  (With K a run-time value the
+// K members known at compile time: pointers and the 16-byte vectors live in registers.  (With K a run-time value the
 // per-member arrays were indexed dynamically and lived in local memory: 0.7 TB/s of algorithmic traffic on a B200.)
+// The kernel was bound by its conversions (u8 -> f64, f32 -> f64, f64 -> f32: nine per byte for K = 3, on the 16-lane XU pipe), so the
+// products come from shared-memory tables built once per block with the same instruction the per-byte path used:
+//   s_prod[m][b] = __dmul_rn(f64(b), w[m])                     (the reference's  img.astype(f32) * weights[m], a float64 product)
+//   s_first[b]   = f32(f64(0.f) + s_prod[0][b])                (the first member's step: 0 + P is exact, so this is f32(P))
+// and a later member's step is  acc = f32(f64(acc) + s_prod[m][b])  -- the same roundings in the same order, bit for bit.
 // Two independent 16-byte vectors per member are in flight per thread and iteration.
 template <int K>
 __global__ void __launch_bounds__(256) blend_kernel_k(const BlendParams p, const int vec_ok) {
+  __shared__ double s_prod[K][256];
+  __shared__ float s_first[256];
+  for (int i = threadIdx.x; i < 256 * K; i += 256) s_prod[i >> 8][i & 255] = __dmul_rn(static_cast<double>(i & 255), p.weights[i >> 8]);
+  __syncthreads();
+  s_first[threadIdx.x] = static_cast<float>(__dadd_rn(0.0, s_prod[0][threadIdx.x]));
+  __syncthreads();
   const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const int64_t nvec = vec_ok ? p.nbytes / 16 : 0;
   const uint4* src[K];
-  double w[K];
 #pragma unroll
-  for (int m = 0; m < K; ++m) { src[m] = reinterpret_cast<const uint4*>(p.members[m]); w[m] = p.weights[m]; }
+  for (int m = 0; m < K; ++m) src[m] = reinterpret_cast<const uint4*>(p.members[m]);
   uint4* dst = reinterpret_cast<uint4*>(p.out);
+  auto blend1 = [&](const uint32_t (&b)[K]) {                   // one output byte from the K member bytes
+    float acc = s_first[b[0]];
+#pragma unroll
+    for (int m = 1; m < K; ++m) acc = static_cast<float>(__dadd_rn(static_cast<double>(acc), s_prod[m][b[m]]));
+    return static_cast<uint32_t>(static_cast<uint8_t>(acc));    // astype(uint8): truncation (acc >= 0)
+  };
   auto blend16 = [&](const uint4 (&in)[K]) {
     uint4 o;
     uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
@@ -47,10 +63,10 @@ __global__ void __launch_bounds__(256) blend_kernel_k(const BlendParams p, const
       uint32_t word = 0;
 #pragma unroll
       for (int by = 0; by < 4; ++by) {
-        float acc = 0.f;
+        uint32_t b[K];
 #pragma unroll
-        for (int m = 0; m < K; ++m) acc = blend_step(acc, (reinterpret_cast<const uint32_t*>(&in[m])[wd] >> (8 * by)) & 0xFF, w[m]);
-        word |= static_cast<uint32_t>(static_cast<uint8_t>(acc)) << (8 * by);   // astype(uint8): truncation (acc >= 0)
+        for (int m = 0; m < K; ++m) b[m] = (reinterpret_cast<const uint32_t*>(&in[m])[wd] >> (8 * by)) & 0xFF;
+        word |= blend1(b) << (8 * by);
       }
       ow[wd] = word;
     }
@@ -71,10 +87,10 @@ __global__ void __launch_bounds__(256) blend_kernel_k(const BlendParams p, const
     __stcs(dst + i, blend16(a));
   }
   for (int64_t j = nvec * 16 + tid; j < p.nbytes; j += nthreads) {
-    float acc = 0.f;
+    uint32_t b[K];
 #pragma unroll
-    for (int m = 0; m < K; ++m) acc = blend_step(acc, p.members[m][j], w[m]);
-    p.out[j] = static_cast<uint8_t>(acc);
+    for (int m = 0; m < K; ++m) b[m] = p.members[m][j];
+    p.out[j] = static_cast<uint8_t>(blend1(b));
   }
 }
 
