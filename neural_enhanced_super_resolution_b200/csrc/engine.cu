@@ -85,12 +85,14 @@ struct Arena {
   float* trunk = nullptr;     // [P0][64] fp32 residual trunk
   float* rrdb = nullptr;      // [P0][64] fp32 RRDB input
   float* feat = nullptr;      // [P0][64] fp32 conv_first output (long skip)
+  void* g1 = nullptr;         // [P0][64] conv_body's output (+ long skip) on the feature grid: conv_up1 reads it up-sampled (src_up)
   void* g2 = nullptr;         // [P1][64]
   void* g4[2] = {nullptr, nullptr};  // [P2][64]
   int64_t P[3] = {0, 0, 0};
   CUtensorMap m_x0, m_d[2], m_g2, m_g4[2];             // box 128 px (per-tap kernel)
   CUtensorMap f_x0, f_d[2], f_g2, f_g4[2];             // box 136 px (row-folded kernel, full strips)
   CUtensorMap e_x0, e_d[2], e_g2, e_g4[2];             // box 8 px (row-folded kernel, packed remainder strips)
+  CUtensorMap u_g1[2], u_g2[2];                        // "every pixel twice" views (zero-stride dimension) of g1 / g2: boxes of 68 and 4 source pixels
   CUtensorMap b_d[2][4];                               // boxes 8 / 16 / 32 / 64 px of the dense-block buffers (trunk kernel)
   CUtensorMap hf_d[2], hb_d[2][4];                     // the same as 32-channel (64-byte, SWIZZLE_64B) boxes: 136 px and 8 / 16 / 32 / 64 px
   bool shared_g = false;                               // growth planes shared by both dense buffers (see build_plan)
@@ -355,6 +357,19 @@ int make_map(nesr_b200_handle* h, CUtensorMap* m, void* base, int64_t channels, 
   return NESR_OK;
 }
 
+// (64 channels, 2 copies at stride ZERO, rows pixels): a box of `box_px` source pixels lands in shared memory as 2 * box_px rows of 128
+// bytes, every pixel twice -- nearest x2 along x done by the TMA engine (tools/tma_dup_probe.cu).
+int make_dup_map(nesr_b200_handle* h, CUtensorMap* m, void* base, int64_t rows, int box_px) {
+  const cuuint64_t gdim[3] = {64, 2, (cuuint64_t)rows};
+  const cuuint64_t gstride[2] = {0, 128};
+  const cuuint32_t box[3] = {64u, 2u, (cuuint32_t)box_px};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, NESR_E_CUDA, "cuTensorMapEncodeTiled (pixel-twice view) failed (%d) rows=%lld", (int)r, (long long)rows);
+  return NESR_OK;
+}
+
 // ----------------------------------------------------------------------------------------------
 // tile plan (upstream RealESRGANer.pre_process + tile_process geometry, oracle/realesrganer.py)
 // ----------------------------------------------------------------------------------------------
@@ -438,7 +453,9 @@ bool build_fold_schedule(Batch& b, int level, int num_sms, int max_rows = 0, int
   for (size_t ti = 0; ti < b.tiles.size(); ++ti) {
     const LevelGeom& g = b.tiles[ti].lv[level];
     const int rem = g.w % kBlockPixels;
-    if (rem) cols.push_back(Piece{(int32_t)ti, g.w - rem, rem, (rem + 2 + 7) / 8 * 8, 0, g.h});
+    // slab lanes of a piece: its pixels plus one halo pixel on either side -- plus one more on the levels whose layers may read their
+    // input nearest-x2 up-sampled (src_up: a slab row then starts at the even pixel x0 - 2), rounded to the 8-pixel TMA box
+    if (rem) cols.push_back(Piece{(int32_t)ti, g.w - rem, rem, (rem + 2 + (level > 0 ? 1 : 0) + 7) / 8 * 8, 0, g.h});
   }
   if (!cols.empty()) {
     // every piece costs the TMA producer at least one more operation per slab row; with 8 pieces a packed strip's
@@ -819,8 +836,8 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
     const int64_t p0 = bb.lv[0].pixels, p1 = bb.lv[1].pixels, p2 = bb.lv[2].pixels;
     const size_t sz_x0 = round_up(p0 * 64 * 2, 1024), sz_d = round_up(p0 * kDense * 2, 1024);
     const size_t sz_f = round_up(p0 * 64 * 4, 1024), sz_g2 = round_up(p1 * 64 * 2, 1024), sz_g4 = round_up(p2 * 64 * 2, 1024);
-    if (zero) *zero = sz_x0 + 2 * sz_d + sz_g2 + 2 * sz_g4;
-    return sz_x0 + 2 * sz_d + 3 * sz_f + sz_g2 + 2 * sz_g4;
+    if (zero) *zero = 2 * sz_x0 + 2 * sz_d + sz_g2 + 2 * sz_g4;
+    return 2 * sz_x0 + 2 * sz_d + 3 * sz_f + sz_g2 + 2 * sz_g4;            // x0 and g1 have the same size
   };
   size_t total = 0, largest = 0;
   for (const Batch& bb : h->batches) { const size_t n = slice_bytes(bb, nullptr); total += n; largest = std::max(largest, n); }
@@ -850,6 +867,7 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
     uint8_t* p = h->arena_shared ? h->arena_base : cursor;
     a.base = p;
     a.x0 = p; p += sz_x0;
+    a.g1 = p; p += sz_x0;
     // Dense-block buffers.  Classic layout: two [3][P0][64] buffers that ping-pong between blocks.  Shared-growth layout (trunk
     // kernel only, NESR_B200_SHARED_G): only x needs the ping-pong -- a block's conv1 overwrites the previous block's growth
     // channels only after every halo neighbour has published that block's conv5, i.e. has finished reading them -- so the planes
@@ -890,6 +908,8 @@ int build_plan(nesr_b200_handle* h, const PlanKey& key, int out_h, int out_w) {
     }
     if ((rc = make_map(h, &a.e_g2, a.g2, 64, Pb[1], 8))) return rc;
     for (int i2 = 0; i2 < 2; ++i2) if ((rc = make_map(h, &a.e_g4[i2], a.g4[i2], 64, Pb[2], 8))) return rc;
+    if ((rc = make_dup_map(h, &a.u_g1[0], a.g1, Pb[0], kSlab / 2)) || (rc = make_dup_map(h, &a.u_g1[1], a.g1, Pb[0], 4))) return rc;
+    if ((rc = make_dup_map(h, &a.u_g2[0], a.g2, Pb[1], kSlab / 2)) || (rc = make_dup_map(h, &a.u_g2[1], a.g2, Pb[1], 4))) return rc;
   }
   h->stats.arena_bytes = (int64_t)h->arena_bytes;
   if (h->cfg.conv_impl == 0 || h->cfg.conv_impl == 4)
@@ -1128,35 +1148,71 @@ int forward_batch(nesr_b200_handle* h, const Batch& b, const PackParams& pack_in
       cur ^= 1;
     }
   }
-  {  // conv_body + long skip, stored nearest-x2 upsampled into level 1
-    ConvParams p{};
-    p.res1 = a.feat; p.s1 = 1.0f;
-    p.dst16 = a.g2; p.dst16_plane_px = (int)a.P[1]; p.dst16_fmt = c.edge_format; p.dst16_up = 1;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_d[cur], &a.f_d[cur], &a.e_d[cur], a.d[cur], 3, 0}, p, s))) return rc;
-  }
-  {  // conv_up1 + lrelu, stored upsampled into level 2
-    ConvParams p{};
-    p.lrelu = 1;
-    p.dst16 = a.g4[0]; p.dst16_plane_px = (int)a.P[2]; p.dst16_fmt = c.edge_format; p.dst16_up = 1;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g2, &a.f_g2, &a.e_g2, a.g2, 1, 1}, p, s))) return rc;
-  }
-  {  // conv_up2 + lrelu
-    ConvParams p{};
-    p.lrelu = 1;
-    p.dst16 = a.g4[1]; p.dst16_plane_px = (int)a.P[2]; p.dst16_fmt = c.edge_format;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], &a.f_g4[0], &a.e_g4[0], a.g4[0], 1, 2}, p, s))) return rc;
-  }
-  {  // conv_hr + lrelu
-    ConvParams p{};
-    p.lrelu = 1;
-    p.dst16 = a.g4[0]; p.dst16_plane_px = (int)a.P[2]; p.dst16_fmt = c.edge_format;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[1], &a.f_g4[1], &a.e_g4[1], a.g4[1], 1, 2}, p, s))) return rc;
+  // nearest x2 (upstream F.interpolate(scale_factor=2, mode='nearest') in front of conv_up1 and conv_up2) on the READ side: the producing
+  // layer stores its own resolution and the consuming layer's TMA loads deliver every source pixel twice (zero-stride tensor-map
+  // dimension) from source row y >> 1 -- a quarter of the stores and loads of the write-side form (four replicated stores), which the
+  // CUDA-core validation kernel (conv_impl 1: it reads `src` directly) keeps.  Index arithmetic only: same bits either way.
+  const bool read_up = c.conv_impl != 1;
+  const void* last_src = nullptr;
+  const CUtensorMap *last_m = nullptr, *last_f = nullptr, *last_e = nullptr;
+  if (read_up) {
+    {  // conv_body + long skip -> g1 (feature grid)
+      ConvParams p{};
+      p.res1 = a.feat; p.s1 = 1.0f;
+      p.dst16 = a.g1; p.dst16_plane_px = (int)a.P[0]; p.dst16_fmt = c.edge_format;
+      if ((rc = run_conv(h, b, next(), ConvIO{&a.m_d[cur], &a.f_d[cur], &a.e_d[cur], a.d[cur], 3, 0}, p, s))) return rc;
+    }
+    {  // conv_up1 + lrelu on level 1, reading g1 up-sampled -> g2
+      ConvParams p{};
+      p.lrelu = 1; p.src_up = 1;
+      p.dst16 = a.g2; p.dst16_plane_px = (int)a.P[1]; p.dst16_fmt = c.edge_format;
+      if ((rc = run_conv(h, b, next(), ConvIO{nullptr, &a.u_g1[0], &a.u_g1[1], a.g1, 1, 1}, p, s))) return rc;
+    }
+    {  // conv_up2 + lrelu on level 2, reading g2 up-sampled -> g4[0]
+      ConvParams p{};
+      p.lrelu = 1; p.src_up = 1;
+      p.dst16 = a.g4[0]; p.dst16_plane_px = (int)a.P[2]; p.dst16_fmt = c.edge_format;
+      if ((rc = run_conv(h, b, next(), ConvIO{nullptr, &a.u_g2[0], &a.u_g2[1], a.g2, 1, 2}, p, s))) return rc;
+    }
+    {  // conv_hr + lrelu: g4[0] -> g4[1]
+      ConvParams p{};
+      p.lrelu = 1;
+      p.dst16 = a.g4[1]; p.dst16_plane_px = (int)a.P[2]; p.dst16_fmt = c.edge_format;
+      if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], &a.f_g4[0], &a.e_g4[0], a.g4[0], 1, 2}, p, s))) return rc;
+    }
+    last_src = a.g4[1]; last_m = &a.m_g4[1]; last_f = &a.f_g4[1]; last_e = &a.e_g4[1];
+  } else {
+    {  // conv_body + long skip, stored nearest-x2 upsampled into level 1
+      ConvParams p{};
+      p.res1 = a.feat; p.s1 = 1.0f;
+      p.dst16 = a.g2; p.dst16_plane_px = (int)a.P[1]; p.dst16_fmt = c.edge_format; p.dst16_up = 1;
+      if ((rc = run_conv(h, b, next(), ConvIO{&a.m_d[cur], &a.f_d[cur], &a.e_d[cur], a.d[cur], 3, 0}, p, s))) return rc;
+    }
+    {  // conv_up1 + lrelu, stored upsampled into level 2
+      ConvParams p{};
+      p.lrelu = 1;
+      p.dst16 = a.g4[0]; p.dst16_plane_px = (int)a.P[2]; p.dst16_fmt = c.edge_format; p.dst16_up = 1;
+      if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g2, &a.f_g2, &a.e_g2, a.g2, 1, 1}, p, s))) return rc;
+    }
+    {  // conv_up2 + lrelu
+      ConvParams p{};
+      p.lrelu = 1;
+      p.dst16 = a.g4[1]; p.dst16_plane_px = (int)a.P[2]; p.dst16_fmt = c.edge_format;
+      if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], &a.f_g4[0], &a.e_g4[0], a.g4[0], 1, 2}, p, s))) return rc;
+    }
+    {  // conv_hr + lrelu
+      ConvParams p{};
+      p.lrelu = 1;
+      p.dst16 = a.g4[0]; p.dst16_plane_px = (int)a.P[2]; p.dst16_fmt = c.edge_format;
+      if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[1], &a.f_g4[1], &a.e_g4[1], a.g4[1], 1, 2}, p, s))) return rc;
+    }
+    last_src = a.g4[0]; last_m = &a.m_g4[0]; last_f = &a.f_g4[0]; last_e = &a.e_g4[0];
   }
   {  // conv_last -> clamp, BGR, u8, halo crop + stitch  (or unclamped fp32 NCHW)
     ConvParams p{};
     p.out_u8 = sink.out_u8; p.out_stride = sink.out_stride; p.out_frame_stride = sink.out_frame_stride; p.out_trunc = sink.out_trunc;
     p.out_f32 = sink.out_f32; p.out_h = sink.out_h; p.out_w = sink.out_w;
-    if ((rc = run_conv(h, b, next(), ConvIO{&a.m_g4[0], &a.f_g4[0], &a.e_g4[0], a.g4[0], 1, 2}, p, s))) return rc;
+    if ((rc = run_conv(h, b, next(), ConvIO{last_m, last_f, last_e, last_src, 1, 2}, p, s))) return rc;
   }
   if (time_end) cudaEventRecord(h->evc1, s);
   h->stats.tiles_processed += (int64_t)b.tiles.size();
@@ -1529,10 +1585,11 @@ int nesr_b200_debug_plan(int32_t n_frames, int32_t H, int32_t W, int32_t tile, i
           for (int sgi = 0; sgi < band.nseg; ++sgi) {
             const FoldSeg& sg = lp.segs[band.seg0 + sgi];
             const LevelGeom& g = b.tiles[sg.tile].lv[level];
-            if (sg.lane0 < lanes || (sg.lane0 & 7) || sg.lane0 + sg.width > kBlockPixels || sg.lane0 + sg.width + 2 > 136 ||
-                sg.x0 < 0 || sg.x0 + sg.width > g.w || sg.y0 < 0 || sg.y0 + sg.h > g.h)
+            const int halo = 2 + (level > 0 ? 1 : 0);      // levels above 0 may be read up-sampled: slab rows start at the even pixel x0 - 2
+            if (sg.lane0 < lanes || (sg.lane0 & 7) || sg.lane0 + sg.width > kBlockPixels || sg.lane0 + sg.width + halo > 136 ||
+                sg.x0 < 0 || sg.x0 + sg.width > g.w || sg.y0 < 0 || sg.y0 + sg.h > g.h || (level > 0 && (sg.x0 & 1)))
               return fail(nullptr, NESR_E_STATE, "group %zu level %d: segment %d out of range", bi, level, band.seg0 + sgi);
-            lanes = sg.lane0 + (sg.width + 2 + 7) / 8 * 8;
+            lanes = sg.lane0 + (sg.width + halo + 7) / 8 * 8;
             for (int r = band.r0; r < band.r0 + band.rows && r < sg.h; ++r)
               for (int x = sg.x0; x < sg.x0 + sg.width; ++x)
                 if (++cover[sg.tile][(size_t)(sg.y0 + r) * g.w + x] != 1)

@@ -156,7 +156,7 @@ __device__ __forceinline__ void load_weights(const ConvParams& p, const CUtensor
 __device__ __forceinline__ void producer_bands(const ConvParams& p, const CUtensorMap* amap, const CUtensorMap* amap8,
                                                const Pipe& s, RingPos& rp, int band_begin, int band_end) {
   const int nchunk = (p.cin + kChunkChannels - 1) / kChunkChannels;
-  const int plane_px = p.src_plane_px, level = p.level, dbg = dbg_flags(p);
+  const int plane_px = p.src_plane_px, level = p.level, dbg = dbg_flags(p), up = p.src_up;
   const FoldBand* const bands = p.bands;
   const FoldSeg* const segs = p.segs;
   const TileGeom* const tiles = p.tiles;
@@ -172,19 +172,23 @@ __device__ __forceinline__ void producer_bands(const ConvParams& p, const CUtens
   for (int bi = band_begin; bi < band_end; ++bi) {
     const FoldBand band = bands[bi];
     // per segment: flat pixel of (row r0-1, x0-1), row pitch, slab byte offset, number of 8-pixel boxes
-    int seg_px[kMaxFoldSegs], seg_pitch[kMaxFoldSegs], seg_off[kMaxFoldSegs], seg_n8[kMaxFoldSegs];
+    // read-side nearest x2 (up): the source is the level below; slab row i is source row (r0 - 1 + y0 + i) >> 1 and starts at the EVEN
+    // up-sampled pixel x0 - 2 (a "pixel twice" box starts on a pair), one pixel before the usual x0 - 1: seg_px = flat source pixel of
+    // (row 0, (x0 - 2) / 2), seg_y0 = up-sampled row of slab row 0.  x0 is even on every level above 0 (tile widths are fw << level).
+    int seg_px[kMaxFoldSegs], seg_pitch[kMaxFoldSegs], seg_off[kMaxFoldSegs], seg_n8[kMaxFoldSegs], seg_y0[kMaxFoldSegs];
     bool full_strip = false;
     uint32_t row_bytes = 0;
 #pragma unroll
     for (int sgi = 0; sgi < kMaxFoldSegs; ++sgi) {
-      seg_px[sgi] = seg_pitch[sgi] = seg_off[sgi] = seg_n8[sgi] = 0;
+      seg_px[sgi] = seg_pitch[sgi] = seg_off[sgi] = seg_n8[sgi] = seg_y0[sgi] = 0;
       if (sgi < band.nseg) {
         const FoldSeg sg = segs[band.seg0 + sgi];
-        const LevelGeom g = tiles[sg.tile].lv[level];
-        seg_px[sgi] = g.base + (band.r0 - 1 + sg.y0) * g.pitch + sg.x0 - 1;
+        const LevelGeom g = tiles[sg.tile].lv[up ? level - 1 : level];
+        seg_px[sgi] = up ? g.base + ((sg.x0 - 2) >> 1) : g.base + (band.r0 - 1 + sg.y0) * g.pitch + sg.x0 - 1;
+        seg_y0[sgi] = band.r0 - 1 + sg.y0;
         seg_pitch[sgi] = g.pitch;
         seg_off[sgi] = sg.lane0 * 128;
-        seg_n8[sgi] = (sg.width + 2 + 7) >> 3;
+        seg_n8[sgi] = (sg.width + 2 + up + 7) >> 3;
         if (sg.width == kBlockPixels) full_strip = true;      // a 128-pixel segment is always alone
         row_bytes += seg_n8[sgi] * 1024;
       }
@@ -202,7 +206,17 @@ __device__ __forceinline__ void producer_bands(const ConvParams& p, const CUtens
             mbar_arrive_expect_tx(&s.full[rp.stage], row_bytes);
             uint8_t* slab = s.ring + rp.stage * kSlabBytes;
             const int plane = c * plane_px;
-            if (hints) {
+            if (up) {                                            // one chunk, no L2 hints: 68 (or 4) source pixels become 136 (8) slab rows
+              if (full_strip) {
+                tma_load_3d(slab, amap, &s.full[rp.stage], 0, 0, seg_px[0] + ((seg_y0[0] + i) >> 1) * seg_pitch[0]);
+              } else {
+#pragma unroll
+                for (int sgi = 0; sgi < kMaxFoldSegs; ++sgi)
+                  for (int k = 0; k < seg_n8[sgi]; ++k)
+                    tma_load_3d(slab + seg_off[sgi] + k * 1024, amap8, &s.full[rp.stage], 0, 0,
+                                seg_px[sgi] + ((seg_y0[sgi] + i) >> 1) * seg_pitch[sgi] + k * 4);
+              }
+            } else if (hints) {
               const uint64_t pol = c < pin_chunks ? pol_keep : pol_stream;
               if (full_strip) {
                 tma_load_2d_hint(slab, amap, &s.full[rp.stage], 0, plane + seg_px[0] + i * seg_pitch[0], pol);
@@ -252,7 +266,7 @@ __device__ __forceinline__ void mma_bands(const ConvParams& p, const Pipe& s, Ri
   const uint32_t hw = (p.idesc >> 7) & 7u;                 // operand format bits of the layer
   const uint32_t idesc1 = umma_idesc_f16(hw, COUT), idesc2 = umma_idesc_f16(hw, 2 * COUT), idesc3 = umma_idesc_f16(hw, 3 * COUT);
   const uint32_t hi = umma_desc_hi_sw128();
-  const uint32_t a_lo0 = umma_desc_lo(smem_u32(s.ring));
+  const uint32_t a_lo0 = umma_desc_lo(smem_u32(s.ring)) + (p.src_up ? 8u : 0u);   // read-side x2: slabs start one pixel (128 B) early
   const uint32_t w_lo0 = umma_desc_lo(smem_u32(s.wsm));
   const uint32_t tmem_base = s.tmem_base;
   const int nstage = s.nstage;

@@ -108,6 +108,8 @@ struct ConvParams {
   const int32_t* cta_band_off; // [grid + 1] first band of each CTA
   int32_t c_off;               // first output channel of this pass inside the 64-channel fp32 buffers
   int32_t fold_stages;         // activation ring depth (host-computed from the shared-memory budget)
+  int32_t src_up;              // 1: `src` is the layer BELOW this level and is read nearest-x2 up-sampled (in[y >> 1, x >> 1]): the tensor maps are
+                               // the zero-stride "every pixel twice" views of it, slab rows start one pixel early (at the even pixel x0 - 2)
   // persistent trunk kernel (conv3x3_body.cu)
   int32_t src_sel;             // which of the two dense-block buffers (tensor maps) this pass reads
   int32_t sync_passes;         // passes [0, sync_passes) of every CTA must be complete before this pass loads activations

@@ -102,6 +102,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 3-D tiled load.  Used with a ZERO-stride middle dimension (channels, 2 copies @ stride 0, pixels): the TMA engine writes every source
+// pixel twice, i.e. it delivers the nearest-x2 up-sampled row (tools/tma_dup_probe.cu: the driver accepts the stride, also with the
+// 128-byte swizzle) -- the read-side form of upstream's F.interpolate(scale_factor=2, mode='nearest') for conv_up1 / conv_up2.
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // L2 eviction policies.  The dense-block activations of a tile group are re-read by every layer pass and should
 // stay in the 126 MB L2 (evict_last); the fp32 trunk streams through once per dense block and must not push them
 // out (evict_first on those loads / stores, see epilogue.cuh).
