@@ -36,6 +36,7 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
     tma_prefetch_desc(&amap8);
     tma_prefetch_desc(&wmap);
   }
+  if (threadIdx.x < 64) s.bias[threadIdx.x] = threadIdx.x < COUT ? p.bias[threadIdx.x] : 0.f;   // constants of the network: no need to wait for the previous layer
   pipe_setup<COUT>(s, warp, lane, !(dbg_flags(p) & 128));
 
   const int band_begin = p.cta_band_off[blockIdx.x];

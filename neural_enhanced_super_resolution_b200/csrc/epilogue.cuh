@@ -147,7 +147,7 @@ __device__ __forceinline__ void epilogue16(const Params& p, const TileGeom& tg, 
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 b = __ldg(b4 + i);
+      const float4 b = b4[i];                                  // global or shared memory (conv3x3_fold.cu stages the layer's biases)
       v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
     }
   }

@@ -56,7 +56,7 @@ constexpr int kSlabBytes = kSlabPx * 128;          // 17408 = 17 * 1024
 constexpr int kMaxStages = 8;
 constexpr int kMaxSlots = 16;
 constexpr int kSmemBudget = 232448;                // 227 KB
-constexpr int kBarrierBytes = (1 + 2 * kMaxStages + 2 * kMaxSlots) * 8 + 16;
+constexpr int kBarrierBytes = (1 + 2 * kMaxStages + 2 * kMaxSlots) * 8 + 32 + 256;   // mbarriers, TMEM slot word (+ pad to 16 B), the layer's 64 biases
 
 template <int COUT>
 struct FoldCfg {
@@ -74,6 +74,7 @@ struct Pipe {
   uint8_t* ring;
   uint64_t *wbar, *full, *empty, *tfull, *tempty;
   uint32_t* tmem_slot;
+  float* bias;               // [64] biases of the layer pass (conv3x3_fold.cu copies them once per launch: the per-row epilogue reads them here)
   int nstage;
   uint32_t tmem_base;
 };
@@ -88,6 +89,7 @@ __device__ __forceinline__ Pipe carve_pipe(uint8_t* smem, int wbytes, int nstage
   s.tfull = s.empty + kMaxStages;
   s.tempty = s.tfull + kMaxSlots;
   s.tmem_slot = reinterpret_cast<uint32_t*>(s.tempty + kMaxSlots);
+  s.bias = reinterpret_cast<float*>(s.tmem_slot + 6);        // 49 mbarriers = 392 bytes, + 24: 16-byte aligned
   s.nstage = nstage;
   s.tmem_base = 0;
   return s;
@@ -354,7 +356,9 @@ template <int COUT, bool kTrunk>
 __device__ __forceinline__ void epilogue_bands(const ConvParams& p, const Pipe& s, uint32_t& u, int warp, int lane,
                                                int band_begin, int band_end) {
   using Cfg = FoldCfg<COUT>;
-  const EpiRegs e = make_epi_regs<kTrunk>(p);
+  EpiRegs e = make_epi_regs<kTrunk>(p);
+  if (!kTrunk) e.bias = s.bias;                              // one-layer launch: biases staged in shared memory (four global loads per 16
+                                                             // channels and row sat behind the accumulator wait: profiles/r2_edge_readside.txt)
   const FoldBand* const bands = p.bands;
   const FoldSeg* const segs = p.segs;
   const TileGeom* const tiles = p.tiles;
