@@ -363,6 +363,15 @@ __device__ __forceinline__ void epilogue_bands(const ConvParams& p, const Pipe& 
   const FoldSeg* const segs = p.segs;
   const TileGeom* const tiles = p.tiles;
   const int level = e.level, dbg = dbg_flags(p);
+  // The plain layer -- bias, LeakyReLU, one 16-bit store at the layer's own resolution: conv_up1, conv_up2, conv_hr, i.e. every
+  // 64-channel layer of the two up-sampled levels -- gets a straight-line epilogue.  The general path re-evaluates a dozen
+  // warp-uniform conditions per 16 channels (residuals, fp32 copies, up-sampled store, frame output, operand format): measured on
+  // conv_up2 it executed 600 instructions per warp and row, 280 of them branches and uniform compares, and the two epilogue groups --
+  // not the MMAs, not the memory system -- set the layer's pace (profiles/r2_edge_readside.txt).
+  const bool plain = !kTrunk && e.lrelu && !e.res1 && !e.res2 && !e.dst32a && !e.dst32b && e.dst16 && !e.dst16_up && !e.out_u8 &&
+                     !e.out_f32 && (e.dst16_coff & 63) + COUT <= 64 && e.cout == COUT && !(NESR_PROF && dbg);
+  uint16_t* const plain_dst = reinterpret_cast<uint16_t*>(e.dst16) + static_cast<size_t>(e.dst16_coff >> 6) * e.dst16_plane_px * 64 + (e.dst16_coff & 63);
+  const bool plain_fp16 = e.dst16_fmt != 0;
   const int quarter = warp & 3;
   const int group = (warp - 2) >> 2;                         // rows alternate between the epilogue groups
   const int m = quarter * 32 + lane;                         // A row == TMEM lane == pixel x0 + m
@@ -420,7 +429,32 @@ __device__ __forceinline__ void epilogue_bands(const ConvParams& p, const Pipe& 
       tc_fence_before();
       mbar_arrive(&s.tempty[slot]);
       PROF_END(1);
-      if (active) {
+      if (plain) {
+        if (active) {
+          uint16_t* const d = plain_dst + static_cast<size_t>(px.P) * 64;
+#pragma unroll
+          for (int c = 0; c < COUT / 16; ++c) {
+            float v[16];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float4 b = reinterpret_cast<const float4*>(s.bias)[c * 4 + q4];
+              v[4 * q4 + 0] = __uint_as_float(r[c][4 * q4 + 0]) + b.x; v[4 * q4 + 1] = __uint_as_float(r[c][4 * q4 + 1]) + b.y;
+              v[4 * q4 + 2] = __uint_as_float(r[c][4 * q4 + 2]) + b.z; v[4 * q4 + 3] = __uint_as_float(r[c][4 * q4 + 3]) + b.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.2f * v[k]);      // LeakyReLU(0.2): v >= 0 ? v : 0.2 v, the same bits without a predicate
+            uint32_t w[8];
+            if (plain_fp16) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) w[k] = pack2(v[2 * k], v[2 * k + 1], 1);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) w[k] = pack2(v[2 * k], v[2 * k + 1], 0);
+            }
+            stg256(d + c * 16, w);
+          }
+        }
+      } else if (active) {
 #pragma unroll
         for (int c = 0; c < COUT / 16; ++c) {
           if (c * 16 < e.cout) {
