@@ -369,7 +369,7 @@ __device__ __forceinline__ void epilogue_bands(const ConvParams& p, const Pipe& 
   // conv_up2 it executed 600 instructions per warp and row, 280 of them branches and uniform compares, and the two epilogue groups --
   // not the MMAs, not the memory system -- set the layer's pace (profiles/r2_edge_readside.txt).
   const bool plain = !kTrunk && e.lrelu && !e.res1 && !e.res2 && !e.dst32a && !e.dst32b && e.dst16 && !e.dst16_up && !e.out_u8 &&
-                     !e.out_f32 && (e.dst16_coff & 63) + COUT <= 64 && e.cout == COUT && !(NESR_PROF && dbg);
+                     !e.out_f32 && (e.dst16_coff & 63) + COUT <= 64 && e.cout == COUT && !(NESR_PROF && (dbg & ~32));   // timing switches other than the role timer use the general path
   uint16_t* const plain_dst = reinterpret_cast<uint16_t*>(e.dst16) + static_cast<size_t>(e.dst16_coff >> 6) * e.dst16_plane_px * 64 + (e.dst16_coff & 63);
   const bool plain_fp16 = e.dst16_fmt != 0;
   const int quarter = warp & 3;
