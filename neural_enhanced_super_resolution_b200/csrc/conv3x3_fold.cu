@@ -50,9 +50,11 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
     producer_bands(p, &amap, &amap8, s, rp, band_begin, band_end);
     __syncwarp();
   } else if (warp == 1) {
-    RingPos rp;
-    uint32_t u = 0;
-    mma_bands<COUT>(p, s, rp, u, 0, band_begin, band_end);
+    if (elect_one()) {             // single-thread issuer (fold_roles.cuh mma_bands, kSingle)
+      RingPos rp;
+      uint32_t u = 0;
+      mma_bands<COUT, true>(p, s, rp, u, 0, band_begin, band_end);
+    }
     __syncwarp();
   } else {
     pdl_wait();                    // residual reads / stores must not overtake the previous layer

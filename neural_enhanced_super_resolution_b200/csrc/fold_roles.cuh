@@ -257,7 +257,11 @@ __device__ __forceinline__ void producer_bands(const ConvParams& p, const CUtens
 // bubble in the MMA stream.  One input row is therefore ONE elected region: the barrier waits for all
 // of the row's slabs come first (warp-wide), then a single lane issues the row's 3 x k-steps MMAs of
 // every chunk, the commits that free the slabs and the commit that completes the output row.
-template <int COUT>
+// kSingle: the caller runs the role in ONE thread (the one-layer kernel): no elect / __syncwarp per row, and the barriers of the NEXT input
+// row are looked at (mbarrier.test_wait, non-blocking) between the MMA groups of the current one, so that in the steady state the thread goes
+// from a row's last commit straight to the next row's first MMA -- the tensor pipe queues only ~2 MMAs (tools/commit_probe.cu), and the
+// warp-wide version left it idle for ~0.9k of the 2.4k cycles a row took on the level-2 edge layers (profiles/r2_edge_readside.txt).
+template <int COUT, bool kSingle = false>
 __device__ __forceinline__ void mma_bands(const ConvParams& p, const Pipe& s, RingPos& rp, uint32_t& u, uint32_t wphase,
                                           int band_begin, int band_end) {
   using Cfg = FoldCfg<COUT>;
@@ -286,14 +290,15 @@ __device__ __forceinline__ void mma_bands(const ConvParams& p, const Pipe& s, Ri
       const uint32_t v = u + j;
       mbar_wait(&s.tempty[v % Cfg::kSlots], ((v / Cfg::kSlots) & 1) ^ 1);
     }
+    bool ready = false;                                    // kSingle: this row's barriers were seen complete during the previous row
     for (int i = 0; i < rows + 2; ++i) {
       PROF_BEGIN();
-      {                                                    // slot of output row i+2 must be drained + zeroed
+      if (!ready) {                                        // slot of output row i+2 must be drained + zeroed
         const uint32_t v = u + i + 2;
         mbar_wait(&s.tempty[v % Cfg::kSlots], ((v / Cfg::kSlots) & 1) ^ 1);
       }
       PROF_END(0);
-      {                                                    // every slab of this input row has landed
+      if (!ready) {                                        // every slab of this input row has landed
         int st = rp.stage;
         uint32_t ph = rp.phase;
         for (int c = 0; c < nchunk; ++c) {
@@ -309,7 +314,7 @@ __device__ __forceinline__ void mma_bands(const ConvParams& p, const Pipe& s, Ri
       uint32_t id0 = idesc3, id1 = 0, b1 = 0;
       if (q + 2 == Cfg::kSlots) { id0 = idesc2; id1 = idesc1; b1 = (2 * COUT * 128) >> 4; }
       else if (q + 1 == Cfg::kSlots) { id0 = idesc1; id1 = idesc2; b1 = (COUT * 128) >> 4; }
-      if (elect_one()) {
+      if (kSingle || elect_one()) {
         int st = rp.stage;
         for (int c = 0; c < nchunk; ++c) {
           const uint32_t a_lo = a_lo0 + st * kSlabLo;
@@ -318,6 +323,20 @@ __device__ __forceinline__ void mma_bands(const ConvParams& p, const Pipe& s, Ri
             if (c + 1 < nchunk || last_ks == 4) {
 #pragma unroll
               for (int dxi = 0; dxi < 3; ++dxi) {
+                if (kSingle && dxi == 2 && c + 1 == nchunk) {   // with two MMA groups queued: are the next row's slot and slabs there?
+                  ready = false;
+                  if (i + 1 < rows + 2) {
+                    const uint32_t v = u + i + 3;
+                    ready = mbar_test_wait(&s.tempty[v % Cfg::kSlots], ((v / Cfg::kSlots) & 1) ^ 1);
+                    int st2 = rp.stage + nchunk;
+                    uint32_t ph2 = rp.phase;
+                    if (st2 >= nstage) { st2 -= nstage; ph2 ^= 1; }
+                    for (int c2 = 0; c2 < nchunk && ready; ++c2) {
+                      ready = mbar_test_wait(&s.full[st2], ph2);
+                      if (++st2 == nstage) { st2 = 0; ph2 ^= 1; }
+                    }
+                  }
+                }
                 umma_f16_ksteps<4>(d0, a_lo + dxi * 8, b_lo + dxi * dx_lo, hi, id0);
                 if (id1) umma_f16_ksteps<4>(tmem_base, a_lo + dxi * 8, b_lo + dxi * dx_lo + b1, hi, id1);
               }
@@ -338,7 +357,7 @@ __device__ __forceinline__ void mma_bands(const ConvParams& p, const Pipe& s, Ri
           umma_commit(&s.tfull[(u + i + 2) % Cfg::kSlots]);
         }
       }
-      __syncwarp();
+      if (!kSingle) __syncwarp();
       PROF_END(2);
       rp.stage += nchunk;
       if (rp.stage >= nstage) { rp.stage -= nstage; rp.phase ^= 1; }

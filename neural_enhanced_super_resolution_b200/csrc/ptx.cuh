@@ -70,6 +70,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking look: mbarrier.try_wait suspends the thread for a hardware time limit before it answers "not yet"; test_wait answers at once.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU box.
 #ifndef NESR_HANG_GUARD_CYCLES
 #define NESR_HANG_GUARD_CYCLES (4000000000LL)   // ~2-3 s at B200 clocks
