@@ -3,7 +3,7 @@
 // The roles (TMA producer, MMA issuer, epilogue warps) and the reasoning behind the row fold live in
 // fold_roles.cuh.  This kernel runs the six edge layers of the network (conv_first, conv_body,
 // conv_up1/2, conv_hr, conv_last); the 69 residual dense blocks in between run inside the persistent
-// kernel of conv3x3_body.cu, which uses the same roles.  (conv_impl = 3 runs every layer through this
+// kernels (conv3x3_trunk.cu; conv3x3_body.cu, which uses the same roles).  (conv_impl = 3 runs every layer through this
 // kernel -- the previous production path, kept as a cross-check.)
 //
 // Layers with Cout = 64 and Cin > 64 (RDB conv5) run as two passes of 32 output channels so that

@@ -24,6 +24,13 @@
 // epilogue warps drain rows in order while the MMAs run ahead: tcgen05.ld -> fused epilogue
 // (epilogue.cuh) -> tcgen05.st zeros (every MMA accumulates; a slot is handed back zeroed).
 // Rows just outside a band are "virtual": they receive partial sums and are dropped.
+//
+// One-layer kernel only (end of round 2, profiles/r2_edge_readside.txt):
+//   * src_up: the layer reads its input nearest-x2 up-sampled (conv_up1 / conv_up2).  The producer loads through a zero-stride
+//     "every pixel twice" tensor map of the layer BELOW, from source row y >> 1; slabs start at the even pixel x0 - 2 and the A
+//     descriptors one pixel later.  The TMA engine does the replication: no instruction and no shared-memory traffic on the SM.
+//   * the MMA role runs in one thread and looks at the next row's barriers between the MMA groups of the current row;
+//   * plain layers (bias, LeakyReLU, one 16-bit store) have a straight-line epilogue; the layer's biases sit in shared memory.
 #pragma once
 #include <stdio.h>
 
