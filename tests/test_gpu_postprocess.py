@@ -118,3 +118,32 @@ def test_blend_lattice_and_sizes(engine, golden):
     assert np.array_equal(engine.blend_u8(dev).cpu().numpy(), O.ensemble_results(ms))
     with pytest.raises(RuntimeError):
         engine.blend_u8([ms[0]])
+
+
+@pytest.mark.skipif(torch.cuda.is_available() and torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_engine_on_another_gpu_leaves_the_current_device_alone():
+    """Every C-ABI entry sets the handle's device for the duration of the call and restores the caller's (csrc/engine.cu DeviceGuard):
+    an engine on cuda:1 must not move torch's current device, and its results are the ones of an engine on cuda:0."""
+    assert torch.cuda.current_device() == 0
+    img = natural_image(70, 90, seed=4)
+    other = np.ascontiguousarray(img[::-1])
+    eng1 = _ffi.Engine(device=1, num_block=1)
+    try:
+        assert torch.cuda.current_device() == 0
+        a = eng1.sharpen_u8(img)
+        assert torch.cuda.current_device() == 0
+        b = eng1.blend_u8([img, other])
+        c = eng1.preprocess_u8(img, denoise_level=0.3)
+        d = eng1.sharpen_u8(torch.from_numpy(img).to("cuda:1"))
+        assert torch.cuda.current_device() == 0 and d.device.index == 1
+        with pytest.raises(ValueError):
+            eng1.sharpen_u8(torch.from_numpy(img).to("cuda:0"))          # a tensor on another GPU is an error, not a peer access
+        t = torch.ones(4, device="cuda")                                    # torch still allocates on cuda:0
+        assert t.device.index == 0
+    finally:
+        eng1.close()
+    assert torch.cuda.current_device() == 0
+    assert np.array_equal(a, O.postprocess_image(img)) and np.array_equal(b, O.ensemble_results([img, other]))
+    assert np.array_equal(d.cpu().numpy(), a)
+    from oracle import preprocess as P
+    assert np.array_equal(c, P.preprocess_image(img, 0.3))
