@@ -179,39 +179,50 @@ __global__ void __launch_bounds__(256) sharpen_mma_kernel(const uint8_t* __restr
 #pragma unroll
   for (int vb = 0; vb < kTH / 16; ++vb) {
     const int cb = warp;
-    int blur[4][4];                                              // [plane][accumulator]
-#pragma unroll
-    for (int plane = 0; plane < 4; ++plane) {
-      if (kExtMask && plane == 3) continue;
+    const int ox = 8 * cb + 2 * t;
+    auto column_blur = [&](int plane, const uint32_t (&af)[4], int (&out4)[4]) {      // the block's four blurred values of one plane
       const uint32_t* hi = reinterpret_cast<const uint32_t*>(&s_t[plane][0][8 * cb + g][16 * vb + 4 * t]);
       const uint32_t* lo = reinterpret_cast<const uint32_t*>(&s_t[plane][1][8 * cb + g][16 * vb + 4 * t]);
       int dh[4] = {0, 0, 0, 0}, dl[4] = {32768, 32768, 32768, 32768};   // the rounding constant rides in the accumulator
-      if (plane == 3) { imma(dh, a2, hi[0], hi[4]); imma(dl, a2, lo[0], lo[4]); }
-      else { imma(dh, a3, hi[0], hi[4]); imma(dl, a3, lo[0], lo[4]); }
+      imma(dh, af, hi[0], hi[4]);
+      imma(dl, af, lo[0], lo[4]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) blur[plane][i] = static_cast<int>((static_cast<uint32_t>(dh[i]) * 256u + static_cast<uint32_t>(dl[i])) >> 16);
-    }
-    const int ox = 8 * cb + 2 * t;
+      for (int i = 0; i < 4; ++i) out4[i] = static_cast<int>((static_cast<uint32_t>(dh[i]) * 256u + static_cast<uint32_t>(dl[i])) >> 16);
+    };
+    // the mask of the thread's four pixels first: where no pixel of the warp's 16 x 8 block is selected (flat regions of a photo, most of
+    // a segmentation mask's background) the three colour blurs are not needed and the block is a copy
+    bool mask[2][2];
+    if (kExtMask) {
 #pragma unroll
-    for (int hrow = 0; hrow < 2; ++hrow) {
-      const int oy = 16 * vb + g + 8 * hrow;
-      const int gy = y0 + oy;
-      bool mask[2];
-      if (kExtMask) {
+      for (int hrow = 0; hrow < 2; ++hrow)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int gx = x0 + ox + e;
+          const int gy = y0 + 16 * vb + g + 8 * hrow, gx = x0 + ox + e;
           int m = 0;
           if (gy < H && gx < W)
             for (int yy = max(gy - 1, 0); yy <= min(gy + 1, H - 1); ++yy)
               for (int xx = max(gx - 1, 0); xx <= min(gx + 1, W - 1); ++xx) m = max(m, static_cast<int>(__ldg(ext_mask + static_cast<size_t>(yy) * W + xx)));
-          mask[e] = m == 1;                                      // np.where(mask == 1, ...): another label selects nothing
+          mask[hrow][e] = m == 1;                                // np.where(mask == 1, ...): another label selects nothing
         }
-      } else {
-        const uint32_t gray2 = *reinterpret_cast<const uint16_t*>(&s_in[3][oy + kHalo][ox + kHalo]);
-        mask[0] = static_cast<int>(gray2 & 255) - blur[3][2 * hrow] > 10;          // saturating subtract, then threshold
-        mask[1] = static_cast<int>(gray2 >> 8) - blur[3][2 * hrow + 1] > 10;
+    } else {
+      int g2[4];
+      column_blur(3, a2, g2);
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        const uint32_t gray2 = *reinterpret_cast<const uint16_t*>(&s_in[3][16 * vb + g + 8 * hrow + kHalo][ox + kHalo]);
+        mask[hrow][0] = static_cast<int>(gray2 & 255) - g2[2 * hrow] > 10;             // saturating subtract, then threshold
+        mask[hrow][1] = static_cast<int>(gray2 >> 8) - g2[2 * hrow + 1] > 10;
       }
+    }
+    const bool any = __any_sync(0xffffffffu, mask[0][0] | mask[0][1] | mask[1][0] | mask[1][1]);
+    int blur[3][4] = {};
+    if (any) {                                                   // warp-uniform: the MMAs below are warp-wide
+#pragma unroll
+      for (int plane = 0; plane < 3; ++plane) column_blur(plane, a3, blur[plane]);
+    }
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int oy = 16 * vb + g + 8 * hrow;
       uint32_t res[2][3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -220,7 +231,7 @@ __global__ void __launch_bounds__(256) sharpen_mma_kernel(const uint8_t* __restr
         for (int e = 0; e < 2; ++e) {
           const int a = static_cast<int>((a2px >> (8 * e)) & 255);
           int v = a;
-          if (mask[e]) {
+          if (mask[hrow][e]) {
             const int t2 = 3 * a - blur[c][2 * hrow + e];        // twice (1.5 a - 0.5 b)
             const int half = t2 >> 1;                            // floor
             v = half + ((t2 & 1) & (half & 1));                  // ties to even

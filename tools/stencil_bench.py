@@ -35,3 +35,22 @@ for (H, W) in ((2160, 3840), (4320, 7680)):
         t = float(np.median(ms[3:]))
         gbs = bytes_px * H * W / (t * 1e-3) / 1e9
         print(f"{name:10s} {W}x{H}: {t:.3f} ms  {H * W / t / 1e3:.0f} Mpix/s  algorithmic {gbs:.0f} GB/s = {100 * gbs / peak:.1f} % of the measured HBM peak ({peak:.0f} GB/s)")
+
+# the sharpen kernel skips the colour blurs of 16 x 8 blocks without a selected pixel: a photo-like image (smooth structure + mild noise) beside the noise above
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from gpu_common import natural_image  # noqa: E402
+H, W = 2160, 3840
+import cv2  # noqa: E402
+base = natural_image(H, W, seed=1)
+for name, host in (("photo-like", base), ("smooth (the photo-like image blurred, sigma 3)", cv2.GaussianBlur(base, (0, 0), 3))):
+    photo = torch.from_numpy(host).cuda()
+    out = torch.empty_like(photo)
+    ms = []
+    for it in range(8):
+        flush.fill_(it)
+        eng.sharpen_u8(photo, out=out)
+        ms.append(eng.stats()["last_device_ms"])
+    t = float(np.median(ms[3:]))
+    sel = float((out != photo).any(dim=2).float().mean())
+    print(f"sharpen    {W}x{H} {name} ({100 * sel:.1f} % of the pixels changed): {t:.3f} ms  algorithmic {6 * H * W / (t * 1e-3) / 1e9:.0f} GB/s = "
+          f"{100 * 6 * H * W / (t * 1e-3) / 1e9 / peak:.1f} % of the measured HBM peak")
