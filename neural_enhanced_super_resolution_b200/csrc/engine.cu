@@ -60,6 +60,9 @@ struct LevelPlan {
   FoldSeg* d_segs = nullptr;
   int32_t* d_cta_off = nullptr;
   int fold_grid = 0;
+  bool row_capped = false;     // level 0: the schedule was built under the trunk kernel's rules (<= 8 rows per CTA, pieces of a packed strip cut at
+                               // multiples of 8 tile rows).  The free schedule a group falls back to may also keep every CTA at <= 8 rows, but its
+                               // pieces are not phase aligned: it must never run on the trunk kernel.
   std::vector<int32_t> deps;   // level 0 only: [grid][kTrunkMaxDeps] CTAs owning pixels of a CTA's input slab rows (empty: too many)
   int32_t* d_deps = nullptr;
   std::vector<uint8_t> need;   // level 0 only: [grid][kTrunkMaxSlabRows][kTrunkMaxDeps] rows each dependency must have stored per slab row
@@ -486,10 +489,13 @@ bool build_fold_schedule(Batch& b, int level, int num_sms, int max_rows = 0, int
     };
     int best_T = 1 << 30;
     int64_t best = plan(best_T, nullptr);                       // no cutting
+    std::vector<int> tried;                                     // a T is evaluated once (same order, same winner: many columns share a height)
     for (const Piece& c : cols)
       for (int n = 2; n <= 16; ++n) {
         const int T = (c.h + n - 1) / n;
         if (T < 8) break;
+        if (std::find(tried.begin(), tried.end(), T) != tried.end()) continue;
+        tried.push_back(T);
         const int64_t cost = plan(T, nullptr);
         if (cost < best) { best = cost; best_T = T; }
       }
@@ -731,9 +737,10 @@ int plan_groups_with_cap(nesr_b200_handle* h, const PlanKey& key, int out_h, int
   // level-0 schedule of a group and whether the TMEM-resident trunk kernel can run it
   auto sched0 = [&](Batch& bb) {                                // row-capped for the trunk kernel; a group that cannot fit keeps the free schedule
     layout_level(bb, 0);
-    if (!l2_groups || !build_fold_schedule(bb, 0, h->num_sms, kTrunkMaxRows, pieces)) build_fold_schedule(bb, 0, h->num_sms);
+    bb.lv[0].row_capped = l2_groups && build_fold_schedule(bb, 0, h->num_sms, kTrunkMaxRows, pieces);
+    if (!bb.lv[0].row_capped) build_fold_schedule(bb, 0, h->num_sms);
   };
-  auto fits0 = [&](const Batch& bb) { return trunk_schedule_fits(bb.lv[0]); };
+  auto fits0 = [&](const Batch& bb) { return bb.lv[0].row_capped && trunk_schedule_fits(bb.lv[0]); };
   auto tile_px = [&](const TileGeom& t) { return (int64_t)t.lv[0].h * t.lv[0].pitch; };
   std::vector<std::vector<int>> groups;                         // tile indices (into `all`) of every group
   if (l2_groups) {
@@ -743,20 +750,30 @@ int plan_groups_with_cap(nesr_b200_handle* h, const PlanKey& key, int out_h, int
     std::vector<int> order(all.size());
     for (size_t i = 0; i < all.size(); ++i) order[i] = (int)i;
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tile_px(all[x]) > tile_px(all[y]); });
-    std::vector<int64_t> gpx;
+    // A probe builds the group's whole level-0 schedule; with hundreds of small tiles (tile 128 on a 4K frame: 510) probing every open
+    // group for every tile took minutes.  Strip rows a tile needs AT LEAST -- its full strips, plus its remainder column's lanes at the
+    // 136 slab lanes of a packed strip row -- bound a group from below: a group whose bound exceeds the TMEM row budget cannot fit.
+    auto min_rows = [&](const TileGeom& t) {
+      const int w = t.lv[0].w, h = t.lv[0].h, rem = w % kBlockPixels;
+      return (int64_t)h * (w / kBlockPixels) + (rem ? (int64_t)h * ((rem + 2 + 7) / 8 * 8) / 136 : 0);   // rounded DOWN: a bound, never an estimate
+    };
+    const int64_t row_budget = (int64_t)kTrunkMaxRows * h->num_sms;
+    std::vector<int64_t> gpx, grows;
     for (int ti : order) {
-      const int64_t n = tile_px(all[ti]);
+      const int64_t n = tile_px(all[ti]), nr = min_rows(all[ti]);
       bool placed = false;
       for (size_t g = 0; g < groups.size() && !placed; ++g) {
         if (gpx[g] + n > cap) continue;
+        if (h->cfg.max_batch_pixels == 0 && grows[g] + nr > row_budget) continue;      // (an explicit pixel cap keeps the probes: groups may
+                                                                                       // exceed the trunk kernel's budget there on purpose)
         Batch probe;
         for (int k : groups[g]) probe.tiles.push_back(all[k]);
         probe.tiles.push_back(all[ti]);
         sched0(probe);
         if (!fits0(probe)) continue;
-        groups[g].push_back(ti); gpx[g] += n; placed = true;
+        groups[g].push_back(ti); gpx[g] += n; grows[g] += nr; placed = true;
       }
-      if (!placed) { groups.push_back({ti}); gpx.push_back(n); }
+      if (!placed) { groups.push_back({ti}); gpx.push_back(n); grows.push_back(nr); }
     }
     for (auto& g : groups) std::sort(g.begin(), g.end());
     std::sort(groups.begin(), groups.end(), [](const std::vector<int>& x, const std::vector<int>& y) { return x.front() < y.front(); });
@@ -1641,7 +1658,14 @@ int nesr_b200_debug_plan(int32_t n_frames, int32_t H, int32_t W, int32_t tile, i
               for (int sgi = 0; sgi < band.nseg; ++sgi) {
                 const FoldSeg& sg = lp.segs[band.seg0 + sgi];
                 if (band.r0 >= sg.h) continue;
-                if (res >= 0 && res != ((sg.y0 + band.r0) & 7)) return fail(nullptr, NESR_E_STATE, "group %zu: packed pieces out of phase", bi);
+                if (res >= 0 && res != ((sg.y0 + band.r0) & 7)) {
+                  if (getenv("NESR_B200_PLAN_DEBUG"))
+                    for (int k2 = 0; k2 < band.nseg; ++k2) {
+                      const FoldSeg& s2 = lp.segs[band.seg0 + k2];
+                      fprintf(stderr, "  band r0 %d rows %d: seg %d tile %d x0 %d width %d lane0 %d y0 %d h %d\n", band.r0, band.rows, k2, s2.tile, s2.x0, s2.width, s2.lane0, s2.y0, s2.h);
+                    }
+                  return fail(nullptr, NESR_E_STATE, "group %zu: packed pieces out of phase", bi);
+                }
                 res = (sg.y0 + band.r0) & 7;
               }
             }

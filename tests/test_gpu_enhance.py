@@ -162,6 +162,20 @@ def test_c2_crop_1024_tile512_within_tolerance():
     _check_tolerance(out, want, "C2 crop 1024x1024 tile=512 halo=10")
 
 
+def test_group_that_only_fits_with_unaligned_pieces_is_split():
+    """952 x 670, tile 300, halo 10: eight of its tiles fit one tile group only under the FREE level-0 schedule (remainder pieces cut every
+    31 rows); the trunk kernel's schedule (pieces cut at multiples of 8 tile rows: layout.h trunk_order) needs a few rows more than 148 x 8.
+    The planner used to accept the free schedule because every CTA still had <= 8 rows (found by the seeded planner sweep of
+    tests/test_plan_cpu.py); now the group is split.  Index work bit-exact, product kernel against per-layer launches, repeatable."""
+    img = natural_image(952, 670, seed=3)
+    assert np.array_equal(gpu_up("identity", 300, 10).enhance(img)[0], identity_expected(img))
+    a, _ = gpu_up("calibrated", 300, 10).enhance(img)
+    b, _ = gpu_up("calibrated", 300, 10, conv_impl=3).enhance(img)
+    d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 5e-2
+    assert np.array_equal(a, gpu_up("calibrated", 300, 10).enhance(img)[0])
+
+
 def test_c2_full_frame_product_kernel_vs_per_layer_launches():
     """1920x1080, tile 512, halo 10 (12 tiles, three tile groups): the product trunk kernel (conv_impl 0: neighbour
     progress words, TMEM-resident bands) against one launch per layer pass (conv_impl 3: stream order is the only
